@@ -1,0 +1,45 @@
+"""Shared fixtures for the parity tests: the small synthetic world the golden vectors were generated on
+(must mirror oracle/gen_golden.py: RASTER_KW / EXTENT / weight seed 0)."""
+import os
+
+import numpy as np
+import torch
+
+from strive_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+RASTER_KW = dict(seed=3, M=2, H=1280, W=1280)
+EXTENT = (90.0, 230.0)
+REFINE_W = {'coll_veh': 100.0, 'coll_env': 100.0, 'motion_prior': 1.0, 'init_z': 0.01}
+ADV_W = {'coll_veh': 20.0, 'coll_veh_plan': 20.0, 'coll_env': 20.0, 'init_z': 0.5, 'init_z_atk': 0.05,
+         'motion_prior': 1.0, 'motion_prior_atk': 0.005, 'motion_prior_ext': 0.0001, 'match_ext': 10.0,
+         'adv_crash': 2.0}
+SOL_W = {'motion_prior': 0.005, 'coll_veh': 10.0, 'coll_env': 10.0, 'motion_prior_ext': 0.001,
+         'match_ext': 10.0, 'init_z': 0.0}
+
+_cache = {}
+
+
+def world():
+    """raster, dx, weights for the golden world; verifies the regenerated inputs against stored checksums."""
+    if 'w' not in _cache:
+        raster, dx = synth.make_raster(**RASTER_KW)
+        sd = synth.make_weights(0)
+        meta = np.load(os.path.join(GOLD, 'meta.npz'))
+        assert float(raster.double().sum()) == float(meta['raster_sum'])
+        wsum = synth.checksum(torch.cat([v.reshape(-1) for v in sd.values()]))
+        assert abs(wsum - float(meta['weights_sum'])) < 1e-9, 'seeded weights did not regenerate identically'
+        assert np.array_equal(dx.numpy(), meta['dx'])
+        _cache['w'] = (raster, dx, sd)
+    return _cache['w']
+
+
+def golden(name):
+    return np.load(os.path.join(GOLD, name + '.npz'))
+
+
+def scene_for(g, **kw):
+    sizes = [int(v) for v in g['sizes']]
+    args = dict(map_extent_m=EXTENT, M=2, FT=int(g['FT']), collide_frac=1.0, offroad_frac=1.0)
+    args.update(kw)
+    return synth.make_scenes(int(g['seed']), sizes, **args)
