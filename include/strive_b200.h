@@ -1,0 +1,166 @@
+/*
+ * strive_b200 -- C ABI of the B200-native STRIVE latent-optimisation hot path.
+ *
+ * The reference (nv-tlabs/STRIVE) has no native/FFI boundary: its hot path is the Python method surface
+ *   TrafficModel.decode_embedding                 src/models/traffic_model.py:405-414 (-> 589-704)
+ *   TrafficModel.encode_map                       src/models/traffic_model.py:416-451
+ *   AvoidCollLoss / AdvGenLoss / TgtMatchingLoss  src/losses/adv_gen_nusc.py:14-341
+ *   torch.optim.Adam on z                         src/refine_traffic_optim.py:163-218, utils/*_optim.py
+ * These entry points are what a ctypes binding under those methods calls (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch) owns all memory,
+ *     including workspaces; the library keeps no state between calls except the opaque model handle.
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), one device per process.
+ *   - return 0 on success; otherwise an error code and strive_last_error() describes it (the Python wrapper
+ *     raises RuntimeError so the drivers' `except RuntimeError` batch-skip keeps working,
+ *     src/refine_traffic_optim.py:381-388).
+ *   - float = fp32, state/feature layouts are row-major exactly as the reference tensors.
+ */
+#ifndef STRIVE_B200_H
+#define STRIVE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STRIVE_ABI_VERSION 1
+
+typedef struct StriveModel StriveModel;
+
+/* ---- error handling ---------------------------------------------------------------------------------- */
+const char* strive_last_error(void);
+int strive_abi_version(void);
+/* sizeof/offsetof table of the ABI structs so foreign bindings can verify their layout (returns count) */
+int strive_struct_layout(int64_t* out, int max_n);
+
+/* ---- model weights -------------------------------------------------------------------------------------
+ * Replaces: torch state_dict of decoder_net.*, decoder_memory.*, map_conv.*, map_feature.* loaded by
+ * utils/torch.py:32-60 (load_state).  `blob` is a device buffer packed by strive_b200/weights.py in the
+ * segment order returned by strive_model_layout(); seg_sizes_host (n_segs int64) is checked against it. */
+int strive_model_layout(int num_classes, int64_t* seg_sizes_host, int max_segs, int* n_segs_out);
+int strive_model_create(const float* blob, int64_t blob_floats, const int64_t* seg_sizes_host, int n_segs,
+                        int num_classes, StriveModel** out);
+void strive_model_destroy(StriveModel* m);
+
+/* ---- scene description (all device) --------------------------------------------------------------------
+ * Mirrors the torch_geometric Batch the drivers build (src/datasets/nuscenes_dataset.py:609-687): edges are
+ * the full directed clique inside each scene, so only `ptr` is needed. */
+typedef struct StriveScene {
+  int32_t num_agents;          /* NA */
+  int32_t num_scenes;          /* S  */
+  int32_t max_scene_agents;    /* host-known max(ptr[s+1]-ptr[s]); must be <= 255 */
+  int32_t num_classes;         /* NC */
+  const int32_t* ptr;          /* (S+1) */
+  const int32_t* scene_of;     /* (NA) scene id per agent (= Batch.batch) */
+  const int32_t* map_idx;      /* (S) map id per scene */
+  const float* past_last;      /* (NA,6) normalised last past state  = scene_graph.past[:, -1, :] */
+  const float* lw;             /* (NA,2) normalised length/width */
+  const float* sem;            /* (NA,NC) one-hot class */
+} StriveScene;
+
+typedef struct StriveMap {
+  const uint8_t* raster;       /* (M,C,H,W) uint8 = NuScenesMapEnv.nusc_raster, src/datasets/map_env.py:165 */
+  const double* dx;            /* (M,2) float64 metres/pixel = nusc_dx, map_env.py:166 */
+  int32_t M, C, H, W;
+  const float* lin_l;          /* (256) torch.linspace(bounds[0], bounds[2], 256) float32, nuscenes_utils.py:219 */
+  const float* lin_w;          /* (256) torch.linspace(bounds[1], bounds[3], 256) float32, nuscenes_utils.py:220 */
+} StriveMap;
+
+/* ---- map encoder ---------------------------------------------------------------------------------------
+ * Replaces TrafficModel.encode_map + NuScenesMapEnv.get_map_crop + get_map_obs + map_conv + map_feature.
+ * pose_un: (N,4) UNNORMALISED (x,y,hx,hy); map_of: (N) map id per pose; out: (N,64).
+ * workspace: strive_mapenc_workspace_bytes(N) bytes. */
+int64_t strive_mapenc_workspace_bytes(int32_t n);
+int strive_mapenc_fwd(const StriveModel* m, const StriveMap* map, const float* pose_un, const int32_t* map_of,
+                      int32_t n, float* out_feat, void* workspace, int64_t workspace_bytes, void* stream);
+/* test hook: the gathered crop itself, (N,4,256,256) uint8 (reference get_map_obs output) */
+int strive_map_crop(const StriveMap* map, const float* pose_un, const int32_t* map_of, int32_t n,
+                    uint8_t* out_crop, void* stream);
+
+/* ---- decoder rollout -----------------------------------------------------------------------------------
+ * Replaces TrafficModel.decode_embedding -> autoregressive_decoder (traffic_model.py:589-704), single-sample
+ * branch (z (NA,32)); the NS=1 3-D z of sol_optim.py:38-44 is the same computation on a view.
+ *   z, map_feat0, past_feat0: (NA,32),(NA,64),(NA,64); ext_future: (S,FT,4) normalised or NULL
+ *   traj_out: (NA,FT,4) normalised global (x,y,hx,hy) = 'future_pred'
+ *   tape: strive_decode_tape_bytes(NA,FT) bytes, consumed by strive_decode_bwd.
+ * strive_decode_bwd may be called several times per forward with different d_traj seeds (adv/sol loops decode
+ * twice with identical values and different detach masks, utils/adv_gen_optim.py:119-130); d_z is OVERWRITTEN. */
+int64_t strive_decode_tape_bytes(int32_t num_agents, int32_t ft);
+int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, const StriveMap* map, const float* z,
+                      const float* map_feat0, const float* past_feat0, const float* ext_future, int32_t ft,
+                      float* traj_out, void* tape, int64_t tape_bytes, void* stream);
+int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, int32_t ft, const float* ext_future,
+                      const float* d_traj, float* d_z, void* tape, int64_t tape_bytes, void* stream);
+/* test hook: copies one named tape tensor of step t to `out` (float). names: x,P,Q,aggr,past_feat,map_feat,prev,pos,loc,mem */
+int strive_decode_tape_read(const void* tape, int32_t num_agents, int32_t ft, const char* name, int32_t t,
+                            float* out, void* stream);
+
+/* ---- losses --------------------------------------------------------------------------------------------
+ * One fused forward+backward evaluation of the reference loss modules on a decoded future.
+ * Loss-normalisation groups = the batches the reference driver would have formed (every .mean() in
+ * adv_gen_nusc.py is over one such batch); a group is a contiguous range of scenes (hence of agents).
+ * Collision blocks = the sets of agents that may collide with each other: the whole group for
+ * AvoidCollLoss(ptr=None) as built by refine_traffic_optim.py:176-181; one scene when ptr is given
+ * (adv_gen_optim.py:76-84, sol_optim.py:57-63).  Blocks are contiguous agent ranges. */
+#define STRIVE_LOSS_AVOID 1   /* AvoidCollLoss.forward      adv_gen_nusc.py:303-341 */
+#define STRIVE_LOSS_ADV   2   /* AdvGenLoss.forward         adv_gen_nusc.py:93-262  */
+#define STRIVE_LOSS_MATCH 4   /* TgtMatchingLoss.forward    adv_gen_nusc.py:27-51 (incl. the :46 quirk) */
+
+typedef struct StriveLossCfg {
+  int32_t kind;                /* bitmask of STRIVE_LOSS_*; AVOID and ADV are mutually exclusive */
+  int32_t traj_unnormalized;   /* 1: traj/targets/d_traj are in UNNORMALISED units (the reference loss modules' own
+                                  calling convention); 0: normalised decoder output (fused loop) */
+  int32_t num_groups;
+  const int32_t* group_agent_ptr; /* (G+1) agent ranges of the groups */
+  const int32_t* group_of;     /* (NA) group per agent */
+  const int32_t* agent_map;    /* (NA) map id per agent (= mapixes of the reference loss constructors) */
+  const int32_t* group_zrows;  /* (G) number of latent rows that enter the prior/init means of the group */
+  const int32_t* group_match_rows; /* (G) number of (agent,t) rows in the match mean, or NULL */
+  const int32_t* cblock_ptr;   /* (NB+1) agent ranges of collision blocks */
+  const int32_t* cblock_of;    /* (NA) collision block per agent */
+  float w_coll_veh, w_coll_env, w_motion_prior, w_init_z;
+  float w_coll_veh_plan, w_init_z_atk, w_motion_prior_atk, w_adv_crash, w_match_ext, w_motion_prior_ext;
+  float veh_coll_buffer;
+  int32_t single_veh_idx;      /* -1 = all agents; k = only pairs/rows involving agent ptr[s]+k (sol_optim.py:57-63) */
+  int32_t crash_min_t;
+  int32_t use_infront;         /* crash_loss_min_infront is not None */
+  float crash_min_infront;
+  const int32_t* attack_mask;  /* (NA) 1 = allowed attacker (attack_agt_idx), or NULL = all */
+  int32_t* adv_min_out;        /* (S,2) OUT: (min_agt local index, min_t) of the softmin arg-max, or NULL (:137-138) */
+  const int32_t* env_L;        /* (G) get_coll_point grid, nuscenes_utils.py:351-354, computed on host per group */
+  const int32_t* env_W;
+  const float* env_lin_l;      /* (G,128) torch.linspace(-1,1,L) zero padded */
+  const float* env_lin_w;      /* (G,128) */
+  const float* circ_cx;        /* (NA,5) VehCollLoss centre offsets, adv_gen_nusc.py:432-437 (torch.linspace) */
+  const float* lw_un;          /* (NA,2) unnormalised length/width */
+} StriveLossCfg;
+
+#define STRIVE_TERMS 16
+/* terms (G,16) float: [0] loss of the AVOID/ADV module  [1] coll_veh mean [2] coll_veh count [3] coll_env mean
+ * [4] coll_env count [5] motion_prior mean [6] init term (mean for AVOID, weighted sum for ADV) [7] coll_veh_plan mean
+ * [8] coll_veh_plan count [9] adv_crash mean [10] match_ext mean [11] loss of the MATCH module */
+int64_t strive_loss_workspace_bytes(int32_t num_agents, int32_t ft, int32_t num_groups);
+/* traj: (NA,FT,4) NORMALISED decoder output.  z/prior_mu/prior_var/init_z: (NA,32) rows in graph order; rows with
+ * z_mask[a]==0 carry no latent term (z_mask NULL = all rows).  match_tgt (NA,FT,4) normalised + match_mask (NA,FT)
+ * select the rows of the MATCH mean.  adv_tgt (S,FT,4) normalised = planner trajectory attacked by ADV.
+ * outputs: d_traj / d_traj_match (NA,FT,4) gradients wrt the NORMALISED traj of the AVOID|ADV and MATCH modules
+ * (separate seeds: the reference routes them to different latents), d_z_direct (NA,32). */
+int strive_loss_fwd_bwd(const StriveLossCfg* cfg, const StriveScene* sc, const StriveMap* map, int32_t ft,
+                        const float* traj, const float* z, const float* prior_mu, const float* prior_var,
+                        const float* init_z, const uint8_t* z_mask, const float* match_tgt,
+                        const uint8_t* match_mask, const float* adv_tgt,
+                        float* d_traj, float* d_traj_match, float* d_z_direct, float* terms,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- fused Adam on z (torch.optim.Adam defaults: betas (0.9,0.999), eps 1e-8, no weight decay) ---------
+ * g = g_a + g_b (g_b may be NULL); step_count is the 1-based step number. */
+int strive_adam_step(float* z, const float* g_a, const float* g_b, float* exp_avg, float* exp_avg_sq,
+                     int64_t n, int32_t step_count, float lr, float beta1, float beta2, float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

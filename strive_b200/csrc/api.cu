@@ -1,0 +1,140 @@
+// C-ABI glue: error string, model handle (packed weights), fused Adam.
+#include <stdarg.h>
+#include <string.h>
+#include <new>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void strive_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* strive_last_error(void) { return g_err; }
+extern "C" int strive_abi_version(void) { return STRIVE_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------------------
+// segment sizes (floats); the order is enum Seg in common.cuh
+// ------------------------------------------------------------------------------------------------------
+static void seg_sizes(int nc, int64_t* sz) {
+  const int chans[7] = {4, 16, 32, 64, 64, 128, 128};
+  const int ks[6] = {7, 5, 5, 3, 3, 3};
+  for (int l = 0; l < 6; l++) {
+    sz[S_CW0 + 4 * l] = (int64_t)chans[l] * ks[l] * ks[l] * chans[l + 1];
+    sz[S_CB0 + 4 * l] = chans[l + 1];
+    sz[S_GG0 + 4 * l] = chans[l + 1];
+    sz[S_GB0 + 4 * l] = chans[l + 1];
+  }
+  sz[S_FCW] = 512 * 64; sz[S_FCB] = 64;
+  const int in0 = round_up4(64 + 64 + nc + ZDIM + 2);
+  const int u0 = round_up4(64 + 64 + nc);
+  sz[S_IN0_T] = (int64_t)in0 * 128; sz[S_IN0_B] = 128; sz[S_IN_LN1_G] = 128; sz[S_IN_LN1_B] = 128;
+  sz[S_IN3_T] = 128 * 128; sz[S_IN3_B] = 128; sz[S_IN_LN4_G] = 128; sz[S_IN_LN4_B] = 128;
+  sz[S_IN6_T] = 128 * 64; sz[S_IN6_B] = 64;
+  sz[S_IN0_N_PF] = 128 * 64; sz[S_IN0_N_Z] = 128 * 32; sz[S_IN3_N] = 128 * 128; sz[S_IN6_N] = 64 * 128;
+  sz[S_E0_T_XI] = 64 * 128; sz[S_E0_T_XJ] = 64 * 128; sz[S_E0_T_SEMI] = nc * 128; sz[S_E0_T_SEMJ] = nc * 128;
+  sz[S_E0_T_REL] = 4 * 128; sz[S_E0_B] = 128; sz[S_E0_N_XI] = 128 * 64; sz[S_E0_N_XJ] = 128 * 64;
+  sz[S_E_LN1_G] = 128; sz[S_E_LN1_B] = 128; sz[S_E3_T] = 128 * 128; sz[S_E3_N] = 128 * 128; sz[S_E3_B] = 128;
+  sz[S_E_LN4_G] = 128; sz[S_E_LN4_B] = 128; sz[S_E6_T] = 128 * 64; sz[S_E6_N] = 64 * 128; sz[S_E6_B] = 64;
+  sz[S_U0_T] = (int64_t)u0 * 128; sz[S_U0_B] = 128; sz[S_U_LN1_G] = 128; sz[S_U_LN1_B] = 128;
+  sz[S_U3_T] = 128 * 64; sz[S_U3_B] = 64; sz[S_U0_N_X] = 128 * 64; sz[S_U0_N_AGGR] = 128 * 64; sz[S_U3_N] = 64 * 128;
+  sz[S_O0_T] = 64 * 128; sz[S_O0_B] = 128; sz[S_O_LN1_G] = 128; sz[S_O_LN1_B] = 128;
+  sz[S_O3_T] = 128 * 128; sz[S_O3_B] = 128; sz[S_O_LN4_G] = 128; sz[S_O_LN4_B] = 128;
+  sz[S_O6_N] = 2 * 128; sz[S_O6_B] = 2; sz[S_O0_N] = 128 * 64; sz[S_O3_N] = 128 * 128;
+  for (int l = 0; l < 3; l++) {
+    const int kin = (l == 0) ? 4 : 64;
+    sz[S_GI_T0 + 6 * l] = (int64_t)kin * 192; sz[S_GH_T0 + 6 * l] = 64 * 192;
+    sz[S_GBI0 + 6 * l] = 192; sz[S_GBH0 + 6 * l] = 192;
+    sz[S_GI_N0 + 6 * l] = (int64_t)192 * kin; sz[S_GH_N0 + 6 * l] = 192 * 64;
+  }
+}
+
+extern "C" int strive_model_layout(int num_classes, int64_t* seg_sizes_host, int max_segs, int* n_segs_out) {
+  STRIVE_CHECK(num_classes >= 1 && num_classes <= 16, STRIVE_EINVAL, "num_classes=%d out of range", num_classes);
+  STRIVE_CHECK(seg_sizes_host && n_segs_out && max_segs >= (int)S_COUNT, STRIVE_EINVAL, "layout buffer too small (%d < %d)", max_segs, (int)S_COUNT);
+  seg_sizes(num_classes, seg_sizes_host);
+  *n_segs_out = S_COUNT;
+  return 0;
+}
+
+extern "C" int strive_model_create(const float* blob, int64_t blob_floats, const int64_t* seg_sizes_host, int n_segs,
+                                   int num_classes, StriveModel** out) {
+  STRIVE_CHECK(blob && seg_sizes_host && out, STRIVE_EINVAL, "strive_model_create: null argument");
+  STRIVE_CHECK(n_segs == (int)S_COUNT, STRIVE_ESIZE, "segment count %d != %d", n_segs, (int)S_COUNT);
+  STRIVE_CHECK(num_classes >= 1 && num_classes <= 16, STRIVE_EINVAL, "num_classes=%d out of range", num_classes);
+  int64_t want[S_COUNT];
+  seg_sizes(num_classes, want);
+  StriveModel* m = new (std::nothrow) StriveModel();
+  STRIVE_CHECK(m != nullptr, STRIVE_EINVAL, "out of host memory");
+  int64_t off = 0;
+  for (int i = 0; i < S_COUNT; i++) {
+    if (seg_sizes_host[i] != want[i]) {
+      strive_set_error("segment %d has %lld floats, expected %lld", i, (long long)seg_sizes_host[i], (long long)want[i]);
+      delete m;
+      return STRIVE_ESIZE;
+    }
+    m->seg[i] = blob + off;
+    m->seg_size[i] = want[i];
+    off += (want[i] + 3) & ~(int64_t)3;   // every segment starts 16-byte aligned
+  }
+  if (off != blob_floats) {
+    strive_set_error("weight blob has %lld floats, expected %lld", (long long)blob_floats, (long long)off);
+    delete m;
+    return STRIVE_ESIZE;
+  }
+  m->nc = num_classes;
+  m->in0_rows = round_up4(64 + 64 + num_classes + ZDIM + 2);
+  m->u0_rows = round_up4(64 + 64 + num_classes);
+  *out = m;
+  return 0;
+}
+
+extern "C" void strive_model_destroy(StriveModel* m) { delete m; }
+
+// ------------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam, amsgrad=False, weight_decay=0, maximize=False) as used by the latent loops
+// (refine_traffic_optim.py:166, init_optim.py:21, adv_gen_optim.py:72, sol_optim.py:47)
+// ------------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ z, const float* __restrict__ ga, const float* __restrict__ gb,
+                            float* __restrict__ m, float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2_sqrt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float g = ga[i];
+  if (gb != nullptr) g += gb[i];
+  const float mi = m[i] + (g - m[i]) * (1.0f - b1);          // exp_avg.lerp_(grad, 1-beta1)
+  const float vi = v[i] * b2 + (1.0f - b2) * g * g;          // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  z[i] = z[i] - (lr / bc1) * (mi / denom);
+}
+
+extern "C" int strive_adam_step(float* z, const float* g_a, const float* g_b, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                int32_t step_count, float lr, float beta1, float beta2, float eps, void* stream) {
+  STRIVE_CHECK(z && g_a && exp_avg && exp_avg_sq && n > 0 && step_count >= 1, STRIVE_EINVAL, "strive_adam_step: bad arguments");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step_count);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step_count);
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z, g_a, g_b, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                             (float)bc1, (float)sqrt(bc2));
+  STRIVE_LAUNCH_CHECK();
+  return 0;
+}
+
+// layout self-check for foreign-function bindings (tests compare against ctypes.sizeof / offsets)
+#include <stddef.h>
+extern "C" int strive_struct_layout(int64_t* out, int max_n) {
+  const int64_t v[] = {(int64_t)sizeof(StriveScene), (int64_t)offsetof(StriveScene, ptr), (int64_t)offsetof(StriveScene, sem),
+                       (int64_t)sizeof(StriveMap), (int64_t)offsetof(StriveMap, lin_l),
+                       (int64_t)sizeof(StriveLossCfg), (int64_t)offsetof(StriveLossCfg, group_agent_ptr),
+                       (int64_t)offsetof(StriveLossCfg, w_coll_veh), (int64_t)offsetof(StriveLossCfg, attack_mask),
+                       (int64_t)offsetof(StriveLossCfg, lw_un)};
+  const int n = (int)(sizeof(v) / sizeof(v[0]));
+  if (max_n < n) return -1;
+  for (int i = 0; i < n; i++) out[i] = v[i];
+  return n;
+}

@@ -1,0 +1,1218 @@
+// Decoder rollout (forward + BPTT w.r.t. z) of the STRIVE traffic prior.
+//
+// Restates reference src/models/traffic_model.py:589-704 (autoregressive_decoder), :714-733 (sim_traj),
+// src/models/interaction_net.py:52-218 (SceneInteractionNet / AgentInteractionConv with max aggregation),
+// src/models/common.py:8-67 (MLP, car_dynamics), nn.GRU(4,64,3) one step, utils/transforms.py:78-139.
+//
+// Per rollout step t (forward):   node_fwd -> edge_fwd -> post_fwd -> gru_fwd -> [map encoder, mapenc.cu]
+// Per rollout step t (backward):  gru_bwd -> post_bwd -> edge_bwd -> node_bwd      (t = FT-1 .. 0)
+//
+// Work decomposition: one warp owns R rows (agents, or edges of one target agent); a row's activations live
+// in per-warp shared memory (broadcast reads), each lane owns OUT/32 output columns, weights are read
+// coalesced from global ([in][out] layout) and are L1/L2 resident (<1 MB for the whole decoder).
+// The first edge-MLP layer is factorised:  W1 [x_i|x_j|sem_i|sem_j|rel] = P_i + Q_j + W_rel rel  (node terms
+// P,Q computed once per node), which removes 40 % of the per-edge MACs.
+//
+// Backward recomputes edge/node activations from the tape (node-level tensors only) instead of storing
+// per-edge activations (E x 320 floats per step would be 4 GB at BASELINE config 5).
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------------
+// tape layout (floats unless noted), all [t][agent][...]
+// ------------------------------------------------------------------------------------------------------
+struct Tape {
+  float* pastfeat;  // [FT][NA][64]   past_feat input of step t
+  float* mapfeat;   // [FT][NA][64]   map_feat input of step t
+  float* mem;       // [FT][NA][3][64] GRU hidden at the start of step t
+  float* prev;      // [FT][NA][6]    prev_state input of step t (normalised)
+  float* pos;       // [FT][NA][4]    pos used for edge transforms at step t (normalised)
+  float* loc;       // [FT][NA][4]    local-frame delta fed to the GRU at step t
+  float* x;         // [FT][NA][64]   mlp_in output
+  float* P;         // [FT][NA][128]
+  float* Q;         // [FT][NA][128]
+  float* aggr;      // [FT][NA][64]
+  uint8_t* arg;     // [FT][NA][64]   local index (within scene) of the arg-max source, 255 = none
+  float* z;         // [NA][32]       copy of the latent the forward pass ran on (node recompute in backward)
+  // backward carries / scratch, [NA][...]
+  float* g_prev;    // [NA][6]
+  float* g_pos;     // [NA][4]
+  float* g_pf;      // [NA][64]
+  float* g_mem;     // [NA][3][64]
+  float* d_loc;     // [NA][4]
+  float* d_xupd;    // [NA][64]
+  float* d_aggr;    // [NA][64]
+  float* dP;        // [NA][128]
+  float* dQ;        // [NA][128]
+  float* pose;      // [NA][4]  unnormalised crop pose for the map encoder
+  int32_t* map_of;  // [NA]
+  void* mapenc_ws;  // map encoder workspace
+  int64_t mapenc_ws_bytes;
+};
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int64_t tape_carve(Tape* tp, char* base, int NA, int FT) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align256(bytes);
+    return p;
+  };
+  const size_t n = (size_t)NA, T = (size_t)FT;
+  tp->pastfeat = (float*)take(T * n * 64 * 4);
+  tp->mapfeat = (float*)take(T * n * 64 * 4);
+  tp->mem = (float*)take(T * n * 192 * 4);
+  tp->prev = (float*)take(T * n * 6 * 4);
+  tp->pos = (float*)take(T * n * 4 * 4);
+  tp->loc = (float*)take(T * n * 4 * 4);
+  tp->x = (float*)take(T * n * 64 * 4);
+  tp->P = (float*)take(T * n * 128 * 4);
+  tp->Q = (float*)take(T * n * 128 * 4);
+  tp->aggr = (float*)take(T * n * 64 * 4);
+  tp->arg = (uint8_t*)take(T * n * 64);
+  tp->z = (float*)take(n * 32 * 4);
+  tp->g_prev = (float*)take(n * 6 * 4);
+  tp->g_pos = (float*)take(n * 4 * 4);
+  tp->g_pf = (float*)take(n * 64 * 4);
+  tp->g_mem = (float*)take(n * 192 * 4);
+  tp->d_loc = (float*)take(n * 4 * 4);
+  tp->d_xupd = (float*)take(n * 64 * 4);
+  tp->d_aggr = (float*)take(n * 64 * 4);
+  tp->dP = (float*)take(n * 128 * 4);
+  tp->dQ = (float*)take(n * 128 * 4);
+  tp->pose = (float*)take(n * 4 * 4);
+  tp->map_of = (int32_t*)take(n * 4);
+  tp->mapenc_ws_bytes = strive_mapenc_workspace_bytes(NA);
+  tp->mapenc_ws = (void*)take((size_t)tp->mapenc_ws_bytes);
+  return (int64_t)off;
+}
+
+extern "C" int64_t strive_decode_tape_bytes(int32_t num_agents, int32_t ft) {
+  Tape tp;
+  return tape_carve(&tp, nullptr, num_agents, ft);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// kernel parameter blocks
+// ------------------------------------------------------------------------------------------------------
+struct ModelDev {
+  const float* seg[S_COUNT];
+  int nc, in0_rows, u0_rows;
+};
+
+struct StepArgs {
+  int NA, t, FT, NC;
+  const int32_t* ptr;
+  const int32_t* scene_of;
+  const float* lw;
+  const float* sem;
+  const float* z;
+  const float* ext;     // (S,FT,4) or null
+  float* traj;          // (NA,FT,4)
+  const float* d_traj;  // (NA,FT,4)
+  float* d_z;           // (NA,32)
+  Tape tp;
+};
+
+#define NODE_R 4
+#define NODE_WARPS 4
+#define EDGE_R 8
+#define EDGE_WARPS 4
+#define LDA 172   // >= 168, multiple of 4
+#define LDH 132   // 128 + 4
+
+// ------------------------------------------------------------------------------------------------------
+// node phase: f -> mlp_in -> x, P, Q           (interaction_net.py:61 ; factorised first edge layer)
+// ------------------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void stage_node_feat(float* bufA, const StepArgs& a, const int (&row)[R], int lane, int in0_rows) {
+  const int NA = a.NA, NC = a.NC;
+  const float* pf = a.tp.pastfeat + (size_t)a.t * NA * 64;
+  const float* mf = a.tp.mapfeat + (size_t)a.t * NA * 64;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int ag = row[r];
+    for (int k = lane; k < in0_rows; k += 32) {
+      float v;
+      if (k < 64) v = pf[(size_t)ag * 64 + k];
+      else if (k < 128) v = mf[(size_t)ag * 64 + k - 64];
+      else if (k < 128 + NC) v = a.sem[(size_t)ag * NC + k - 128];
+      else if (k < 128 + NC + ZDIM) v = a.z[(size_t)ag * ZDIM + k - 128 - NC];
+      else if (k < 128 + NC + ZDIM + 2) v = a.lw[(size_t)ag * 2 + k - 128 - NC - ZDIM];
+      else v = 0.f;
+      bufA[r * LDA + k] = v;
+    }
+  }
+}
+
+// forward of mlp_in on R staged rows. Leaves h2 (post LN/ReLU of layer 2) in bufA (ld LDA) and, if keep, the
+// pre-LN activations a1 in pre1 and a2 in pre2 (ld LDH). Returns x in xacc.
+template <int R>
+__device__ __forceinline__ void mlp_in_fwd(const ModelDev& M, float* bufA, float* bufB, float* pre1, float* pre2,
+                                           float (&xacc)[R][2], int lane) {
+  float acc[R][4];
+  init_bias<4, R>(acc, M.seg[S_IN0_B], lane);
+  warp_gemm<128, R>(M.seg[S_IN0_T], M.in0_rows, bufA, LDA, acc, lane);
+  __syncwarp();
+  ln_relu_store<R>(acc, M.seg[S_IN_LN1_G], M.seg[S_IN_LN1_B], bufB, LDH, pre1, LDH, lane);
+  __syncwarp();
+  init_bias<4, R>(acc, M.seg[S_IN3_B], lane);
+  warp_gemm<128, R>(M.seg[S_IN3_T], 128, bufB, LDH, acc, lane);
+  __syncwarp();
+  ln_relu_store<R>(acc, M.seg[S_IN_LN4_G], M.seg[S_IN_LN4_B], bufA, LDA, pre2, LDH, lane);
+  __syncwarp();
+  init_bias<2, R>(xacc, M.seg[S_IN6_B], lane);
+  warp_gemm<64, R>(M.seg[S_IN6_T], 128, bufA, LDA, xacc, lane);
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(NODE_WARPS * 32) node_fwd_kernel(ModelDev M, StepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* bufA = smem + warp * (NODE_R * (LDA + LDH));
+  float* bufB = bufA + NODE_R * LDA;
+  const int NA = a.NA;
+  int row[NODE_R];
+  bool valid[NODE_R];
+  const int base = (blockIdx.x * NODE_WARPS + warp) * NODE_R;
+  if (base >= NA) return;
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++) {
+    valid[r] = (base + r) < NA;
+    row[r] = valid[r] ? base + r : NA - 1;
+  }
+  stage_node_feat<NODE_R>(bufA, a, row, lane, M.in0_rows);
+  __syncwarp();
+  float xacc[NODE_R][2];
+  mlp_in_fwd<NODE_R>(M, bufA, bufB, nullptr, nullptr, xacc, lane);
+  // x -> tape + shared (bufB as [R][LDH], first 64 cols)
+  float* xg = a.tp.x + (size_t)a.t * NA * 64;
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++) {
+    stvec<2>(bufB + r * LDH + lane * 2, xacc[r]);
+    if (valid[r]) stvec<2>(xg + (size_t)row[r] * 64 + lane * 2, xacc[r]);
+  }
+  __syncwarp();
+  // P = W_xi x + W_semi sem + b ; Q = W_xj x + W_semj sem
+  float acc[NODE_R][4];
+  init_bias<4, NODE_R>(acc, M.seg[S_E0_B], lane);
+  warp_gemm<128, NODE_R>(M.seg[S_E0_T_XI], 64, bufB, LDH, acc, lane);
+  for (int c = 0; c < a.NC; c++) {
+    float w[4];
+    ldvec<4>(w, M.seg[S_E0_T_SEMI] + c * 128 + lane * 4);
+#pragma unroll
+    for (int r = 0; r < NODE_R; r++) {
+      const float s = a.sem[(size_t)row[r] * a.NC + c];
+#pragma unroll
+      for (int v = 0; v < 4; v++) acc[r][v] = fmaf(s, w[v], acc[r][v]);
+    }
+  }
+  float* Pg = a.tp.P + (size_t)a.t * NA * 128;
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++)
+    if (valid[r]) stvec<4>(Pg + (size_t)row[r] * 128 + lane * 4, acc[r]);
+  init_zero<4, NODE_R>(acc);
+  warp_gemm<128, NODE_R>(M.seg[S_E0_T_XJ], 64, bufB, LDH, acc, lane);
+  for (int c = 0; c < a.NC; c++) {
+    float w[4];
+    ldvec<4>(w, M.seg[S_E0_T_SEMJ] + c * 128 + lane * 4);
+#pragma unroll
+    for (int r = 0; r < NODE_R; r++) {
+      const float s = a.sem[(size_t)row[r] * a.NC + c];
+#pragma unroll
+      for (int v = 0; v < 4; v++) acc[r][v] = fmaf(s, w[v], acc[r][v]);
+    }
+  }
+  float* Qg = a.tp.Q + (size_t)a.t * NA * 128;
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++)
+    if (valid[r]) stvec<4>(Qg + (size_t)row[r] * 128 + lane * 4, acc[r]);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// edge phase: one CTA per target agent i; rows = incoming edges (j -> i), max-aggregate with arg-max
+// (interaction_net.py:139-184 message(), aggr='max' at :92, zeros for edge-less nodes :187-188)
+// ------------------------------------------------------------------------------------------------------
+struct EdgeCtx {
+  int i, p0, n, ne, li;
+  float pos_i[4];
+};
+
+// first edge layer for R rows of one chunk: h1pre = P_i + Q_j + W_rel rel  (lane cols)
+template <int R>
+__device__ __forceinline__ void edge_layer0(const StepArgs& a, const EdgeCtx& c, int chunk, const float (&Pi)[4],
+                                            const float (&Wrel)[4][4], float (&acc)[R][4], int (&lj)[R], bool (&valid)[R],
+                                            float (&rel)[R][4], int lane) {
+  const int NA = a.NA;
+  const float* Qg = a.tp.Q + (size_t)a.t * NA * 128;
+  const float* posg = a.tp.pos + (size_t)a.t * NA * 4;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int e = chunk * R + r;
+    valid[r] = e < c.ne;
+    const int ee = valid[r] ? e : 0;
+    lj[r] = ee + (ee >= c.li ? 1 : 0);
+    const int j = c.p0 + lj[r];
+    const float4 pj4 = __ldg(reinterpret_cast<const float4*>(posg + (size_t)j * 4));
+    const float pj[4] = {pj4.x, pj4.y, pj4.z, pj4.w};
+    t2f_fwd(c.pos_i, pj, rel[r]);
+#pragma unroll
+    for (int d = 0; d < 4; d++)
+      if (isnan(rel[r][d])) rel[r][d] = 0.f;   // interaction_net.py:162
+    float q[4];
+    ldvec<4>(q, Qg + (size_t)j * 128 + lane * 4);
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      float h = Pi[v] + q[v];
+#pragma unroll
+      for (int d = 0; d < 4; d++) h = fmaf(rel[r][d], Wrel[d][v], h);
+      acc[r][v] = h;
+    }
+  }
+}
+
+__device__ __forceinline__ bool edge_ctx_init(const StepArgs& a, EdgeCtx& c) {
+  c.i = blockIdx.x;
+  const int s = a.scene_of[c.i];
+  c.p0 = a.ptr[s];
+  c.n = a.ptr[s + 1] - c.p0;
+  c.ne = c.n - 1;
+  c.li = c.i - c.p0;
+  const float4 p = __ldg(reinterpret_cast<const float4*>(a.tp.pos + ((size_t)a.t * a.NA + c.i) * 4));
+  c.pos_i[0] = p.x; c.pos_i[1] = p.y; c.pos_i[2] = p.z; c.pos_i[3] = p.w;
+  return true;
+}
+
+__global__ void __launch_bounds__(EDGE_WARPS * 32) edge_fwd_kernel(ModelDev M, StepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red_val[EDGE_WARPS][64];
+  __shared__ int red_idx[EDGE_WARPS][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* bufA = smem + warp * (2 * EDGE_R * LDH);
+  float* bufB = bufA + EDGE_R * LDH;
+  EdgeCtx c;
+  edge_ctx_init(a, c);
+  const int NA = a.NA;
+  float Pi[4], Wrel[4][4];
+  ldvec<4>(Pi, a.tp.P + ((size_t)a.t * NA + c.i) * 128 + lane * 4);
+#pragma unroll
+  for (int d = 0; d < 4; d++) ldvec<4>(Wrel[d], M.seg[S_E0_T_REL] + d * 128 + lane * 4);
+  float best[2] = {-INFINITY, -INFINITY};
+  int bidx[2] = {255, 255};
+  const int nchunks = (c.ne + EDGE_R - 1) / EDGE_R;
+  for (int chunk = warp; chunk < nchunks; chunk += EDGE_WARPS) {
+    float acc[EDGE_R][4], rel[EDGE_R][4];
+    int lj[EDGE_R];
+    bool valid[EDGE_R];
+    edge_layer0<EDGE_R>(a, c, chunk, Pi, Wrel, acc, lj, valid, rel, lane);
+    __syncwarp();
+    ln_relu_store<EDGE_R>(acc, M.seg[S_E_LN1_G], M.seg[S_E_LN1_B], bufA, LDH, nullptr, 0, lane);
+    __syncwarp();
+    init_bias<4, EDGE_R>(acc, M.seg[S_E3_B], lane);
+    warp_gemm<128, EDGE_R>(M.seg[S_E3_T], 128, bufA, LDH, acc, lane);
+    __syncwarp();
+    ln_relu_store<EDGE_R>(acc, M.seg[S_E_LN4_G], M.seg[S_E_LN4_B], bufB, LDH, nullptr, 0, lane);
+    __syncwarp();
+    float m[EDGE_R][2];
+    init_bias<2, EDGE_R>(m, M.seg[S_E6_B], lane);
+    warp_gemm<64, EDGE_R>(M.seg[S_E6_T], 128, bufB, LDH, m, lane);
+#pragma unroll
+    for (int r = 0; r < EDGE_R; r++) {
+      if (valid[r]) {
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+          if (m[r][v] > best[v] || (m[r][v] == best[v] && lj[r] < bidx[v])) {
+            best[v] = m[r][v];
+            bidx[v] = lj[r];
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  red_val[warp][lane * 2] = best[0];
+  red_val[warp][lane * 2 + 1] = best[1];
+  red_idx[warp][lane * 2] = bidx[0];
+  red_idx[warp][lane * 2 + 1] = bidx[1];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int ch = threadIdx.x;
+    float bv = red_val[0][ch];
+    int bi = red_idx[0][ch];
+#pragma unroll
+    for (int w = 1; w < EDGE_WARPS; w++) {
+      const float v = red_val[w][ch];
+      const int ix = red_idx[w][ch];
+      if (ix != 255 && (bi == 255 || v > bv || (v == bv && ix < bi))) {
+        bv = v;
+        bi = ix;
+      }
+    }
+    if (bi == 255) bv = 0.f;
+    a.tp.aggr[((size_t)a.t * NA + c.i) * 64 + ch] = bv;
+    a.tp.arg[((size_t)a.t * NA + c.i) * 64 + ch] = (uint8_t)bi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// post phase: update_mlp -> mlp_out -> bicycle -> local-frame delta   (interaction_net.py:186-218, :69;
+// traffic_model.py:640-680; models/common.py:47-67)
+// ------------------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void stage_update_in(float* bufA, const StepArgs& a, const int (&row)[R], int lane, int u0_rows) {
+  const int NA = a.NA, NC = a.NC;
+  const float* xg = a.tp.x + (size_t)a.t * NA * 64;
+  const float* ag = a.tp.aggr + (size_t)a.t * NA * 64;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int agn = row[r];
+    for (int k = lane; k < u0_rows; k += 32) {
+      float v;
+      if (k < 64) v = xg[(size_t)agn * 64 + k];
+      else if (k < 128) v = ag[(size_t)agn * 64 + k - 64];
+      else if (k < 128 + NC) v = a.sem[(size_t)agn * NC + k - 128];
+      else v = 0.f;
+      bufA[r * LDA + k] = v;
+    }
+  }
+}
+
+// update_mlp + mlp_out forward on R staged rows; returns o (2 per row, replicated in every lane).
+// If keep: preU (a_u), pre1 (a_1), pre2 (a_2) pre-LN activations (ld LDH) are kept for the backward pass.
+template <int R>
+__device__ __forceinline__ void post_mlps_fwd(const ModelDev& M, float* bufA, float* bufB, float* preU, float* pre1,
+                                              float* pre2, float (&o)[R][2], int lane) {
+  float acc[R][4];
+  init_bias<4, R>(acc, M.seg[S_U0_B], lane);
+  warp_gemm<128, R>(M.seg[S_U0_T], M.u0_rows, bufA, LDA, acc, lane);
+  __syncwarp();
+  ln_relu_store<R>(acc, M.seg[S_U_LN1_G], M.seg[S_U_LN1_B], bufB, LDH, preU, LDH, lane);
+  __syncwarp();
+  float xu[R][2];
+  init_bias<2, R>(xu, M.seg[S_U3_B], lane);
+  warp_gemm<64, R>(M.seg[S_U3_T], 128, bufB, LDH, xu, lane);
+  __syncwarp();
+  store_rows<2, R>(xu, bufA, LDA, lane);
+  __syncwarp();
+  init_bias<4, R>(acc, M.seg[S_O0_B], lane);
+  warp_gemm<128, R>(M.seg[S_O0_T], 64, bufA, LDA, acc, lane);
+  __syncwarp();
+  ln_relu_store<R>(acc, M.seg[S_O_LN1_G], M.seg[S_O_LN1_B], bufB, LDH, pre1, LDH, lane);
+  __syncwarp();
+  init_bias<4, R>(acc, M.seg[S_O3_B], lane);
+  warp_gemm<128, R>(M.seg[S_O3_T], 128, bufB, LDH, acc, lane);
+  __syncwarp();
+  ln_relu_store<R>(acc, M.seg[S_O_LN4_G], M.seg[S_O_LN4_B], bufA, LDA, pre2, LDH, lane);
+  __syncwarp();
+  float w0[4], w1[4];
+  ldvec<4>(w0, M.seg[S_O6_N] + lane * 4);
+  ldvec<4>(w1, M.seg[S_O6_N] + 128 + lane * 4);
+  const float b0 = __ldg(M.seg[S_O6_B]), b1 = __ldg(M.seg[S_O6_B] + 1);
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const float4 h = *reinterpret_cast<const float4*>(bufA + r * LDA + lane * 4);
+    float p0 = h.x * w0[0] + h.y * w0[1] + h.z * w0[2] + h.w * w0[3];
+    float p1 = h.x * w1[0] + h.y * w1[1] + h.z * w1[2] + h.w * w1[3];
+    o[r][0] = warp_sum(p0) + b0;
+    o[r][1] = warp_sum(p1) + b1;
+  }
+}
+
+struct BikeFwd {
+  float un[6];        // unnormalised prev state
+  float h, newh, sn, cs, news, newhdot, pre_s, pre_hd, len;
+};
+
+// sim_traj one step (traffic_model.py:714-733 + common.py:47-67); cur = normalised new state (6)
+__device__ __forceinline__ void bicycle_fwd(const float prev[6], float o0, float o1, float lw_l_norm, float cur[6], BikeFwd& b) {
+  const float acc = o0 * A_STD + A_MEAN;          // traffic_model.py:645
+  const float ddh = o1 * DDH_STD + DDH_MEAN;      // :646
+#pragma unroll
+  for (int k = 0; k < 6; k++) b.un[k] = prev[k] * kStateStd[k] + kStateMean[k];
+  b.len = lw_l_norm * ATT_STD_L + ATT_MEAN_L;     // :601
+  b.h = atan2f(b.un[3], b.un[2]);
+  b.pre_hd = b.un[5] + ddh * BIKE_DT;
+  b.newhdot = fminf(fmaxf(b.pre_hd, -BIKE_MAXHDOT), BIKE_MAXHDOT);
+  b.newh = b.h + BIKE_DT * fabsf(b.un[4]) / b.len * b.newhdot;
+  b.pre_s = b.un[4] + acc * BIKE_DT;
+  b.news = fminf(fmaxf(b.pre_s, 0.0f), BIKE_MAXS);
+  b.sn = sinf(b.newh);
+  b.cs = cosf(b.newh);
+  const float out[6] = {b.un[0] + b.news * b.cs * BIKE_DT, b.un[1] + b.news * b.sn * BIKE_DT, b.cs, b.sn, b.news, b.newhdot};
+#pragma unroll
+  for (int k = 0; k < 6; k++) cur[k] = (out[k] - kStateMean[k]) / kStateStd[k];
+}
+
+__global__ void __launch_bounds__(NODE_WARPS * 32) post_fwd_kernel(ModelDev M, StepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* bufA = smem + warp * (NODE_R * (LDA + LDH));
+  float* bufB = bufA + NODE_R * LDA;
+  const int NA = a.NA, t = a.t, FT = a.FT;
+  int row[NODE_R];
+  const int base = (blockIdx.x * NODE_WARPS + warp) * NODE_R;
+  if (base >= NA) return;
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++) row[r] = (base + r) < NA ? base + r : NA - 1;
+  stage_update_in<NODE_R>(bufA, a, row, lane, M.u0_rows);
+  __syncwarp();
+  float o[NODE_R][2];
+  post_mlps_fwd<NODE_R>(M, bufA, bufB, nullptr, nullptr, nullptr, o, lane);
+  float my_o0 = 0.f, my_o1 = 0.f;
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++)
+    if (lane == r) { my_o0 = o[r][0]; my_o1 = o[r][1]; }
+  if (lane < NODE_R && base + lane < NA) {
+    const int ag = base + lane;
+    const float* pv = a.tp.prev + ((size_t)t * NA + ag) * 6;
+    float prev[6], cur[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) prev[k] = pv[k];
+    BikeFwd b;
+    bicycle_fwd(prev, my_o0, my_o1, a.lw[(size_t)ag * 2], cur, b);
+    float* tr = a.traj + ((size_t)ag * FT + t) * 4;
+    *reinterpret_cast<float4*>(tr) = make_float4(cur[0], cur[1], cur[2], cur[3]);   // :665
+    float glob[4] = {cur[0], cur[1], cur[2], cur[3]};
+    const int s = a.scene_of[ag];
+    if (a.ext != nullptr && ag == a.ptr[s]) {                                        // :667-675
+      const float* e = a.ext + ((size_t)s * FT + t) * 4;
+#pragma unroll
+      for (int k = 0; k < 4; k++) glob[k] = e[k];
+    }
+    float loc[4];
+    t2f_fwd(prev, glob, loc);                                                        // :654 / :674
+    *reinterpret_cast<float4*>(a.tp.loc + ((size_t)t * NA + ag) * 4) = make_float4(loc[0], loc[1], loc[2], loc[3]);
+    if (t + 1 < FT) {
+      float* pn = a.tp.prev + ((size_t)(t + 1) * NA + ag) * 6;                       // :680
+#pragma unroll
+      for (int k = 0; k < 6; k++) pn[k] = cur[k];
+      *reinterpret_cast<float4*>(a.tp.pos + ((size_t)(t + 1) * NA + ag) * 4) = make_float4(glob[0], glob[1], glob[2], glob[3]);  // :698
+      // crop pose: unnormalise (encode_map -> normalize_scene_graph(unnorm=True)), separate mul and add as torch does
+      float4 pu;
+      pu.x = __fadd_rn(__fmul_rn(glob[0], kStateStd[0]), kStateMean[0]);
+      pu.y = __fadd_rn(__fmul_rn(glob[1], kStateStd[1]), kStateMean[1]);
+      pu.z = __fadd_rn(__fmul_rn(glob[2], kStateStd[2]), kStateMean[2]);
+      pu.w = __fadd_rn(__fmul_rn(glob[3], kStateStd[3]), kStateMean[3]);
+      *reinterpret_cast<float4*>(a.tp.pose + (size_t)ag * 4) = pu;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// GRU memory: one step of nn.GRU(4,64,3) (traffic_model.py:152-156, 686-688)
+// ------------------------------------------------------------------------------------------------------
+#define GRU_R 4
+// per-warp shared: xin [R][68], h [3][R][68], gate stash for backward [3][R][4][64]
+#define LDG 68
+
+template <int R>
+__device__ __forceinline__ void gru_layer_fwd(const ModelDev& M, int l, const float* xin, const float* loc /*[R][4] if l==0*/,
+                                              const float* hprev, float (&hnew)[R][2], float* stash /*[R][4][64] or null*/,
+                                              int lane) {
+  const int so = l * 6;
+  float gi[R][6], gh[R][6];
+  // biases
+  {
+    const float* bi = M.seg[S_GBI0 + so];
+    const float* bh = M.seg[S_GBH0 + so];
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const float2 a = __ldg(reinterpret_cast<const float2*>(bi + g * 64 + lane * 2));
+      const float2 b = __ldg(reinterpret_cast<const float2*>(bh + g * 64 + lane * 2));
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        gi[r][g * 2] = a.x; gi[r][g * 2 + 1] = a.y;
+        gh[r][g * 2] = b.x; gh[r][g * 2 + 1] = b.y;
+      }
+    }
+  }
+  if (l == 0) {
+    const float* W = M.seg[S_GI_T0];   // [4][192]
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+      for (int g = 0; g < 3; g++) {
+        const float2 w = __ldg(reinterpret_cast<const float2*>(W + k * 192 + g * 64 + lane * 2));
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const float xv = loc[r * 4 + k];
+          gi[r][g * 2] = fmaf(xv, w.x, gi[r][g * 2]);
+          gi[r][g * 2 + 1] = fmaf(xv, w.y, gi[r][g * 2 + 1]);
+        }
+      }
+    }
+  } else {
+    warp_gemm_gru<R>(M.seg[S_GI_T0 + so], 64, xin, LDG, gi, lane);
+  }
+  warp_gemm_gru<R>(M.seg[S_GH_T0 + so], 64, hprev, LDG, gh, lane);
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const float rg = sigmoidf_(gi[r][e] + gh[r][e]);
+      const float zg = sigmoidf_(gi[r][2 + e] + gh[r][2 + e]);
+      const float ng = tanhf(gi[r][4 + e] + rg * gh[r][4 + e]);
+      const float hp = hprev[r * LDG + lane * 2 + e];
+      hnew[r][e] = (1.0f - zg) * ng + zg * hp;
+      if (stash != nullptr) {
+        float* st = stash + (size_t)r * 4 * 64 + lane * 2 + e;
+        st[0] = rg; st[64] = zg; st[128] = ng; st[192] = gh[r][4 + e];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NODE_WARPS * 32) gru_fwd_kernel(ModelDev M, StepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* xin = smem + warp * (GRU_R * LDG * 4 + GRU_R * 4);
+  float* hbuf = xin + GRU_R * LDG;          // [3][R][LDG]
+  float* locs = hbuf + 3 * GRU_R * LDG;     // [R][4]
+  const int NA = a.NA, t = a.t;
+  const int base = (blockIdx.x * NODE_WARPS + warp) * GRU_R;
+  if (base >= NA) return;
+  int row[GRU_R];
+  bool valid[GRU_R];
+#pragma unroll
+  for (int r = 0; r < GRU_R; r++) { valid[r] = base + r < NA; row[r] = valid[r] ? base + r : NA - 1; }
+  const float* memg = a.tp.mem + (size_t)t * NA * 192;
+#pragma unroll
+  for (int r = 0; r < GRU_R; r++) {
+    for (int k = lane; k < 192; k += 32) hbuf[((k >> 6) * GRU_R + r) * LDG + (k & 63)] = memg[(size_t)row[r] * 192 + k];
+    if (lane < 4) locs[r * 4 + lane] = a.tp.loc[((size_t)t * NA + row[r]) * 4 + lane];
+  }
+  __syncwarp();
+  float* memn = a.tp.mem + (size_t)(t + 1) * NA * 192;
+  float* pfn = a.tp.pastfeat + (size_t)(t + 1) * NA * 64;
+  for (int l = 0; l < 3; l++) {
+    float hnew[GRU_R][2];
+    gru_layer_fwd<GRU_R>(M, l, xin, locs, hbuf + l * GRU_R * LDG, hnew, nullptr, lane);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < GRU_R; r++) {
+      stvec<2>(xin + r * LDG + lane * 2, hnew[r]);
+      if (valid[r]) {
+        stvec<2>(memn + (size_t)row[r] * 192 + l * 64 + lane * 2, hnew[r]);
+        if (l == 2) stvec<2>(pfn + (size_t)row[r] * 64 + lane * 2, hnew[r]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ======================================================================================================
+// backward
+// ======================================================================================================
+
+// GRU backward. In: g_mem (grad wrt mem_{t+1}), g_pf (grad wrt past_feat_{t+1} = top output). Out: g_mem <- grad wrt
+// mem_t, d_loc. (Not launched for t = FT-1: no GRU step there.)
+__global__ void __launch_bounds__(NODE_WARPS * 32) gru_bwd_kernel(ModelDev M, StepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per-warp: xin[3][R][LDG] (inputs of layers 1,2 = new h of layers 0,1; slot 0 unused), h[3][R][LDG], loc[R][4],
+  //           stash[3][R][4][64], dg [R][196]
+  constexpr int PER_WARP = 6 * GRU_R * LDG + GRU_R * 4 + 3 * GRU_R * 256 + GRU_R * 196;
+  float* xin = smem + warp * PER_WARP;
+  float* hbuf = xin + 3 * GRU_R * LDG;
+  float* locs = hbuf + 3 * GRU_R * LDG;
+  float* stash = locs + GRU_R * 4;
+  float* dgb = stash + 3 * GRU_R * 256;   // [R][196] gate grads staged for the native GEMMs
+  const int NA = a.NA, t = a.t;
+  const int base = (blockIdx.x * NODE_WARPS + warp) * GRU_R;
+  if (base >= NA) return;
+  int row[GRU_R];
+  bool valid[GRU_R];
+#pragma unroll
+  for (int r = 0; r < GRU_R; r++) { valid[r] = base + r < NA; row[r] = valid[r] ? base + r : NA - 1; }
+  const float* memg = a.tp.mem + (size_t)t * NA * 192;
+#pragma unroll
+  for (int r = 0; r < GRU_R; r++) {
+    for (int k = lane; k < 192; k += 32) hbuf[((k >> 6) * GRU_R + r) * LDG + (k & 63)] = memg[(size_t)row[r] * 192 + k];
+    if (lane < 4) locs[r * 4 + lane] = a.tp.loc[((size_t)t * NA + row[r]) * 4 + lane];
+  }
+  __syncwarp();
+  // recompute forward, stash gates
+  for (int l = 0; l < 3; l++) {
+    float hnew[GRU_R][2];
+    gru_layer_fwd<GRU_R>(M, l, xin + l * GRU_R * LDG, locs, hbuf + l * GRU_R * LDG, hnew, stash + l * GRU_R * 256, lane);
+    __syncwarp();
+    if (l < 2) {
+#pragma unroll
+      for (int r = 0; r < GRU_R; r++) stvec<2>(xin + ((l + 1) * GRU_R + r) * LDG + lane * 2, hnew[r]);
+    }
+    __syncwarp();
+  }
+  // backward, top layer first. dh[r][e]: grad wrt new hidden of layer l for this lane's units.
+  float dx_next[GRU_R][2];   // grad wrt the input of layer l+1 (= new hidden of layer l)
+#pragma unroll
+  for (int r = 0; r < GRU_R; r++) dx_next[r][0] = dx_next[r][1] = 0.f;
+  float dloc_acc[GRU_R][4];
+#pragma unroll
+  for (int r = 0; r < GRU_R; r++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) dloc_acc[r][k] = 0.f;
+  for (int l = 2; l >= 0; l--) {
+    const int so = l * 6;
+    float dhp[GRU_R][2];   // grad wrt previous hidden (direct z-path part)
+#pragma unroll
+    for (int r = 0; r < GRU_R; r++) {
+      float2 gm = *reinterpret_cast<const float2*>(a.tp.g_mem + (size_t)row[r] * 192 + l * 64 + lane * 2);
+      float dh[2] = {gm.x + dx_next[r][0], gm.y + dx_next[r][1]};
+      if (l == 2) {
+        float2 gp = *reinterpret_cast<const float2*>(a.tp.g_pf + (size_t)row[r] * 64 + lane * 2);
+        dh[0] += gp.x; dh[1] += gp.y;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const float* st = stash + ((size_t)l * GRU_R + r) * 256 + lane * 2 + e;
+        const float rg = st[0], zg = st[64], ng = st[128], ghn = st[192];
+        const float hp = hbuf[(l * GRU_R + r) * LDG + lane * 2 + e];
+        const float dn = dh[e] * (1.0f - zg);
+        const float dz = dh[e] * (hp - ng);
+        dhp[r][e] = dh[e] * zg;
+        const float dpn = dn * (1.0f - ng * ng);
+        const float dr = dpn * ghn;
+        const float dpz = dz * zg * (1.0f - zg);
+        const float dpr = dr * rg * (1.0f - rg);
+        // gate pre-activation grads: input side (dgi) = [dpr, dpz, dpn], hidden side (dgh) = [dpr, dpz, dpn*r]
+        float* dgi = dgb + r * 196;   // reuse the same row buffer for gi then gh sequentially below
+        dgi[lane * 2 + e] = dpr;
+        dgi[64 + lane * 2 + e] = dpz;
+        dgi[128 + lane * 2 + e] = dpn;
+        // stash hidden-side n-gate grad in the stash slot of ghn (no longer needed)
+        const_cast<float*>(st)[192] = dpn * rg;
+      }
+    }
+    __syncwarp();
+    // input grad: dx = dgi . GI_N[l] ([192][Kin])
+    if (l > 0) {
+      float dx[GRU_R][2];
+      init_zero<2, GRU_R>(dx);
+      warp_gemm<64, GRU_R>(M.seg[S_GI_N0 + so], 192, dgb, 196, dx, lane);
+#pragma unroll
+      for (int r = 0; r < GRU_R; r++) { dx_next[r][0] = dx[r][0]; dx_next[r][1] = dx[r][1]; }
+    } else {
+      const float* W = M.seg[S_GI_N0];   // [192][4]
+#pragma unroll
+      for (int r = 0; r < GRU_R; r++) {
+        float p[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int n = lane; n < 192; n += 32) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(W + n * 4));
+          const float g = dgb[r * 196 + n];
+          p[0] = fmaf(g, w.x, p[0]); p[1] = fmaf(g, w.y, p[1]); p[2] = fmaf(g, w.z, p[2]); p[3] = fmaf(g, w.w, p[3]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) dloc_acc[r][k] = warp_sum(p[k]);
+      }
+    }
+    __syncwarp();
+    // hidden grad: dh_prev += dgh . GH_N[l]; dgh differs from dgi only in the n-gate block
+#pragma unroll
+    for (int r = 0; r < GRU_R; r++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) dgb[r * 196 + 128 + lane * 2 + e] = stash[((size_t)l * GRU_R + r) * 256 + 192 + lane * 2 + e];
+    }
+    __syncwarp();
+    warp_gemm<64, GRU_R>(M.seg[S_GH_N0 + so], 192, dgb, 196, dhp, lane);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < GRU_R; r++)
+      if (valid[r]) stvec<2>(a.tp.g_mem + (size_t)row[r] * 192 + l * 64 + lane * 2, dhp[r]);
+  }
+  if (lane < 4) {
+#pragma unroll
+    for (int r = 0; r < GRU_R; r++)
+      if (valid[r]) a.tp.d_loc[(size_t)row[r] * 4 + lane] = lane == 0 ? dloc_acc[r][0] : lane == 1 ? dloc_acc[r][1] : lane == 2 ? dloc_acc[r][2] : dloc_acc[r][3];
+  }
+}
+
+// post backward: (d_traj[t], g_prev, g_pos, d_loc) -> bicycle/transform adjoint -> mlp_out/update_mlp adjoint
+// outputs: g_prev <- grad wrt prev_state_t, d_xupd, d_aggr; zeroes g_pos and dQ rows for the edge phase.
+__global__ void __launch_bounds__(NODE_WARPS * 32) post_bwd_kernel(ModelDev M, StepArgs a, int has_gru) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int PER_WARP = NODE_R * (LDA + LDH) + 3 * NODE_R * LDH;
+  float* bufA = smem + warp * PER_WARP;
+  float* bufB = bufA + NODE_R * LDA;
+  float* preU = bufB + NODE_R * LDH;
+  float* pre1 = preU + NODE_R * LDH;
+  float* pre2 = pre1 + NODE_R * LDH;
+  const int NA = a.NA, t = a.t, FT = a.FT;
+  const int base = (blockIdx.x * NODE_WARPS + warp) * NODE_R;
+  if (base >= NA) return;
+  int row[NODE_R];
+  bool valid[NODE_R];
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++) { valid[r] = base + r < NA; row[r] = valid[r] ? base + r : NA - 1; }
+  stage_update_in<NODE_R>(bufA, a, row, lane, M.u0_rows);
+  __syncwarp();
+  float o[NODE_R][2];
+  post_mlps_fwd<NODE_R>(M, bufA, bufB, preU, pre1, pre2, o, lane);
+  // scalar adjoint: lane r handles row r, then d_o is broadcast to the warp
+  float my_o0 = 0.f, my_o1 = 0.f;
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++)
+    if (lane == r) { my_o0 = o[r][0]; my_o1 = o[r][1]; }
+  float d_o0 = 0.f, d_o1 = 0.f;
+  if (lane < NODE_R && base + lane < NA) {
+    const int ag = base + lane;
+    const float* pv = a.tp.prev + ((size_t)t * NA + ag) * 6;
+    float prev[6], cur[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) prev[k] = pv[k];
+    BikeFwd b;
+    bicycle_fwd(prev, my_o0, my_o1, a.lw[(size_t)ag * 2], cur, b);
+    const int s = a.scene_of[ag];
+    const bool is_ext = (a.ext != nullptr && ag == a.ptr[s]);
+    float dcur[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) dcur[k] = a.tp.g_prev[(size_t)ag * 6 + k];
+    const float4 dt = *reinterpret_cast<const float4*>(a.d_traj + ((size_t)ag * FT + t) * 4);
+    dcur[0] += dt.x; dcur[1] += dt.y; dcur[2] += dt.z; dcur[3] += dt.w;
+    float dprev[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (!is_ext) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) dcur[k] += a.tp.g_pos[(size_t)ag * 4 + k];
+    }
+    if (has_gru) {
+      float gl[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) gl[k] = a.tp.d_loc[(size_t)ag * 4 + k];
+      float glob[4] = {cur[0], cur[1], cur[2], cur[3]};
+      if (is_ext) {
+        const float* e = a.ext + ((size_t)s * FT + t) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) glob[k] = e[k];
+      }
+      float dpose[4] = {0.f, 0.f, 0.f, 0.f};
+      t2f_bwd(prev, glob, gl, dprev, dpose);
+      if (!is_ext) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) dcur[k] += dpose[k];
+      }
+    }
+    // normalise adjoint
+    float db[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) db[k] = dcur[k] / kStateStd[k];
+    float d_newh = -b.sn * db[2] + b.cs * db[3];
+    float d_news = db[4];
+    float d_newhdot = db[5];
+    float dun[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    dun[0] += db[0];
+    d_news += db[0] * b.cs * BIKE_DT;
+    d_newh += -db[0] * b.news * b.sn * BIKE_DT;
+    dun[1] += db[1];
+    d_news += db[1] * b.sn * BIKE_DT;
+    d_newh += db[1] * b.news * b.cs * BIKE_DT;
+    const float pass_s = (b.pre_s >= 0.0f && b.pre_s <= BIKE_MAXS) ? 1.0f : 0.0f;
+    dun[4] += pass_s * d_news;
+    const float d_a = pass_s * d_news * BIKE_DT;
+    float d_h = d_newh;
+    const float sg = (b.un[4] > 0.f) ? 1.0f : ((b.un[4] < 0.f) ? -1.0f : 0.0f);
+    dun[4] += d_newh * BIKE_DT * sg / b.len * b.newhdot;
+    d_newhdot += d_newh * BIKE_DT * fabsf(b.un[4]) / b.len;
+    const float pass_h = (b.pre_hd >= -BIKE_MAXHDOT && b.pre_hd <= BIKE_MAXHDOT) ? 1.0f : 0.0f;
+    dun[5] += pass_h * d_newhdot;
+    const float d_ddh = pass_h * d_newhdot * BIKE_DT;
+    const float nrm = b.un[2] * b.un[2] + b.un[3] * b.un[3];
+    dun[2] += d_h * (-b.un[3] / nrm);
+    dun[3] += d_h * (b.un[2] / nrm);
+#pragma unroll
+    for (int k = 0; k < 6; k++) dprev[k] += dun[k] * kStateStd[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) a.tp.g_prev[(size_t)ag * 6 + k] = dprev[k];
+    // hand g_pos over to the edge phase as a zeroed accumulator
+#pragma unroll
+    for (int k = 0; k < 4; k++) a.tp.g_pos[(size_t)ag * 4 + k] = 0.f;
+    d_o0 = d_a * A_STD;
+    d_o1 = d_ddh * DDH_STD;
+  }
+  // zero dQ rows (edge_bwd accumulates into them atomically)
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++)
+    if (valid[r]) *reinterpret_cast<float4*>(a.tp.dQ + (size_t)row[r] * 128 + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  // mlp_out backward
+  float dh[NODE_R][4];
+  {
+    float w0[4], w1[4];
+    ldvec<4>(w0, M.seg[S_O6_N] + lane * 4);
+    ldvec<4>(w1, M.seg[S_O6_N] + 128 + lane * 4);
+#pragma unroll
+    for (int r = 0; r < NODE_R; r++) {
+      const float g0 = __shfl_sync(0xffffffffu, d_o0, r);
+      const float g1 = __shfl_sync(0xffffffffu, d_o1, r);
+#pragma unroll
+      for (int v = 0; v < 4; v++) dh[r][v] = g0 * w0[v] + g1 * w1[v];
+    }
+  }
+  ln_relu_bwd<NODE_R>(dh, pre2, LDH, M.seg[S_O_LN4_G], M.seg[S_O_LN4_B], lane);
+  __syncwarp();
+  store_rows<4, NODE_R>(dh, bufB, LDH, lane);
+  __syncwarp();
+  init_zero<4, NODE_R>(dh);
+  warp_gemm<128, NODE_R>(M.seg[S_O3_N], 128, bufB, LDH, dh, lane);
+  ln_relu_bwd<NODE_R>(dh, pre1, LDH, M.seg[S_O_LN1_G], M.seg[S_O_LN1_B], lane);
+  __syncwarp();
+  store_rows<4, NODE_R>(dh, bufB, LDH, lane);
+  __syncwarp();
+  float dxu[NODE_R][2];
+  init_zero<2, NODE_R>(dxu);
+  warp_gemm<64, NODE_R>(M.seg[S_O0_N], 128, bufB, LDH, dxu, lane);
+  __syncwarp();
+  // update_mlp backward
+  store_rows<2, NODE_R>(dxu, bufA, LDA, lane);
+  __syncwarp();
+  init_zero<4, NODE_R>(dh);
+  warp_gemm<128, NODE_R>(M.seg[S_U3_N], 64, bufA, LDA, dh, lane);
+  ln_relu_bwd<NODE_R>(dh, preU, LDH, M.seg[S_U_LN1_G], M.seg[S_U_LN1_B], lane);
+  __syncwarp();
+  store_rows<4, NODE_R>(dh, bufB, LDH, lane);
+  __syncwarp();
+  float dxx[NODE_R][2], dag[NODE_R][2];
+  init_zero<2, NODE_R>(dxx);
+  init_zero<2, NODE_R>(dag);
+  warp_gemm<64, NODE_R>(M.seg[S_U0_N_X], 128, bufB, LDH, dxx, lane);
+  warp_gemm<64, NODE_R>(M.seg[S_U0_N_AGGR], 128, bufB, LDH, dag, lane);
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++) {
+    if (valid[r]) {
+      stvec<2>(a.tp.d_xupd + (size_t)row[r] * 64 + lane * 2, dxx[r]);
+      stvec<2>(a.tp.d_aggr + (size_t)row[r] * 64 + lane * 2, dag[r]);
+    }
+  }
+}
+
+// edge backward: recompute the edge MLP per chunk, route d_aggr to the arg-max edges, back through the MLP.
+// dP_i written (exclusive), dQ_j / g_pos_j accumulated atomically, g_pos_i accumulated atomically.
+__global__ void __launch_bounds__(EDGE_WARPS * 32) edge_bwd_kernel(ModelDev M, StepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ float red_dp[EDGE_WARPS][128];
+  __shared__ float red_pos[EDGE_WARPS][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* bufA = smem + warp * (4 * EDGE_R * LDH);
+  float* bufB = bufA + EDGE_R * LDH;
+  float* pre1 = bufB + EDGE_R * LDH;
+  float* pre2 = pre1 + EDGE_R * LDH;
+  EdgeCtx c;
+  edge_ctx_init(a, c);
+  const int NA = a.NA;
+  float Pi[4], Wrel[4][4];
+  ldvec<4>(Pi, a.tp.P + ((size_t)a.t * NA + c.i) * 128 + lane * 4);
+#pragma unroll
+  for (int d = 0; d < 4; d++) ldvec<4>(Wrel[d], M.seg[S_E0_T_REL] + d * 128 + lane * 4);
+  const float2 dagg = *reinterpret_cast<const float2*>(a.tp.d_aggr + (size_t)c.i * 64 + lane * 2);
+  const uchar2 am = *reinterpret_cast<const uchar2*>(a.tp.arg + ((size_t)a.t * NA + c.i) * 64 + lane * 2);
+  float dP[4] = {0.f, 0.f, 0.f, 0.f};
+  float dposi[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* posg = a.tp.pos + (size_t)a.t * NA * 4;
+  const int nchunks = (c.ne + EDGE_R - 1) / EDGE_R;
+  for (int chunk = warp; chunk < nchunks; chunk += EDGE_WARPS) {
+    float acc[EDGE_R][4], rel[EDGE_R][4];
+    int lj[EDGE_R];
+    bool valid[EDGE_R];
+    edge_layer0<EDGE_R>(a, c, chunk, Pi, Wrel, acc, lj, valid, rel, lane);
+    __syncwarp();
+    ln_relu_store<EDGE_R>(acc, M.seg[S_E_LN1_G], M.seg[S_E_LN1_B], bufA, LDH, pre1, LDH, lane);
+    __syncwarp();
+    init_bias<4, EDGE_R>(acc, M.seg[S_E3_B], lane);
+    warp_gemm<128, EDGE_R>(M.seg[S_E3_T], 128, bufA, LDH, acc, lane);
+    __syncwarp();
+    ln_relu_store<EDGE_R>(acc, M.seg[S_E_LN4_G], M.seg[S_E_LN4_B], bufB, LDH, pre2, LDH, lane);
+    __syncwarp();
+    // d_m rows (64 wide) into bufA (ld LDH)
+#pragma unroll
+    for (int r = 0; r < EDGE_R; r++) {
+      float dm[2];
+      dm[0] = (valid[r] && (int)am.x == lj[r]) ? dagg.x : 0.f;
+      dm[1] = (valid[r] && (int)am.y == lj[r]) ? dagg.y : 0.f;
+      stvec<2>(bufA + r * LDH + lane * 2, dm);
+    }
+    __syncwarp();
+    float dh[EDGE_R][4];
+    init_zero<4, EDGE_R>(dh);
+    warp_gemm<128, EDGE_R>(M.seg[S_E6_N], 64, bufA, LDH, dh, lane);
+    ln_relu_bwd<EDGE_R>(dh, pre2, LDH, M.seg[S_E_LN4_G], M.seg[S_E_LN4_B], lane);
+    __syncwarp();
+    store_rows<4, EDGE_R>(dh, bufA, LDH, lane);
+    __syncwarp();
+    init_zero<4, EDGE_R>(dh);
+    warp_gemm<128, EDGE_R>(M.seg[S_E3_N], 128, bufA, LDH, dh, lane);
+    ln_relu_bwd<EDGE_R>(dh, pre1, LDH, M.seg[S_E_LN1_G], M.seg[S_E_LN1_B], lane);
+    __syncwarp();
+    // dh = grad wrt h1pre = P_i + Q_j + W_rel rel
+#pragma unroll
+    for (int r = 0; r < EDGE_R; r++) {
+      if (!valid[r]) continue;   // warp-uniform
+      const int j = c.p0 + lj[r];
+      float drel[4];
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        float p = dh[r][0] * Wrel[d][0] + dh[r][1] * Wrel[d][1] + dh[r][2] * Wrel[d][2] + dh[r][3] * Wrel[d][3];
+        drel[d] = warp_sum(p);
+      }
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        dP[v] += dh[r][v];
+        atomicAdd(a.tp.dQ + (size_t)j * 128 + lane * 4 + v, dh[r][v]);
+      }
+      const float4 pj4 = __ldg(reinterpret_cast<const float4*>(posg + (size_t)j * 4));
+      const float pj[4] = {pj4.x, pj4.y, pj4.z, pj4.w};
+      float relchk[4];
+      t2f_fwd(c.pos_i, pj, relchk);
+#pragma unroll
+      for (int d = 0; d < 4; d++)
+        if (isnan(relchk[d])) drel[d] = 0.f;
+      float dpj[4] = {0.f, 0.f, 0.f, 0.f};
+      t2f_bwd(c.pos_i, pj, drel, dposi, dpj);
+      if (lane < 4) atomicAdd(a.tp.g_pos + (size_t)j * 4 + lane, lane == 0 ? dpj[0] : lane == 1 ? dpj[1] : lane == 2 ? dpj[2] : dpj[3]);
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int v = 0; v < 4; v++) red_dp[warp][lane * 4 + v] = dP[v];
+  if (lane < 4) red_pos[warp][lane] = lane == 0 ? dposi[0] : lane == 1 ? dposi[1] : lane == 2 ? dposi[2] : dposi[3];
+  __syncthreads();
+  {
+    const int ch = threadIdx.x;   // 128 threads, 128 columns
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < EDGE_WARPS; w++) s += red_dp[w][ch];
+    a.tp.dP[(size_t)c.i * 128 + ch] = s;
+    if (ch < 4) {
+      float p = 0.f;
+#pragma unroll
+      for (int w = 0; w < EDGE_WARPS; w++) p += red_pos[w][ch];
+      atomicAdd(a.tp.g_pos + (size_t)c.i * 4 + ch, p);
+    }
+  }
+}
+
+// node backward: d_x = d_xupd + dP.W_xi + dQ.W_xj ; back through mlp_in; d_z += ; g_pf <- grad wrt past_feat_t
+__global__ void __launch_bounds__(NODE_WARPS * 32) node_bwd_kernel(ModelDev M, StepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int PER_WARP = NODE_R * (LDA + LDH) + 2 * NODE_R * LDH;
+  float* bufA = smem + warp * PER_WARP;
+  float* bufB = bufA + NODE_R * LDA;
+  float* pre1 = bufB + NODE_R * LDH;
+  float* pre2 = pre1 + NODE_R * LDH;
+  const int NA = a.NA;
+  const int base = (blockIdx.x * NODE_WARPS + warp) * NODE_R;
+  if (base >= NA) return;
+  int row[NODE_R];
+  bool valid[NODE_R];
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++) { valid[r] = base + r < NA; row[r] = valid[r] ? base + r : NA - 1; }
+  stage_node_feat<NODE_R>(bufA, a, row, lane, M.in0_rows);
+  __syncwarp();
+  float xacc[NODE_R][2];
+  mlp_in_fwd<NODE_R>(M, bufA, bufB, pre1, pre2, xacc, lane);
+  // d_x
+  float dx[NODE_R][2];
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++) {
+    const float2 u = *reinterpret_cast<const float2*>(a.tp.d_xupd + (size_t)row[r] * 64 + lane * 2);
+    dx[r][0] = u.x; dx[r][1] = u.y;
+    *reinterpret_cast<float4*>(bufB + r * LDH + lane * 4) = *reinterpret_cast<const float4*>(a.tp.dP + (size_t)row[r] * 128 + lane * 4);
+  }
+  __syncwarp();
+  warp_gemm<64, NODE_R>(M.seg[S_E0_N_XI], 128, bufB, LDH, dx, lane);
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++)
+    *reinterpret_cast<float4*>(bufB + r * LDH + lane * 4) = *reinterpret_cast<const float4*>(a.tp.dQ + (size_t)row[r] * 128 + lane * 4);
+  __syncwarp();
+  warp_gemm<64, NODE_R>(M.seg[S_E0_N_XJ], 128, bufB, LDH, dx, lane);
+  __syncwarp();
+  store_rows<2, NODE_R>(dx, bufA, LDA, lane);
+  __syncwarp();
+  float dh[NODE_R][4];
+  init_zero<4, NODE_R>(dh);
+  warp_gemm<128, NODE_R>(M.seg[S_IN6_N], 64, bufA, LDA, dh, lane);
+  ln_relu_bwd<NODE_R>(dh, pre2, LDH, M.seg[S_IN_LN4_G], M.seg[S_IN_LN4_B], lane);
+  __syncwarp();
+  store_rows<4, NODE_R>(dh, bufB, LDH, lane);
+  __syncwarp();
+  init_zero<4, NODE_R>(dh);
+  warp_gemm<128, NODE_R>(M.seg[S_IN3_N], 128, bufB, LDH, dh, lane);
+  ln_relu_bwd<NODE_R>(dh, pre1, LDH, M.seg[S_IN_LN1_G], M.seg[S_IN_LN1_B], lane);
+  __syncwarp();
+  store_rows<4, NODE_R>(dh, bufB, LDH, lane);
+  __syncwarp();
+  float dpf[NODE_R][2], dz[NODE_R][1];
+  init_zero<2, NODE_R>(dpf);
+  init_zero<1, NODE_R>(dz);
+  warp_gemm<64, NODE_R>(M.seg[S_IN0_N_PF], 128, bufB, LDH, dpf, lane);
+  warp_gemm<32, NODE_R>(M.seg[S_IN0_N_Z], 128, bufB, LDH, dz, lane);
+#pragma unroll
+  for (int r = 0; r < NODE_R; r++) {
+    if (valid[r]) {
+      stvec<2>(a.tp.g_pf + (size_t)row[r] * 64 + lane * 2, dpf[r]);
+      a.d_z[(size_t)row[r] * ZDIM + lane] += dz[r][0];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// small utility kernels
+// ------------------------------------------------------------------------------------------------------
+__global__ void init_tape_kernel(StepArgs a, const float* past_last, const float* map_feat0, const float* past_feat0,
+                                 const int32_t* map_idx) {
+  const int NA = a.NA;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NA * 64) return;
+  const int ag = i >> 6, k = i & 63;
+  const float pf = past_feat0[i];
+  a.tp.pastfeat[i] = pf;
+  a.tp.mapfeat[i] = map_feat0[i];
+  a.tp.mem[(size_t)ag * 192 + k] = pf;            // traffic_model.py:625 hidden init = past_feat x 3 layers
+  a.tp.mem[(size_t)ag * 192 + 64 + k] = pf;
+  a.tp.mem[(size_t)ag * 192 + 128 + k] = pf;
+  if (k < 6) a.tp.prev[(size_t)ag * 6 + k] = past_last[(size_t)ag * 6 + k];
+  if (k < 4) a.tp.pos[(size_t)ag * 4 + k] = past_last[(size_t)ag * 6 + k];   // :604
+  if (k == 0) a.tp.map_of[ag] = map_idx[a.scene_of[ag]];
+  if (k < ZDIM) a.tp.z[(size_t)ag * ZDIM + k] = a.z[(size_t)ag * ZDIM + k];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------------
+static ModelDev model_dev(const StriveModel* m) {
+  ModelDev d;
+  for (int i = 0; i < S_COUNT; i++) d.seg[i] = m->seg[i];
+  d.nc = m->nc;
+  d.in0_rows = m->in0_rows;
+  d.u0_rows = m->u0_rows;
+  return d;
+}
+
+static const size_t SM_NODE = NODE_WARPS * NODE_R * (LDA + LDH) * 4;
+static const size_t SM_EDGE_F = EDGE_WARPS * 2 * EDGE_R * LDH * 4;
+static const size_t SM_EDGE_B = EDGE_WARPS * 4 * EDGE_R * LDH * 4;
+static const size_t SM_GRU_F = NODE_WARPS * (GRU_R * LDG * 4 + GRU_R * 4) * 4;
+static const size_t SM_GRU_B = NODE_WARPS * (6 * GRU_R * LDG + GRU_R * 4 + 3 * GRU_R * 256 + GRU_R * 196) * 4;
+static const size_t SM_POST_B = NODE_WARPS * (NODE_R * (LDA + LDH) + 3 * NODE_R * LDH) * 4;
+static const size_t SM_NODE_B = NODE_WARPS * (NODE_R * (LDA + LDH) + 2 * NODE_R * LDH) * 4;
+
+static int set_smem_attrs() {
+  static bool done = false;
+  if (done) return 0;
+  STRIVE_CUDA(cudaFuncSetAttribute(edge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_EDGE_B));
+  STRIVE_CUDA(cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GRU_B));
+  STRIVE_CUDA(cudaFuncSetAttribute(post_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_POST_B));
+  STRIVE_CUDA(cudaFuncSetAttribute(node_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE_B));
+  done = true;
+  return 0;
+}
+
+static int check_scene(const StriveModel* m, const StriveScene* sc, int ft) {
+  STRIVE_CHECK(m != nullptr && sc != nullptr, STRIVE_EINVAL, "null model/scene");
+  STRIVE_CHECK(sc->num_agents > 0 && sc->num_scenes > 0 && ft > 0, STRIVE_EINVAL, "empty scene batch (NA=%d S=%d FT=%d)",
+               sc->num_agents, sc->num_scenes, ft);
+  STRIVE_CHECK(sc->max_scene_agents <= 255, STRIVE_EUNSUPPORTED, "scene with %d agents > 255 unsupported", sc->max_scene_agents);
+  STRIVE_CHECK(sc->num_classes == m->nc, STRIVE_EINVAL, "scene NC=%d != model NC=%d", sc->num_classes, m->nc);
+  return 0;
+}
+
+extern "C" int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, const StriveMap* map, const float* z,
+                                 const float* map_feat0, const float* past_feat0, const float* ext_future, int32_t ft,
+                                 float* traj_out, void* tape, int64_t tape_bytes, void* stream_) {
+  int rc = check_scene(m, sc, ft);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int NA = sc->num_agents;
+  StepArgs a;
+  const int64_t need = tape_carve(&a.tp, (char*)tape, NA, ft);
+  STRIVE_CHECK(tape_bytes >= need, STRIVE_ESIZE, "tape too small: %lld < %lld", (long long)tape_bytes, (long long)need);
+  rc = set_smem_attrs();
+  if (rc) return rc;
+  a.NA = NA; a.FT = ft; a.NC = sc->num_classes; a.t = 0;
+  a.ptr = sc->ptr; a.scene_of = sc->scene_of; a.lw = sc->lw; a.sem = sc->sem; a.z = z; a.ext = ext_future;
+  a.traj = traj_out; a.d_traj = nullptr; a.d_z = nullptr;
+  ModelDev M = model_dev(m);
+  init_tape_kernel<<<(NA * 64 + 255) / 256, 256, 0, stream>>>(a, sc->past_last, map_feat0, past_feat0, sc->map_idx);
+  STRIVE_LAUNCH_CHECK();
+  const int node_blocks = (NA + NODE_WARPS * NODE_R - 1) / (NODE_WARPS * NODE_R);
+  for (int t = 0; t < ft; t++) {
+    a.t = t;
+    node_fwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_NODE, stream>>>(M, a);
+    STRIVE_LAUNCH_CHECK();
+    edge_fwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_F, stream>>>(M, a);
+    STRIVE_LAUNCH_CHECK();
+    post_fwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_NODE, stream>>>(M, a);
+    STRIVE_LAUNCH_CHECK();
+    if (t + 1 < ft) {
+      gru_fwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_GRU_F, stream>>>(M, a);
+      STRIVE_LAUNCH_CHECK();
+      rc = strive_mapenc_fwd(m, map, a.tp.pose, a.tp.map_of, NA, a.tp.mapfeat + (size_t)(t + 1) * NA * 64, a.tp.mapenc_ws,
+                             a.tp.mapenc_ws_bytes, stream_);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+extern "C" int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, int32_t ft, const float* ext_future,
+                                 const float* d_traj, float* d_z, void* tape, int64_t tape_bytes, void* stream_) {
+  int rc = check_scene(m, sc, ft);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int NA = sc->num_agents;
+  StepArgs a;
+  const int64_t need = tape_carve(&a.tp, (char*)tape, NA, ft);
+  STRIVE_CHECK(tape_bytes >= need, STRIVE_ESIZE, "tape too small: %lld < %lld", (long long)tape_bytes, (long long)need);
+  rc = set_smem_attrs();
+  if (rc) return rc;
+  a.NA = NA; a.FT = ft; a.NC = sc->num_classes; a.t = 0;
+  a.ptr = sc->ptr; a.scene_of = sc->scene_of; a.lw = sc->lw; a.sem = sc->sem; a.z = nullptr; a.ext = ext_future;
+  a.traj = nullptr; a.d_traj = d_traj; a.d_z = d_z;
+  a.z = a.tp.z;   // the latent the forward pass ran on
+  ModelDev M = model_dev(m);
+  STRIVE_CUDA(cudaMemsetAsync(d_z, 0, (size_t)NA * ZDIM * 4, stream));
+  STRIVE_CUDA(cudaMemsetAsync(a.tp.g_prev, 0, (size_t)NA * 6 * 4, stream));
+  STRIVE_CUDA(cudaMemsetAsync(a.tp.g_pos, 0, (size_t)NA * 4 * 4, stream));
+  STRIVE_CUDA(cudaMemsetAsync(a.tp.g_pf, 0, (size_t)NA * 64 * 4, stream));
+  STRIVE_CUDA(cudaMemsetAsync(a.tp.g_mem, 0, (size_t)NA * 192 * 4, stream));
+  STRIVE_CUDA(cudaMemsetAsync(a.tp.d_loc, 0, (size_t)NA * 4 * 4, stream));
+  const int node_blocks = (NA + NODE_WARPS * NODE_R - 1) / (NODE_WARPS * NODE_R);
+  for (int t = ft - 1; t >= 0; t--) {
+    a.t = t;
+    const int has_gru = (t + 1 < ft) ? 1 : 0;
+    if (has_gru) {
+      gru_bwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_GRU_B, stream>>>(M, a);
+      STRIVE_LAUNCH_CHECK();
+    }
+    post_bwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_POST_B, stream>>>(M, a, has_gru);
+    STRIVE_LAUNCH_CHECK();
+    edge_bwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_B, stream>>>(M, a);
+    STRIVE_LAUNCH_CHECK();
+    node_bwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_NODE_B, stream>>>(M, a);
+    STRIVE_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int strive_decode_tape_read(const void* tape, int32_t num_agents, int32_t ft, const char* name, int32_t t,
+                                       float* out, void* stream_) {
+  Tape tp;
+  tape_carve(&tp, (char*)tape, num_agents, ft);
+  STRIVE_CHECK(t >= 0 && t < ft, STRIVE_EINVAL, "tape_read: step %d out of range", t);
+  const size_t n = (size_t)num_agents;
+  const float* src = nullptr;
+  size_t w = 0;
+  struct { const char* nm; const float* base; size_t width; } tab[] = {
+      {"x", tp.x, 64}, {"P", tp.P, 128}, {"Q", tp.Q, 128}, {"aggr", tp.aggr, 64}, {"past_feat", tp.pastfeat, 64},
+      {"map_feat", tp.mapfeat, 64}, {"prev", tp.prev, 6}, {"pos", tp.pos, 4}, {"loc", tp.loc, 4}, {"mem", tp.mem, 192}};
+  for (auto& e : tab) {
+    bool eq = true;
+    for (int i = 0;; i++) {
+      if (e.nm[i] != name[i]) { eq = false; break; }
+      if (e.nm[i] == 0) break;
+    }
+    if (eq) { src = e.base + (size_t)t * n * e.width; w = e.width; }
+  }
+  STRIVE_CHECK(src != nullptr, STRIVE_EINVAL, "tape_read: unknown tensor '%s'", name);
+  STRIVE_CUDA(cudaMemcpyAsync(out, src, n * w * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+  return 0;
+}

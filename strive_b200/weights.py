@@ -1,0 +1,89 @@
+"""Packs the decode-path tensors of a STRIVE `TrafficModel.state_dict()` into the kernel layout.
+
+Segment order = `enum Seg` in csrc/common.cuh (checked at load time against strive_model_layout()).
+`_T` segments are [in][out] (transposed nn.Linear weights: coalesced forward GEMVs), `_N` segments are the
+native [out][in] matrices (or column slices) used by the data-gradient GEMVs of the backward pass.
+Reference key names: src/models/traffic_model.py:69-156, src/models/interaction_net.py:29-119, models/common.py:8-39.
+"""
+import torch
+
+
+def _pad_rows(t, rows):
+    if t.size(0) == rows:
+        return t
+    out = torch.zeros((rows, t.size(1)), dtype=t.dtype, device=t.device)
+    out[:t.size(0)] = t
+    return out
+
+
+def _r4(x):
+    return (x + 3) & ~3
+
+
+def decode_segments(sd, NC):
+    """List of (name, 2-D/1-D float32 CPU tensor) in enum Seg order."""
+    g = lambda k: sd[k].detach().to(torch.float32).cpu()
+    segs = []
+    for l in range(6):
+        w = g('map_conv.%d.weight' % (3 * l))                       # (Cout,Cin,k,k)
+        segs.append(('CW%d' % l, w.permute(1, 2, 3, 0).reshape(-1, w.size(0))))
+        segs.append(('CB%d' % l, g('map_conv.%d.bias' % (3 * l))))
+        segs.append(('GG%d' % l, g('map_conv.%d.weight' % (3 * l + 1))))
+        segs.append(('GB%d' % l, g('map_conv.%d.bias' % (3 * l + 1))))
+    segs.append(('FCW', g('map_feature.weight').t()))
+    segs.append(('FCB', g('map_feature.bias')))
+    p = 'decoder_net.mlp_in.net.'
+    w0 = g(p + '0.weight')                                           # (128, 64+64+NC+32+2)
+    in0_rows = _r4(64 + 64 + NC + 32 + 2)
+    assert w0.size(1) == 64 + 64 + NC + 32 + 2, 'decoder_net.mlp_in input width does not match num_classes'
+    segs += [('IN0_T', _pad_rows(w0.t(), in0_rows)), ('IN0_B', g(p + '0.bias')),
+             ('IN_LN1_G', g(p + '1.weight')), ('IN_LN1_B', g(p + '1.bias')),
+             ('IN3_T', g(p + '3.weight').t()), ('IN3_B', g(p + '3.bias')),
+             ('IN_LN4_G', g(p + '4.weight')), ('IN_LN4_B', g(p + '4.bias')),
+             ('IN6_T', g(p + '6.weight').t()), ('IN6_B', g(p + '6.bias')),
+             ('IN0_N_PF', w0[:, 0:64]), ('IN0_N_Z', w0[:, 128 + NC:128 + NC + 32]),
+             ('IN3_N', g(p + '3.weight')), ('IN6_N', g(p + '6.weight'))]
+    p = 'decoder_net.msg.0.edge_mlp.net.'
+    w1 = g(p + '0.weight')                                           # (128, 2*(64+NC)+4)
+    assert w1.size(1) == 2 * (64 + NC) + 4
+    segs += [('E0_T_XI', w1[:, 0:64].t()), ('E0_T_XJ', w1[:, 64:128].t()),
+             ('E0_T_SEMI', w1[:, 128:128 + NC].t()), ('E0_T_SEMJ', w1[:, 128 + NC:128 + 2 * NC].t()),
+             ('E0_T_REL', w1[:, 128 + 2 * NC:].t()), ('E0_B', g(p + '0.bias')),
+             ('E0_N_XI', w1[:, 0:64]), ('E0_N_XJ', w1[:, 64:128]),
+             ('E_LN1_G', g(p + '1.weight')), ('E_LN1_B', g(p + '1.bias')),
+             ('E3_T', g(p + '3.weight').t()), ('E3_N', g(p + '3.weight')), ('E3_B', g(p + '3.bias')),
+             ('E_LN4_G', g(p + '4.weight')), ('E_LN4_B', g(p + '4.bias')),
+             ('E6_T', g(p + '6.weight').t()), ('E6_N', g(p + '6.weight')), ('E6_B', g(p + '6.bias'))]
+    p = 'decoder_net.msg.0.update_mlp.net.'
+    wu = g(p + '0.weight')                                           # (128, 64+64+NC)
+    u0_rows = _r4(64 + 64 + NC)
+    segs += [('U0_T', _pad_rows(wu.t(), u0_rows)), ('U0_B', g(p + '0.bias')),
+             ('U_LN1_G', g(p + '1.weight')), ('U_LN1_B', g(p + '1.bias')),
+             ('U3_T', g(p + '3.weight').t()), ('U3_B', g(p + '3.bias')),
+             ('U0_N_X', wu[:, 0:64]), ('U0_N_AGGR', wu[:, 64:128]), ('U3_N', g(p + '3.weight'))]
+    p = 'decoder_net.mlp_out.net.'
+    segs += [('O0_T', g(p + '0.weight').t()), ('O0_B', g(p + '0.bias')),
+             ('O_LN1_G', g(p + '1.weight')), ('O_LN1_B', g(p + '1.bias')),
+             ('O3_T', g(p + '3.weight').t()), ('O3_B', g(p + '3.bias')),
+             ('O_LN4_G', g(p + '4.weight')), ('O_LN4_B', g(p + '4.bias')),
+             ('O6_N', g(p + '6.weight')), ('O6_B', g(p + '6.bias')),
+             ('O0_N', g(p + '0.weight')), ('O3_N', g(p + '3.weight'))]
+    for l in range(3):
+        wi, wh = g('decoder_memory.weight_ih_l%d' % l), g('decoder_memory.weight_hh_l%d' % l)
+        segs += [('GI_T%d' % l, wi.t()), ('GH_T%d' % l, wh.t()),
+                 ('GBI%d' % l, g('decoder_memory.bias_ih_l%d' % l)), ('GBH%d' % l, g('decoder_memory.bias_hh_l%d' % l)),
+                 ('GI_N%d' % l, wi), ('GH_N%d' % l, wh)]
+    return segs
+
+
+def pack_decode_weights(sd, NC):
+    """-> (blob float32 CPU 1-D, [segment sizes])  every segment starts on a 16-byte boundary."""
+    segs = decode_segments(sd, NC)
+    sizes = [int(t.numel()) for _, t in segs]
+    total = sum(_r4(s) for s in sizes)
+    blob = torch.zeros(total, dtype=torch.float32)
+    off = 0
+    for (_, t), s in zip(segs, sizes):
+        blob[off:off + s] = t.contiguous().reshape(-1)
+        off += _r4(s)
+    return blob, sizes

@@ -1,0 +1,363 @@
+"""GPU parity tests: the CUDA path (called through the C-ABI / drop-in modules) against the CPU oracle and the
+golden vectors generated from the unmodified reference.
+
+Stated tolerances (DESIGN.md 'Tolerances'):
+  * integer / byte work (map crop, arg-max indices): bit exact.
+  * single functions in fp32 (CNN feature, one GNN step, loss terms, per-step adjoints): <= 2e-5 abs on O(1) values
+    (fp32 re-association only).
+  * rollouts: the autoregressive decoder amplifies fp32 rounding ~1.6x per step (nearest-pixel crop), for the
+    reference itself as much as for us; a rollout passes if its error against the fp64 oracle is within 10x the
+    error of the fp32 oracle (= reference precision) against the same fp64 oracle, plus 1e-5.
+Every test appends what it measured to gpurun_out/diag_gpu.txt.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import strive_oracle as O
+from tests.common import world, golden, scene_for, REFINE_W, ADV_W, SOL_W, EXTENT
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DIAG = os.path.join(ROOT, 'gpurun_out', 'diag_gpu.txt')
+
+
+def diag(msg):
+    os.makedirs(os.path.dirname(DIAG), exist_ok=True)
+    with open(DIAG, 'a') as f:
+        f.write(msg + '\n')
+    print(msg)
+
+
+class Graph(object):
+    pass
+
+
+def to_graph(sc, dev):
+    g = Graph()
+    for k in ('past', 'lw', 'sem', 'ptr', 'batch', 'edge_index'):
+        setattr(g, k, sc[k].to(dev))
+    g.past_vis = torch.ones(sc['past'].shape[:2], device=dev)
+    return g
+
+
+_ctx = {}
+
+
+def ctx():
+    if not _ctx:
+        import strive_b200
+        dev = torch.device('cuda:0')
+        raster, dx, sd = world()
+        _ctx['dev'] = dev
+        _ctx['model'] = strive_b200.make_model(nfuture=20, state_dict=sd, device=dev)
+        _ctx['env'] = strive_b200.MapEnv(raster, dx, device=dev)
+        _ctx['sd64'] = {k: v.double() for k, v in sd.items()}
+    return _ctx['dev'], _ctx['model'], _ctx['env']
+
+
+def o_decode(sd, raster, dx, sc, z, FT, ext=None, taps=None, dtype=torch.float32):
+    c = lambda t: t.to(dtype) if t.is_floating_point() else t
+    return O.decode(sd, c(z), c(sc['map_feat']), c(sc['past_feat']), c(sc['past'][:, -1, :]), c(sc['lw']), c(sc['sem']),
+                    sc['ptr'], sc['edge_index'], sc['map_idx'], raster, dx, FT, ext_future=None if ext is None else c(ext), taps=taps)
+
+
+def gpu_decode(sc, FT, ext=None, z=None):
+    dev, model, env = ctx()
+    g = to_graph(sc, dev)
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev)}
+    zz = (sc['z'] if z is None else z).to(dev)
+    return model.decode_embedding(zz, embed, g, sc['map_idx'].to(dev), env, ext_future=None if ext is None else ext.to(dev),
+                                  nfuture=FT)['future_pred'], g
+
+
+# ----------------------------------------------------------------------------------------------------------
+def test_library_loaded_is_in_tree():
+    from strive_b200 import _cabi
+    L = _cabi.lib()
+    assert os.path.dirname(_cabi.LIB_PATH).endswith('strive_b200') and L.strive_abi_version() == 1
+
+
+def test_map_crop_bit_exact():
+    dev, model, env = ctx()
+    raster, dx, sd = world()
+    g = golden('encode_map')
+    pos_n = torch.from_numpy(g['pos_n'])
+    mapix = torch.from_numpy(g['mapix'])
+    gen = torch.Generator().manual_seed(5)
+    extra = torch.rand(26, 2, generator=gen) * 300.0 + 10.0
+    ang = torch.rand(26, generator=gen) * 6.28318
+    pose_un = torch.cat([O.unnorm_state(pos_n), torch.cat([extra, torch.cos(ang)[:, None], torch.sin(ang)[:, None]], 1)], 0).contiguous()
+    mapix = torch.cat([mapix, torch.randint(0, 2, (26,), generator=gen)])
+    ref = O.map_crop(raster, dx, pose_un, mapix)
+    got = env.crop_poses(pose_un.to(dev), mapix.to(dev)).cpu()
+    nbad = int((ref != got).sum())
+    diag('map_crop: %d poses, mismatching pixels = %d of %d' % (pose_un.size(0), nbad, ref.numel()))
+    assert nbad == 0
+    assert np.array_equal(got[:6].long().sum(dim=3).numpy(), g['crop_rowsum'])
+
+
+def test_map_encoder_feature():
+    dev, model, env = ctx()
+    raster, dx, sd = world()
+    g = golden('encode_map')
+    pos_n = torch.from_numpy(g['pos_n'])
+    mapix = torch.from_numpy(g['mapix'])
+    gen = torch.Generator().manual_seed(6)
+    extra = torch.rand(58, 2, generator=gen) * 250.0 + 30.0
+    ang = torch.rand(58, generator=gen) * 6.28318
+    pose_un = torch.cat([O.unnorm_state(pos_n), torch.cat([extra, torch.cos(ang)[:, None], torch.sin(ang)[:, None]], 1)], 0).contiguous()
+    mapix = torch.cat([mapix, torch.randint(0, 2, (58,), generator=gen)])
+    got = model.encode_map_poses(pose_un.to(dev), mapix.to(dev), env).cpu()
+    crop = O.map_crop(raster, dx, pose_un, mapix)
+    ref32 = O.map_cnn(sd, crop.float())
+    ref64 = O.map_cnn(_ctx['sd64'], crop.double())
+    e_gpu = (got.double() - ref64).abs().max().item()
+    e_ref = (ref32.double() - ref64).abs().max().item()
+    e_gold = np.abs(got[:6].numpy() - g['map_feat']).max()
+    diag('map_encoder: |gpu-fp64|=%.3e |fp32oracle-fp64|=%.3e |gpu-golden|=%.3e feat_absmax=%.3f' % (e_gpu, e_ref, e_gold, ref64.abs().max().item()))
+    assert e_gpu < 2e-5 and e_gold < 2e-5
+
+
+def _tape(model_scene_tape, name, t, NA, FT, width):
+    from strive_b200 import _cabi
+    tape = model_scene_tape
+    out = torch.empty((NA, width), dtype=torch.float32, device=tape.device)
+    _cabi.check(_cabi.lib().strive_decode_tape_read(_cabi.dptr(tape), NA, FT, name.encode(), t, _cabi.dptr(out), _cabi.stream_ptr()))
+    return out.cpu()
+
+
+def test_decode_per_step_intermediates():
+    """Every tape tensor of every step against the oracle's intermediates (fp32 oracle)."""
+    import ctypes as C
+    from strive_b200 import _cabi
+    dev, model, env = ctx()
+    raster, dx, sd = world()
+    g = golden('decode_small')
+    sc = scene_for(g)
+    FT = int(g['FT'])
+    taps = {}
+    with torch.no_grad():
+        ref = o_decode(sd, raster, dx, sc, sc['z'], FT, taps=taps)
+    graph = to_graph(sc, dev)
+    scene = model.scene_batch(graph, sc['map_idx'].to(dev))
+    L = _cabi.lib()
+    NA = scene.NA
+    nb = L.strive_decode_tape_bytes(NA, FT)
+    tape = torch.empty(nb, dtype=torch.uint8, device=dev)
+    traj = torch.empty((NA, FT, 4), dtype=torch.float32, device=dev)
+    z = sc['z'].to(dev).contiguous()
+    mf, pf = sc['map_feat'].to(dev).contiguous(), sc['past_feat'].to(dev).contiguous()
+    _cabi.check(L.strive_decode_fwd(model.device_model().handle, C.byref(scene.cstruct), C.byref(env.cstruct), _cabi.dptr(z),
+                                    _cabi.dptr(mf), _cabi.dptr(pf), None, FT, _cabi.dptr(traj), _cabi.dptr(tape), nb, _cabi.stream_ptr()))
+    torch.cuda.synchronize()
+    worst0 = 0.0
+    for t in range(FT):
+        st = taps['steps'][t]
+        row = []
+        for name, width, refv in (('past_feat', 64, st['past_feat']), ('map_feat', 64, st['map_feat']), ('x', 64, st['x']),
+                                  ('aggr', 64, st['aggr']), ('pos', 4, st['pos_in']), ('loc', 4, st['loc']),
+                                  ('mem', 192, st['mem'].permute(1, 0, 2).reshape(NA, 192))):
+            got = _tape(tape, name, t, NA, FT, width)
+            d = (got - refv).abs().max().item()
+            row.append('%s=%.1e' % (name, d))
+            if t == 0:
+                worst0 = max(worst0, d)
+        dtraj = (traj[:, t].cpu() - ref[:, t]).abs().max().item()
+        if t == 0:
+            worst0 = max(worst0, dtraj)
+        diag('decode step %d: traj=%.1e %s' % (t, dtraj, ' '.join(row)))
+    assert worst0 < 2e-5, 'first rollout step (no amplification) must match to fp32 re-association'
+
+
+@pytest.mark.parametrize('name', ['decode_small', 'decode_ext', 'decode_c1'])
+def test_decode_rollout_vs_golden_and_fp64(name):
+    dev, model, env = ctx()
+    raster, dx, sd = world()
+    g = golden(name)
+    sc = scene_for(g)
+    FT = int(g['FT'])
+    ext = sc['ext_future'] if int(g['with_ext']) else None
+    traj, _ = gpu_decode(sc, FT, ext)
+    traj = traj.detach().cpu()
+    with torch.no_grad():
+        r32 = o_decode(sd, raster, dx, sc, sc['z'], FT, ext)
+        r64 = o_decode(_ctx['sd64'], raster, dx, sc, sc['z'], FT, ext, dtype=torch.float64)
+    e_gpu = (traj.double() - r64).abs().amax(dim=(0, 2))
+    e_ref = (r32.double() - r64).abs().amax(dim=(0, 2))
+    e_gold = np.abs(traj.numpy() - g['traj']).max(axis=(0, 2))
+    diag('%s: per-step |gpu-fp64| %s' % (name, ' '.join('%.1e' % v for v in e_gpu.tolist())))
+    diag('%s: per-step |ref32-fp64| %s' % (name, ' '.join('%.1e' % v for v in e_ref.tolist())))
+    diag('%s: per-step |gpu-golden| %s' % (name, ' '.join('%.1e' % v for v in e_gold.tolist())))
+    assert e_gold[0] < 2e-6
+    # cumulative-max envelope: rounding noise is amplified step by step
+    env_ref = torch.cummax(e_ref, 0)[0]
+    assert bool((e_gpu <= 10.0 * env_ref + 1e-5).all())
+
+
+@pytest.mark.parametrize('FT,with_ext', [(1, False), (2, False), (4, False), (4, True), (6, False)])
+def test_decode_backward_vs_autograd(FT, with_ext):
+    dev, model, env = ctx()
+    raster, dx, sd = world()
+    g = golden('decode_small')
+    sc = scene_for(g)
+    ext = sc['ext_future'][:, :FT].contiguous() if with_ext else None
+    gen = torch.Generator().manual_seed(100 + FT)
+    seed = torch.randn(sc['z'].size(0), FT, 4, generator=gen)
+    z = sc['z'].clone().to(dev).requires_grad_(True)
+    traj, _ = gpu_decode(sc, FT, ext, z=z)
+    traj.backward(seed.to(dev))
+    got = z.grad.cpu()
+    z64 = sc['z'].double().requires_grad_(True)
+    r64 = o_decode(_ctx['sd64'], raster, dx, sc, z64, FT, ext, dtype=torch.float64)
+    r64.backward(seed.double())
+    z32 = sc['z'].clone().requires_grad_(True)
+    r32 = o_decode(sd, raster, dx, sc, z32, FT, ext)
+    r32.backward(seed)
+    scale = z64.grad.abs().max().item()
+    e_gpu = (got.double() - z64.grad).abs().max().item()
+    e_ref = (z32.grad.double() - z64.grad).abs().max().item()
+    diag('decode_bwd FT=%d ext=%d: |gpu-fp64|=%.3e |ref32-fp64|=%.3e grad_absmax=%.3e' % (FT, int(with_ext), e_gpu, e_ref, scale))
+    assert e_gpu <= 10.0 * e_ref + 2e-5 * max(1.0, scale)
+
+
+def test_avoid_loss_terms_and_grads_refine():
+    """AvoidCollLoss as refine_traffic_optim builds it (no ptr: one collision block), drop-in module, on the golden traj."""
+    from strive_b200.losses import AvoidCollLoss
+    dev, model, env = ctx()
+    raster, dx, sd = world()
+    g = golden('refine')
+    sc = scene_for(g)
+    fut_n = torch.from_numpy(g['traj0'])
+    lw_un = O.unnorm_att(sc['lw'])
+    mapixes = sc['map_idx'][sc['batch']]
+    fut = O.unnorm_state(fut_n).requires_grad_(True)
+    z = sc['z'].clone().requires_grad_(True)
+    ref = O.avoid_coll_loss(fut, z, (sc['prior_mu'], sc['prior_var']), sc['z'] + 0.1, REFINE_W, lw_un, mapixes, None, raster, dx,
+                            veh_coll_buffer=0.2)
+    ref['loss'].backward()
+    mod = AvoidCollLoss(REFINE_W, lw_un.to(dev), mapixes.to(dev), env, (sc['z'] + 0.1).to(dev), veh_coll_buffer=0.2)
+    futd = O.unnorm_state(fut_n).to(dev).requires_grad_(True)
+    zd = sc['z'].clone().to(dev).requires_grad_(True)
+    out = mod(futd, zd, (sc['prior_mu'].to(dev), sc['prior_var'].to(dev)))
+    out['loss'].backward()
+    t = out['_terms'][0].cpu()
+    diag('avoid(refine): loss gpu %.6f ref %.6f | veh mean %.6f/%.6f cnt %d/%d | env mean %.6f/%.6f cnt %d/%d | prior %.5f/%.5f init %.6f/%.6f' % (
+        float(out['loss']), float(ref['loss']), t[1], float(ref['coll_veh_loss'].mean()), int(t[2]), ref['coll_veh_loss'].numel(),
+        t[3], float(ref['coll_env_loss'].mean()), int(t[4]), ref['coll_env_loss'].numel(), t[5], float(ref['motion_prior_loss'].mean()),
+        t[6], float(ref['init_loss'].mean())))
+    e_f = (futd.grad.cpu() - fut.grad).abs().max().item()
+    e_z = (zd.grad.cpu() - z.grad).abs().max().item()
+    diag('avoid(refine): |d_fut| err %.3e (max %.3e)  |d_z| err %.3e (max %.3e)' % (e_f, fut.grad.abs().max().item(), e_z, z.grad.abs().max().item()))
+    assert int(t[2]) == ref['coll_veh_loss'].numel() and int(t[4]) == ref['coll_env_loss'].numel()
+    assert abs(float(out['loss']) - float(ref['loss'])) < 1e-4 * abs(float(ref['loss']))
+    assert e_f < 1e-4 * max(1.0, fut.grad.abs().max().item()) and e_z < 1e-5 * max(1.0, z.grad.abs().max().item())
+
+
+def test_adv_and_sol_losses_vs_golden():
+    from strive_b200.losses import AdvGenLoss, AvoidCollLoss, TgtMatchingLoss
+    dev, model, env = ctx()
+    raster, dx, sd = world()
+    g = golden('losses')
+    sc = scene_for(g)
+    ptr = sc['ptr']
+    NA = int(ptr[-1])
+    ego = torch.zeros(NA, dtype=torch.bool)
+    ego[ptr[:-1]] = True
+    FT = int(g['FT'])
+    fut_n = torch.from_numpy(g['fut_n'])
+    lw_un = O.unnorm_att(sc['lw']).to(dev)
+    mapixes = sc['map_idx'][sc['batch']].to(dev)
+    tgt = O.unnorm_state(sc['ext_future'][:, :FT]).to(dev)
+    # adversarial loss
+    fut = O.unnorm_state(fut_n).to(dev).requires_grad_(True)
+    z_o = sc['z'][~ego].clone().to(dev).requires_grad_(True)
+    prior_o = (sc['prior_mu'][~ego].to(dev), sc['prior_var'][~ego].to(dev))
+    adv = AdvGenLoss(ADV_W, lw_un, mapixes, env, (sc['z'][~ego] + 0.05).to(dev), ptr.to(dev), veh_coll_buffer=0.1,
+                     crash_loss_min_time=2, crash_loss_min_infront=-0.5)
+    ld = adv(fut, tgt, z_o, prior_o, return_mins=True)
+    ld['loss'].backward()
+    t = ld['_terms'][0].cpu()
+    diag('adv: loss gpu %.4f golden %.4f | means gpu [init %.4f prior %.4f veh %.5f plan %.5f env %.5f crash %.4f] golden %s | mins %s %s vs %s %s' % (
+        float(ld['loss']), float(g['adv_loss']), t[6], t[5], t[1], t[7], t[3], t[9], np.array2string(g['adv_means'], precision=4),
+        ld['min_agt'], ld['min_t'], g['adv_min_agt'], g['adv_min_t']))
+    e_f = np.abs(fut.grad.cpu().numpy() - g['adv_d_fut']).max()
+    e_z = np.abs(z_o.grad.cpu().numpy() - g['adv_d_z']).max()
+    diag('adv: |d_fut| err %.3e (max %.3e) |d_z| err %.3e (max %.3e)' % (e_f, np.abs(g['adv_d_fut']).max(), e_z, np.abs(g['adv_d_z']).max()))
+    assert abs(float(ld['loss']) - float(g['adv_loss'])) < 1e-4 * abs(float(g['adv_loss']))
+    assert e_f < 1e-3 * np.abs(g['adv_d_fut']).max() and e_z < 1e-4 * max(1.0, np.abs(g['adv_d_z']).max())
+    assert list(ld['min_agt']) == list(g['adv_min_agt']) and list(ld['min_t']) == list(g['adv_min_t'])
+    # matching loss
+    futm = O.unnorm_state(fut_n)[ego].to(dev).requires_grad_(True)
+    lm = TgtMatchingLoss(ADV_W)(futm, tgt, sc['z'][ego].to(dev), (sc['prior_mu'][ego].to(dev), sc['prior_var'][ego].to(dev)))
+    lm['loss'].backward()
+    assert abs(float(lm['loss']) - float(g['match_loss'])) < 1e-5 * abs(float(g['match_loss']))
+    assert np.abs(futm.grad.cpu().numpy() - g['match_d_fut']).max() < 1e-5 * max(1.0, np.abs(g['match_d_fut']).max())
+    # solution-phase avoid loss (single_veh_idx=0)
+    futs = O.unnorm_state(fut_n).to(dev).requires_grad_(True)
+    zs = sc['prior_mu'][ego].clone().to(dev).requires_grad_(True)
+    av = AvoidCollLoss(SOL_W, lw_un, mapixes, env, zs.detach().clone(), veh_coll_buffer=0.5, single_veh_idx=0, ptr=ptr.to(dev))
+    ls = av(futs, zs, (sc['prior_mu'][ego].to(dev), sc['prior_var'][ego].to(dev)))
+    ls['loss'].backward()
+    e_f = np.abs(futs.grad.cpu().numpy() - g['sol_d_fut']).max()
+    e_z = np.abs(zs.grad.cpu().numpy() - g['sol_d_z']).max()
+    diag('sol avoid: loss gpu %.6f golden %.6f | |d_fut| err %.3e (max %.3e) |d_z| err %.3e' % (float(ls['loss']), float(g['sol_loss']), e_f, np.abs(g['sol_d_fut']).max(), e_z))
+    assert abs(float(ls['loss']) - float(g['sol_loss'])) < 1e-4 * abs(float(g['sol_loss']))
+    assert e_f < 1e-3 * max(1.0, np.abs(g['sol_d_fut']).max()) and e_z < 1e-5
+
+
+def test_refine_loop_vs_golden_adam_trajectory():
+    """Fused device loop (decode -> loss -> d/dz -> Adam) against the reference's own 5-iteration Adam trajectory."""
+    from strive_b200.optim import RefineLoop
+    dev, model, env = ctx()
+    raster, dx, sd = world()
+    g = golden('refine')
+    sc = scene_for(g)
+    FT, iters, lr = int(g['FT']), int(g['iters']), float(g['lr'])
+    graph = to_graph(sc, dev)
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev),
+             'prior_out': (sc['prior_mu'].to(dev), sc['prior_var'].to(dev))}
+    loop = RefineLoop(model, graph, sc['map_idx'].to(dev), env, embed, sc['z'].to(dev), REFINE_W, lr, FT, veh_coll_buffer=0.2)
+    for it in range(iters):
+        loop._forward(); loop._loss(); loop._backward()
+        torch.cuda.synchronize()
+        gerr = np.abs(loop.grad().cpu().numpy() - g['grad'][it]).max()
+        lerr = abs(float(loop.terms[:, 0].sum()) - g['loss'][it])
+        loop._adam()
+        torch.cuda.synchronize()
+        zerr = np.abs(loop.z.cpu().numpy() - g['z'][it]).max()
+        diag('refine iter %d: loss gpu %.5f golden %.5f | |grad err| %.3e (max %.3e) | |z err| %.3e' % (
+            it, float(loop.terms[:, 0].sum()), g['loss'][it], gerr, np.abs(g['grad'][it]).max(), zerr))
+        if it == 0:
+            assert lerr < 1e-3 * abs(g['loss'][0]) and gerr < 2e-3 * np.abs(g['grad'][0]).max()
+    assert zerr < 2e-3
+
+
+def test_dropin_api_equals_fused_loop():
+    """decode_embedding + AvoidCollLoss + torch.optim.Adam (the reference driver's own loop body) == RefineLoop."""
+    from strive_b200.optim import RefineLoop
+    from strive_b200.losses import AvoidCollLoss
+    dev, model, env = ctx()
+    g = golden('refine')
+    sc = scene_for(g)
+    FT, lr = int(g['FT']), float(g['lr'])
+    graph = to_graph(sc, dev)
+    midx = sc['map_idx'].to(dev)
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev),
+             'prior_out': (sc['prior_mu'].to(dev), sc['prior_var'].to(dev))}
+    loop = RefineLoop(model, graph, midx, env, embed, sc['z'].to(dev), REFINE_W, lr, FT, veh_coll_buffer=0.2)
+    loop.run(3)
+    z = sc['z'].clone().to(dev).requires_grad_(True)
+    opt = torch.optim.Adam([z], lr=lr)
+    lossm = AvoidCollLoss(REFINE_W, model.get_att_normalizer().unnormalize(graph.lw), midx[graph.batch], env, z.clone().detach(), veh_coll_buffer=0.2)
+    for _ in range(3):
+        opt.zero_grad()
+        fut = model.get_normalizer().unnormalize(model.decode_embedding(z, embed, graph, midx, env, nfuture=FT)['future_pred'])
+        lossm(fut, z, embed['prior_out'])['loss'].backward()
+        opt.step()
+    d = (z.detach() - loop.z).abs().max().item()
+    diag('dropin-vs-fused: |z| diff after 3 iters %.3e' % d)
+    assert d < 1e-4

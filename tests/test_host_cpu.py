@@ -1,0 +1,68 @@
+"""CPU: the C-ABI library loads and exports every symbol include/strive_b200.h declares, binding layouts match,
+weight packing matches the library's segment table, host-side exact helpers match torch."""
+import os
+import re
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build():
+    import __graft_entry__ as ge
+    ge.build()
+
+
+def test_library_exports_every_declared_symbol():
+    _build()
+    from strive_b200 import _cabi
+    L = _cabi.lib()      # also verifies struct layouts against the library
+    hdr = open(os.path.join(ROOT, 'include', 'strive_b200.h')).read()
+    names = sorted(set(re.findall(r'\b(strive_[a-z0-9_]+)\s*\(', hdr)))
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), 'missing export %s' % n
+    assert sorted(_cabi.EXPORTS) == names
+
+
+def test_weight_packing_matches_library_layout():
+    _build()
+    import ctypes as C
+    from strive_b200 import _cabi, synth, weights
+    sd = synth.make_weights(0)
+    blob, sizes = weights.pack_decode_weights(sd, 2)
+    want = (C.c_int64 * 256)()
+    n = C.c_int(0)
+    _cabi.check(_cabi.lib().strive_model_layout(2, want, 256, C.byref(n)))
+    assert list(want[:n.value]) == sizes
+    # a transposed segment really is the transpose of the reference tensor
+    segs = dict(weights.decode_segments(sd, 2))
+    assert torch.equal(segs['E3_T'], sd['decoder_net.msg.0.edge_mlp.net.3.weight'].t())
+    assert torch.equal(segs['CW1'][(3 * 5 + 2) * 5 + 4], sd['map_conv.3.weight'][:, 3, 2, 4])
+    assert torch.equal(segs['FCW'][5 * 4 + 1 * 2 + 1], sd['map_feature.weight'][:, 5 * 4 + 3])
+
+
+def test_product_path_refuses_cpu_tensors():
+    _build()
+    import pytest
+    from strive_b200 import _cabi
+    with pytest.raises(RuntimeError):
+        _cabi.dptr(torch.zeros(4))
+
+
+def test_linspace5_matches_torch_linspace_bitwise():
+    from strive_b200.losses import linspace5
+    g = torch.Generator().manual_seed(0)
+    lo = -(torch.rand(200, generator=g) * 4 + 1)
+    hi = -lo + torch.rand(200, generator=g) * 0.1
+    mine = linspace5(lo, hi)
+    ref = torch.stack([torch.linspace(lo[i].item(), hi[i].item(), 5) for i in range(200)])
+    assert torch.equal(mine, ref)
+
+
+def test_oracle_is_not_imported_by_the_product():
+    pkg = os.path.join(ROOT, 'strive_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert 'oracle' not in src.replace('the oracle', '').replace('CPU oracle', ''), fn
