@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- agent*timestep*iters/sec of the STRIVE latent Adam loop (refine_traffic_optim) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm's CPU path (oracle port) on host cores
+
+A "step" is one Adam iteration of the refine loop (decode -> AvoidCollLoss -> dL/dz -> Adam.step,
+reference src/refine_traffic_optim.py:185-218) over one batch of synthetic scenes.
+Workload at every N (weak scaling, scenes are independent): BASELINE.json configs[1] per GPU =
+64 scenes x 32 agents x 20 future steps, loss-normalisation groups of 4 scenes, refine weights.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'agent_timestep_iters_per_sec'
+UNIT = 'agent*timestep*iter/s'
+REFINE_W = {'coll_veh': 100.0, 'coll_env': 100.0, 'motion_prior': 1.0, 'init_z': 0.01}   # configs/refine_traffic_optim.cfg:26-29
+LR = 0.05
+WORK = dict(scenes=64, agents=32, FT=20, group=4, raster=4096)
+# algorithmic MACs per crop of each map-encoder kernel
+CNN_MAC = {'conv1_gather': 49.0e6, 'conv2': 47.63e6, 'conv3': 43.06e6, 'conv4': 7.23e6, 'conv5': 2.65e6, 'conv6': 0.59e6, 'fc': 0.03e6}
+MAPENC_CHUNK = 512
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], bf16_burst=d['bf16_tflops'], bf16_sustained=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    source='measured')
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source='fallback')
+
+
+class Graph(object):
+    pass
+
+
+def make_workload(seed, dev=None, scenes=None, agents=None):
+    from strive_b200 import synth
+    S = WORK['scenes'] if scenes is None else scenes
+    n = WORK['agents'] if agents is None else agents
+    raster, dx = synth.make_raster(seed=1, M=1, H=WORK['raster'], W=WORK['raster'])
+    sd = synth.make_weights(0)
+    sc = synth.make_scenes(1000 + seed, [n] * S, map_extent_m=(200.0, 800.0), M=1, FT=WORK['FT'], collide_frac=0.25, offroad_frac=0.25)
+    return raster, dx, sd, sc
+
+
+def to_graph(sc, dev):
+    g = Graph()
+    for k in ('past', 'lw', 'sem', 'ptr', 'batch', 'edge_index'):
+        setattr(g, k, sc[k].to(dev))
+    return g
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU path (oracle port of the reference algorithm) -- cpu_baseline leg and --impl reference
+# ----------------------------------------------------------------------------------------------------------
+def cpu_refine_rate(budget_s, steps, warmup, seed=0):
+    """Times `steps` refine iterations of the oracle port on a bounded sample of the bench workload with all host threads.
+    Weights keep requires_grad=True as in the reference drivers (model.train(), no freezing: refine_traffic_optim.py:487)."""
+    from oracle import strive_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    raster, dx, sd, sc_full = make_workload(seed, scenes=1)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    FT = WORK['FT']
+
+    def sub(n):
+        from strive_b200 import synth
+        keep = slice(0, n)
+        sc = {k: (v[keep] if (isinstance(v, torch.Tensor) and v.dim() > 0 and v.size(0) == WORK['agents']) else v) for k, v in sc_full.items()}
+        sc['ptr'] = torch.tensor([0, n])
+        sc['batch'] = torch.zeros(n, dtype=torch.long)
+        sc['edge_index'] = synth.clique_edges([0, n])
+        return sc
+
+    def run(sc, iters, ft):
+        z = sc['z'].clone().requires_grad_(True)
+        opt = torch.optim.Adam([z], lr=LR)
+        lw_un = O.unnorm_att(sc['lw'])
+        mapixes = sc['map_idx'][sc['batch']]
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            opt.zero_grad()
+            for p in sd.values():
+                p.grad = None
+            fut = O.decode(sd, z, sc['map_feat'], sc['past_feat'], sc['past'][:, -1, :], sc['lw'], sc['sem'], sc['ptr'], sc['edge_index'],
+                           sc['map_idx'], raster, dx, ft)
+            ld = O.avoid_coll_loss(O.unnorm_state(fut), z, (sc['prior_mu'], sc['prior_var']), sc['z'], REFINE_W, lw_un, mapixes, None,
+                                   raster, dx, veh_coll_buffer=0.2)
+            ld['loss'].backward()
+            opt.step()
+        return time.perf_counter() - t0
+
+    # probe: 4 agents x 3 steps -> units/s estimate -> choose the sample size that fits the budget
+    run(sub(4), 1, 2)
+    tp = run(sub(4), 1, 3)
+    rate = 4 * 3 / tp
+    per_step_budget = budget_s / max(1, steps + warmup)
+    n = int(max(2, min(WORK['agents'], rate * per_step_budget / FT)))
+    sc = sub(n)
+    if warmup > 0:
+        run(sc, warmup, FT)
+    t = run(sc, steps, FT)
+    units = n * FT * steps
+    return dict(value=units / t, cores=cores, agents=n, FT=FT, steps=steps, seconds=t,
+                sample='%d refine iteration(s) of 1 scene x %d agents x %d steps of the bench workload, fp32, %d torch threads, '
+                       'weights requires_grad as in the reference drivers' % (steps, n, FT, cores))
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    r = cpu_refine_rate(budget_s=150.0, steps=args.steps, warmup=args.warmup)
+    out = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+           'warmup': args.warmup, 'ms_per_step': 1000.0 * r['seconds'] / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+           'config': {'workload': 'refine_traffic_optim latent Adam loop, BASELINE configs[1] (64 scenes x 32 agents x 20 steps); '
+                                  'CPU step = bounded sample (see cpu_baseline.sample)'},
+           'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
+           'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU path
+# ----------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import __graft_entry__ as ge
+    ge.build()
+    import strive_b200
+    from strive_b200 import _cabi
+    from strive_b200.optim import RefineLoop
+    from strive_b200.losses import AvoidCollLoss
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback on the product path)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    raster, dx, sd, sc = make_workload(rank)
+    model = strive_b200.make_model(nfuture=WORK['FT'], state_dict=sd, device=dev)
+    env = strive_b200.MapEnv(raster, dx, device=dev)
+    graph = to_graph(sc, dev)
+    midx = sc['map_idx'].to(dev)
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev),
+             'prior_out': (sc['prior_mu'].to(dev), sc['prior_var'].to(dev))}
+    S, FT = WORK['scenes'], WORK['FT']
+    gptr = list(range(0, S + 1, WORK['group']))
+    loop = RefineLoop(model, graph, midx, env, embed, sc['z'].to(dev), REFINE_W, LR, FT, veh_coll_buffer=0.2, group_scene_ptr=gptr)
+    NA = loop.NA
+    units_per_step = NA * FT
+
+    # ---- device-resident loop: `value`
+    for _ in range(args.warmup):
+        loop.step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loop.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    barrier()
+    t = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * units_per_step * args.steps / (ms / 1000.0)
+    loss_now = float(loop.terms[:, 0].sum())
+
+    # ---- end to end through the public drop-in API with HOST buffers (pinned), H2D/D2H inside the timed region
+    host = {k: sc[k].clone().pin_memory() for k in ('z', 'map_feat', 'past_feat', 'prior_mu', 'prior_var')}
+    devb = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    z_dev = devb['z'].requires_grad_(True)
+    opt = torch.optim.Adam([z_dev], lr=LR)
+    lossm = AvoidCollLoss(REFINE_W, model.get_att_normalizer().unnormalize(graph.lw), midx[graph.batch], env, sc['z'].to(dev),
+                          veh_coll_buffer=0.2, group_scene_ptr=gptr, ptr_for_groups=sc['ptr'])
+    loss_host = torch.zeros((len(gptr) - 1, 16)).pin_memory()
+    z_host_out = torch.zeros_like(host['z']).pin_memory()
+    h2d = sum(v.numel() * 4 for v in host.values())
+    d2h = loss_host.numel() * 4 + z_host_out.numel() * 4
+
+    def api_step():
+        with torch.no_grad():
+            for k, v in host.items():
+                devb[k].copy_(v, non_blocking=True)
+        em = {'map_feat': devb['map_feat'], 'past_feat': devb['past_feat'], 'prior_out': (devb['prior_mu'], devb['prior_var'])}
+        opt.zero_grad()
+        fut = model.get_normalizer().unnormalize(model.decode_embedding(z_dev, em, graph, midx, env, nfuture=FT)['future_pred'])
+        ld = lossm(fut, z_dev, em['prior_out'])
+        ld['loss'].backward()
+        opt.step()
+        loss_host.copy_(ld['_terms'], non_blocking=True)
+        z_host_out.copy_(z_dev.detach(), non_blocking=True)
+        torch.cuda.synchronize()
+        host['z'].copy_(z_host_out)
+
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(min(args.warmup, 2)):
+        api_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        api_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e = e0.elapsed_time(e1)
+    barrier()
+    t = torch.tensor([ms_e], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e = float(t.item())
+    e2e_value = world * units_per_step * e2e_steps / (ms_e / 1000.0)
+
+    # ---- per-kernel device times (CUDA events on the launch stream) -> roofline of the dominant kernel
+    _cabi.profile_enable(True)
+    prof_steps = 2
+    for _ in range(prof_steps):
+        loop.step()
+    prof = _cabi.profile_report()
+    _cabi.profile_enable(False)
+    tot = sum(v[1] for v in prof.values())
+    top = max(prof.items(), key=lambda kv: kv[1][1])
+    peaks = measured_peaks()
+    roof = None
+    if top[0] in CNN_MAC:
+        launches, tms = top[1]
+        crops_total = NA * (FT - 1) * prof_steps
+        flops = 2.0 * CNN_MAC[top[0]] * crops_total
+        achieved = flops / (tms / 1000.0) / 1e12
+        roof = {'kernel': top[0], 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
+                'frac': achieved / peaks['bf16_sustained'], 'traffic': None, 'peak_source': peaks['source'] + ' bf16 sustained (cuBLAS 8192^3)',
+                'share_of_step': tms / tot, 'avg_launch_ms': tms / launches,
+                'note': 'fp32 SIMT direct-conv kernel measured against the dense bf16 tensor peak; algorithmic FLOPs = 2*MAC*crops'}
+    enc = sum(prof[k][1] for k in CNN_MAC if k in prof)
+    shares = {k: round(v[1] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
+
+    out = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_refine_rate(budget_s=20.0, steps=1, warmup=0)
+            cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
+        out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+               'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+               'data': 'synthetic',
+               'config': {'workload': 'refine_traffic_optim latent Adam loop: %d scenes x %d agents x %d steps per GPU (BASELINE configs[1]), '
+                                      'loss groups of %d scenes, random-init weights, synthetic %dx%d raster' % (S, WORK['agents'], FT, WORK['group'], WORK['raster'], WORK['raster']),
+                          'agents_per_gpu': NA, 'FT': FT, 'parallelism': 'scene-sharded replicas x%d, no collective in the loop' % world,
+                          'l2': 'per-step working set (tape %.0f MB + encoder activations %.0f MB) exceeds the 126 MB L2; no explicit flush' % (
+                              loop.tape_bytes / 1e6, _cabi.lib().strive_mapenc_workspace_bytes(NA) / 1e6),
+                          'loss_after_timed_steps': loss_now},
+               'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
+                       'ms_per_step': ms_e / e2e_steps,
+                       'api': 'TrafficModel.decode_embedding + losses.AvoidCollLoss + torch.optim.Adam, inputs from pinned host memory every step'},
+               'gpu_launches': loop.launches_per_iter * args.steps,
+               'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+               'kernel_time_shares': shares, 'map_encoder_share': enc / tot}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='strive_b200', choices=['strive_b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != 'reference':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -36,6 +36,12 @@ int strive_abi_version(void);
 /* sizeof/offsetof table of the ABI structs so foreign bindings can verify their layout (returns count) */
 int strive_struct_layout(int64_t* out, int max_n);
 
+/* ---- per-kernel timing (bench.py) ----------------------------------------------------------------------
+ * When enabled every kernel launch is bracketed by CUDA events on its stream; strive_profile_report
+ * synchronises and writes "kernel_name launches total_ms" lines. Not for use under CUDA-graph capture. */
+int strive_profile_enable(int on);
+int64_t strive_profile_report(char* buf, int64_t cap);
+
 /* ---- model weights -------------------------------------------------------------------------------------
  * Replaces: torch state_dict of decoder_net.*, decoder_memory.*, map_conv.*, map_feature.* loaded by
  * utils/torch.py:32-60 (load_state).  `blob` is a device buffer packed by strive_b200/weights.py in the

@@ -43,7 +43,7 @@ class StriveLossCfg(C.Structure):
                 ('circ_cx', C.c_void_p), ('lw_un', C.c_void_p)]
 
 
-EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy',
+EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy',
            'strive_mapenc_workspace_bytes', 'strive_mapenc_fwd', 'strive_map_crop', 'strive_decode_tape_bytes',
            'strive_decode_fwd', 'strive_decode_bwd', 'strive_decode_tape_read', 'strive_loss_workspace_bytes',
            'strive_loss_fwd_bwd', 'strive_adam_step']
@@ -80,6 +80,9 @@ def lib():
                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     L.strive_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, i32, f32, f32, f32, f32, vp]
     L.strive_struct_layout.argtypes = [C.POINTER(i64), C.c_int]
+    L.strive_profile_enable.argtypes = [C.c_int]
+    L.strive_profile_report.argtypes = [C.c_char_p, i64]
+    L.strive_profile_report.restype = i64
     if L.strive_abi_version() != 1:
         raise RuntimeError('strive_b200: ABI version mismatch')
     _verify_layout(L)
@@ -117,3 +120,20 @@ def _verify_layout(L):
             StriveLossCfg.attack_mask.offset, StriveLossCfg.lw_un.offset]
     if n != len(mine) or list(buf[:n]) != mine:
         raise RuntimeError('strive_b200: ctypes struct layout %s does not match the library %s' % (mine, list(buf[:max(n, 0)])))
+
+
+def profile_enable(on):
+    lib().strive_profile_enable(int(bool(on)))
+
+
+def profile_report():
+    """{kernel_name: (launches, total_ms)} since the last report (synchronises the device)."""
+    buf = C.create_string_buffer(1 << 16)
+    n = lib().strive_profile_report(buf, len(buf))
+    if n < 0:
+        raise RuntimeError('strive_b200: profile report buffer too small')
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out

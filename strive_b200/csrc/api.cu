@@ -119,8 +119,8 @@ extern "C" int strive_adam_step(float* z, const float* g_a, const float* g_b, fl
   STRIVE_CHECK(z && g_a && exp_avg && exp_avg_sq && n > 0 && step_count >= 1, STRIVE_EINVAL, "strive_adam_step: bad arguments");
   const double bc1 = 1.0 - pow((double)beta1, (double)step_count);
   const double bc2 = 1.0 - pow((double)beta2, (double)step_count);
-  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z, g_a, g_b, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                                             (float)bc1, (float)sqrt(bc2));
+  KPROF("adam", (cudaStream_t)stream, adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(z, g_a, g_b, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                             (float)bc1, (float)sqrt(bc2)));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
@@ -137,4 +137,57 @@ extern "C" int strive_struct_layout(int64_t* out, int max_n) {
   if (max_n < n) return -1;
   for (int i = 0; i < n; i++) out[i] = v[i];
   return n;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// per-kernel device timing with CUDA events on the launching stream (bench.py roofline numbers)
+// ------------------------------------------------------------------------------------------------------
+#include <vector>
+#include <string>
+#include <map>
+int g_strive_profile_on = 0;
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_pool;
+static cudaEvent_t prof_event() {
+  if (!g_pool.empty()) { cudaEvent_t e = g_pool.back(); g_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void strive_prof_begin(const char* name, cudaStream_t s) {
+  ProfRec r;
+  r.name = name; r.e0 = prof_event(); r.e1 = prof_event();
+  cudaEventRecord(r.e0, s);
+  g_prof.push_back(r);
+}
+void strive_prof_end(cudaStream_t s) { cudaEventRecord(g_prof.back().e1, s); }
+
+extern "C" int strive_profile_enable(int on) {
+  g_strive_profile_on = on ? 1 : 0;
+  return 0;
+}
+// Synchronises the device, aggregates "name count total_ms" lines into buf, clears the records. Returns bytes written.
+extern "C" int64_t strive_profile_report(char* buf, int64_t cap) {
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<long long, double>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    auto& a = agg[r.name];
+    a.first += 1;
+    a.second += ms;
+    g_pool.push_back(r.e0);
+    g_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+  std::string out;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if ((int64_t)out.size() + 1 > cap) return -1;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (int64_t)out.size();
 }

@@ -32,6 +32,17 @@ void strive_set_error(const char* fmt, ...);
 
 #define STRIVE_LAUNCH_CHECK() STRIVE_CUDA(cudaGetLastError())
 
+// optional per-launch CUDA-event timing (strive_profile_enable); zero overhead when disabled
+extern int g_strive_profile_on;
+void strive_prof_begin(const char* name, cudaStream_t s);
+void strive_prof_end(cudaStream_t s);
+#define KPROF(name, stream, ...)                              \
+  do {                                                        \
+    if (g_strive_profile_on) strive_prof_begin(name, stream); \
+    __VA_ARGS__;                                              \
+    if (g_strive_profile_on) strive_prof_end(stream);         \
+  } while (0)
+
 enum StriveErr { STRIVE_OK = 0, STRIVE_EINVAL = 1, STRIVE_ESIZE = 2, STRIVE_EUNSUPPORTED = 3 };
 
 // ------------------------------------------------------------------------------------------------------

@@ -629,20 +629,20 @@ extern "C" int strive_loss_fwd_bwd(const StriveLossCfg* cfg, const StriveScene* 
   const int NA = a.NA, T3 = a.T3;
   {
     const int nz = max(NA, cfg->num_groups * A_N);
-    loss_zero_kernel<<<(nz + 255) / 256, 256, 0, stream>>>(a);
+    KPROF("loss_zero", stream, loss_zero_kernel<<<(nz + 255) / 256, 256, 0, stream>>>(a));
     STRIVE_LAUNCH_CHECK();
   }
   if (main_term) {
-    interp_kernel<<<(NA * T3 + 255) / 256, 256, 0, stream>>>(a);
+    KPROF("interp", stream, interp_kernel<<<(NA * T3 + 255) / 256, 256, 0, stream>>>(a));
     STRIVE_LAUNCH_CHECK();
     if (kind & STRIVE_LOSS_ADV) {
-      adv_dist_kernel<<<(NA + 127) / 128, 128, 0, stream>>>(a);
+      KPROF("adv_dist", stream, adv_dist_kernel<<<(NA + 127) / 128, 128, 0, stream>>>(a));
       STRIVE_LAUNCH_CHECK();
-      adv_crash_kernel<<<a.S, 256, 0, stream>>>(a, cfg->adv_min_out);
+      KPROF("adv_crash", stream, adv_crash_kernel<<<a.S, 256, 0, stream>>>(a, cfg->adv_min_out));
       STRIVE_LAUNCH_CHECK();
     }
     if (cfg->w_coll_veh > 0.f || ((kind & STRIVE_LOSS_ADV) && cfg->w_coll_veh_plan > 0.f)) {
-      veh_coll_kernel<<<(NA * T3 + 127) / 128, 128, 0, stream>>>(a);
+      KPROF("veh_coll", stream, veh_coll_kernel<<<(NA * T3 + 127) / 128, 128, 0, stream>>>(a));
       STRIVE_LAUNCH_CHECK();
     } else {
       STRIVE_CUDA(cudaMemsetAsync(a.ws.gA, 0, (size_t)NA * T3 * 16, stream));
@@ -650,21 +650,21 @@ extern "C" int strive_loss_fwd_bwd(const StriveLossCfg* cfg, const StriveScene* 
     }
     if (cfg->w_coll_env > 0.f) {
       const long long threads = (long long)NA * T3 * 32;
-      env_coll_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a);
+      KPROF("env_coll", stream, env_coll_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a));
       STRIVE_LAUNCH_CHECK();
     } else {
       STRIVE_CUDA(cudaMemsetAsync(a.ws.gE, 0, (size_t)NA * T3 * 8, stream));
     }
-    latent_terms_kernel<<<(NA * 32 + 255) / 256, 256, 0, stream>>>(a);
+    KPROF("latent_terms", stream, latent_terms_kernel<<<(NA * 32 + 255) / 256, 256, 0, stream>>>(a));
     STRIVE_LAUNCH_CHECK();
   }
   if (kind & STRIVE_LOSS_MATCH) {
-    match_sum_kernel<<<(NA * ft + 255) / 256, 256, 0, stream>>>(a);
+    KPROF("match_sum", stream, match_sum_kernel<<<(NA * ft + 255) / 256, 256, 0, stream>>>(a));
     STRIVE_LAUNCH_CHECK();
   }
-  finalize_kernel<<<(NA * ft + 255) / 256, 256, 0, stream>>>(a);
+  KPROF("finalize", stream, finalize_kernel<<<(NA * ft + 255) / 256, 256, 0, stream>>>(a));
   STRIVE_LAUNCH_CHECK();
-  terms_kernel<<<(cfg->num_groups + 63) / 64, 64, 0, stream>>>(a);
+  KPROF("terms", stream, terms_kernel<<<(cfg->num_groups + 63) / 64, 64, 0, stream>>>(a));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }

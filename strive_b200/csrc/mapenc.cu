@@ -58,7 +58,7 @@ extern "C" int strive_map_crop(const StriveMap* map, const float* pose_un, const
                                uint8_t* out_crop, void* stream) {
   STRIVE_CHECK(map && pose_un && map_of && out_crop && n > 0, STRIVE_EINVAL, "strive_map_crop: bad arguments");
   dim3 grid((CROP * CROP + 255) / 256, n);
-  map_crop_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*map, pose_un, map_of, n, out_crop);
+  KPROF("map_crop", (cudaStream_t)stream, map_crop_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*map, pose_un, map_of, n, out_crop));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
@@ -305,7 +305,7 @@ conv_gn_kernel(const float* __restrict__ in, const double* __restrict__ in_stats
 }
 
 template <int CIN, int COUT, int KS, int HIN, int HOUT, int TH, int TW, int G, int CC, int COC, int PXT, bool FINAL>
-static int launch_conv(const float* in, const double* in_stats, const float* gam, const float* bet, const float* Wk,
+static int launch_conv(const char* name, const float* in, const double* in_stats, const float* gam, const float* bet, const float* Wk,
                        const float* bias, float* out, double* out_stats, int n, cudaStream_t stream) {
   using Cfg = ConvCfg<CIN, COUT, KS, HIN, HOUT, TH, TW, G, CC, COC, PXT, FINAL>;
   static_assert(CIN % CC == 0 && COUT % COC == 0 && COC % 4 == 0 && (TH % PXT) == 0, "bad conv tiling");
@@ -316,7 +316,7 @@ static int launch_conv(const float* in, const double* in_stats, const float* gam
     attr_done = true;
   }
   dim3 grid(Cfg::TILES, (n + G - 1) / G, COUT / COC);
-  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, Wk, bias, out, out_stats, n);
+  KPROF(name, stream, kern<<<grid, Cfg::NTHREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, Wk, bias, out, out_stats, n));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
@@ -359,21 +359,21 @@ extern "C" int strive_mapenc_fwd(const StriveModel* m, const StriveMap* map, con
     const float* pose = pose_un + (size_t)start * 4;
     const int32_t* mo = map_of + start;
     dim3 g1(C1_TILES * C1_TILES, cn);
-    conv1_gather_kernel<<<g1, 256, 0, stream>>>(*map, pose, mo, sg[S_CW0], sg[S_CB0], act[0], st[0], cn);
+    KPROF("conv1_gather", stream, conv1_gather_kernel<<<g1, 256, 0, stream>>>(*map, pose, mo, sg[S_CW0], sg[S_CB0], act[0], st[0], cn));
     STRIVE_LAUNCH_CHECK();
     int rc;
     //             CIN COUT KS HIN HOUT TH  TW  G  CC COC PXT FINAL
-    rc = launch_conv<16, 32, 5, 125, 61, 16, 16, 1, 8, 32, 2, false>(act[0], st[0], sg[S_GG0], sg[S_GB0], sg[S_CW1], sg[S_CB1], act[1], st[1], cn, stream);
+    rc = launch_conv<16, 32, 5, 125, 61, 16, 16, 1, 8, 32, 2, false>("conv2", act[0], st[0], sg[S_GG0], sg[S_GB0], sg[S_CW1], sg[S_CB1], act[1], st[1], cn, stream);
     if (rc) return rc;
-    rc = launch_conv<32, 64, 5, 61, 29, 16, 16, 1, 8, 32, 2, false>(act[1], st[1], sg[S_GG1], sg[S_GB1], sg[S_CW2], sg[S_CB2], act[2], st[2], cn, stream);
+    rc = launch_conv<32, 64, 5, 61, 29, 16, 16, 1, 8, 32, 2, false>("conv3", act[1], st[1], sg[S_GG1], sg[S_GB1], sg[S_CW2], sg[S_CB2], act[2], st[2], cn, stream);
     if (rc) return rc;
-    rc = launch_conv<64, 64, 3, 29, 14, 14, 14, 1, 16, 32, 2, false>(act[2], st[2], sg[S_GG2], sg[S_GB2], sg[S_CW3], sg[S_CB3], act[3], st[3], cn, stream);
+    rc = launch_conv<64, 64, 3, 29, 14, 14, 14, 1, 16, 32, 2, false>("conv4", act[2], st[2], sg[S_GG2], sg[S_GB2], sg[S_CW3], sg[S_CB3], act[3], st[3], cn, stream);
     if (rc) return rc;
-    rc = launch_conv<64, 128, 3, 14, 6, 6, 6, 4, 16, 32, 2, false>(act[3], st[3], sg[S_GG3], sg[S_GB3], sg[S_CW4], sg[S_CB4], act[4], st[4], cn, stream);
+    rc = launch_conv<64, 128, 3, 14, 6, 6, 6, 4, 16, 32, 2, false>("conv5", act[3], st[3], sg[S_GG3], sg[S_GB3], sg[S_CW4], sg[S_CB4], act[4], st[4], cn, stream);
     if (rc) return rc;
-    rc = launch_conv<128, 128, 3, 6, 2, 2, 2, 32, 16, 32, 2, false>(act[4], st[4], sg[S_GG4], sg[S_GB4], sg[S_CW5], sg[S_CB5], act[5], st[5], cn, stream);
+    rc = launch_conv<128, 128, 3, 6, 2, 2, 2, 32, 16, 32, 2, false>("conv6", act[4], st[4], sg[S_GG4], sg[S_GB4], sg[S_CW5], sg[S_CB5], act[5], st[5], cn, stream);
     if (rc) return rc;
-    rc = launch_conv<128, 64, 2, 2, 1, 1, 1, 64, 16, 32, 1, true>(act[5], st[5], sg[S_GG5], sg[S_GB5], sg[S_FCW], sg[S_FCB], out_feat + (size_t)start * 64, nullptr, cn, stream);
+    rc = launch_conv<128, 64, 2, 2, 1, 1, 1, 64, 16, 32, 1, true>("fc", act[5], st[5], sg[S_GG5], sg[S_GB5], sg[S_FCW], sg[S_FCB], out_feat + (size_t)start * 64, nullptr, cn, stream);
     if (rc) return rc;
   }
   return 0;

@@ -1131,19 +1131,19 @@ extern "C" int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, co
   a.ptr = sc->ptr; a.scene_of = sc->scene_of; a.lw = sc->lw; a.sem = sc->sem; a.z = z; a.ext = ext_future;
   a.traj = traj_out; a.d_traj = nullptr; a.d_z = nullptr;
   ModelDev M = model_dev(m);
-  init_tape_kernel<<<(NA * 64 + 255) / 256, 256, 0, stream>>>(a, sc->past_last, map_feat0, past_feat0, sc->map_idx);
+  KPROF("init_tape", stream, init_tape_kernel<<<(NA * 64 + 255) / 256, 256, 0, stream>>>(a, sc->past_last, map_feat0, past_feat0, sc->map_idx));
   STRIVE_LAUNCH_CHECK();
   const int node_blocks = (NA + NODE_WARPS * NODE_R - 1) / (NODE_WARPS * NODE_R);
   for (int t = 0; t < ft; t++) {
     a.t = t;
-    node_fwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_NODE, stream>>>(M, a);
+    KPROF("node_fwd", stream, node_fwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_NODE, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();
-    edge_fwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_F, stream>>>(M, a);
+    KPROF("edge_fwd", stream, edge_fwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_F, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();
-    post_fwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_NODE, stream>>>(M, a);
+    KPROF("post_fwd", stream, post_fwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_NODE, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();
     if (t + 1 < ft) {
-      gru_fwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_GRU_F, stream>>>(M, a);
+      KPROF("gru_fwd", stream, gru_fwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_GRU_F, stream>>>(M, a));
       STRIVE_LAUNCH_CHECK();
       rc = strive_mapenc_fwd(m, map, a.tp.pose, a.tp.map_of, NA, a.tp.mapfeat + (size_t)(t + 1) * NA * 64, a.tp.mapenc_ws,
                              a.tp.mapenc_ws_bytes, stream_);
@@ -1180,14 +1180,14 @@ extern "C" int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, in
     a.t = t;
     const int has_gru = (t + 1 < ft) ? 1 : 0;
     if (has_gru) {
-      gru_bwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_GRU_B, stream>>>(M, a);
+      KPROF("gru_bwd", stream, gru_bwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_GRU_B, stream>>>(M, a));
       STRIVE_LAUNCH_CHECK();
     }
-    post_bwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_POST_B, stream>>>(M, a, has_gru);
+    KPROF("post_bwd", stream, post_bwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_POST_B, stream>>>(M, a, has_gru));
     STRIVE_LAUNCH_CHECK();
-    edge_bwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_B, stream>>>(M, a);
+    KPROF("edge_bwd", stream, edge_bwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_B, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();
-    node_bwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_NODE_B, stream>>>(M, a);
+    KPROF("node_bwd", stream, node_bwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_NODE_B, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();
   }
   return 0;

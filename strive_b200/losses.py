@@ -240,7 +240,11 @@ class _Base(nn.Module):
 
 
 class AvoidCollLoss(_Base):
-    def __init__(self, loss_weights, veh_att, mapixes, map_env, init_z, veh_coll_buffer=0.0, single_veh_idx=None, ptr=None):
+    def __init__(self, loss_weights, veh_att, mapixes, map_env, init_z, veh_coll_buffer=0.0, single_veh_idx=None, ptr=None,
+                 group_scene_ptr=None, ptr_for_groups=None):
+        """Reference signature (adv_gen_nusc.py:268-271) plus one extension: `group_scene_ptr` (+ `ptr_for_groups`, the scene
+        ptr) evaluates several independent reference batches ("loss-normalisation groups") in one call; every mean and,
+        when ptr is None, every collision block is then per group.  Default None = exactly one reference batch."""
         super().__init__()
         dev = veh_att.device
         self.NA = int(veh_att.size(0))
@@ -248,10 +252,17 @@ class AvoidCollLoss(_Base):
         self.init_z = init_z
         if single_veh_idx is not None and ptr is None:
             raise RuntimeError('single_veh_idx requires ptr (adv_gen_nusc.py:294-295)')
-        ptr_host = torch.tensor([0, self.NA]) if ptr is None else ptr.detach().cpu()
+        if group_scene_ptr is not None:
+            src = ptr if ptr is not None else ptr_for_groups
+            if src is None:
+                raise RuntimeError('group_scene_ptr needs the scene ptr (ptr or ptr_for_groups)')
+            ptr_host = src.detach().cpu()
+        else:
+            ptr_host = torch.tensor([0, self.NA]) if ptr is None else ptr.detach().cpu()
         # ptr=None: the whole batch is ONE collision block (VehCollLoss :443-451), as refine_traffic_optim.py:176-181 builds it
         self.plan = LossPlan(_cabi.LOSS_AVOID, loss_weights, veh_att, mapixes, map_env, ptr_host, dev, coll_by_scene=ptr is not None,
-                             veh_coll_buffer=veh_coll_buffer, single_veh_idx=single_veh_idx, traj_unnormalized=True)
+                             veh_coll_buffer=veh_coll_buffer, single_veh_idx=single_veh_idx, traj_unnormalized=True,
+                             group_scene_ptr=group_scene_ptr)
         self.scene_struct, self._keep = _mini_scene(ptr_host, mapixes, dev)
         self.row_idx = torch.nonzero(self.plan.z_mask.bool(), as_tuple=False).flatten()
 

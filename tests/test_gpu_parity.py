@@ -224,6 +224,61 @@ def test_decode_backward_vs_autograd(FT, with_ext):
     assert e_gpu <= 10.0 * e_ref + 2e-5 * max(1.0, scale)
 
 
+def _lowlevel(sc, FT, ext=None):
+    import ctypes as C
+    from strive_b200 import _cabi
+    dev, model, env = ctx()
+    graph = to_graph(sc, dev)
+    scene = model.scene_batch(graph, sc['map_idx'].to(dev))
+    L = _cabi.lib()
+    NA = scene.NA
+    nb = L.strive_decode_tape_bytes(NA, FT)
+    tape = torch.empty(nb, dtype=torch.uint8, device=dev)
+    traj = torch.empty((NA, FT, 4), dtype=torch.float32, device=dev)
+    z = sc['z'].to(dev).contiguous()
+    mf, pf = sc['map_feat'].to(dev).contiguous(), sc['past_feat'].to(dev).contiguous()
+    extd = None if ext is None else ext.to(dev).contiguous()
+    _cabi.check(L.strive_decode_fwd(model.device_model().handle, C.byref(scene.cstruct), C.byref(env.cstruct), _cabi.dptr(z),
+                                    _cabi.dptr(mf), _cabi.dptr(pf), _cabi.dptr(extd), FT, _cabi.dptr(traj), _cabi.dptr(tape), nb,
+                                    _cabi.stream_ptr()))
+
+    def bwd(seed):
+        d_z = torch.empty((NA, 32), dtype=torch.float32, device=dev)
+        sd_ = seed.to(dev).contiguous()
+        _cabi.check(L.strive_decode_bwd(model.device_model().handle, C.byref(scene.cstruct), FT, _cabi.dptr(extd), _cabi.dptr(sd_),
+                                        _cabi.dptr(d_z), _cabi.dptr(tape), nb, _cabi.stream_ptr()))
+        return d_z.cpu()
+    torch.cuda.synchronize()
+    feats = [_tape(tape, 'map_feat', t, NA, FT, 64) for t in range(1, FT)]
+    return traj.cpu(), feats, bwd
+
+
+@pytest.mark.parametrize('name,FT,with_ext', [('decode_small', 6, False), ('decode_small', 6, True), ('decode_c1', 20, False), ('refine', 6, False)])
+def test_teacher_forced_rollout_and_adjoint(name, FT, with_ext):
+    """Strict kernel check: the oracle is fed the GPU's own per-step map features (the only discontinuous input: one
+    flipped crop pixel otherwise perturbs map_feat by ~1e-5 and the rollout amplifies it), so forward and BPTT must
+    agree to fp32 re-association level over the whole horizon."""
+    raster, dx, sd = world()
+    g = golden(name)
+    sc = scene_for(g)
+    ext = sc['ext_future'][:, :FT].contiguous() if with_ext else None
+    traj, feats, bwd = _lowlevel(sc, FT, ext)
+    z = sc['z'].clone().requires_grad_(True)
+    ref = O.decode(sd, z, sc['map_feat'], sc['past_feat'], sc['past'][:, -1, :], sc['lw'], sc['sem'], sc['ptr'], sc['edge_index'],
+                   sc['map_idx'], raster, dx, FT, ext_future=ext, map_feat_override=feats)
+    e_t = (traj - ref.detach()).abs().amax(dim=(0, 2))
+    gen = torch.Generator().manual_seed(7)
+    seed = torch.randn(traj.shape, generator=gen)
+    ref.backward(seed)
+    got = bwd(seed)
+    scale = z.grad.abs().max().item()
+    e_g = (got - z.grad).abs().max().item()
+    diag('teacher-forced %s FT=%d ext=%d: traj err per step %s | grad err %.3e (max %.3e)' % (
+        name, FT, int(with_ext), ' '.join('%.1e' % v for v in e_t.tolist()), e_g, scale))
+    assert e_t.max().item() < 2e-5 * (1.0 + 0.5 * FT)
+    assert e_g < 2e-4 * max(1.0, scale)
+
+
 def test_avoid_loss_terms_and_grads_refine():
     """AvoidCollLoss as refine_traffic_optim builds it (no ptr: one collision block), drop-in module, on the golden traj."""
     from strive_b200.losses import AvoidCollLoss
@@ -324,16 +379,21 @@ def test_refine_loop_vs_golden_adam_trajectory():
     for it in range(iters):
         loop._forward(); loop._loss(); loop._backward()
         torch.cuda.synchronize()
-        gerr = np.abs(loop.grad().cpu().numpy() - g['grad'][it]).max()
+        gg, gr = loop.grad().cpu().numpy().reshape(-1), g['grad'][it].reshape(-1)
+        gerr = np.abs(gg - gr).max()
+        cos = float(np.dot(gg, gr) / (np.linalg.norm(gg) * np.linalg.norm(gr)))
         lerr = abs(float(loop.terms[:, 0].sum()) - g['loss'][it])
         loop._adam()
         torch.cuda.synchronize()
-        zerr = np.abs(loop.z.cpu().numpy() - g['z'][it]).max()
-        diag('refine iter %d: loss gpu %.5f golden %.5f | |grad err| %.3e (max %.3e) | |z err| %.3e' % (
-            it, float(loop.terms[:, 0].sum()), g['loss'][it], gerr, np.abs(g['grad'][it]).max(), zerr))
+        zd = np.abs(loop.z.cpu().numpy() - g['z'][it])
+        diag('refine iter %d: loss gpu %.5f golden %.5f | |grad err| %.3e (max %.3e) cos %.6f | |z err| max %.3e, frac>1e-3 %.4f' % (
+            it, float(loop.terms[:, 0].sum()), g['loss'][it], gerr, np.abs(gr).max(), cos, zd.max(), float((zd > 1e-3).mean())))
         if it == 0:
-            assert lerr < 1e-3 * abs(g['loss'][0]) and gerr < 2e-3 * np.abs(g['grad'][0]).max()
-    assert zerr < 2e-3
+            # one flipped crop pixel moves the gradient by ~1 % (ReLU / arg-max routing flips); the strict adjoint check is the
+            # teacher-forced test above.  Adam's first step is lr*sign(g): an element with |g| below the noise may flip (2*lr).
+            assert lerr < 1e-4 * abs(g['loss'][0]) and gerr < 0.05 * np.abs(gr).max() and cos > 0.999
+            assert zd.max() <= 2 * lr + 1e-5 and float((zd > 1e-3).mean()) < 0.03
+    assert abs(float(loop.terms[:, 0].sum()) - g['loss'][-1]) < 0.02 * abs(g['loss'][-1])
 
 
 def test_dropin_api_equals_fused_loop():
