@@ -42,6 +42,10 @@ int strive_struct_layout(int64_t* out, int max_n);
 int strive_profile_enable(int on);
 int64_t strive_profile_report(char* buf, int64_t cap);
 
+/* ---- tcgen05 primitive self-test (tests only): A (128,32), B (32,32), X0/X1 (144,8) fp32 (rounded to bf16 inside);
+ * D0 = A B^T, D1[m] = [X0[m+1] | X1[m+3]] B[:, :16]^T, both (128,32) fp32. */
+int strive_tc_selftest(const float* A, const float* B, const float* X0, const float* X1, float* D0, float* D1, void* stream);
+
 /* ---- model weights -------------------------------------------------------------------------------------
  * Replaces: torch state_dict of decoder_net.*, decoder_memory.*, map_conv.*, map_feature.* loaded by
  * utils/torch.py:32-60 (load_state).  `blob` is a device buffer packed by strive_b200/weights.py in the

@@ -43,7 +43,7 @@ class StriveLossCfg(C.Structure):
                 ('circ_cx', C.c_void_p), ('lw_un', C.c_void_p)]
 
 
-EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy',
+EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy',
            'strive_mapenc_workspace_bytes', 'strive_mapenc_fwd', 'strive_map_crop', 'strive_decode_tape_bytes',
            'strive_decode_fwd', 'strive_decode_bwd', 'strive_decode_tape_read', 'strive_loss_workspace_bytes',
            'strive_loss_fwd_bwd', 'strive_adam_step']
@@ -81,6 +81,7 @@ def lib():
     L.strive_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, i32, f32, f32, f32, f32, vp]
     L.strive_struct_layout.argtypes = [C.POINTER(i64), C.c_int]
     L.strive_profile_enable.argtypes = [C.c_int]
+    L.strive_tc_selftest.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.strive_profile_report.argtypes = [C.c_char_p, i64]
     L.strive_profile_report.restype = i64
     if L.strive_abi_version() != 1:
