@@ -54,6 +54,12 @@ int strive_model_layout(int num_classes, int64_t* seg_sizes_host, int max_segs, 
 int strive_model_create(const float* blob, int64_t blob_floats, const int64_t* seg_sizes_host, int n_segs,
                         int num_classes, StriveModel** out);
 void strive_model_destroy(StriveModel* m);
+/* bf16 hi/lo split conv1..conv4 weights in the tcgen05 K-major operand layout (packed by strive_b200/weights.py
+ * pack_tc_weights; derived from the same map_conv.* tensors).  Without it the map encoder refuses the tensor-core path. */
+int64_t strive_model_tc_bytes(void);
+int strive_model_set_tc_weights(StriveModel* m, const void* blob, int64_t bytes);
+/* 1 = tensor-core map encoder (default), 0 = fp32 SIMT kernels (A/B verification only) */
+int strive_mapenc_set_impl(int impl);
 
 /* ---- scene description (all device) --------------------------------------------------------------------
  * Mirrors the torch_geometric Batch the drivers build (src/datasets/nuscenes_dataset.py:609-687): edges are

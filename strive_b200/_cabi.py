@@ -43,7 +43,7 @@ class StriveLossCfg(C.Structure):
                 ('circ_cx', C.c_void_p), ('lw_un', C.c_void_p)]
 
 
-EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy',
+EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl',
            'strive_mapenc_workspace_bytes', 'strive_mapenc_fwd', 'strive_map_crop', 'strive_decode_tape_bytes',
            'strive_decode_fwd', 'strive_decode_bwd', 'strive_decode_tape_read', 'strive_loss_workspace_bytes',
            'strive_loss_fwd_bwd', 'strive_adam_step']
@@ -65,6 +65,9 @@ def lib():
     L.strive_model_create.argtypes = [vp, i64, C.POINTER(i64), C.c_int, C.c_int, C.POINTER(vp)]
     L.strive_model_destroy.argtypes = [vp]
     L.strive_model_destroy.restype = None
+    L.strive_model_tc_bytes.restype = i64
+    L.strive_model_set_tc_weights.argtypes = [vp, vp, i64]
+    L.strive_mapenc_set_impl.argtypes = [C.c_int]
     L.strive_mapenc_workspace_bytes.argtypes = [i32]
     L.strive_mapenc_workspace_bytes.restype = i64
     L.strive_mapenc_fwd.argtypes = [vp, C.POINTER(StriveMap), vp, vp, i32, vp, vp, i64, vp]
@@ -138,3 +141,8 @@ def profile_report():
         name, cnt, ms = line.split()
         out[name] = (int(cnt), float(ms))
     return out
+
+
+def set_mapenc_impl(tensor_core):
+    """True (default): tcgen05 map encoder; False: fp32 SIMT kernels (A/B verification)."""
+    lib().strive_mapenc_set_impl(int(bool(tensor_core)))

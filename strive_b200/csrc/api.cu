@@ -87,6 +87,7 @@ extern "C" int strive_model_create(const float* blob, int64_t blob_floats, const
     return STRIVE_ESIZE;
   }
   m->nc = num_classes;
+  m->tc_blob = nullptr;
   m->in0_rows = round_up4(64 + 64 + num_classes + ZDIM + 2);
   m->u0_rows = round_up4(64 + 64 + num_classes);
   *out = m;
@@ -94,6 +95,20 @@ extern "C" int strive_model_create(const float* blob, int64_t blob_floats, const
 }
 
 extern "C" void strive_model_destroy(StriveModel* m) { delete m; }
+
+// tensor-core weight blob: [conv1 14336 B][conv2 51200 B][conv3 2 x 102400 B][conv4 2 x 73728 B]  (layouts in mapenc_tc.cu)
+static const int64_t kTcBytes[4] = {7 * 2 * 2 * 512, 1 * (1 * 25 * 2 * 1024), 2 * (2 * 25 * 2 * 1024), 2 * (4 * 9 * 2 * 1024)};
+extern "C" int64_t strive_model_tc_bytes(void) { return kTcBytes[0] + kTcBytes[1] + kTcBytes[2] + kTcBytes[3]; }
+extern "C" int strive_model_set_tc_weights(StriveModel* m, const void* blob, int64_t bytes) {
+  STRIVE_CHECK(m != nullptr, STRIVE_EINVAL, "null model");
+  STRIVE_CHECK(blob != nullptr && bytes == strive_model_tc_bytes(), STRIVE_ESIZE, "tc weight blob has %lld bytes, expected %lld", (long long)bytes,
+               (long long)strive_model_tc_bytes());
+  STRIVE_CHECK(((uintptr_t)blob & 15) == 0, STRIVE_EINVAL, "tc weight blob must be 16-byte aligned");
+  m->tc_blob = (const uint8_t*)blob;
+  int64_t off = 0;
+  for (int i = 0; i < 4; i++) { m->tc_off[i] = off; off += kTcBytes[i]; }
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // Adam (torch.optim.Adam, amsgrad=False, weight_decay=0, maximize=False) as used by the latent loops

@@ -180,7 +180,7 @@ struct ConvCfg {
   static constexpr size_t SMEM = (size_t)(PATCH_FLOATS + W_FLOATS + 4 * G) * 4;
 };
 
-template <int CIN, int COUT, int KS, int HIN, int HOUT, int TH, int TW, int G, int CC, int COC, int PXT, bool FINAL>
+template <int CIN, int COUT, int KS, int HIN, int HOUT, int TH, int TW, int G, int CC, int COC, int PXT, bool FINAL, bool IN_NHWC>
 __global__ void __launch_bounds__(ConvCfg<CIN, COUT, KS, HIN, HOUT, TH, TW, G, CC, COC, PXT, FINAL>::NTHREADS)
 conv_gn_kernel(const float* __restrict__ in, const double* __restrict__ in_stats, const float* __restrict__ gam,
                const float* __restrict__ bet, const float* __restrict__ Wk, const float* __restrict__ bias,
@@ -237,7 +237,8 @@ conv_gn_kernel(const float* __restrict__ in, const double* __restrict__ in_stats
       const int iy = ty0 * S + row, ix = tx0 * S + col;
       float v = 0.f;
       if (crop < n && iy < HIN && ix < HIN) {
-        const float x = __ldg(in + (((size_t)crop * CIN + c0 + c) * HIN + iy) * HIN + ix);
+        const float x = IN_NHWC ? __ldg(in + (((size_t)crop * HIN + iy) * HIN + ix) * CIN + c0 + c)
+                                : __ldg(in + (((size_t)crop * CIN + c0 + c) * HIN + iy) * HIN + ix);
         const float xn = (x - gstat[gg * 2]) * gstat[gg * 2 + 1];
         v = fmaxf(fmaf(xn, __ldg(gam + c0 + c), __ldg(bet + c0 + c)), 0.f);
       }
@@ -304,12 +305,12 @@ conv_gn_kernel(const float* __restrict__ in, const double* __restrict__ in_stats
   }
 }
 
-template <int CIN, int COUT, int KS, int HIN, int HOUT, int TH, int TW, int G, int CC, int COC, int PXT, bool FINAL>
+template <int CIN, int COUT, int KS, int HIN, int HOUT, int TH, int TW, int G, int CC, int COC, int PXT, bool FINAL, bool IN_NHWC = false>
 static int launch_conv(const char* name, const float* in, const double* in_stats, const float* gam, const float* bet, const float* Wk,
                        const float* bias, float* out, double* out_stats, int n, cudaStream_t stream) {
   using Cfg = ConvCfg<CIN, COUT, KS, HIN, HOUT, TH, TW, G, CC, COC, PXT, FINAL>;
   static_assert(CIN % CC == 0 && COUT % COC == 0 && COC % 4 == 0 && (TH % PXT) == 0, "bad conv tiling");
-  auto kern = conv_gn_kernel<CIN, COUT, KS, HIN, HOUT, TH, TW, G, CC, COC, PXT, FINAL>;
+  auto kern = conv_gn_kernel<CIN, COUT, KS, HIN, HOUT, TH, TW, G, CC, COC, PXT, FINAL, IN_NHWC>;
   static bool attr_done = false;
   if (!attr_done) {
     STRIVE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -325,6 +326,20 @@ static int launch_conv(const char* name, const float* in, const double* in_stats
 // workspace + driver
 // ------------------------------------------------------------------------------------------------------
 #define MAPENC_CHUNK 512
+// 1 = tensor-core conv1..4 (default), 0 = fp32 SIMT reference kernels (kept for A/B verification, strive_mapenc_set_impl)
+static int g_mapenc_impl = 1;
+extern "C" int strive_mapenc_set_impl(int impl) {
+  g_mapenc_impl = impl ? 1 : 0;
+  return 0;
+}
+int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_of, const uint8_t* wpack, const float* bias, float* out,
+                    double* out_stats, int n, cudaStream_t stream);
+int tc_launch_conv2(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+                    float* out, double* out_stats, int n, cudaStream_t stream);
+int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+                    float* out, double* out_stats, int n, cudaStream_t stream);
+int tc_launch_conv4(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+                    float* out, double* out_stats, int n, cudaStream_t stream);
 static const size_t kActFloats[6] = {16 * 125 * 125, 32 * 61 * 61, 64 * 29 * 29, 64 * 14 * 14, 128 * 6 * 6, 128 * 2 * 2};
 
 extern "C" int64_t strive_mapenc_workspace_bytes(int32_t n) {
@@ -358,19 +373,34 @@ extern "C" int strive_mapenc_fwd(const StriveModel* m, const StriveMap* map, con
     for (int i = 0; i < 6; i++) st[i] = stats + (size_t)i * c * 2;
     const float* pose = pose_un + (size_t)start * 4;
     const int32_t* mo = map_of + start;
-    dim3 g1(C1_TILES * C1_TILES, cn);
-    KPROF("conv1_gather", stream, conv1_gather_kernel<<<g1, 256, 0, stream>>>(*map, pose, mo, sg[S_CW0], sg[S_CB0], act[0], st[0], cn));
-    STRIVE_LAUNCH_CHECK();
     int rc;
-    //             CIN COUT KS HIN HOUT TH  TW  G  CC COC PXT FINAL
-    rc = launch_conv<16, 32, 5, 125, 61, 16, 16, 1, 8, 32, 2, false>("conv2", act[0], st[0], sg[S_GG0], sg[S_GB0], sg[S_CW1], sg[S_CB1], act[1], st[1], cn, stream);
-    if (rc) return rc;
-    rc = launch_conv<32, 64, 5, 61, 29, 16, 16, 1, 8, 32, 2, false>("conv3", act[1], st[1], sg[S_GG1], sg[S_GB1], sg[S_CW2], sg[S_CB2], act[2], st[2], cn, stream);
-    if (rc) return rc;
-    rc = launch_conv<64, 64, 3, 29, 14, 14, 14, 1, 16, 32, 2, false>("conv4", act[2], st[2], sg[S_GG2], sg[S_GB2], sg[S_CW3], sg[S_CB3], act[3], st[3], cn, stream);
-    if (rc) return rc;
-    rc = launch_conv<64, 128, 3, 14, 6, 6, 6, 4, 16, 32, 2, false>("conv5", act[3], st[3], sg[S_GG3], sg[S_GB3], sg[S_CW4], sg[S_CB4], act[4], st[4], cn, stream);
-    if (rc) return rc;
+    if (g_mapenc_impl == 1 && m->tc_blob != nullptr) {
+      // tensor-core path (mapenc_tc.cu): conv1..conv4 on tcgen05, activations NHWC fp32
+      rc = tc_launch_conv1(map, pose, mo, m->tc_blob + m->tc_off[0], sg[S_CB0], act[0], st[0], cn, stream);
+      if (rc) return rc;
+      rc = tc_launch_conv2(act[0], st[0], sg[S_GG0], sg[S_GB0], m->tc_blob + m->tc_off[1], sg[S_CB1], act[1], st[1], cn, stream);
+      if (rc) return rc;
+      rc = tc_launch_conv3(act[1], st[1], sg[S_GG1], sg[S_GB1], m->tc_blob + m->tc_off[2], sg[S_CB2], act[2], st[2], cn, stream);
+      if (rc) return rc;
+      rc = tc_launch_conv4(act[2], st[2], sg[S_GG2], sg[S_GB2], m->tc_blob + m->tc_off[3], sg[S_CB3], act[3], st[3], cn, stream);
+      if (rc) return rc;
+      // conv5 reads the NHWC conv4 output
+      rc = launch_conv<64, 128, 3, 14, 6, 6, 6, 4, 16, 32, 2, false, true>("conv5", act[3], st[3], sg[S_GG3], sg[S_GB3], sg[S_CW4], sg[S_CB4], act[4], st[4], cn, stream);
+      if (rc) return rc;
+    } else {
+      dim3 g1(C1_TILES * C1_TILES, cn);
+      KPROF("conv1_gather", stream, conv1_gather_kernel<<<g1, 256, 0, stream>>>(*map, pose, mo, sg[S_CW0], sg[S_CB0], act[0], st[0], cn));
+      STRIVE_LAUNCH_CHECK();
+      //             CIN COUT KS HIN HOUT TH  TW  G  CC COC PXT FINAL
+      rc = launch_conv<16, 32, 5, 125, 61, 16, 16, 1, 8, 32, 2, false>("conv2", act[0], st[0], sg[S_GG0], sg[S_GB0], sg[S_CW1], sg[S_CB1], act[1], st[1], cn, stream);
+      if (rc) return rc;
+      rc = launch_conv<32, 64, 5, 61, 29, 16, 16, 1, 8, 32, 2, false>("conv3", act[1], st[1], sg[S_GG1], sg[S_GB1], sg[S_CW2], sg[S_CB2], act[2], st[2], cn, stream);
+      if (rc) return rc;
+      rc = launch_conv<64, 64, 3, 29, 14, 14, 14, 1, 16, 32, 2, false>("conv4", act[2], st[2], sg[S_GG2], sg[S_GB2], sg[S_CW3], sg[S_CB3], act[3], st[3], cn, stream);
+      if (rc) return rc;
+      rc = launch_conv<64, 128, 3, 14, 6, 6, 6, 4, 16, 32, 2, false>("conv5", act[3], st[3], sg[S_GG3], sg[S_GB3], sg[S_CW4], sg[S_CB4], act[4], st[4], cn, stream);
+      if (rc) return rc;
+    }
     rc = launch_conv<128, 128, 3, 6, 2, 2, 2, 32, 16, 32, 2, false>("conv6", act[4], st[4], sg[S_GG4], sg[S_GB4], sg[S_CW5], sg[S_CB5], act[5], st[5], cn, stream);
     if (rc) return rc;
     rc = launch_conv<128, 64, 2, 2, 1, 1, 1, 64, 16, 32, 1, true>("fc", act[5], st[5], sg[S_GG5], sg[S_GB5], sg[S_FCW], sg[S_FCB], out_feat + (size_t)start * 64, nullptr, cn, stream);

@@ -7,7 +7,7 @@ import ctypes as C
 import torch
 
 from . import _cabi
-from .weights import pack_decode_weights
+from .weights import pack_decode_weights, pack_tc_weights
 
 CROP_BOUNDS = (-17.0, -38.5, 60.0, 38.5)     # reference src/datasets/map_env.py:23
 
@@ -33,6 +33,11 @@ class DeviceModel(object):
         h = C.c_void_p()
         _cabi.check(L.strive_model_create(_cabi.dptr(self.blob), self.blob.numel(), arr, len(sizes), num_classes, C.byref(h)))
         self.handle = h
+        tcb = pack_tc_weights(state_dict)
+        if tcb.numel() != L.strive_model_tc_bytes():
+            raise RuntimeError('strive_b200: tensor-core weight packing size mismatch')
+        self.tc_blob = tcb.to(device)
+        _cabi.check(L.strive_model_set_tc_weights(h, _cabi.dptr(self.tc_blob), self.tc_blob.numel()))
 
     def __del__(self):
         try:

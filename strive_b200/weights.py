@@ -87,3 +87,39 @@ def pack_decode_weights(sd, NC):
         blob[off:off + s] = t.contiguous().reshape(-1)
         off += _r4(s)
     return blob, sizes
+
+
+def _split(w):
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.to(torch.float32)).to(torch.bfloat16)
+    return hi, lo
+
+
+def _bytes(t):
+    return t.contiguous().view(torch.int16).reshape(-1).view(torch.uint8)
+
+
+def pack_tc_weights(sd):
+    """bf16 hi/lo split conv1..conv4 weights in the tcgen05 K-major no-swizzle operand layout (csrc/mapenc_tc.cu).
+    conv1: [ky 7][kq 2][prec 2][khalf 2][ngroup 2][r 8][k 8], k = (kx_l % 2) * 4 + c, taps kx = 4 kq + kx_l (kx = 7 is zero);
+    conv2..4: [nchunk][c2][tap][prec 2][khalf 2][ngroup 4][r 8][k 8], n = 32 nchunk + 8 ngroup + r, c = 16 c2 + 8 khalf + k."""
+    g = lambda k: sd[k].detach().to(torch.float32).cpu()
+    out = []
+    w = g('map_conv.0.weight')                                              # (16,4,7,7)
+    w = torch.cat([w, torch.zeros(16, 4, 7, 1)], dim=3)                     # pad kx to 8
+    parts = []
+    for p in _split(w):
+        t = p.reshape(2, 8, 4, 7, 2, 2, 2)                                  # (ngroup, r, c, ky, kq, khalf, kxh)
+        parts.append(t.permute(3, 4, 5, 0, 1, 6, 2))                        # (ky, kq, khalf, ngroup, r, kxh, c)
+    t = torch.stack(parts, dim=2)                                           # (ky, kq, prec, khalf, ngroup, r, kxh, c)
+    out.append(_bytes(t))
+    for li, ks in ((1, 5), (2, 5), (3, 3)):
+        w = g('map_conv.%d.weight' % (3 * li))                              # (Cout, Cin, ks, ks)
+        cout, cin = w.size(0), w.size(1)
+        parts = []
+        for p in _split(w):
+            t = p.reshape(cout // 32, 4, 8, cin // 16, 2, 8, ks * ks)       # (nchunk, ngroup, r, c2, khalf, k, tap)
+            parts.append(t.permute(0, 3, 6, 4, 1, 2, 5))                    # (nchunk, c2, tap, khalf, ngroup, r, k)
+        t = torch.stack(parts, dim=3)                                       # (nchunk, c2, tap, prec, khalf, ngroup, r, k)
+        out.append(_bytes(t))
+    return torch.cat(out)

@@ -111,15 +111,24 @@ def test_map_encoder_feature():
     ang = torch.rand(58, generator=gen) * 6.28318
     pose_un = torch.cat([O.unnorm_state(pos_n), torch.cat([extra, torch.cos(ang)[:, None], torch.sin(ang)[:, None]], 1)], 0).contiguous()
     mapix = torch.cat([mapix, torch.randint(0, 2, (58,), generator=gen)])
-    got = model.encode_map_poses(pose_un.to(dev), mapix.to(dev), env).cpu()
+    from strive_b200 import _cabi
     crop = O.map_crop(raster, dx, pose_un, mapix)
     ref32 = O.map_cnn(sd, crop.float())
     ref64 = O.map_cnn(_ctx['sd64'], crop.double())
-    e_gpu = (got.double() - ref64).abs().max().item()
     e_ref = (ref32.double() - ref64).abs().max().item()
-    e_gold = np.abs(got[:6].numpy() - g['map_feat']).max()
-    diag('map_encoder: |gpu-fp64|=%.3e |fp32oracle-fp64|=%.3e |gpu-golden|=%.3e feat_absmax=%.3f' % (e_gpu, e_ref, e_gold, ref64.abs().max().item()))
-    assert e_gpu < 2e-5 and e_gold < 2e-5
+    res = {}
+    for name, tcflag, tol in (('simt', False, 2e-5), ('tensor-core', True, 1e-4)):
+        _cabi.set_mapenc_impl(tcflag)
+        try:
+            got = model.encode_map_poses(pose_un.to(dev), mapix.to(dev), env).cpu()
+        finally:
+            _cabi.set_mapenc_impl(True)
+        e_gpu = (got.double() - ref64).abs().max().item()
+        e_gold = np.abs(got[:6].numpy() - g['map_feat']).max()
+        diag('map_encoder[%s]: |gpu-fp64|=%.3e |fp32oracle-fp64|=%.3e |gpu-golden|=%.3e feat_absmax=%.3f' % (name, e_gpu, e_ref, e_gold, ref64.abs().max().item()))
+        res[name] = (e_gpu, e_gold, tol)
+    for name, (e_gpu, e_gold, tol) in res.items():
+        assert e_gpu < tol and e_gold < tol, name
 
 
 def _tape(model_scene_tape, name, t, NA, FT, width):
