@@ -29,7 +29,8 @@ REFINE_W = {'coll_veh': 100.0, 'coll_env': 100.0, 'motion_prior': 1.0, 'init_z':
 LR = 0.05
 WORK = dict(scenes=64, agents=32, FT=20, group=4, raster=4096)
 # algorithmic MACs per crop of each map-encoder kernel
-CNN_MAC = {'conv1_gather': 49.0e6, 'conv2': 47.63e6, 'conv3': 43.06e6, 'conv4': 7.23e6, 'conv5': 2.65e6, 'conv6': 0.59e6, 'fc': 0.03e6}
+CNN_MAC = {'conv1_gather': 49.0e6, 'conv2': 47.63e6, 'conv3': 43.06e6, 'conv4': 7.23e6, 'conv5': 2.65e6, 'conv6': 0.59e6, 'fc': 0.03e6,
+           'tc_conv1': 49.0e6, 'tc_conv2': 47.63e6, 'tc_conv3': 43.06e6, 'tc_conv4': 7.23e6, 'tc_conv5': 2.65e6, 'tc_conv6': 0.59e6, 'tc_fc': 0.03e6}
 MAPENC_CHUNK = 512
 
 
@@ -305,7 +306,7 @@ def run_gpu(args):
         roof = {'kernel': top[0], 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
                 'frac': achieved / peaks['bf16_sustained'], 'traffic': None, 'peak_source': peaks['source'] + ' bf16 sustained (cuBLAS 8192^3)',
                 'share_of_step': tms / tot, 'avg_launch_ms': tms / launches,
-                'note': 'fp32 SIMT direct-conv kernel measured against the dense bf16 tensor peak; algorithmic FLOPs = 2*MAC*crops'}
+                'note': 'algorithmic FLOPs = 2*MAC*crops (the bf16 hi/lo split issues 2-3x that many tensor MACs), vs dense bf16 peak'}
     enc = sum(prof[k][1] for k in CNN_MAC if k in prof)
     shares = {k: round(v[1] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
 

@@ -83,6 +83,7 @@ typedef struct StriveMap {
   int32_t M, C, H, W;
   const float* lin_l;          /* (256) torch.linspace(bounds[0], bounds[2], 256) float32, nuscenes_utils.py:219 */
   const float* lin_w;          /* (256) torch.linspace(bounds[1], bounds[3], 256) float32, nuscenes_utils.py:220 */
+  const uint8_t* packed;       /* (M,H,W) uint8: bit c = (raster[m,c,y,x] != 0); the raster must be binary (nuScenes get_map_mask) */
 } StriveMap;
 
 /* ---- map encoder ---------------------------------------------------------------------------------------

@@ -96,9 +96,14 @@ extern "C" int strive_model_create(const float* blob, int64_t blob_floats, const
 
 extern "C" void strive_model_destroy(StriveModel* m) { delete m; }
 
-// tensor-core weight blob: [conv1 14336 B][conv2 51200 B][conv3 2 x 102400 B][conv4 2 x 73728 B]  (layouts in mapenc_tc.cu)
-static const int64_t kTcBytes[4] = {7 * 2 * 2 * 512, 1 * (1 * 25 * 2 * 1024), 2 * (2 * 25 * 2 * 1024), 2 * (4 * 9 * 2 * 1024)};
-extern "C" int64_t strive_model_tc_bytes(void) { return kTcBytes[0] + kTcBytes[1] + kTcBytes[2] + kTcBytes[3]; }
+// tensor-core weight blob: [conv1 14336 B][conv2 51200 B][conv3 2 x 102400 B][conv4 2 x 73728 B][conv5][conv6][fc]  (layouts in mapenc_tc.cu)
+static const int64_t kTcBytes[7] = {7 * 2 * 2 * 512, 1 * (1 * 25 * 2 * 1024), 2 * (2 * 25 * 2 * 1024), 2 * (4 * 9 * 2 * 1024),
+                                    9 * 2 * 128 * 64 * 2, 18 * 2 * 128 * 64 * 2, 8 * 2 * 64 * 64 * 2};
+extern "C" int64_t strive_model_tc_bytes(void) {
+  int64_t t = 0;
+  for (int i = 0; i < 7; i++) t += kTcBytes[i];
+  return t;
+}
 extern "C" int strive_model_set_tc_weights(StriveModel* m, const void* blob, int64_t bytes) {
   STRIVE_CHECK(m != nullptr, STRIVE_EINVAL, "null model");
   STRIVE_CHECK(blob != nullptr && bytes == strive_model_tc_bytes(), STRIVE_ESIZE, "tc weight blob has %lld bytes, expected %lld", (long long)bytes,
@@ -106,7 +111,7 @@ extern "C" int strive_model_set_tc_weights(StriveModel* m, const void* blob, int
   STRIVE_CHECK(((uintptr_t)blob & 15) == 0, STRIVE_EINVAL, "tc weight blob must be 16-byte aligned");
   m->tc_blob = (const uint8_t*)blob;
   int64_t off = 0;
-  for (int i = 0; i < 4; i++) { m->tc_off[i] = off; off += kTcBytes[i]; }
+  for (int i = 0; i < 7; i++) { m->tc_off[i] = off; off += kTcBytes[i]; }
   return 0;
 }
 

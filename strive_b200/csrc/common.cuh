@@ -98,7 +98,7 @@ struct StriveModel {
   int in0_rows;   // rows of IN0_T (= 64+64+NC+32+2 rounded up to 4)
   int u0_rows;    // rows of U0_T  (= 64+64+NC rounded up to 4)
   const uint8_t* tc_blob;   // bf16 hi/lo conv weights in UMMA canonical layout (strive_model_set_tc_weights) or null
-  int64_t tc_off[4];        // byte offsets of conv1..conv4 inside tc_blob
+  int64_t tc_off[7];        // byte offsets of conv1..conv6, fc inside tc_blob
 };
 
 __host__ __device__ inline int round_up4(int x) { return (x + 3) & ~3; }

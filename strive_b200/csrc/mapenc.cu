@@ -340,6 +340,12 @@ int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, c
                     float* out, double* out_stats, int n, cudaStream_t stream);
 int tc_launch_conv4(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
                     float* out, double* out_stats, int n, cudaStream_t stream);
+int tc_launch_conv5(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+                    float* out, double* out_stats, int n, cudaStream_t stream);
+int tc_launch_conv6(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+                    float* out, double* out_stats, int n, cudaStream_t stream);
+int tc_launch_fc(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+                 float* out, int n, cudaStream_t stream);
 static const size_t kActFloats[6] = {16 * 125 * 125, 32 * 61 * 61, 64 * 29 * 29, 64 * 14 * 14, 128 * 6 * 6, 128 * 2 * 2};
 
 extern "C" int64_t strive_mapenc_workspace_bytes(int32_t n) {
@@ -384,9 +390,13 @@ extern "C" int strive_mapenc_fwd(const StriveModel* m, const StriveMap* map, con
       if (rc) return rc;
       rc = tc_launch_conv4(act[2], st[2], sg[S_GG2], sg[S_GB2], m->tc_blob + m->tc_off[3], sg[S_CB3], act[3], st[3], cn, stream);
       if (rc) return rc;
-      // conv5 reads the NHWC conv4 output
-      rc = launch_conv<64, 128, 3, 14, 6, 6, 6, 4, 16, 32, 2, false, true>("conv5", act[3], st[3], sg[S_GG3], sg[S_GB3], sg[S_CW4], sg[S_CB4], act[4], st[4], cn, stream);
+      rc = tc_launch_conv5(act[3], st[3], sg[S_GG3], sg[S_GB3], m->tc_blob + m->tc_off[4], sg[S_CB4], act[4], st[4], cn, stream);
       if (rc) return rc;
+      rc = tc_launch_conv6(act[4], st[4], sg[S_GG4], sg[S_GB4], m->tc_blob + m->tc_off[5], sg[S_CB5], act[5], st[5], cn, stream);
+      if (rc) return rc;
+      rc = tc_launch_fc(act[5], st[5], sg[S_GG5], sg[S_GB5], m->tc_blob + m->tc_off[6], sg[S_FCB], out_feat + (size_t)start * 64, cn, stream);
+      if (rc) return rc;
+      continue;
     } else {
       dim3 g1(C1_TILES * C1_TILES, cn);
       KPROF("conv1_gather", stream, conv1_gather_kernel<<<g1, 256, 0, stream>>>(*map, pose, mo, sg[S_CW0], sg[S_CB0], act[0], st[0], cn));

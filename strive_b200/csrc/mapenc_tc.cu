@@ -26,9 +26,18 @@
 
 struct CropFrameTc {
   float px, py, hc, hs;
-  double dx0, dx1;
+  double dx0, dx1, inv0, inv1;
   const uint8_t* base;
 };
+
+// round-half-even(g / dx) exactly as torch.round(float64 quotient): multiply by the reciprocal and fall back to the true
+// division only when the product lands within 1e-6 of a .5 boundary (the only case where the two could round differently).
+__device__ __forceinline__ long long round_div_exact(float g, double dx, double inv) {
+  const double q = (double)g * inv;
+  const double fr = q - floor(q);
+  if (fabs(fr - 0.5) < 1e-6) return __double2ll_rn((double)g / dx);
+  return __double2ll_rn(q);
+}
 
 __device__ __forceinline__ void crop_pixel_tc(const CropFrameTc& f, float l, float w, int H, int W, long long& xp, long long& yp) {
   // exact restatement of get_map_obs (reference datasets/nuscenes_utils.py:248-263); see mapenc.cu crop_pixel
@@ -36,8 +45,8 @@ __device__ __forceinline__ void crop_pixel_tc(const CropFrameTc& f, float l, flo
   float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, f.hs), __fmul_rn(w, f.hc)), f.py);
   if (isnan(gx)) gx = 0.f;
   if (isnan(gy)) gy = 0.f;
-  xp = (long long)rint((double)gx / f.dx0);
-  yp = (long long)rint((double)gy / f.dx1);
+  xp = round_div_exact(gx, f.dx0, f.inv0);
+  yp = round_div_exact(gy, f.dx1, f.inv1);
   if (yp < 0 || yp >= H || xp < 0 || xp >= W) { xp = 0; yp = 0; }
 }
 
@@ -75,8 +84,8 @@ __global__ void __launch_bounds__(T1_THREADS) tc_conv1_kernel(StriveMap map, con
       CropFrameTc f;
       f.px = pose[crop * 4 + 0]; f.py = pose[crop * 4 + 1]; f.hc = pose[crop * 4 + 2]; f.hs = pose[crop * 4 + 3];
       f.dx0 = map.dx[m * 2 + 0]; f.dx1 = map.dx[m * 2 + 1];
-      f.base = map.raster + (size_t)m * 4 * map.H * map.W;
-      const size_t plane = (size_t)map.H * map.W;
+      f.inv0 = 1.0 / f.dx0; f.inv1 = 1.0 / f.dx1;
+      f.base = map.packed + (size_t)m * map.H * map.W;     // bit c of a byte = layer c (binary raster)
       for (int i = tid; i < T1_PH * T1_PW; i += T1_THREADS) {
         const int r = i / T1_PW, c = i % T1_PW;
         const int iy = oy0 * 2 + r, ix = ox0 * 2 + c;
@@ -84,10 +93,10 @@ __global__ void __launch_bounds__(T1_THREADS) tc_conv1_kernel(StriveMap map, con
         if (iy < 256 && ix < 256) {
           long long xp, yp;
           crop_pixel_tc(f, __ldg(map.lin_l + iy), __ldg(map.lin_w + ix), map.H, map.W, xp, yp);
-          const uint8_t* p = f.base + (size_t)yp * map.W + xp;
+          const uint32_t bits = __ldg(f.base + (size_t)yp * map.W + xp);
           const uint32_t one = 0x3F80u;   // bf16(1.0)
-          lo = (__ldg(p) ? one : 0u) | ((__ldg(p + plane) ? one : 0u) << 16);
-          hi = (__ldg(p + 2 * plane) ? one : 0u) | ((__ldg(p + 3 * plane) ? one : 0u) << 16);
+          lo = ((bits & 1u) ? one : 0u) | ((bits & 2u) ? (one << 16) : 0u);
+          hi = ((bits & 4u) ? one : 0u) | ((bits & 8u) ? (one << 16) : 0u);
         }
         *reinterpret_cast<uint2*>(sP + (size_t)i * 8) = make_uint2(lo, hi);
       }
@@ -181,8 +190,9 @@ struct TcCfg {
   static constexpr size_t SMEM = (size_t)W_BYTES + (size_t)NBUF * A_BYTES;
 };
 
+#define T2_THREADS 512
 template <int CIN, int KS, int HIN, int HOUT, int COUT, int NBUF>
-__global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
+__global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
                                                       const float* __restrict__ gam, const float* __restrict__ bet,
                                                       const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
                                                       float* __restrict__ out, double* __restrict__ out_stats, int n) {
@@ -198,9 +208,9 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   const int nchunk = blockIdx.y;
   {
     const int4* src = reinterpret_cast<const int4*>(wpack + (size_t)nchunk * Cfg::W_BYTES);
-    for (int i = tid; i < Cfg::W_BYTES / 16; i += 128) reinterpret_cast<int4*>(sW)[i] = __ldg(src + i);
+    for (int i = tid; i < Cfg::W_BYTES / 16; i += T2_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(src + i);
   }
-  for (int i = tid; i < CIN; i += 128) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
+  for (int i = tid; i < CIN; i += T2_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
   if (tid < 32) s_bias[tid] = bias[nchunk * 32 + tid];
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
@@ -227,6 +237,7 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
     }
   };
   auto epilogue = [&](int crop, int ty0, int tx0) {
+    if (warp >= 4) return;   // TMEM lanes 0..127 are read by warps 0..3
     const int m = warp * 32 + lane;
     const int oy = ty0 + (m >> 3), ox = tx0 + (m & 7);
     float s1 = 0.f, s2 = 0.f;
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
       wait_buf(b);
       uint8_t* dst = sA + (size_t)b * Cfg::A_BYTES;
       const float* src = in + (size_t)crop * HIN * HIN * CIN + c2 * 16;
-      for (int p = tid; p < PH * PW; p += 128) {
+      for (int p = tid; p < PH * PW; p += T2_THREADS) {
         const int row = p / PW, col = p % PW;
         const int iy = 2 * ty0 + row, ix = 2 * tx0 + col;
         uint32_t hi[8], lo[8];
@@ -353,6 +364,189 @@ __global__ void __launch_bounds__(128) tc_conv_kernel(const float* __restrict__ 
   if (warp == 0) tc::tmem_dealloc(tm, 32);
 }
 
+
+// ======================================================================================================
+// conv5 / conv6 / fc: small spatial extent (6x6, 2x2, 1x1 outputs) -> rows of many crops are packed into M = 128 tiles and
+// the A operand is gathered explicitly (im2col rows written straight into the canonical K-major layout, 64-wide K chunks).
+// GEMM:  out[m][n] = sum_k relu(GN(in))[row m, tap(k), c(k)] * W[n][k],   k = tap * CIN + c,  NHWC in/out.
+// ======================================================================================================
+template <int CIN, int KS, int HIN, int HOUT, int COUT, bool FINAL>
+struct Tc3Cfg {
+  static constexpr int PIX = HOUT * HOUT;
+  static constexpr int K = KS * KS * CIN;
+  static constexpr int NCH = K / 64;
+  static constexpr int A_PREC = 128 * 64 * 2;
+  static constexpr int W_PREC = COUT * 64 * 2;
+  static constexpr int STAGE = 2 * A_PREC + 2 * W_PREC;
+  static constexpr size_t SMEM = 2 * (size_t)STAGE;
+};
+
+template <int CIN, int KS, int HIN, int HOUT, int COUT, bool FINAL>
+__global__ void __launch_bounds__(T2_THREADS) tc_gemm_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
+                                                             const float* __restrict__ gam, const float* __restrict__ bet,
+                                                             const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
+                                                             float* __restrict__ out, double* __restrict__ out_stats, int n) {
+  using Cfg = Tc3Cfg<CIN, KS, HIN, HOUT, COUT, FINAL>;
+  constexpr int PIX = Cfg::PIX, NCH = Cfg::NCH;
+  static_assert(CIN % 64 == 0 && COUT % 16 == 0, "tc_gemm tiling");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_base;
+  __shared__ float s_gam[CIN], s_bet[CIN], s_bias[COUT];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < CIN; i += T2_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
+  for (int i = tid; i < COUT; i += T2_THREADS) s_bias[i] = bias[i];
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base, COUT < 32 ? 32 : COUT);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm = tmem_base;
+  const uint32_t idesc = tc::idesc_bf16_f32(128, COUT);
+  int counter = 0;
+  bool pend[2] = {false, false};
+  uint32_t ph[2] = {0, 0};
+  bool have_prev = false;
+  int p_tile = 0, p_b = 0;
+  auto wait_buf = [&](int b) {
+    if (pend[b]) {
+      tc::mbar_wait(&bars[b], ph[b]);
+      ph[b] ^= 1;
+      pend[b] = false;
+    }
+  };
+  const long long rows_total = (long long)n * PIX;
+  auto epilogue = [&](int tile) {
+    if (warp >= 4) return;
+    const long long gm = (long long)tile * 128 + warp * 32 + lane;
+    const bool valid = gm < rows_total;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+    for (int h = 0; h < COUT / 16; h++) {
+      float v[16];
+      tc::tmem_ld16(tm + ((uint32_t)(warp * 32) << 16) + h * 16, v);
+      if (valid) {
+        float* o = out + (size_t)gm * COUT + h * 16;
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          v[c] += s_bias[h * 16 + c];
+          s1 += v[c];
+          s2 = fmaf(v[c], v[c], s2);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      }
+    }
+    if (!FINAL && valid) {
+      const int crop = (int)(gm / PIX);
+      atomicAdd(out_stats + (size_t)crop * 2, (double)s1);
+      atomicAdd(out_stats + (size_t)crop * 2 + 1, (double)s2);
+    }
+  };
+
+  const int tiles = (int)((rows_total + 127) / 128);
+  const int m = tid & 127;          // every thread stages a fixed row of the tile, k-groups (tid>>7) and (tid>>7)+4
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long gm = (long long)tile * 128 + m;
+    const bool valid = gm < rows_total;
+    int crop = 0, oy = 0, ox = 0;
+    float mean = 0.f, rstd = 0.f;
+    if (valid) {
+      crop = (int)(gm / PIX);
+      const int pix = (int)(gm % PIX);
+      oy = pix / HOUT; ox = pix % HOUT;
+      const double cnt = (double)CIN * HIN * HIN;
+      const double mu = in_stats[(size_t)crop * 2] / cnt;
+      double var = in_stats[(size_t)crop * 2 + 1] / cnt - mu * mu;
+      if (var < 0.0) var = 0.0;
+      mean = (float)mu;
+      rstd = (float)(1.0 / sqrt(var + 1e-5));
+    }
+#pragma unroll 1
+    for (int kc = 0; kc < NCH; kc++) {
+      const int b = counter & 1;
+      wait_buf(b);
+      uint8_t* sA = smem + (size_t)b * Cfg::STAGE;
+      uint8_t* sWt = sA + 2 * Cfg::A_PREC;
+      {
+        const int4* src = reinterpret_cast<const int4*>(wpack + (size_t)kc * 2 * Cfg::W_PREC);
+        for (int i = tid; i < 2 * Cfg::W_PREC / 16; i += T2_THREADS) reinterpret_cast<int4*>(sWt)[i] = __ldg(src + i);
+      }
+      const int k0 = kc * 64;
+      const int tap = k0 / CIN, c0 = k0 % CIN;
+      const int ky = tap / KS, kx = tap % KS;
+      const float* src = in + (((size_t)crop * HIN + 2 * oy + ky) * HIN + 2 * ox + kx) * CIN + c0;
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        const int kg = (tid >> 7) + half * 4;
+        uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+        if (valid) {
+          const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + kg * 8));
+          const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + kg * 8 + 4));
+          const float x[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) {
+            const int ch = c0 + kg * 8 + c;
+            float h0, l0, h1, l1;
+            const float y0 = fmaxf(fmaf((x[c] - mean) * rstd, s_gam[ch], s_bet[ch]), 0.f);
+            const float y1 = fmaxf(fmaf((x[c + 1] - mean) * rstd, s_gam[ch + 1], s_bet[ch + 1]), 0.f);
+            tc::split_bf16(y0, h0, l0);
+            tc::split_bf16(y1, h1, l1);
+            hi[c >> 1] = tc::pack_bf16(h0, h1);
+            lo[c >> 1] = tc::pack_bf16(l0, l1);
+          }
+        }
+        const int unit = (kg * 16 + (m >> 3)) * 8 + (m & 7);
+        *reinterpret_cast<uint4*>(sA + (size_t)unit * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(sA + Cfg::A_PREC + (size_t)unit * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      tc::fence_async_smem();
+      if (kc == 0 && have_prev) {
+        wait_buf(p_b);
+        tc::tc_fence_after();
+        epilogue(p_tile);
+        tc::tc_fence_before();
+      }
+      __syncthreads();
+      if (tid == 0) {
+        tc::tc_fence_after();
+        const uint32_t abase = tc::smem_u32(sA), wbase = tc::smem_u32(sWt);
+        constexpr uint32_t LBO_W = (COUT / 8) * 128;
+        uint32_t acc = (kc > 0) ? 1u : 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const uint64_t ah = tc::smem_desc(abase + j * 2 * 2048, 2048, 128);
+          const uint64_t al = tc::smem_desc(abase + Cfg::A_PREC + j * 2 * 2048, 2048, 128);
+          const uint64_t bh = tc::smem_desc(wbase + j * 2 * LBO_W, LBO_W, 128);
+          const uint64_t bl = tc::smem_desc(wbase + Cfg::W_PREC + j * 2 * LBO_W, LBO_W, 128);
+          tc::mma_bf16(tm, ah, bh, idesc, acc);
+          tc::mma_bf16(tm, al, bh, idesc, 1);
+          tc::mma_bf16(tm, ah, bl, idesc, 1);
+          acc = 1;
+        }
+        tc::mma_commit(&bars[b]);
+      }
+      pend[b] = true;
+      counter++;
+    }
+    have_prev = true;
+    p_tile = tile;
+    p_b = (counter - 1) & 1;
+  }
+  if (have_prev) {
+    wait_buf(p_b);
+    tc::tc_fence_after();
+    epilogue(p_tile);
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tm, COUT < 32 ? 32 : COUT);
+}
+
 // ------------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------------
@@ -400,7 +594,7 @@ static int tc_launch(const char* name, const float* in, const double* in_stats, 
   if (gx < 1) gx = 1;
   if (gx > items) gx = items;
   dim3 grid(gx, COUT / 32);
-  KPROF(name, stream, kern<<<grid, 128, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
+  KPROF(name, stream, kern<<<grid, T2_THREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
@@ -416,4 +610,36 @@ int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, c
 int tc_launch_conv4(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {
   return tc_launch<64, 3, 29, 14, 64, 2>("tc_conv4", in, in_stats, gam, bet, wpack, bias, out, out_stats, n, stream);
+}
+
+template <int CIN, int KS, int HIN, int HOUT, int COUT, bool FINAL>
+static int tc3_launch(const char* name, const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack,
+                      const float* bias, float* out, double* out_stats, int n, cudaStream_t stream) {
+  using Cfg = Tc3Cfg<CIN, KS, HIN, HOUT, COUT, FINAL>;
+  static_assert(Cfg::SMEM <= 227 * 1024, "tc gemm shared memory");
+  auto kern = tc_gemm_kernel<CIN, KS, HIN, HOUT, COUT, FINAL>;
+  static bool attr = false;
+  if (!attr) {
+    STRIVE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    attr = true;
+  }
+  const long long rows = (long long)n * Cfg::PIX;
+  const int tiles = (int)((rows + 127) / 128);
+  const int gx = tiles < num_sms() ? tiles : num_sms();
+  KPROF(name, stream, kern<<<gx, T2_THREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
+  STRIVE_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc_launch_conv5(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+                    float* out, double* out_stats, int n, cudaStream_t stream) {
+  return tc3_launch<64, 3, 14, 6, 128, false>("tc_conv5", in, in_stats, gam, bet, wpack, bias, out, out_stats, n, stream);
+}
+int tc_launch_conv6(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+                    float* out, double* out_stats, int n, cudaStream_t stream) {
+  return tc3_launch<128, 3, 6, 2, 128, false>("tc_conv6", in, in_stats, gam, bet, wpack, bias, out, out_stats, n, stream);
+}
+int tc_launch_fc(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+                 float* out, int n, cudaStream_t stream) {
+  return tc3_launch<128, 2, 2, 1, 64, true>("tc_fc", in, in_stats, gam, bet, wpack, bias, out, nullptr, n, stream);
 }

@@ -67,8 +67,14 @@ class MapEnv(object):
         self._lin_l = torch.linspace(bounds[0], bounds[2], L, dtype=torch.float32).to(self.device)
         self._lin_w = torch.linspace(bounds[1], bounds[3], W, dtype=torch.float32).to(self.device)
         M, Cc, H, Wd = self.nusc_raster.shape
+        if int(self.nusc_raster.max()) > 1:
+            raise RuntimeError('strive_b200: the map raster must be binary (0/1 layers as produced by get_map_mask, map_env.py:106-118)')
+        # one byte per pixel, bit c = layer c: the crop gather then touches 1 byte instead of C scattered bytes
+        self._packed = torch.zeros((M, H, Wd), dtype=torch.uint8, device=self.device)
+        for c in range(min(Cc, 8)):
+            self._packed |= (self.nusc_raster[:, c] << c)
         self.cstruct = _cabi.StriveMap(_cabi.dptr(self.nusc_raster), _cabi.dptr(self.nusc_dx), M, Cc, H, Wd,
-                                       _cabi.dptr(self._lin_l), _cabi.dptr(self._lin_w))
+                                       _cabi.dptr(self._lin_l), _cabi.dptr(self._lin_w), _cabi.dptr(self._packed))
 
     def crop_poses(self, pose_un, mapixes):
         """(N,4) unnormalised poses -> (N,C,256,256) uint8 (reference get_map_obs, nuscenes_utils.py:236-264)."""

@@ -122,4 +122,17 @@ def pack_tc_weights(sd):
             parts.append(t.permute(0, 3, 6, 4, 1, 2, 5))                    # (nchunk, c2, tap, khalf, ngroup, r, k)
         t = torch.stack(parts, dim=3)                                       # (nchunk, c2, tap, prec, khalf, ngroup, r, k)
         out.append(_bytes(t))
+    # conv5 / conv6 / fc as GEMMs with K = tap * Cin + c in 64-wide chunks: [kchunk][prec][kg 8][ng Cout/8][r 8][kk 8]
+    def gemm_pack(wk):                                                      # wk (Cout, K)
+        cout, K = wk.shape
+        parts = []
+        for p in _split(wk):
+            t = p.reshape(cout // 8, 8, K // 64, 8, 8)                      # (ng, r, kchunk, kg, kk)
+            parts.append(t.permute(2, 3, 0, 1, 4))                          # (kchunk, kg, ng, r, kk)
+        return _bytes(torch.stack(parts, dim=1))                            # (kchunk, prec, kg, ng, r, kk)
+    for li in (4, 5):
+        w = g('map_conv.%d.weight' % (3 * li))                              # (Cout, Cin, 3, 3) -> k = (ky*3+kx)*Cin + c
+        out.append(gemm_pack(w.permute(0, 2, 3, 1).reshape(w.size(0), -1)))
+    wf = g('map_feature.weight').reshape(64, 128, 2, 2)                     # flatten index of the reference = c*4 + y*2 + x
+    out.append(gemm_pack(wf.permute(0, 2, 3, 1).reshape(64, -1)))           # NHWC order: k = (y*2+x)*128 + c
     return torch.cat(out)
