@@ -1,0 +1,28 @@
+"""Runs the map encoder alone on N random poses (profiling target for ncu)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import strive_b200
+from strive_b200 import synth
+N = int(os.environ.get('N', '512'))
+REPS = int(os.environ.get('REPS', '3'))
+dev = torch.device('cuda:0')
+raster, dx = synth.make_raster(seed=1, M=1, H=4096, W=4096)
+sd = synth.make_weights(0)
+model = strive_b200.make_model(nfuture=20, state_dict=sd, device=dev)
+env = strive_b200.MapEnv(raster, dx, device=dev)
+g = torch.Generator().manual_seed(0)
+xy = torch.rand(N, 2, generator=g) * 600 + 200
+ang = torch.rand(N, generator=g) * 6.2831853
+pose = torch.cat([xy, torch.cos(ang)[:, None], torch.sin(ang)[:, None]], 1).to(dev).contiguous()
+mapix = torch.zeros(N, dtype=torch.int32, device=dev)
+for _ in range(REPS):
+    f = model.encode_map_poses(pose, mapix, env)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(REPS):
+    f = model.encode_map_poses(pose, mapix, env)
+e1.record()
+torch.cuda.synchronize()
+print('mapenc: %d crops, %.3f ms per call, %.3f us per crop, feat checksum %.6f' % (N, e0.elapsed_time(e1) / REPS, 1000 * e0.elapsed_time(e1) / REPS / N, float(f.double().sum())))
