@@ -31,7 +31,7 @@ WORK = dict(scenes=64, agents=32, FT=20, group=4, raster=4096)
 # algorithmic MACs per crop of each map-encoder kernel
 CNN_MAC = {'conv1_gather': 49.0e6, 'conv2': 47.63e6, 'conv3': 43.06e6, 'conv4': 7.23e6, 'conv5': 2.65e6, 'conv6': 0.59e6, 'fc': 0.03e6,
            'tc_conv1': 49.0e6, 'tc_conv2': 47.63e6, 'tc_conv3': 43.06e6, 'tc_conv4': 7.23e6, 'tc_conv5': 2.65e6, 'tc_conv6': 0.59e6, 'tc_fc': 0.03e6}
-MAPENC_CHUNK = 512
+MAPENC_CHUNK = 2048
 
 
 def measured_peaks():

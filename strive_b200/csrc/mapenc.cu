@@ -325,7 +325,7 @@ static int launch_conv(const char* name, const float* in, const double* in_stats
 // ------------------------------------------------------------------------------------------------------
 // workspace + driver
 // ------------------------------------------------------------------------------------------------------
-#define MAPENC_CHUNK 512
+#define MAPENC_CHUNK 2048
 // 1 = tensor-core conv1..4 (default), 0 = fp32 SIMT reference kernels (kept for A/B verification, strive_mapenc_set_impl)
 static int g_mapenc_impl = 1;
 extern "C" int strive_mapenc_set_impl(int impl) {

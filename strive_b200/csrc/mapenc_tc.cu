@@ -1,145 +1,186 @@
-// Tensor-core (tcgen05 + TMEM) implicit-GEMM convolutions of the map encoder.
+// Tensor-core (tcgen05 + TMEM) implicit-GEMM convolutions of the map encoder, warp-specialised:
+//   warps 0..10  producers  : stage operand tiles into a shared-memory ring (GroupNorm + ReLU + bf16 hi/lo split fused)
+//   warp  11     MMA issuer : one elected thread issues tcgen05.mma, frees ring slots with tcgen05.commit
+//   warps 12..15 epilogue   : TMEM -> registers -> +bias -> NHWC fp32 store + fp64 GroupNorm statistics
+// Two TMEM accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1; all hand-offs are mbarriers.
 //
 // Numerics: bf16 operand SPLITTING with fp32 accumulation in TMEM.  x = hi + lo (hi = bf16(x), lo = bf16(x - hi)).
 //   conv1: the input is the binary crop (exact in bf16); weights are split -> 2 MMAs per K step (error 2^-17 relative).
-//   conv2..: activations and weights are both split -> hi*hi + lo*hi + hi*lo (3 MMAs, dropped lo*lo term 2^-18).
-// This keeps the encoder at fp32-level accuracy (tests: <= 1e-4 abs on O(1) features; measured ~1e-5) at 1/3 of the
-// dense bf16 tensor peak; see DESIGN.md.
+//   conv2..fc: activations and weights both split -> hi*hi + lo*hi + hi*lo (3 MMAs, dropped lo*lo term 2^-18).
+// Measured against the fp64 oracle: 1.4e-5 abs on O(1) features (tests allow 1e-4), at 1/3 of the dense bf16 tensor rate.
 //
-// Operand addressing ("shifted window"): the GroupNorm'ed/ReLU'ed input tile is written to shared memory ONCE, with the
-// columns de-interleaved by parity (stride-2 convolution -> consecutive output pixels are consecutive 16-byte rows of a
-// parity plane).  Every filter tap is then just a different start address / the same LBO,SBO in the K-major no-swizzle
-// matrix descriptor, so there is no im2col expansion in shared memory at all.
+// Operand addressing ("shifted window", conv1..conv4): the input tile is written to shared memory ONCE, columns
+// de-interleaved by parity (stride-2 conv -> consecutive output pixels are consecutive 16-byte rows of a parity plane).
+// Every filter tap is then only a different start address in the K-major no-swizzle matrix descriptor: no im2col copy.
 #include "common.cuh"
 #include "tc.cuh"
 
+#define TC_NPROD 11
+#define TC_MMA_WARP 11
+#define TC_EPI_WARP0 12
+#define TC_THREADS 512
+#define TC_PROD_THREADS (TC_NPROD * 32)
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+__device__ __forceinline__ void gn_stats(const double* __restrict__ st, int crop, double cnt, float& mean, float& rstd) {
+  const double mu = st[(size_t)crop * 2] / cnt;
+  double var = st[(size_t)crop * 2 + 1] / cnt - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean = (float)mu;
+  rstd = (float)(1.0 / sqrt(var + 1e-5));
+}
+
 // ======================================================================================================
-// conv1: 4 -> 16, k7 s2, input gathered from the raster.  CTA = 32x32 outputs = 8 MMA sub-tiles (16 rows x 8 cols).
-// A tile: [row][col][4 ch] bf16 (8 B / pixel); one K=16 MMA = 4 taps (kx..kx+3) x 4 channels at fixed ky.
+// conv1: 4 -> 16, k7 s2, input gathered from the packed binary raster.  CTA tile = 32x32 outputs = 8 MMA sub-tiles
+// (16 rows x 8 cols each, own TMEM accumulator).  A tile: [row][col][4 ch] bf16 (8 B / pixel); one K=16 MMA = 4 taps
+// (kx..kx+3) x 4 channels at fixed ky.
 // ======================================================================================================
 #define T1_PH 69
 #define T1_PW 70
 #define T1_WBYTES (7 * 2 * 2 * 512)
 #define T1_PATCH_BYTES (T1_PH * T1_PW * 8)
-#define T1_THREADS 256
 #define T1_SUPER 4   // 4 x 4 super-tiles of 32 x 32 outputs cover 125 x 125
+#define T1_NBUF 2
 
-struct CropFrameTc {
-  float px, py, hc, hs;
-  double dx0, dx1, inv0, inv1;
-  const uint8_t* base;
-};
-
-// round-half-even(g / dx) exactly as torch.round(float64 quotient): multiply by the reciprocal and fall back to the true
-// division only when the product lands within 1e-6 of a .5 boundary (the only case where the two could round differently).
-__device__ __forceinline__ long long round_div_exact(float g, double dx, double inv) {
-  const double q = (double)g * inv;
-  const double fr = q - floor(q);
-  if (fabs(fr - 0.5) < 1e-6) return __double2ll_rn((double)g / dx);
-  return __double2ll_rn(q);
+// round-half-even(g / dx) exactly as torch.round(float64 quotient) (reference datasets/nuscenes_utils.py:254-255): multiply by
+// the reciprocal; only when the product lands within 1e-6 of a .5 boundary (where the two could round differently) divide.
+__device__ __forceinline__ int round_div_exact(float g, double dx, double inv) {
+  const double gd = (double)g;
+  const double q = gd * inv;
+  int r = __double2int_rn(q);
+  const double fr = fabs(q - (double)r);
+  if (fr > 0.499999) r = __double2int_rn(gd / dx);
+  return r;
 }
 
-__device__ __forceinline__ void crop_pixel_tc(const CropFrameTc& f, float l, float w, int H, int W, long long& xp, long long& yp) {
-  // exact restatement of get_map_obs (reference datasets/nuscenes_utils.py:248-263); see mapenc.cu crop_pixel
-  float gx = __fadd_rn(__fsub_rn(__fmul_rn(l, f.hc), __fmul_rn(w, f.hs)), f.px);
-  float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, f.hs), __fmul_rn(w, f.hc)), f.py);
-  if (isnan(gx)) gx = 0.f;
-  if (isnan(gy)) gy = 0.f;
-  xp = round_div_exact(gx, f.dx0, f.inv0);
-  yp = round_div_exact(gy, f.dx1, f.inv1);
-  if (yp < 0 || yp >= H || xp < 0 || xp >= W) { xp = 0; yp = 0; }
-}
-
-__global__ void __launch_bounds__(T1_THREADS) tc_conv1_kernel(StriveMap map, const float* __restrict__ pose,
+__global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(StriveMap map, const float* __restrict__ pose,
                                                               const int32_t* __restrict__ map_of, const uint8_t* __restrict__ wpack,
                                                               const float* __restrict__ bias, float* __restrict__ out,
                                                               double* __restrict__ out_stats, int n) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sP = smem + T1_WBYTES;
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t full[T1_NBUF], empty[T1_NBUF], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
   __shared__ float s_bias[16];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < T1_WBYTES / 16; i += T1_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(reinterpret_cast<const int4*>(wpack) + i);
+  for (int i = tid; i < T1_WBYTES / 16; i += TC_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(reinterpret_cast<const int4*>(wpack) + i);
   if (tid < 16) s_bias[tid] = bias[tid];
   if (tid == 0) {
-    tc::mbar_init(&bar, 1);
+    for (int b = 0; b < T1_NBUF; b++) { tc::mbar_init(&full[b], TC_PROD_THREADS); tc::mbar_init(&empty[b], 1); }
+    for (int a = 0; a < 2; a++) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 128); }
     tc::fence_mbar_init();
   }
-  if (warp == 0) tc::tmem_alloc(&tmem_base, 128);
+  if (warp == TC_MMA_WARP) tc::tmem_alloc(&tmem_base, 256);
+  tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tm = tmem_base;
-  const uint32_t idesc = tc::idesc_bf16_f32(128, 16);
-  uint32_t phase = 0;
   const int items = n * T1_SUPER * T1_SUPER;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int crop = item / (T1_SUPER * T1_SUPER);
-    const int st = item % (T1_SUPER * T1_SUPER);
-    const int oy0 = (st / T1_SUPER) * 32, ox0 = (st % T1_SUPER) * 32;
-    {
+
+  if (warp < TC_NPROD) {
+    // ---------------- producers: gather the crop tile (exact get_map_obs arithmetic) ----------------
+    int cnt = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, cnt++) {
+      const int crop = item / (T1_SUPER * T1_SUPER), st = item % (T1_SUPER * T1_SUPER);
+      const int oy0 = (st / T1_SUPER) * 32, ox0 = (st % T1_SUPER) * 32;
+      const int b = cnt % T1_NBUF;
+      tc::mbar_wait(&empty[b], ((cnt / T1_NBUF) & 1) ^ 1);
+      uint8_t* dst = sP + (size_t)b * T1_PATCH_BYTES;
       const int m = map_of[crop];
-      CropFrameTc f;
-      f.px = pose[crop * 4 + 0]; f.py = pose[crop * 4 + 1]; f.hc = pose[crop * 4 + 2]; f.hs = pose[crop * 4 + 3];
-      f.dx0 = map.dx[m * 2 + 0]; f.dx1 = map.dx[m * 2 + 1];
-      f.inv0 = 1.0 / f.dx0; f.inv1 = 1.0 / f.dx1;
-      f.base = map.packed + (size_t)m * map.H * map.W;     // bit c of a byte = layer c (binary raster)
-      for (int i = tid; i < T1_PH * T1_PW; i += T1_THREADS) {
-        const int r = i / T1_PW, c = i % T1_PW;
+      const float px = pose[crop * 4 + 0], py = pose[crop * 4 + 1], hc = pose[crop * 4 + 2], hs = pose[crop * 4 + 3];
+      const double dx0 = map.dx[m * 2 + 0], dx1 = map.dx[m * 2 + 1];
+      const double inv0 = 1.0 / dx0, inv1 = 1.0 / dx1;
+      const uint8_t* base = map.packed + (size_t)m * map.H * map.W;
+      const int H = map.H, W = map.W;
+      for (int i = tid; i < T1_PH * T1_PW; i += TC_PROD_THREADS) {
+        const int r = i / T1_PW, c = i - r * T1_PW;
         const int iy = oy0 * 2 + r, ix = ox0 * 2 + c;
         uint32_t lo = 0, hi = 0;
         if (iy < 256 && ix < 256) {
-          long long xp, yp;
-          crop_pixel_tc(f, __ldg(map.lin_l + iy), __ldg(map.lin_w + ix), map.H, map.W, xp, yp);
-          const uint32_t bits = __ldg(f.base + (size_t)yp * map.W + xp);
+          const float l = __ldg(map.lin_l + iy), w = __ldg(map.lin_w + ix);
+          // gen_car_coords (:232-233): (l*hcos - w*hsin) + x ; (l*hsin + w*hcos) + y  -- separate fp32 roundings, no FMA
+          float gx = __fadd_rn(__fsub_rn(__fmul_rn(l, hc), __fmul_rn(w, hs)), px);
+          float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, hs), __fmul_rn(w, hc)), py);
+          if (isnan(gx)) gx = 0.f;
+          if (isnan(gy)) gy = 0.f;
+          int xp = round_div_exact(gx, dx0, inv0), yp = round_div_exact(gy, dx1, inv1);
+          if (yp < 0 || yp >= H || xp < 0 || xp >= W) { xp = 0; yp = 0; }     // :260-262
+          const uint32_t bits = __ldg(base + (size_t)yp * W + xp);
           const uint32_t one = 0x3F80u;   // bf16(1.0)
           lo = ((bits & 1u) ? one : 0u) | ((bits & 2u) ? (one << 16) : 0u);
           hi = ((bits & 4u) ? one : 0u) | ((bits & 8u) ? (one << 16) : 0u);
         }
-        *reinterpret_cast<uint2*>(sP + (size_t)i * 8) = make_uint2(lo, hi);
+        *reinterpret_cast<uint2*>(dst + (size_t)i * 8) = make_uint2(lo, hi);
+      }
+      tc::fence_async_smem();
+      tc::mbar_arrive(&full[b]);
+    }
+  } else if (warp == TC_MMA_WARP) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_bf16_f32(128, 16);
+      const uint32_t wbase = tc::smem_u32(sW);
+      int cnt = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, cnt++) {
+        const int b = cnt % T1_NBUF, a = cnt & 1;
+        tc::mbar_wait(&acc_empty[a], ((cnt >> 1) & 1) ^ 1);
+        tc::mbar_wait(&full[b], (cnt / T1_NBUF) & 1);
+        tc::tc_fence_after();
+        const uint32_t pbase = tc::smem_u32(sP + (size_t)b * T1_PATCH_BYTES);
+#pragma unroll 1
+        for (int sub = 0; sub < 8; sub++) {
+          const int sy = sub >> 2, sx = sub & 3;
+          const uint32_t abase = pbase + ((sy * 32) * T1_PW + sx * 16) * 8;
+          const uint32_t d = tm + a * 128 + sub * 16;
+          uint32_t acc = 0;
+#pragma unroll 1
+          for (int ky = 0; ky < 7; ky++) {
+#pragma unroll
+            for (int kq = 0; kq < 2; kq++) {
+              const uint64_t ad = tc::smem_desc(abase + (ky * T1_PW + 4 * kq) * 8, 16, 2 * T1_PW * 8);
+              const uint32_t wb = wbase + ((ky * 2 + kq) * 2) * 512;
+              tc::mma_bf16(d, ad, tc::smem_desc(wb, 256, 128), idesc, acc);
+              tc::mma_bf16(d, ad, tc::smem_desc(wb + 512, 256, 128), idesc, 1);
+              acc = 1;
+            }
+          }
+        }
+        tc::mma_commit(&empty[b]);
+        tc::mma_commit(&acc_full[a]);
       }
     }
-    tc::fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
+  } else {
+    // ---------------- epilogue: warp q reads TMEM lanes 32q..32q+31 of all 8 sub-tiles ----------------
+    const int q = warp - TC_EPI_WARP0;
+    const int m = q * 32 + lane, oyl = m >> 3, oxl = m & 7;
+    int cnt = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, cnt++) {
+      const int crop = item / (T1_SUPER * T1_SUPER), st = item % (T1_SUPER * T1_SUPER);
+      const int oy0 = (st / T1_SUPER) * 32, ox0 = (st % T1_SUPER) * 32;
+      const int a = cnt & 1;
+      tc::mbar_wait(&acc_full[a], (cnt >> 1) & 1);
       tc::tc_fence_after();
-      const uint32_t pbase = tc::smem_u32(sP), wbase = tc::smem_u32(sW);
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
       for (int sub = 0; sub < 8; sub++) {
         const int sy = sub >> 2, sx = sub & 3;
-        const uint32_t abase = pbase + ((sy * 32) * T1_PW + sx * 16) * 8;
-        uint32_t acc = 0;
-#pragma unroll 1
-        for (int ky = 0; ky < 7; ky++) {
-#pragma unroll
-          for (int kq = 0; kq < 2; kq++) {
-            const uint64_t ad = tc::smem_desc(abase + (ky * T1_PW + 4 * kq) * 8, 16, 2 * T1_PW * 8);
-            const uint32_t wb = wbase + ((ky * 2 + kq) * 2) * 512;
-            tc::mma_bf16(tm + sub * 16, ad, tc::smem_desc(wb, 256, 128), idesc, acc);
-            tc::mma_bf16(tm + sub * 16, ad, tc::smem_desc(wb + 512, 256, 128), idesc, 1);
-            acc = 1;
-          }
-        }
-      }
-      tc::mma_commit(&bar);
-    }
-    tc::mbar_wait(&bar, phase);
-    phase ^= 1;
-    tc::tc_fence_after();
-    // epilogue: warp w handles TMEM lanes (w%4)*32.. of sub-tiles (w/4)*4 .. +3
-    float s1 = 0.f, s2 = 0.f;
-    {
-      const int q = warp & 3;
-      const int m = q * 32 + lane;              // row of the 128-row sub-tile = oy_l*8 + ox_l
-      const int oyl = m >> 3, oxl = m & 7;
-#pragma unroll 1
-      for (int k = 0; k < 4; k++) {
-        const int sub = (warp >> 2) * 4 + k;
-        const int sy = sub >> 2, sx = sub & 3;
         float v[16];
-        tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + sub * 16, v);
+        tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * 128 + sub * 16, v);
+        if (sub == 7) {
+          tc::tc_fence_before();
+          tc::mbar_arrive(&acc_empty[a]);
+        }
         const int oy = oy0 + sy * 16 + oyl, ox = ox0 + sx * 8 + oxl;
         if (oy < 125 && ox < 125) {
           float* o = out + (((size_t)crop * 125 + oy) * 125 + ox) * 16;
@@ -153,25 +194,26 @@ __global__ void __launch_bounds__(T1_THREADS) tc_conv1_kernel(StriveMap map, con
           for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
         }
       }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        atomicAdd(out_stats + (size_t)crop * 2, (double)s1);
+        atomicAdd(out_stats + (size_t)crop * 2 + 1, (double)s2);
+      }
     }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) {
-      atomicAdd(out_stats + (size_t)crop * 2, (double)s1);
-      atomicAdd(out_stats + (size_t)crop * 2 + 1, (double)s2);
-    }
-    tc::tc_fence_before();
-    __syncthreads();   // TMEM + patch are free again
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tm, 128);
+  if (warp == TC_MMA_WARP) {
+    __syncwarp();
+    tc::tmem_dealloc(tm, 256);
+  }
 }
 
 // ======================================================================================================
 // conv2..4: stride-2 kxk conv, CIN multiple of 16, output-channel chunks of N=32 (blockIdx.y), NHWC fp32 in/out.
 // CTA tile = 16 x 8 outputs (M = 128).  Weights of the chunk stay resident in shared memory; the input tile is staged
-// per 16-channel chunk into an NBUF-deep ring so staging of chunk i+1 overlaps the (asynchronous) MMAs of chunk i.
+// per 16-channel chunk into an NBUF-deep ring.
 // ======================================================================================================
 template <int CIN, int KS, int HIN, int HOUT, int COUT, int NBUF>
 struct TcCfg {
@@ -190,180 +232,195 @@ struct TcCfg {
   static constexpr size_t SMEM = (size_t)W_BYTES + (size_t)NBUF * A_BYTES;
 };
 
-#define T2_THREADS 512
 template <int CIN, int KS, int HIN, int HOUT, int COUT, int NBUF>
-__global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
-                                                      const float* __restrict__ gam, const float* __restrict__ bet,
-                                                      const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
-                                                      float* __restrict__ out, double* __restrict__ out_stats, int n) {
+__global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
+                                                             const float* __restrict__ gam, const float* __restrict__ bet,
+                                                             const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
+                                                             float* __restrict__ out, double* __restrict__ out_stats, int n) {
   using Cfg = TcCfg<CIN, KS, HIN, HOUT, COUT, NBUF>;
   constexpr int PH = Cfg::PH, PW = Cfg::PW, PQ = Cfg::PQ, C2 = Cfg::C2, TAPS = Cfg::TAPS;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sA = smem + Cfg::W_BYTES;
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
   __shared__ float s_gam[CIN], s_bet[CIN], s_bias[32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunk = blockIdx.y;
   {
     const int4* src = reinterpret_cast<const int4*>(wpack + (size_t)nchunk * Cfg::W_BYTES);
-    for (int i = tid; i < Cfg::W_BYTES / 16; i += T2_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(src + i);
+    for (int i = tid; i < Cfg::W_BYTES / 16; i += TC_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(src + i);
   }
-  for (int i = tid; i < CIN; i += T2_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
+  for (int i = tid; i < CIN; i += TC_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
   if (tid < 32) s_bias[tid] = bias[nchunk * 32 + tid];
   if (tid == 0) {
-    tc::mbar_init(&bars[0], 1);
-    tc::mbar_init(&bars[1], 1);
+    for (int b = 0; b < NBUF; b++) { tc::mbar_init(&full[b], TC_PROD_THREADS); tc::mbar_init(&empty[b], 1); }
+    for (int a = 0; a < 2; a++) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 128); }
     tc::fence_mbar_init();
   }
-  if (warp == 0) tc::tmem_alloc(&tmem_base, 32);
+  if (warp == TC_MMA_WARP) tc::tmem_alloc(&tmem_base, 64);
+  tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tm = tmem_base;
-  const uint32_t idesc = tc::idesc_bf16_f32(128, 32);
-  int counter = 0;
-  bool pend[2] = {false, false};
-  uint32_t ph[2] = {0, 0};
-  bool have_prev = false;
-  int p_crop = 0, p_ty0 = 0, p_tx0 = 0, p_b = 0;
+  const int items = n * Cfg::TILES;
 
-  auto wait_buf = [&](int b) {
-    if (pend[b]) {
-      tc::mbar_wait(&bars[b], ph[b]);
-      ph[b] ^= 1;
-      pend[b] = false;
-    }
-  };
-  auto epilogue = [&](int crop, int ty0, int tx0) {
-    if (warp >= 4) return;   // TMEM lanes 0..127 are read by warps 0..3
-    const int m = warp * 32 + lane;
-    const int oy = ty0 + (m >> 3), ox = tx0 + (m & 7);
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      float v[16];
-      tc::tmem_ld16(tm + ((uint32_t)(warp * 32) << 16) + h * 16, v);
-      if (oy < HOUT && ox < HOUT) {
-        float* o = out + (((size_t)crop * HOUT + oy) * HOUT + ox) * COUT + nchunk * 32 + h * 16;
+  if (warp < TC_NPROD) {
+    // ---------------- producers ----------------
+    int cnt = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int crop = item / Cfg::TILES, tile = item % Cfg::TILES;
+      const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
+      float mean, rstd;
+      gn_stats(in_stats, crop, (double)CIN * HIN * HIN, mean, rstd);
+#pragma unroll 1
+      for (int c2 = 0; c2 < C2; c2++, cnt++) {
+        const int b = cnt % NBUF;
+        // y = relu(x * ga + gb)  ==  relu((x - mean) * rstd * gamma + beta)
+        float ga[16], gb[16];
 #pragma unroll
         for (int c = 0; c < 16; c++) {
-          v[c] += s_bias[h * 16 + c];
-          s1 += v[c];
-          s2 = fmaf(v[c], v[c], s2);
+          ga[c] = rstd * s_gam[c2 * 16 + c];
+          gb[c] = fmaf(-mean, ga[c], s_bet[c2 * 16 + c]);
         }
+        tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
+        uint8_t* dst = sA + (size_t)b * Cfg::A_BYTES;
+        const float* src = in + (size_t)crop * HIN * HIN * CIN + c2 * 16;
+        constexpr int NPIX = PH * PW;
+#pragma unroll 1
+        for (int p0 = tid; p0 < NPIX; p0 += 2 * TC_PROD_THREADS) {
+          float4 x[2][4];
+          bool ok[2];
+          int u0[2];
 #pragma unroll
-        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+          for (int k = 0; k < 2; k++) {
+            const int p = p0 + k * TC_PROD_THREADS;
+            const int row = p / PW, col = p - row * PW;
+            const int iy = 2 * ty0 + row, ix = 2 * tx0 + col;
+            ok[k] = (p < NPIX) && iy < HIN && ix < HIN;
+            u0[k] = (p < NPIX) ? ((row * 2 + (col & 1)) * PQ + (col >> 1)) : -1;
+            if (ok[k]) {
+              const float4* s4 = reinterpret_cast<const float4*>(src + ((size_t)iy * HIN + ix) * CIN);
+#pragma unroll
+              for (int q = 0; q < 4; q++) x[k][q] = __ldg(s4 + q);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            if (u0[k] < 0) continue;
+            uint32_t hi[8], lo[8];
+            if (ok[k]) {
+              const float xs[16] = {x[k][0].x, x[k][0].y, x[k][0].z, x[k][0].w, x[k][1].x, x[k][1].y, x[k][1].z, x[k][1].w,
+                                    x[k][2].x, x[k][2].y, x[k][2].z, x[k][2].w, x[k][3].x, x[k][3].y, x[k][3].z, x[k][3].w};
+#pragma unroll
+              for (int c = 0; c < 16; c += 2) {
+                const float y0 = fmaxf(fmaf(xs[c], ga[c], gb[c]), 0.f);
+                const float y1 = fmaxf(fmaf(xs[c + 1], ga[c + 1], gb[c + 1]), 0.f);
+                tc::split_pack2(y0, y1, hi[c >> 1], lo[c >> 1]);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 8; c++) { hi[c] = 0u; lo[c] = 0u; }
+            }
+            uint8_t* d0 = dst + (size_t)u0[k] * 16;
+            constexpr int CG = PH * 2 * PQ * 16;
+            *reinterpret_cast<uint4*>(d0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(d0 + CG) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<uint4*>(d0 + Cfg::A_PREC_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(d0 + Cfg::A_PREC_BYTES + CG) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          }
+        }
+        tc::fence_async_smem();
+        tc::mbar_arrive(&full[b]);
       }
     }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
+  } else if (warp == TC_MMA_WARP) {
     if (lane == 0) {
-      atomicAdd(out_stats + (size_t)crop * 2, (double)s1);
-      atomicAdd(out_stats + (size_t)crop * 2 + 1, (double)s2);
-    }
-  };
-
-  const int items = n * Cfg::TILES;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int crop = item / Cfg::TILES, tile = item % Cfg::TILES;
-    const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
-    float mean, rstd;
-    {
-      const double cnt = (double)CIN * HIN * HIN;
-      const double mu = in_stats[(size_t)crop * 2] / cnt;
-      double var = in_stats[(size_t)crop * 2 + 1] / cnt - mu * mu;
-      if (var < 0.0) var = 0.0;
-      mean = (float)mu;
-      rstd = (float)(1.0 / sqrt(var + 1e-5));
-    }
+      const uint32_t idesc = tc::idesc_bf16_f32(128, 32);
+      constexpr uint32_t LBO_A = PH * 2 * PQ * 16, SBO_A = 64 * PQ;
+      int cnt = 0, it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
+        const int a = it & 1;
+        tc::mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+        const uint32_t d = tm + a * 32;
 #pragma unroll 1
-    for (int c2 = 0; c2 < C2; c2++) {
-      const int b = counter % NBUF;
-      wait_buf(b);
-      uint8_t* dst = sA + (size_t)b * Cfg::A_BYTES;
-      const float* src = in + (size_t)crop * HIN * HIN * CIN + c2 * 16;
-      for (int p = tid; p < PH * PW; p += T2_THREADS) {
-        const int row = p / PW, col = p % PW;
-        const int iy = 2 * ty0 + row, ix = 2 * tx0 + col;
-        uint32_t hi[8], lo[8];
-        if (iy < HIN && ix < HIN) {
-          const float4* s4 = reinterpret_cast<const float4*>(src + ((size_t)iy * HIN + ix) * CIN);
-          float x[16];
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const float4 t = __ldg(s4 + q);
-            x[q * 4] = t.x; x[q * 4 + 1] = t.y; x[q * 4 + 2] = t.z; x[q * 4 + 3] = t.w;
-          }
-#pragma unroll
-          for (int c = 0; c < 16; c += 2) {
-            float h0, l0, h1, l1;
-            const float y0 = fmaxf(fmaf((x[c] - mean) * rstd, s_gam[c2 * 16 + c], s_bet[c2 * 16 + c]), 0.f);
-            const float y1 = fmaxf(fmaf((x[c + 1] - mean) * rstd, s_gam[c2 * 16 + c + 1], s_bet[c2 * 16 + c + 1]), 0.f);
-            tc::split_bf16(y0, h0, l0);
-            tc::split_bf16(y1, h1, l1);
-            hi[c >> 1] = tc::pack_bf16(h0, h1);
-            lo[c >> 1] = tc::pack_bf16(l0, l1);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; c++) { hi[c] = 0u; lo[c] = 0u; }
-        }
-        const int u0 = ((row * 2 + (col & 1)) * PQ + (col >> 1));   // 16-byte unit inside channel-group 0
-        uint8_t* d0 = dst + (size_t)u0 * 16;
-        constexpr int CG = PH * 2 * PQ * 16;
-        *reinterpret_cast<uint4*>(d0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(d0 + CG) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        *reinterpret_cast<uint4*>(d0 + Cfg::A_PREC_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(d0 + Cfg::A_PREC_BYTES + CG) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-      }
-      tc::fence_async_smem();
-      if (c2 == 0 && have_prev) {
-        wait_buf(p_b);
-        tc::tc_fence_after();
-        epilogue(p_crop, p_ty0, p_tx0);
-        tc::tc_fence_before();
-      }
-      __syncthreads();
-      if (tid == 0) {
-        tc::tc_fence_after();
-        const uint32_t abase = tc::smem_u32(dst);
-        const uint32_t wbase = tc::smem_u32(sW) + c2 * TAPS * 2048;
-        constexpr uint32_t LBO_A = PH * 2 * PQ * 16, SBO_A = 64 * PQ;
-        uint32_t acc = (c2 > 0) ? 1u : 0u;
+        for (int c2 = 0; c2 < C2; c2++, cnt++) {
+          const int b = cnt % NBUF;
+          tc::mbar_wait(&full[b], (cnt / NBUF) & 1);
+          tc::tc_fence_after();
+          const uint32_t abase = tc::smem_u32(sA + (size_t)b * Cfg::A_BYTES);
+          const uint32_t wbase = tc::smem_u32(sW) + c2 * TAPS * 2048;
+          uint32_t acc = (c2 > 0) ? 1u : 0u;
 #pragma unroll 1
-        for (int tap = 0; tap < TAPS; tap++) {
-          const int ky = tap / KS, kx = tap % KS;
-          const uint32_t aoff = ((ky * 2 + (kx & 1)) * PQ + (kx >> 1)) * 16;
-          const uint64_t ah = tc::smem_desc(abase + aoff, LBO_A, SBO_A);
-          const uint64_t al = tc::smem_desc(abase + Cfg::A_PREC_BYTES + aoff, LBO_A, SBO_A);
-          const uint64_t bh = tc::smem_desc(wbase + tap * 2048, 512, 128);
-          const uint64_t bl = tc::smem_desc(wbase + tap * 2048 + 1024, 512, 128);
-          tc::mma_bf16(tm, ah, bh, idesc, acc);
-          tc::mma_bf16(tm, al, bh, idesc, 1);
-          tc::mma_bf16(tm, ah, bl, idesc, 1);
-          acc = 1;
+          for (int ky = 0; ky < KS; ky++) {
+#pragma unroll
+            for (int kx = 0; kx < KS; kx++) {
+              const int tap = ky * KS + kx;
+              const uint32_t aoff = ((ky * 2 + (kx & 1)) * PQ + (kx >> 1)) * 16;
+              const uint64_t ah = tc::smem_desc(abase + aoff, LBO_A, SBO_A);
+              const uint64_t al = tc::smem_desc(abase + Cfg::A_PREC_BYTES + aoff, LBO_A, SBO_A);
+              const uint64_t bh = tc::smem_desc(wbase + tap * 2048, 512, 128);
+              const uint64_t bl = tc::smem_desc(wbase + tap * 2048 + 1024, 512, 128);
+              tc::mma_bf16(d, ah, bh, idesc, acc);
+              tc::mma_bf16(d, al, bh, idesc, 1);
+              tc::mma_bf16(d, ah, bl, idesc, 1);
+              acc = 1;
+            }
+          }
+          tc::mma_commit(&empty[b]);
         }
-        tc::mma_commit(&bars[b]);
+        tc::mma_commit(&acc_full[a]);
       }
-      pend[b] = true;
-      counter++;
     }
-    have_prev = true;
-    p_crop = crop; p_ty0 = ty0; p_tx0 = tx0;
-    p_b = (counter - 1) % NBUF;
-  }
-  if (have_prev) {
-    wait_buf(p_b);
-    tc::tc_fence_after();
-    epilogue(p_crop, p_ty0, p_tx0);
+  } else {
+    // ---------------- epilogue ----------------
+    const int q = warp - TC_EPI_WARP0;
+    const int m = q * 32 + lane;
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
+      const int crop = item / Cfg::TILES, tile = item % Cfg::TILES;
+      const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
+      const int a = it & 1;
+      tc::mbar_wait(&acc_full[a], (it >> 1) & 1);
+      tc::tc_fence_after();
+      float v0[16], v1[16];
+      tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * 32, v0);
+      tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * 32 + 16, v1);
+      tc::tc_fence_before();
+      tc::mbar_arrive(&acc_empty[a]);
+      const int oy = ty0 + (m >> 3), ox = tx0 + (m & 7);
+      float s1 = 0.f, s2 = 0.f;
+      if (oy < HOUT && ox < HOUT) {
+        float* o = out + (((size_t)crop * HOUT + oy) * HOUT + ox) * COUT + nchunk * 32;
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+          v0[c] += s_bias[c];
+          v1[c] += s_bias[16 + c];
+          s1 += v0[c] + v1[c];
+          s2 = fmaf(v0[c], v0[c], s2);
+          s2 = fmaf(v1[c], v1[c], s2);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v0[c], v0[c + 1], v0[c + 2], v0[c + 3]);
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(o + 16 + c) = make_float4(v1[c], v1[c + 1], v1[c + 2], v1[c + 3]);
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        atomicAdd(out_stats + (size_t)crop * 2, (double)s1);
+        atomicAdd(out_stats + (size_t)crop * 2 + 1, (double)s2);
+      }
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tm, 32);
+  if (warp == TC_MMA_WARP) {
+    __syncwarp();
+    tc::tmem_dealloc(tm, 64);
+  }
 }
-
 
 // ======================================================================================================
 // conv5 / conv6 / fc: small spatial extent (6x6, 2x2, 1x1 outputs) -> rows of many crops are packed into M = 128 tiles and
@@ -378,200 +435,189 @@ struct Tc3Cfg {
   static constexpr int A_PREC = 128 * 64 * 2;
   static constexpr int W_PREC = COUT * 64 * 2;
   static constexpr int STAGE = 2 * A_PREC + 2 * W_PREC;
-  static constexpr size_t SMEM = 2 * (size_t)STAGE;
+  static constexpr int NBUF = 3;
+  static constexpr size_t SMEM = (size_t)NBUF * STAGE;
 };
 
 template <int CIN, int KS, int HIN, int HOUT, int COUT, bool FINAL>
-__global__ void __launch_bounds__(T2_THREADS) tc_gemm_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
+__global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
                                                              const float* __restrict__ gam, const float* __restrict__ bet,
                                                              const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
                                                              float* __restrict__ out, double* __restrict__ out_stats, int n) {
   using Cfg = Tc3Cfg<CIN, KS, HIN, HOUT, COUT, FINAL>;
-  constexpr int PIX = Cfg::PIX, NCH = Cfg::NCH;
-  static_assert(CIN % 64 == 0 && COUT % 16 == 0, "tc_gemm tiling");
+  constexpr int PIX = Cfg::PIX, NCH = Cfg::NCH, NBUF = Cfg::NBUF;
+  static_assert(CIN % 64 == 0 && COUT % 16 == 0 && 2 * COUT <= 512, "tc_gemm tiling");
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
   __shared__ float s_gam[CIN], s_bet[CIN], s_bias[COUT];
+  __shared__ float s_mean[2][128], s_rstd[2][128];
+  __shared__ int s_off[2][128];     // element offset of the row's (2oy, 2ox) input pixel, -1 = row beyond the batch
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < CIN; i += T2_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
-  for (int i = tid; i < COUT; i += T2_THREADS) s_bias[i] = bias[i];
+  for (int i = tid; i < CIN; i += TC_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
+  for (int i = tid; i < COUT; i += TC_THREADS) s_bias[i] = bias[i];
   if (tid == 0) {
-    tc::mbar_init(&bars[0], 1);
-    tc::mbar_init(&bars[1], 1);
+    for (int b = 0; b < NBUF; b++) { tc::mbar_init(&full[b], TC_PROD_THREADS); tc::mbar_init(&empty[b], 1); }
+    for (int a = 0; a < 2; a++) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 128); }
     tc::fence_mbar_init();
   }
-  if (warp == 0) tc::tmem_alloc(&tmem_base, COUT < 32 ? 32 : COUT);
+  constexpr uint32_t TCOLS = 2 * COUT;   // 256 or 128: a power of two >= 32
+  if (warp == TC_MMA_WARP) tc::tmem_alloc(&tmem_base, TCOLS);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tm = tmem_base;
-  const uint32_t idesc = tc::idesc_bf16_f32(128, COUT);
-  int counter = 0;
-  bool pend[2] = {false, false};
-  uint32_t ph[2] = {0, 0};
-  bool have_prev = false;
-  int p_tile = 0, p_b = 0;
-  auto wait_buf = [&](int b) {
-    if (pend[b]) {
-      tc::mbar_wait(&bars[b], ph[b]);
-      ph[b] ^= 1;
-      pend[b] = false;
-    }
-  };
   const long long rows_total = (long long)n * PIX;
-  auto epilogue = [&](int tile) {
-    if (warp >= 4) return;
-    const long long gm = (long long)tile * 128 + warp * 32 + lane;
-    const bool valid = gm < rows_total;
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-    for (int h = 0; h < COUT / 16; h++) {
-      float v[16];
-      tc::tmem_ld16(tm + ((uint32_t)(warp * 32) << 16) + h * 16, v);
-      if (valid) {
-        float* o = out + (size_t)gm * COUT + h * 16;
-#pragma unroll
-        for (int c = 0; c < 16; c++) {
-          v[c] += s_bias[h * 16 + c];
-          s1 += v[c];
-          s2 = fmaf(v[c], v[c], s2);
-        }
-#pragma unroll
-        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-      }
-    }
-    if (!FINAL && valid) {
-      const int crop = (int)(gm / PIX);
-      atomicAdd(out_stats + (size_t)crop * 2, (double)s1);
-      atomicAdd(out_stats + (size_t)crop * 2 + 1, (double)s2);
-    }
-  };
-
   const int tiles = (int)((rows_total + 127) / 128);
-  const int m = tid & 127;          // every thread stages a fixed row of the tile, k-groups (tid>>7) and (tid>>7)+4
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const long long gm = (long long)tile * 128 + m;
-    const bool valid = gm < rows_total;
-    int crop = 0, oy = 0, ox = 0;
-    float mean = 0.f, rstd = 0.f;
-    if (valid) {
-      crop = (int)(gm / PIX);
-      const int pix = (int)(gm % PIX);
-      oy = pix / HOUT; ox = pix % HOUT;
-      const double cnt = (double)CIN * HIN * HIN;
-      const double mu = in_stats[(size_t)crop * 2] / cnt;
-      double var = in_stats[(size_t)crop * 2 + 1] / cnt - mu * mu;
-      if (var < 0.0) var = 0.0;
-      mean = (float)mu;
-      rstd = (float)(1.0 / sqrt(var + 1e-5));
-    }
+
+  if (warp < TC_NPROD) {
+    int cnt = 0, tpar = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, tpar ^= 1) {
+      if (tid < 128) {
+        const long long gm = (long long)tile * 128 + tid;
+        float mean = 0.f, rstd = 0.f;
+        int off = -1;
+        if (gm < rows_total) {
+          const int crop = (int)(gm / PIX), pix = (int)(gm % PIX);
+          gn_stats(in_stats, crop, (double)CIN * HIN * HIN, mean, rstd);
+          off = ((crop * HIN + 2 * (pix / HOUT)) * HIN + 2 * (pix % HOUT)) * CIN;
+        }
+        s_mean[tpar][tid] = mean; s_rstd[tpar][tid] = rstd; s_off[tpar][tid] = off;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");   // producers only
 #pragma unroll 1
-    for (int kc = 0; kc < NCH; kc++) {
-      const int b = counter & 1;
-      wait_buf(b);
-      uint8_t* sA = smem + (size_t)b * Cfg::STAGE;
-      uint8_t* sWt = sA + 2 * Cfg::A_PREC;
-      {
-        const int4* src = reinterpret_cast<const int4*>(wpack + (size_t)kc * 2 * Cfg::W_PREC);
-        for (int i = tid; i < 2 * Cfg::W_PREC / 16; i += T2_THREADS) reinterpret_cast<int4*>(sWt)[i] = __ldg(src + i);
-      }
-      const int k0 = kc * 64;
-      const int tap = k0 / CIN, c0 = k0 % CIN;
-      const int ky = tap / KS, kx = tap % KS;
-      const float* src = in + (((size_t)crop * HIN + 2 * oy + ky) * HIN + 2 * ox + kx) * CIN + c0;
+      for (int kc = 0; kc < NCH; kc++, cnt++) {
+        const int b = cnt % NBUF;
+        tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
+        uint8_t* sA = smem + (size_t)b * Cfg::STAGE;
+        uint8_t* sWt = sA + 2 * Cfg::A_PREC;
+        {
+          const int4* src = reinterpret_cast<const int4*>(wpack + (size_t)kc * 2 * Cfg::W_PREC);
+          for (int i = tid; i < 2 * Cfg::W_PREC / 16; i += TC_PROD_THREADS) reinterpret_cast<int4*>(sWt)[i] = __ldg(src + i);
+        }
+        const int k0 = kc * 64;
+        const int tap = k0 / CIN, c0 = k0 % CIN;
+        const int ky = tap / KS, kx = tap % KS;
+        for (int idx = tid; idx < 128 * 8; idx += TC_PROD_THREADS) {
+          const int m = idx & 127, kg = idx >> 7;
+          uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+          const int off = s_off[tpar][m];
+          if (off >= 0) {
+            const float mean = s_mean[tpar][m], rstd = s_rstd[tpar][m];
+            const float* src = in + (size_t)off + (ky * HIN + kx) * CIN + c0 + kg * 8;
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(src));
+            const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+            const float x[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-      for (int half = 0; half < 2; half++) {
-        const int kg = (tid >> 7) + half * 4;
-        uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
-        if (valid) {
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(src + kg * 8));
-          const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + kg * 8 + 4));
-          const float x[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-#pragma unroll
-          for (int c = 0; c < 8; c += 2) {
-            const int ch = c0 + kg * 8 + c;
-            float h0, l0, h1, l1;
-            const float y0 = fmaxf(fmaf((x[c] - mean) * rstd, s_gam[ch], s_bet[ch]), 0.f);
-            const float y1 = fmaxf(fmaf((x[c + 1] - mean) * rstd, s_gam[ch + 1], s_bet[ch + 1]), 0.f);
-            tc::split_bf16(y0, h0, l0);
-            tc::split_bf16(y1, h1, l1);
-            hi[c >> 1] = tc::pack_bf16(h0, h1);
-            lo[c >> 1] = tc::pack_bf16(l0, l1);
+            for (int c = 0; c < 8; c += 2) {
+              const int ch = c0 + kg * 8 + c;
+              const float a0 = rstd * s_gam[ch], a1 = rstd * s_gam[ch + 1];
+              const float y0 = fmaxf(fmaf(x[c], a0, fmaf(-mean, a0, s_bet[ch])), 0.f);
+              const float y1 = fmaxf(fmaf(x[c + 1], a1, fmaf(-mean, a1, s_bet[ch + 1])), 0.f);
+              tc::split_pack2(y0, y1, hi[c >> 1], lo[c >> 1]);
+            }
           }
+          const int unit = (kg * 16 + (m >> 3)) * 8 + (m & 7);
+          *reinterpret_cast<uint4*>(sA + (size_t)unit * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(sA + Cfg::A_PREC + (size_t)unit * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        const int unit = (kg * 16 + (m >> 3)) * 8 + (m & 7);
-        *reinterpret_cast<uint4*>(sA + (size_t)unit * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(sA + Cfg::A_PREC + (size_t)unit * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        tc::fence_async_smem();
+        tc::mbar_arrive(&full[b]);
       }
-      tc::fence_async_smem();
-      if (kc == 0 && have_prev) {
-        wait_buf(p_b);
-        tc::tc_fence_after();
-        epilogue(p_tile);
-        tc::tc_fence_before();
-      }
-      __syncthreads();
-      if (tid == 0) {
-        tc::tc_fence_after();
-        const uint32_t abase = tc::smem_u32(sA), wbase = tc::smem_u32(sWt);
-        constexpr uint32_t LBO_W = (COUT / 8) * 128;
-        uint32_t acc = (kc > 0) ? 1u : 0u;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const uint64_t ah = tc::smem_desc(abase + j * 2 * 2048, 2048, 128);
-          const uint64_t al = tc::smem_desc(abase + Cfg::A_PREC + j * 2 * 2048, 2048, 128);
-          const uint64_t bh = tc::smem_desc(wbase + j * 2 * LBO_W, LBO_W, 128);
-          const uint64_t bl = tc::smem_desc(wbase + Cfg::W_PREC + j * 2 * LBO_W, LBO_W, 128);
-          tc::mma_bf16(tm, ah, bh, idesc, acc);
-          tc::mma_bf16(tm, al, bh, idesc, 1);
-          tc::mma_bf16(tm, ah, bl, idesc, 1);
-          acc = 1;
-        }
-        tc::mma_commit(&bars[b]);
-      }
-      pend[b] = true;
-      counter++;
     }
-    have_prev = true;
-    p_tile = tile;
-    p_b = (counter - 1) & 1;
-  }
-  if (have_prev) {
-    wait_buf(p_b);
-    tc::tc_fence_after();
-    epilogue(p_tile);
+  } else if (warp == TC_MMA_WARP) {
+    if (lane == 0) {
+      const uint32_t idesc = tc::idesc_bf16_f32(128, COUT);
+      constexpr uint32_t LBO_W = (COUT / 8) * 128;
+      int cnt = 0, it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+        const int a = it & 1;
+        tc::mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+        const uint32_t d = tm + a * COUT;
+#pragma unroll 1
+        for (int kc = 0; kc < NCH; kc++, cnt++) {
+          const int b = cnt % NBUF;
+          tc::mbar_wait(&full[b], (cnt / NBUF) & 1);
+          tc::tc_fence_after();
+          const uint32_t abase = tc::smem_u32(smem + (size_t)b * Cfg::STAGE);
+          const uint32_t wbase = abase + 2 * Cfg::A_PREC;
+          uint32_t acc = (kc > 0) ? 1u : 0u;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint64_t ah = tc::smem_desc(abase + j * 2 * 2048, 2048, 128);
+            const uint64_t al = tc::smem_desc(abase + Cfg::A_PREC + j * 2 * 2048, 2048, 128);
+            const uint64_t bh = tc::smem_desc(wbase + j * 2 * LBO_W, LBO_W, 128);
+            const uint64_t bl = tc::smem_desc(wbase + Cfg::W_PREC + j * 2 * LBO_W, LBO_W, 128);
+            tc::mma_bf16(d, ah, bh, idesc, acc);
+            tc::mma_bf16(d, al, bh, idesc, 1);
+            tc::mma_bf16(d, ah, bl, idesc, 1);
+            acc = 1;
+          }
+          tc::mma_commit(&empty[b]);
+        }
+        tc::mma_commit(&acc_full[a]);
+      }
+    }
+  } else {
+    const int q = warp - TC_EPI_WARP0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, it++) {
+      const int a = it & 1;
+      const long long gm = (long long)tile * 128 + q * 32 + lane;
+      const bool valid = gm < rows_total;
+      tc::mbar_wait(&acc_full[a], (it >> 1) & 1);
+      tc::tc_fence_after();
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int h = 0; h < COUT / 16; h++) {
+        float v[16];
+        tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * COUT + h * 16, v);
+        if (h == COUT / 16 - 1) {
+          tc::tc_fence_before();
+          tc::mbar_arrive(&acc_empty[a]);
+        }
+        if (valid) {
+          float* o = out + (size_t)gm * COUT + h * 16;
+#pragma unroll
+          for (int c = 0; c < 16; c++) {
+            v[c] += s_bias[h * 16 + c];
+            s1 += v[c];
+            s2 = fmaf(v[c], v[c], s2);
+          }
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        }
+      }
+      if (!FINAL && valid) {
+        const int crop = (int)(gm / PIX);
+        atomicAdd(out_stats + (size_t)crop * 2, (double)s1);
+        atomicAdd(out_stats + (size_t)crop * 2 + 1, (double)s2);
+      }
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tm, COUT < 32 ? 32 : COUT);
+  if (warp == TC_MMA_WARP) {
+    __syncwarp();
+    tc::tmem_dealloc(tm, TCOLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  return g_num_sms;
-}
-
 int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_of, const uint8_t* wpack, const float* bias, float* out,
                     double* out_stats, int n, cudaStream_t stream) {
   static bool attr = false;
-  const size_t smem = T1_WBYTES + T1_PATCH_BYTES;
+  const size_t smem = T1_WBYTES + T1_NBUF * T1_PATCH_BYTES;
   if (!attr) {
     STRIVE_CUDA(cudaFuncSetAttribute(tc_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
+  STRIVE_CHECK(map->packed != nullptr, STRIVE_EINVAL, "tensor-core map encoder needs StriveMap.packed");
   const int items = n * T1_SUPER * T1_SUPER;
-  const int grid = items < num_sms() * 3 ? items : num_sms() * 3;
-  KPROF("tc_conv1", stream, tc_conv1_kernel<<<grid, T1_THREADS, smem, stream>>>(*map, pose, map_of, wpack, bias, out, out_stats, n));
+  const int grid = items < num_sms() * 2 ? items : num_sms() * 2;
+  KPROF("tc_conv1", stream, tc_conv1_kernel<<<grid, TC_THREADS, smem, stream>>>(*map, pose, map_of, wpack, bias, out, out_stats, n));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
@@ -581,7 +627,7 @@ static int tc_launch(const char* name, const float* in, const double* in_stats, 
                      const float* bias, float* out, double* out_stats, int n, cudaStream_t stream) {
   using Cfg = TcCfg<CIN, KS, HIN, HOUT, COUT, NBUF>;
   static_assert(COUT % 32 == 0 && CIN % 16 == 0, "tc conv tiling");
-  static_assert(Cfg::SMEM <= 227 * 1024, "tc conv shared memory");
+  static_assert(Cfg::SMEM <= 226 * 1024, "tc conv shared memory");
   auto kern = tc_conv_kernel<CIN, KS, HIN, HOUT, COUT, NBUF>;
   static bool attr = false;
   if (!attr) {
@@ -589,19 +635,18 @@ static int tc_launch(const char* name, const float* in, const double* in_stats, 
     attr = true;
   }
   const int items = n * Cfg::TILES;
-  const int per_sm = (Cfg::SMEM + 2048) * 2 <= 227 * 1024 ? 2 : 1;
-  int gx = num_sms() * per_sm / (COUT / 32);
+  int gx = num_sms() / (COUT / 32);
   if (gx < 1) gx = 1;
   if (gx > items) gx = items;
   dim3 grid(gx, COUT / 32);
-  KPROF(name, stream, kern<<<grid, T2_THREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
+  KPROF(name, stream, kern<<<grid, TC_THREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
 
 int tc_launch_conv2(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {
-  return tc_launch<16, 5, 125, 61, 32, 2>("tc_conv2", in, in_stats, gam, bet, wpack, bias, out, out_stats, n, stream);
+  return tc_launch<16, 5, 125, 61, 32, 3>("tc_conv2", in, in_stats, gam, bet, wpack, bias, out, out_stats, n, stream);
 }
 int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {
@@ -609,14 +654,14 @@ int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, c
 }
 int tc_launch_conv4(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {
-  return tc_launch<64, 3, 29, 14, 64, 2>("tc_conv4", in, in_stats, gam, bet, wpack, bias, out, out_stats, n, stream);
+  return tc_launch<64, 3, 29, 14, 64, 3>("tc_conv4", in, in_stats, gam, bet, wpack, bias, out, out_stats, n, stream);
 }
 
 template <int CIN, int KS, int HIN, int HOUT, int COUT, bool FINAL>
 static int tc3_launch(const char* name, const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack,
                       const float* bias, float* out, double* out_stats, int n, cudaStream_t stream) {
   using Cfg = Tc3Cfg<CIN, KS, HIN, HOUT, COUT, FINAL>;
-  static_assert(Cfg::SMEM <= 227 * 1024, "tc gemm shared memory");
+  static_assert(Cfg::SMEM <= 226 * 1024, "tc gemm shared memory");
   auto kern = tc_gemm_kernel<CIN, KS, HIN, HOUT, COUT, FINAL>;
   static bool attr = false;
   if (!attr) {
@@ -626,7 +671,7 @@ static int tc3_launch(const char* name, const float* in, const double* in_stats,
   const long long rows = (long long)n * Cfg::PIX;
   const int tiles = (int)((rows + 127) / 128);
   const int gx = tiles < num_sms() ? tiles : num_sms();
-  KPROF(name, stream, kern<<<gx, T2_THREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
+  KPROF(name, stream, kern<<<gx, TC_THREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }

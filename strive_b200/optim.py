@@ -100,7 +100,7 @@ class RefineLoop(object):
 
     def _count_launches(self):
         FT, NA = self.FT, self.NA
-        chunks = (NA + 511) // 512
+        chunks = (NA + 2047) // 2048
         fwd = 1 + FT * 3 + (FT - 1) * (1 + chunks * 7)
         bwd = FT * 3 + (FT - 1)
         loss = 7
