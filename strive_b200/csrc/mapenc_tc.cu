@@ -73,7 +73,12 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(StriveMap map, con
   __shared__ __align__(8) uint64_t full[T1_NBUF], empty[T1_NBUF], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
   __shared__ float s_bias[16];
+  __shared__ uint2 s_lut[16];   // 4 layer bits -> 4 x bf16 {0,1}
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 16) {
+    const uint32_t one = 0x3F80u;
+    s_lut[tid] = make_uint2(((tid & 1) ? one : 0u) | ((tid & 2) ? (one << 16) : 0u), ((tid & 4) ? one : 0u) | ((tid & 8) ? (one << 16) : 0u));
+  }
   for (int i = tid; i < T1_WBYTES / 16; i += TC_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(reinterpret_cast<const int4*>(wpack) + i);
   if (tid < 16) s_bias[tid] = bias[tid];
   if (tid == 0) {
@@ -104,25 +109,33 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(StriveMap map, con
       const double inv0 = 1.0 / dx0, inv1 = 1.0 / dx1;
       const uint8_t* base = map.packed + (size_t)m * map.H * map.W;
       const int H = map.H, W = map.W;
-      for (int i = tid; i < T1_PH * T1_PW; i += TC_PROD_THREADS) {
+      // a NaN coordinate can only come from a non-finite pose (the linspace tables are finite): then every sample is (0,0) (:251)
+      const bool finite_pose = isfinite(px) && isfinite(py) && isfinite(hc) && isfinite(hs);
+      auto sample = [&](int i) -> uint2 {
         const int r = i / T1_PW, c = i - r * T1_PW;
         const int iy = oy0 * 2 + r, ix = ox0 * 2 + c;
-        uint32_t lo = 0, hi = 0;
-        if (iy < 256 && ix < 256) {
+        if (iy >= 256 || ix >= 256) return make_uint2(0u, 0u);
+        int xp = 0, yp = 0;
+        if (finite_pose) {
           const float l = __ldg(map.lin_l + iy), w = __ldg(map.lin_w + ix);
           // gen_car_coords (:232-233): (l*hcos - w*hsin) + x ; (l*hsin + w*hcos) + y  -- separate fp32 roundings, no FMA
-          float gx = __fadd_rn(__fsub_rn(__fmul_rn(l, hc), __fmul_rn(w, hs)), px);
-          float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, hs), __fmul_rn(w, hc)), py);
-          if (isnan(gx)) gx = 0.f;
-          if (isnan(gy)) gy = 0.f;
-          int xp = round_div_exact(gx, dx0, inv0), yp = round_div_exact(gy, dx1, inv1);
-          if (yp < 0 || yp >= H || xp < 0 || xp >= W) { xp = 0; yp = 0; }     // :260-262
-          const uint32_t bits = __ldg(base + (size_t)yp * W + xp);
-          const uint32_t one = 0x3F80u;   // bf16(1.0)
-          lo = ((bits & 1u) ? one : 0u) | ((bits & 2u) ? (one << 16) : 0u);
-          hi = ((bits & 4u) ? one : 0u) | ((bits & 8u) ? (one << 16) : 0u);
+          const float gx = __fadd_rn(__fsub_rn(__fmul_rn(l, hc), __fmul_rn(w, hs)), px);
+          const float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, hs), __fmul_rn(w, hc)), py);
+          xp = round_div_exact(gx, dx0, inv0);
+          yp = round_div_exact(gy, dx1, inv1);
+          if ((unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }     // :260-262
         }
-        *reinterpret_cast<uint2*>(dst + (size_t)i * 8) = make_uint2(lo, hi);
+        const uint32_t bits = __ldg(base + (size_t)((unsigned)yp * (unsigned)W + (unsigned)xp)) & 15u;
+        return s_lut[bits];
+      };
+      constexpr int NPX = T1_PH * T1_PW;
+#pragma unroll 1
+      for (int i = tid; i < NPX; i += 2 * TC_PROD_THREADS) {
+        const int i1 = i + TC_PROD_THREADS;
+        const uint2 v0 = sample(i);
+        const uint2 v1 = (i1 < NPX) ? sample(i1) : make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(dst + (size_t)i * 8) = v0;
+        if (i1 < NPX) *reinterpret_cast<uint2*>(dst + (size_t)i1 * 8) = v1;
       }
       tc::fence_async_smem();
       tc::mbar_arrive(&full[b]);
@@ -265,74 +278,97 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
   tc::tc_fence_after();
   const uint32_t tm = tmem_base;
   const int items = n * Cfg::TILES;
+  // contiguous item range per CTA: consecutive tiles of the same crop share the GroupNorm statistics and L2 lines
+  const int item_lo = (int)(((long long)items * blockIdx.x) / gridDim.x);
+  const int item_hi = (int)(((long long)items * (blockIdx.x + 1)) / gridDim.x);
 
   if (warp < TC_NPROD) {
-    // ---------------- producers ----------------
-    int cnt = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      const int crop = item / Cfg::TILES, tile = item % Cfg::TILES;
-      const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
-      float mean, rstd;
-      gn_stats(in_stats, crop, (double)CIN * HIN * HIN, mean, rstd);
-#pragma unroll 1
-      for (int c2 = 0; c2 < C2; c2++, cnt++) {
-        const int b = cnt % NBUF;
-        // y = relu(x * ga + gb)  ==  relu((x - mean) * rstd * gamma + beta)
-        float ga[16], gb[16];
+    // ---------------- producers: one pixel (16 channels) per step, the next pixel's global loads always in flight ----------------
+    constexpr int NPIX = PH * PW;
+    constexpr int KPT = (NPIX + TC_PROD_THREADS - 1) / TC_PROD_THREADS;
+    constexpr int CG = PH * 2 * PQ * 16;
+    auto load_pixel = [&](int item, int c2, int k, float4 (&x)[4], bool& ok, int& u) {
+      const int p = tid + k * TC_PROD_THREADS;
+      ok = false;
+      u = -1;
+      if (p < NPIX) {
+        const int crop = item / Cfg::TILES, tile = item - crop * Cfg::TILES;
+        const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
+        const int row = p / PW, col = p - row * PW;
+        const int iy = 2 * ty0 + row, ix = 2 * tx0 + col;
+        u = (row * 2 + (col & 1)) * PQ + (col >> 1);
+        if (iy < HIN && ix < HIN) {
+          ok = true;
+          const float4* s4 = reinterpret_cast<const float4*>(in + ((size_t)(crop * HIN + iy) * HIN + ix) * CIN + c2 * 16);
 #pragma unroll
-        for (int c = 0; c < 16; c++) {
-          ga[c] = rstd * s_gam[c2 * 16 + c];
-          gb[c] = fmaf(-mean, ga[c], s_bet[c2 * 16 + c]);
+          for (int q = 0; q < 4; q++) x[q] = __ldg(s4 + q);
         }
+      }
+    };
+    int item = item_lo, c2 = 0, k = 0, cnt = 0, cur_crop = -1, b = 0;
+    float mean = 0.f, rstd = 0.f;
+    float ga[16], gb[16];
+    float4 xn[4];
+    bool okn = false;
+    int un = -1;
+    if (item < item_hi) load_pixel(item, c2, k, xn, okn, un);
+    uint8_t* dst = sA;
+    while (item < item_hi) {
+      float4 xc[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) xc[q] = xn[q];
+      const bool okc = okn;
+      const int uc = un;
+      const int ci = item, cc2 = c2, ck = k;
+      if (++k == KPT) {
+        k = 0;
+        if (++c2 == C2) { c2 = 0; item++; }
+      }
+      if (item < item_hi) load_pixel(item, c2, k, xn, okn, un);
+      if (ck == 0) {
+        const int crop = ci / Cfg::TILES;
+        const bool newcrop = crop != cur_crop;
+        if (newcrop) {
+          gn_stats(in_stats, crop, (double)CIN * HIN * HIN, mean, rstd);
+          cur_crop = crop;
+        }
+        if (newcrop || C2 > 1) {
+          // y = relu(x * ga + gb)  ==  relu((x - mean) * rstd * gamma + beta)
+#pragma unroll
+          for (int c = 0; c < 16; c++) {
+            ga[c] = rstd * s_gam[cc2 * 16 + c];
+            gb[c] = fmaf(-mean, ga[c], s_bet[cc2 * 16 + c]);
+          }
+        }
+        b = cnt % NBUF;
         tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
-        uint8_t* dst = sA + (size_t)b * Cfg::A_BYTES;
-        const float* src = in + (size_t)crop * HIN * HIN * CIN + c2 * 16;
-        constexpr int NPIX = PH * PW;
-#pragma unroll 1
-        for (int p0 = tid; p0 < NPIX; p0 += 2 * TC_PROD_THREADS) {
-          float4 x[2][4];
-          bool ok[2];
-          int u0[2];
+        dst = sA + (size_t)b * Cfg::A_BYTES;
+      }
+      if (uc >= 0) {
+        uint32_t hi[8], lo[8];
+        if (okc) {
+          const float xs[16] = {xc[0].x, xc[0].y, xc[0].z, xc[0].w, xc[1].x, xc[1].y, xc[1].z, xc[1].w,
+                                xc[2].x, xc[2].y, xc[2].z, xc[2].w, xc[3].x, xc[3].y, xc[3].z, xc[3].w};
 #pragma unroll
-          for (int k = 0; k < 2; k++) {
-            const int p = p0 + k * TC_PROD_THREADS;
-            const int row = p / PW, col = p - row * PW;
-            const int iy = 2 * ty0 + row, ix = 2 * tx0 + col;
-            ok[k] = (p < NPIX) && iy < HIN && ix < HIN;
-            u0[k] = (p < NPIX) ? ((row * 2 + (col & 1)) * PQ + (col >> 1)) : -1;
-            if (ok[k]) {
-              const float4* s4 = reinterpret_cast<const float4*>(src + ((size_t)iy * HIN + ix) * CIN);
-#pragma unroll
-              for (int q = 0; q < 4; q++) x[k][q] = __ldg(s4 + q);
-            }
+          for (int c = 0; c < 16; c += 2) {
+            const float y0 = fmaxf(fmaf(xs[c], ga[c], gb[c]), 0.f);
+            const float y1 = fmaxf(fmaf(xs[c + 1], ga[c + 1], gb[c + 1]), 0.f);
+            tc::split_pack2(y0, y1, hi[c >> 1], lo[c >> 1]);
           }
+        } else {
 #pragma unroll
-          for (int k = 0; k < 2; k++) {
-            if (u0[k] < 0) continue;
-            uint32_t hi[8], lo[8];
-            if (ok[k]) {
-              const float xs[16] = {x[k][0].x, x[k][0].y, x[k][0].z, x[k][0].w, x[k][1].x, x[k][1].y, x[k][1].z, x[k][1].w,
-                                    x[k][2].x, x[k][2].y, x[k][2].z, x[k][2].w, x[k][3].x, x[k][3].y, x[k][3].z, x[k][3].w};
-#pragma unroll
-              for (int c = 0; c < 16; c += 2) {
-                const float y0 = fmaxf(fmaf(xs[c], ga[c], gb[c]), 0.f);
-                const float y1 = fmaxf(fmaf(xs[c + 1], ga[c + 1], gb[c + 1]), 0.f);
-                tc::split_pack2(y0, y1, hi[c >> 1], lo[c >> 1]);
-              }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 8; c++) { hi[c] = 0u; lo[c] = 0u; }
-            }
-            uint8_t* d0 = dst + (size_t)u0[k] * 16;
-            constexpr int CG = PH * 2 * PQ * 16;
-            *reinterpret_cast<uint4*>(d0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(d0 + CG) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            *reinterpret_cast<uint4*>(d0 + Cfg::A_PREC_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            *reinterpret_cast<uint4*>(d0 + Cfg::A_PREC_BYTES + CG) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-          }
+          for (int c = 0; c < 8; c++) { hi[c] = 0u; lo[c] = 0u; }
         }
+        uint8_t* d0 = dst + (size_t)uc * 16;
+        *reinterpret_cast<uint4*>(d0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(d0 + CG) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<uint4*>(d0 + Cfg::A_PREC_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(d0 + Cfg::A_PREC_BYTES + CG) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+      }
+      if (ck == KPT - 1) {
         tc::fence_async_smem();
         tc::mbar_arrive(&full[b]);
+        cnt++;
       }
     }
   } else if (warp == TC_MMA_WARP) {
@@ -340,7 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
       const uint32_t idesc = tc::idesc_bf16_f32(128, 32);
       constexpr uint32_t LBO_A = PH * 2 * PQ * 16, SBO_A = 64 * PQ;
       int cnt = 0, it = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
+      for (int item = item_lo; item < item_hi; item++, it++) {
         const int a = it & 1;
         tc::mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
         const uint32_t d = tm + a * 32;
@@ -378,7 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
     const int q = warp - TC_EPI_WARP0;
     const int m = q * 32 + lane;
     int it = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, it++) {
+    for (int item = item_lo; item < item_hi; item++, it++) {
       const int crop = item / Cfg::TILES, tile = item % Cfg::TILES;
       const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
       const int a = it & 1;
