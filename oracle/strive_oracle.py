@@ -548,3 +548,83 @@ def refine_loop(sd, scene, raster, dx, weights, iters, lr, FT, veh_coll_buffer=0
             record.append({'loss': float(total.detach()), 'grad': z.grad.detach().clone(), 'traj': fut.detach().clone()})
         opt.step()
     return z.detach()
+
+
+# --------------------------------------------------------------------------------------------
+# adversarial / solution loops, literal restatements (two decodes per iteration as the reference)
+# --------------------------------------------------------------------------------------------
+def _collate(ptr, tgt_z, other_z):
+    """utils/adv_gen_optim.py:19-36"""
+    out, prev = [], 0
+    for b in range(ptr.numel() - 1):
+        n = int(ptr[b + 1] - ptr[b]) - 1
+        out += [tgt_z[b:b + 1], other_z[prev:prev + n]]
+        prev += n
+    return torch.cat(out, 0)
+
+
+def adv_loop(sd, scene, raster, dx, weights, iters, lr, FT, planner_fut_n, crash_min_t=0, crash_min_infront=None, veh_coll_buffer=0.1,
+             record=None):
+    """utils/adv_gen_optim.py:39-175, planner_name == 'ego' (open-loop replay, planner_inject_traj=True)."""
+    ptr = scene['ptr']
+    NA = int(ptr[-1])
+    ego = torch.zeros(NA, dtype=torch.bool)
+    ego[ptr[:-1]] = True
+    tgt_z = scene['z'][ego].clone().requires_grad_(True)
+    other_z = scene['z'][~ego].clone().requires_grad_(True)
+    init_o = scene['z'][~ego].clone()
+    opt = torch.optim.Adam([tgt_z, other_z], lr=lr)
+    lw_un = unnorm_att(scene['lw'])
+    mapixes = scene['map_idx'][scene['batch']]
+    tprior = (scene['prior_mu'][ego], scene['prior_var'][ego])
+    oprior = (scene['prior_mu'][~ego], scene['prior_var'][~ego])
+    pf_un = unnorm_state(planner_fut_n)
+
+    def dec(z):
+        return decode(sd, z, scene['map_feat'], scene['past_feat'], scene['past'][:, -1, :], scene['lw'], scene['sem'], ptr,
+                      scene['edge_index'], scene['map_idx'], raster, dx, FT, ext_future=planner_fut_n)
+    for it in range(iters):
+        opt.zero_grad()
+        f_t = dec(_collate(ptr, tgt_z, other_z.detach()))
+        f_o = dec(_collate(ptr, tgt_z.detach(), other_z))
+        lt = tgt_matching_loss(unnorm_state(f_t)[ego], pf_un, weights)
+        la = adv_gen_loss(unnorm_state(f_o), pf_un, other_z, oprior, init_o, weights, lw_un, mapixes, ptr, raster, dx,
+                          veh_coll_buffer=veh_coll_buffer, crash_min_t=crash_min_t, crash_min_infront=crash_min_infront)
+        loss = lt['loss'] + la['loss']
+        loss.backward()
+        if record is not None:
+            record.append({'loss': float(loss.detach()), 'g_tgt': tgt_z.grad.clone(), 'g_other': other_z.grad.clone()})
+        opt.step()
+    return _collate(ptr, tgt_z.detach(), other_z.detach())
+
+
+def sol_loop(sd, scene, raster, dx, weights, iters, lr, future_len, FT, other_match_un, record=None):
+    """utils/sol_optim.py:19-123 (weights already stripped of the 'sol_' prefix)."""
+    ptr = scene['ptr']
+    NA = int(ptr[-1])
+    ego = torch.zeros(NA, dtype=torch.bool)
+    ego[ptr[:-1]] = True
+    tgt_z = scene['prior_mu'][ego].clone().requires_grad_(True)
+    other_z = scene['z'][~ego].clone().requires_grad_(True)
+    init_t = tgt_z.detach().clone()
+    opt = torch.optim.Adam([tgt_z, other_z], lr=lr)
+    lw_un = unnorm_att(scene['lw'])
+    mapixes = scene['map_idx'][scene['batch']]
+    tprior = (scene['prior_mu'][ego], scene['prior_var'][ego])
+
+    def dec(z, n):
+        return decode(sd, z, scene['map_feat'], scene['past_feat'], scene['past'][:, -1, :], scene['lw'], scene['sem'], ptr,
+                      scene['edge_index'], scene['map_idx'], raster, dx, n)
+    for it in range(iters):
+        opt.zero_grad()
+        f_t = dec(_collate(ptr, tgt_z, other_z.detach()), future_len)
+        f_o = dec(_collate(ptr, tgt_z.detach(), other_z), FT)
+        lt = avoid_coll_loss(unnorm_state(f_t), tgt_z, tprior, init_t, weights, lw_un, mapixes, ptr, raster, dx, veh_coll_buffer=0.5,
+                             single_veh_idx=0)
+        lo = tgt_matching_loss(unnorm_state(f_o)[~ego], other_match_un, weights)
+        loss = lt['loss'] + lo['loss']
+        loss.backward()
+        if record is not None:
+            record.append({'loss': float(loss.detach()), 'g_tgt': tgt_z.grad.clone(), 'g_other': other_z.grad.clone()})
+        opt.step()
+    return _collate(ptr, tgt_z.detach(), other_z.detach())

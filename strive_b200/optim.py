@@ -142,3 +142,152 @@ class RefineLoop(object):
     def grad(self):
         """dL/dz of the last evaluated iteration (before Adam consumed it)."""
         return self.d_z_bptt + self.d_z_direct
+
+
+# ----------------------------------------------------------------------------------------------------------
+# init / adversarial / solution loops (reference src/utils/init_optim.py, adv_gen_optim.py, sol_optim.py)
+# ----------------------------------------------------------------------------------------------------------
+def collate_tgt_other_z(scene_graph, tgt_z, other_z):
+    """reference adv_gen_optim.py:19-36, without the per-scene Python loop / O(B^2) concatenations: ego rows are
+    scene_graph.ptr[:-1], everything else keeps graph order."""
+    ptr = scene_graph.ptr
+    NA = int(other_z.size(0) + tgt_z.size(0))
+    ego = torch.zeros(NA, dtype=torch.bool, device=other_z.device)
+    ego[ptr[:-1].long()] = True
+    out = torch.empty((NA,) + tuple(other_z.shape[1:]), dtype=other_z.dtype, device=other_z.device)
+    out[ego] = tgt_z
+    out[~ego] = other_z
+    return out
+
+
+def _ego_mask(scene_graph, NA, device):
+    m = torch.zeros(NA, dtype=torch.bool, device=device)
+    m[scene_graph.ptr[:-1].long()] = True
+    return m
+
+
+def run_init_optim(cur_z, init_traj, traj_vis, lr, loss_weights, model, scene_graph, map_env, map_idx, num_iters, embed_info,
+                   prior_distrib, log=None):
+    """reference init_optim.py:11-68: fit z so the decoded future matches the observed one (TgtMatchingLoss with the
+    init_* weights), Adam(lr)."""
+    from .losses import TgtMatchingLoss
+    init_traj = model.get_normalizer().unnormalize(init_traj)[traj_vis == 1.0]
+    cur_z = cur_z.clone().detach()
+    cur_z.requires_grad = True
+    opt = torch.optim.Adam([cur_z], lr=lr)
+    match_loss = TgtMatchingLoss({k[5:]: v for k, v in loss_weights.items() if k[:5] == 'init_'})
+    for it in range(num_iters):
+        opt.zero_grad()
+        dec = model.decode_embedding(cur_z, embed_info, scene_graph, map_idx, map_env)
+        fut = model.get_normalizer().unnormalize(dec['future_pred'])[traj_vis == 1.0]
+        ld = match_loss(fut, init_traj, cur_z, prior_distrib)
+        if log is not None:
+            log(it, {k: float(torch.mean(v)) for k, v in ld.items()})
+        ld['loss'].backward()
+        opt.step()
+    with torch.no_grad():
+        out = model.decode_embedding(cur_z, embed_info, scene_graph, map_idx, map_env)
+    return cur_z, out['future_pred'].clone().detach(), out
+
+
+def run_adv_gen_optim(cur_z, lr, loss_weights, model, scene_graph, map_env, map_idx, num_iters, embed_info, planner_name,
+                      tgt_prior_distrib, other_prior_distrib, feasibility_time, feasibility_infront_min, planner=None,
+                      planner_viz_out=None, attack_agt_idx=None, future_len=None, veh_coll_buffer=0.1, log=None):
+    """reference adv_gen_optim.py:39-211, planner replay mode (planner_name == 'ego').
+
+    The reference decodes twice per iteration with identical forward values (once with other_z detached for the target's
+    matching loss, once with tgt_z detached for the adversarial loss, :119-130).  Here: ONE rollout and TWO adjoint sweeps
+    over its tape (strive_decode_bwd with two seeds), which yields exactly the same gradients."""
+    from .losses import TgtMatchingLoss, AdvGenLoss
+    if planner_name != 'ego':
+        raise RuntimeError('strive_b200: only planner="ego" (open-loop replay) is supported; the closed-loop rule-based planner '
+                           '(adv_gen_optim.py:133-139) is CPU host code outside the scope of this port')
+    NA = cur_z.size(0)
+    dev = cur_z.device
+    ego_mask = _ego_mask(scene_graph, NA, dev)
+    ego_inds = scene_graph.ptr[:-1].long()
+    if attack_agt_idx is not None:
+        attack_agt_idx = torch.as_tensor(attack_agt_idx, device=dev).long() + ego_inds
+    if future_len is None:
+        future_len = model.FT
+    tgt_z = cur_z[ego_mask].clone().detach().requires_grad_(True)
+    other_z = cur_z[~ego_mask].clone().detach().requires_grad_(True)
+    opt = torch.optim.Adam([tgt_z, other_z], lr=lr)
+    nrm = model.get_normalizer()
+    tgt_loss = TgtMatchingLoss(loss_weights)
+    adv_loss = AdvGenLoss(loss_weights, model.get_att_normalizer().unnormalize(scene_graph.lw), map_idx[scene_graph.batch], map_env,
+                          other_z.clone().detach(), scene_graph.ptr, veh_coll_buffer=veh_coll_buffer,
+                          crash_loss_min_time=feasibility_time, crash_loss_min_infront=feasibility_infront_min)
+    planner_fut = scene_graph.future_gt[ego_mask][:, :, :4]
+    assert planner_fut.size(1) == future_len
+    planner_un = nrm.unnormalize(planner_fut)
+    for it in range(num_iters):
+        opt.zero_grad()
+        z_all = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach()).requires_grad_(True)
+        fut = model.decode_embedding(z_all, embed_info, scene_graph, map_idx, map_env, ext_future=planner_fut, nfuture=future_len)['future_pred']
+        fut_un = nrm.unnormalize(fut)
+        ld_t = tgt_loss(fut_un[ego_mask], planner_un, tgt_z, tgt_prior_distrib)
+        ld_a = adv_loss(fut_un, planner_un, other_z, other_prior_distrib, attack_agt_idx=attack_agt_idx)
+        g_t = torch.autograd.grad(ld_t['loss'], z_all, retain_graph=True)[0]          # adjoint sweep 1: target rows
+        g_a, g_o = torch.autograd.grad(ld_a['loss'], [z_all, other_z])               # adjoint sweep 2 + direct latent terms
+        tgt_z.grad = g_t[ego_mask]
+        other_z.grad = g_a[~ego_mask] + g_o
+        if log is not None:
+            d = {'tgt_match_' + k: float(torch.mean(v)) for k, v in ld_t.items()}
+            d.update({'adv_' + k: float(torch.mean(v)) for k, v in ld_a.items() if not k.startswith('_')})
+            log(it, d)
+        opt.step()
+    cur_z = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach())
+    with torch.no_grad():
+        final = model.decode_embedding(cur_z, embed_info, scene_graph, map_idx, map_env, nfuture=future_len)
+    final_traj = final['future_pred'].unsqueeze(1).clone().detach()
+    final_traj[ego_inds, 0] = planner_fut
+    ld = adv_loss(nrm.unnormalize(final['future_pred']), nrm.unnormalize(final_traj[ego_inds, 0]), cur_z[~ego_mask].clone().detach(),
+                  other_prior_distrib, return_mins=True)
+    min_agt = ld['min_agt'] + ego_inds.cpu().numpy()
+    return cur_z, final_traj, final, min_agt, ld['min_t']
+
+
+def run_find_solution_optim(cur_z, final_result_traj, future_len, lr, loss_weights, model, scene_graph, map_env, map_idx,
+                            num_iters, embed_info, tgt_prior_distrib, other_prior_distrib, log=None):
+    """reference sol_optim.py:19-123: the target (node 0 of every scene) avoids collisions (AvoidCollLoss, single_veh_idx=0,
+    rollout of `future_len`) while the others keep matching the adversarial result (TgtMatchingLoss over model.FT steps).
+    One rollout of max(future_len, FT) steps + two adjoint sweeps replaces the reference's two decodes (:73-77); the
+    rollout is causal, so its first FT steps equal the shorter decode."""
+    from .losses import AvoidCollLoss, TgtMatchingLoss
+    NA = final_result_traj.size(0)
+    dev = cur_z.device
+    nrm = model.get_normalizer()
+    tgt_mask = _ego_mask(scene_graph, NA, dev)
+    other_match = nrm.unnormalize(final_result_traj[:, 0][~tgt_mask])            # (NA-B, FT, 4)
+    FTm = other_match.size(1)
+    tgt_z = tgt_prior_distrib[0].clone().detach().requires_grad_(True)             # (B, D)  sol_optim.py:38-40
+    other_z = cur_z[~tgt_mask].reshape(NA - int(tgt_mask.sum()), -1).clone().detach().requires_grad_(True)
+    opt = torch.optim.Adam([tgt_z, other_z], lr=lr)
+    w = {k[4:]: v for k, v in loss_weights.items() if k[:4] == 'sol_'}
+    avoid_loss = AvoidCollLoss(w, model.get_att_normalizer().unnormalize(scene_graph.lw), map_idx[scene_graph.batch], map_env,
+                               tgt_z.clone().detach(), veh_coll_buffer=0.5, single_veh_idx=0, ptr=scene_graph.ptr)
+    match_loss = TgtMatchingLoss(w)
+    FTd = max(int(future_len), int(FTm))
+    for it in range(num_iters):
+        opt.zero_grad()
+        z_all = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach()).requires_grad_(True)
+        fut = model.decode_embedding(z_all, embed_info, scene_graph, map_idx, map_env, nfuture=FTd)['future_pred']
+        fut_un = nrm.unnormalize(fut)
+        ld_t = avoid_loss(fut_un[:, :future_len].contiguous(), tgt_z, tgt_prior_distrib)
+        ld_o = match_loss(fut_un[~tgt_mask][:, :FTm], other_match, other_z, other_prior_distrib)
+        g_t, g_td = torch.autograd.grad(ld_t['loss'], [z_all, tgt_z], retain_graph=True)
+        g_o = torch.autograd.grad(ld_o['loss'], z_all)[0]
+        tgt_z.grad = g_t[tgt_mask] + g_td
+        other_z.grad = g_o[~tgt_mask]
+        if log is not None:
+            d = {'tgt_' + k: float(torch.mean(v)) for k, v in ld_t.items() if not k.startswith('_')}
+            d.update({'other_' + k: float(torch.mean(v)) for k, v in ld_o.items()})
+            log(it, d)
+        opt.step()
+    cur_z = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach())
+    with torch.no_grad():
+        sol = model.decode_embedding(cur_z, embed_info, scene_graph, map_idx, map_env)
+    sol_traj = sol['future_pred'].clone().detach()
+    sol_traj[~tgt_mask] = nrm.normalize(other_match)[:, :sol_traj.size(1)]
+    return cur_z.unsqueeze(1), sol_traj, sol

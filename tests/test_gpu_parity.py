@@ -431,3 +431,81 @@ def test_dropin_api_equals_fused_loop():
     diag('dropin-vs-fused: |z| diff after 3 iters %.3e' % d)
     # same kernels both ways; the only run-to-run difference is the order of the fp64 atomics in the GroupNorm statistics
     assert d < 2e-3
+
+
+def _loops_scene(FT):
+    g = golden('losses')
+    sc = scene_for(g, FT=FT)
+    return sc
+
+
+def test_adv_loop_one_rollout_two_adjoints_equals_reference_two_decodes():
+    """run_adv_gen_optim (planner replay): one CUDA rollout + two adjoint sweeps == the reference's two decodes per iteration."""
+    from strive_b200.optim import run_adv_gen_optim
+    dev, model, env = ctx()
+    raster, dx, sd = world()
+    FT = 5
+    sc = _loops_scene(FT)
+    NA = sc['z'].size(0)
+    ego = torch.zeros(NA, dtype=torch.bool)
+    ego[sc['ptr'][:-1]] = True
+    pf = sc['ext_future'][:, :FT].contiguous()
+    rec = []
+    z_ref = O.adv_loop(sd, sc, raster, dx, ADV_W, 2, 0.05, FT, pf, crash_min_t=1, crash_min_infront=-0.5, veh_coll_buffer=0.1, record=rec)
+    graph = to_graph(sc, dev)
+    fg = torch.zeros(NA, FT, 6)
+    fg[ego, :, :4] = pf
+    graph.future_gt = fg.to(dev)
+    model.FT = FT
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev)}
+    logs = []
+    try:
+        z, traj, out, min_agt, min_t = run_adv_gen_optim(sc['z'].to(dev), 0.05, ADV_W, model, graph, env, sc['map_idx'].to(dev), 2, embed, 'ego',
+                                                          (sc['prior_mu'][ego].to(dev), sc['prior_var'][ego].to(dev)),
+                                                          (sc['prior_mu'][~ego].to(dev), sc['prior_var'][~ego].to(dev)), 1, -0.5,
+                                                          future_len=FT, veh_coll_buffer=0.1, log=lambda it, d: logs.append(d))
+    finally:
+        model.FT = 20
+    l0 = logs[0]['tgt_match_loss'] + logs[0]['adv_loss']
+    dz = (z.cpu() - z_ref).abs()
+    diag('adv loop: loss0 gpu %.4f oracle %.4f | z after 2 iters: max diff %.3e, frac>1e-3 %.4f | traj %s' % (
+        l0, rec[0]['loss'], dz.max().item(), float((dz > 1e-3).float().mean()), tuple(traj.shape)))
+    assert abs(l0 - rec[0]['loss']) < 1e-4 * abs(rec[0]['loss'])
+    assert dz.max().item() <= 2 * 0.05 * 2 + 1e-4 and float((dz > 1e-3).float().mean()) < 0.05
+
+
+def test_solution_loop_vs_oracle():
+    from strive_b200.optim import run_find_solution_optim
+    dev, model, env = ctx()
+    raster, dx, sd = world()
+    FTm, FTs = 4, 6
+    sc = _loops_scene(FTs)
+    NA = sc['z'].size(0)
+    ego = torch.zeros(NA, dtype=torch.bool)
+    ego[sc['ptr'][:-1]] = True
+    w = {k: v for k, v in SOL_W.items()}
+    wfull = {'sol_' + k: v for k, v in SOL_W.items()}
+    with torch.no_grad():
+        adv_traj = o_decode(sd, raster, dx, sc, sc['z'], FTm)              # stands in for the adversarial result
+    other_un = O.unnorm_state(adv_traj[~ego])
+    rec = []
+    z_ref = O.sol_loop(sd, sc, raster, dx, w, 2, 0.05, FTs, FTm, other_un, record=rec)
+    graph = to_graph(sc, dev)
+    model.FT = FTm
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev)}
+    logs = []
+    try:
+        z, sol_traj, out = run_find_solution_optim(sc['z'].to(dev), adv_traj.unsqueeze(1).to(dev), FTs, 0.05, wfull, model, graph, env,
+                                                   sc['map_idx'].to(dev), 2, embed,
+                                                   (sc['prior_mu'][ego].to(dev), sc['prior_var'][ego].to(dev)),
+                                                   (sc['prior_mu'][~ego].to(dev), sc['prior_var'][~ego].to(dev)),
+                                                   log=lambda it, d: logs.append(d))
+    finally:
+        model.FT = 20
+    l0 = logs[0]['tgt_loss'] + logs[0]['other_loss']
+    dz = (z[:, 0].cpu() - z_ref).abs()
+    diag('sol loop: loss0 gpu %.5f oracle %.5f | z after 2 iters: max diff %.3e, frac>1e-3 %.4f' % (
+        l0, rec[0]['loss'], dz.max().item(), float((dz > 1e-3).float().mean())))
+    assert abs(l0 - rec[0]['loss']) < 1e-3 * max(1.0, abs(rec[0]['loss']))
+    assert dz.max().item() <= 2 * 0.05 * 2 + 1e-4 and float((dz > 1e-3).float().mean()) < 0.05
+    assert tuple(z.shape) == (NA, 1, 32) and tuple(sol_traj.shape) == (NA, FTm, 4)
