@@ -14,6 +14,9 @@
 
 #define CROP 256
 
+// 1 = tensor-core conv1..fc (default), 0 = fp32 SIMT reference kernels (kept for A/B verification, strive_mapenc_set_impl)
+static int g_mapenc_impl = 1;
+
 // ------------------------------------------------------------------------------------------------------
 // crop sampling: exact restatement of get_map_obs (nuscenes_utils.py:248-263)
 // ------------------------------------------------------------------------------------------------------
@@ -37,8 +40,33 @@ __device__ __forceinline__ void crop_pixel(const CropFrame& f, float l, float w,
   if (yp < 0 || yp >= H || xp < 0 || xp >= W) { xp = 0; yp = 0; }   // :260-262
 }
 
+// the tensor-core encoder's sampling arithmetic (mapenc_tc.cu): fp32 quotient accepted unless it is near a rounding tie,
+// exact float64 reciprocal/division path otherwise.  Exposed through strive_map_crop so the bit-exactness test covers it.
+__device__ __forceinline__ int round_div_exact_ref(float g, double dx, double inv) {
+  const double gd = (double)g;
+  const double q = gd * inv;
+  int r = __double2int_rn(q);
+  if (fabs(q - (double)r) > 0.499999) r = __double2int_rn(gd / dx);
+  return r;
+}
+__device__ __forceinline__ void crop_pixel_fast(const CropFrame& f, float l, float w, int H, int W, long long& xo, long long& yo) {
+  int xp = 0, yp = 0;
+  if (isfinite(f.px) && isfinite(f.py) && isfinite(f.hc) && isfinite(f.hs)) {
+    const float gx = __fadd_rn(__fsub_rn(__fmul_rn(l, f.hc), __fmul_rn(w, f.hs)), f.px);
+    const float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, f.hs), __fmul_rn(w, f.hc)), f.py);
+    const double inv0 = 1.0 / f.dx0, inv1 = 1.0 / f.dx1;
+    const float qx = gx * (float)inv0, qy = gy * (float)inv1;
+    const float rx = rintf(qx), ry = rintf(qy);
+    const bool slow = !(fabsf(qx - rx) < 0.49f && fabsf(qy - ry) < 0.49f && fabsf(qx) < 6e4f && fabsf(qy) < 6e4f);
+    xp = (int)rx; yp = (int)ry;
+    if (slow) { xp = round_div_exact_ref(gx, f.dx0, inv0); yp = round_div_exact_ref(gy, f.dx1, inv1); }
+    if ((unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }
+  }
+  xo = xp; yo = yp;
+}
+
 __global__ void map_crop_kernel(StriveMap map, const float* __restrict__ pose, const int32_t* __restrict__ map_of, int n,
-                                uint8_t* __restrict__ out) {
+                                uint8_t* __restrict__ out, int fast) {
   const int crop = blockIdx.y;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over 256*256
   if (crop >= n || idx >= CROP * CROP) return;
@@ -49,7 +77,8 @@ __global__ void map_crop_kernel(StriveMap map, const float* __restrict__ pose, c
   f.dx0 = map.dx[m * 2 + 0]; f.dx1 = map.dx[m * 2 + 1];
   f.base = map.raster + (size_t)m * map.C * map.H * map.W;
   long long xp, yp;
-  crop_pixel(f, map.lin_l[iy], map.lin_w[ix], map.H, map.W, xp, yp);
+  if (fast) crop_pixel_fast(f, map.lin_l[iy], map.lin_w[ix], map.H, map.W, xp, yp);
+  else crop_pixel(f, map.lin_l[iy], map.lin_w[ix], map.H, map.W, xp, yp);
   for (int c = 0; c < map.C; c++)
     out[(((size_t)crop * map.C + c) * CROP + iy) * CROP + ix] = f.base[((size_t)c * map.H + yp) * map.W + xp];
 }
@@ -58,7 +87,7 @@ extern "C" int strive_map_crop(const StriveMap* map, const float* pose_un, const
                                uint8_t* out_crop, void* stream) {
   STRIVE_CHECK(map && pose_un && map_of && out_crop && n > 0, STRIVE_EINVAL, "strive_map_crop: bad arguments");
   dim3 grid((CROP * CROP + 255) / 256, n);
-  KPROF("map_crop", (cudaStream_t)stream, map_crop_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*map, pose_un, map_of, n, out_crop));
+  KPROF("map_crop", (cudaStream_t)stream, map_crop_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*map, pose_un, map_of, n, out_crop, g_mapenc_impl));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
@@ -326,8 +355,6 @@ static int launch_conv(const char* name, const float* in, const double* in_stats
 // workspace + driver
 // ------------------------------------------------------------------------------------------------------
 #define MAPENC_CHUNK 2048
-// 1 = tensor-core conv1..4 (default), 0 = fp32 SIMT reference kernels (kept for A/B verification, strive_mapenc_set_impl)
-static int g_mapenc_impl = 1;
 extern "C" int strive_mapenc_set_impl(int impl) {
   g_mapenc_impl = impl ? 1 : 0;
   return 0;

@@ -133,38 +133,51 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(StriveMap map, con
       if (tid == 0) *qn = 0;
       asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
       constexpr int NPX = T1_PH * T1_PW;
+      constexpr int NPT = (NPX + TC_PROD_THREADS - 1) / TC_PROD_THREADS;     // 14 samples per thread
       const int ymax = 256 - oy0 * 2, xmax = 256 - ox0 * 2;   // rows/cols of the tile inside the 256x256 crop
-#pragma unroll 2
-      for (int i = tid; i < NPX; i += TC_PROD_THREADS) {
-        const int r = i / T1_PW, c = i - r * T1_PW;
-        uint2 v = make_uint2(0u, 0u);
-        if (r < ymax && c < xmax) {
-          int xp = 0, yp = 0;
-          bool slow = false;
-          if (finite_pose) {
-            const float2 rt = rowt[r], ct = colt[c];
-            const float gx = __fadd_rn(__fsub_rn(rt.x, ct.x), px);
-            const float gy = __fadd_rn(__fadd_rn(rt.y, ct.y), py);
-            // fp32 quotient is within 0.002 px of the float64 one for |q| < 6e4: accept unless it is near a .5 tie
-            const float qx = gx * inv0f, qy = gy * inv1f;
-            const float rx = rintf(qx), ry = rintf(qy);
-            slow = !(fabsf(qx - rx) < 0.49f && fabsf(qy - ry) < 0.49f && fabsf(qx) < 6e4f && fabsf(qy) < 6e4f);
-            xp = (int)rx; yp = (int)ry;
-            if (slow) {
-              const int k = atomicAdd(qn, 1);
-              if (k < T1_QMAX) {
-                s_queue[b][k] = (unsigned short)i;
-              } else {     // queue full: resolve exactly right here
-                xp = round_div_exact(gx, dx0, inv0);
-                yp = round_div_exact(gy, dx1, inv1);
-                slow = false;
+      // phase A: all coordinates (independent ALU chains), phase B: all raster loads in flight, phase C: expand + store
+      unsigned off[NPT];          // byte offset into the packed raster; 0xffffffff = emit zeros (outside crop or deferred)
+#pragma unroll
+      for (int k = 0; k < NPT; k++) {
+        const int i = tid + k * TC_PROD_THREADS;
+        off[k] = 0xffffffffu;
+        if (i < NPX) {
+          const int r = i / T1_PW, c = i - r * T1_PW;
+          if (r < ymax && c < xmax) {
+            int xp = 0, yp = 0;
+            bool slow = false;
+            if (finite_pose) {
+              const float2 rt = rowt[r], ct = colt[c];
+              const float gx = __fadd_rn(__fsub_rn(rt.x, ct.x), px);
+              const float gy = __fadd_rn(__fadd_rn(rt.y, ct.y), py);
+              // fp32 quotient is within 0.002 px of the float64 one for |q| < 6e4: accept unless it is near a .5 tie
+              const float qx = gx * inv0f, qy = gy * inv1f;
+              const float rx = rintf(qx), ry = rintf(qy);
+              slow = !(fabsf(qx - rx) < 0.49f && fabsf(qy - ry) < 0.49f && fabsf(qx) < 6e4f && fabsf(qy) < 6e4f);
+              xp = (int)rx; yp = (int)ry;
+              if (slow) {
+                const int q = atomicAdd(qn, 1);
+                if (q < T1_QMAX) {
+                  s_queue[b][q] = (unsigned short)i;
+                } else {     // queue full: resolve exactly right here
+                  xp = round_div_exact(gx, dx0, inv0);
+                  yp = round_div_exact(gy, dx1, inv1);
+                  slow = false;
+                }
               }
+              if ((unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }     // :260-262
             }
-            if ((unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }     // :260-262
+            if (!slow) off[k] = (unsigned)yp * (unsigned)W + (unsigned)xp;
           }
-          if (!slow) v = s_lut[__ldg(base + (size_t)((unsigned)yp * (unsigned)W + (unsigned)xp)) & 15u];
         }
-        *reinterpret_cast<uint2*>(dst + (size_t)i * 8) = v;
+      }
+      unsigned bits[NPT];
+#pragma unroll
+      for (int k = 0; k < NPT; k++) bits[k] = (off[k] != 0xffffffffu) ? (unsigned)__ldg(base + off[k]) : 16u;
+#pragma unroll
+      for (int k = 0; k < NPT; k++) {
+        const int i = tid + k * TC_PROD_THREADS;
+        if (i < NPX) *reinterpret_cast<uint2*>(dst + (size_t)i * 8) = (bits[k] < 16u) ? s_lut[bits[k] & 15u] : make_uint2(0u, 0u);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
       // exact float64 path for the few samples near a rounding tie (or far outside the map)
@@ -300,6 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
   __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
   __shared__ float s_gam[CIN], s_bet[CIN], s_bias[32];
+  __shared__ __align__(16) float s_ga[CIN], s_gb[CIN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunk = blockIdx.y;
   {
@@ -329,89 +343,91 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
     constexpr int NPIX = PH * PW;
     constexpr int KPT = (NPIX + TC_PROD_THREADS - 1) / TC_PROD_THREADS;
     constexpr int CG = PH * 2 * PQ * 16;
-    auto load_pixel = [&](int item, int c2, int k, float4 (&x)[4], bool& ok, int& u) {
-      const int p = tid + k * TC_PROD_THREADS;
-      ok = false;
-      u = -1;
-      if (p < NPIX) {
-        const int crop = item / Cfg::TILES, tile = item - crop * Cfg::TILES;
-        const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
-        const int row = p / PW, col = p - row * PW;
-        const int iy = 2 * ty0 + row, ix = 2 * tx0 + col;
-        u = (row * 2 + (col & 1)) * PQ + (col >> 1);
-        if (iy < HIN && ix < HIN) {
-          ok = true;
-          const float4* s4 = reinterpret_cast<const float4*>(in + ((size_t)(crop * HIN + iy) * HIN + ix) * CIN + c2 * 16);
+    // the loads of the NEXT chunk (KPT pixels x 64 B per thread) are always in flight while the current one is transformed
+    auto load_chunk = [&](int item, int c2, float4 (&x)[KPT][4], bool (&ok)[KPT], int (&u)[KPT]) {
+      const int crop = item / Cfg::TILES, tile = item - crop * Cfg::TILES;
+      const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
 #pragma unroll
-          for (int q = 0; q < 4; q++) x[q] = __ldg(s4 + q);
+      for (int k = 0; k < KPT; k++) {
+        const int p = tid + k * TC_PROD_THREADS;
+        ok[k] = false;
+        u[k] = -1;
+        if (p < NPIX) {
+          const int row = p / PW, col = p - row * PW;
+          const int iy = 2 * ty0 + row, ix = 2 * tx0 + col;
+          u[k] = (row * 2 + (col & 1)) * PQ + (col >> 1);
+          if (iy < HIN && ix < HIN) {
+            ok[k] = true;
+            const float4* s4 = reinterpret_cast<const float4*>(in + ((size_t)(crop * HIN + iy) * HIN + ix) * CIN + c2 * 16);
+#pragma unroll
+            for (int q = 0; q < 4; q++) x[k][q] = __ldg(s4 + q);
+          }
         }
       }
     };
-    int item = item_lo, c2 = 0, k = 0, cnt = 0, cur_crop = -1, b = 0;
-    float mean = 0.f, rstd = 0.f;
-    float ga[16], gb[16];
-    float4 xn[4];
-    bool okn = false;
-    int un = -1;
-    if (item < item_hi) load_pixel(item, c2, k, xn, okn, un);
-    uint8_t* dst = sA;
+    int item = item_lo, c2 = 0, cnt = 0, cur_crop = -1;
+    float4 xn[KPT][4];
+    bool okn[KPT];
+    int un[KPT];
+    if (item < item_hi) load_chunk(item, c2, xn, okn, un);
     while (item < item_hi) {
-      float4 xc[4];
+      float4 xc[KPT][4];
+      bool okc[KPT];
+      int uc[KPT];
 #pragma unroll
-      for (int q = 0; q < 4; q++) xc[q] = xn[q];
-      const bool okc = okn;
-      const int uc = un;
-      const int ci = item, cc2 = c2, ck = k;
-      if (++k == KPT) {
-        k = 0;
-        if (++c2 == C2) { c2 = 0; item++; }
+      for (int k = 0; k < KPT; k++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) xc[k][q] = xn[k][q];
+        okc[k] = okn[k];
+        uc[k] = un[k];
       }
-      if (item < item_hi) load_pixel(item, c2, k, xn, okn, un);
-      if (ck == 0) {
-        const int crop = ci / Cfg::TILES;
-        const bool newcrop = crop != cur_crop;
-        if (newcrop) {
+      const int ci = item, cc2 = c2;
+      if (++c2 == C2) { c2 = 0; item++; }
+      if (item < item_hi) load_chunk(item, c2, xn, okn, un);
+      const int crop = ci / Cfg::TILES;
+      if (crop != cur_crop) {
+        // GroupNorm affine of this crop, shared by all producers:  y = relu(x * ga + gb) == relu((x - mean) * rstd * gamma + beta)
+        cur_crop = crop;
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
+        if (tid < CIN) {
+          float mean, rstd;
           gn_stats(in_stats, crop, (double)CIN * HIN * HIN, mean, rstd);
-          cur_crop = crop;
+          const float g = rstd * s_gam[tid];
+          s_ga[tid] = g;
+          s_gb[tid] = fmaf(-mean, g, s_bet[tid]);
         }
-        if (newcrop || C2 > 1) {
-          // y = relu(x * ga + gb)  ==  relu((x - mean) * rstd * gamma + beta)
-#pragma unroll
-          for (int c = 0; c < 16; c++) {
-            ga[c] = rstd * s_gam[cc2 * 16 + c];
-            gb[c] = fmaf(-mean, ga[c], s_bet[cc2 * 16 + c]);
-          }
-        }
-        b = cnt % NBUF;
-        tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
-        dst = sA + (size_t)b * Cfg::A_BYTES;
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
       }
-      if (uc >= 0) {
-        uint32_t hi[8], lo[8];
-        if (okc) {
-          const float xs[16] = {xc[0].x, xc[0].y, xc[0].z, xc[0].w, xc[1].x, xc[1].y, xc[1].z, xc[1].w,
-                                xc[2].x, xc[2].y, xc[2].z, xc[2].w, xc[3].x, xc[3].y, xc[3].z, xc[3].w};
+      const int b = cnt % NBUF;
+      tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
+      uint8_t* dst = sA + (size_t)b * Cfg::A_BYTES;
 #pragma unroll
-          for (int c = 0; c < 16; c += 2) {
-            const float y0 = fmaxf(fmaf(xs[c], ga[c], gb[c]), 0.f);
-            const float y1 = fmaxf(fmaf(xs[c + 1], ga[c + 1], gb[c + 1]), 0.f);
-            tc::split_pack2(y0, y1, hi[c >> 1], lo[c >> 1]);
+      for (int k = 0; k < KPT; k++) {
+        if (uc[k] < 0) continue;
+        uint32_t hi[8], lo[8];
+        if (okc[k]) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const float4 ga = *reinterpret_cast<const float4*>(&s_ga[cc2 * 16 + q * 4]);
+            const float4 gb = *reinterpret_cast<const float4*>(&s_gb[cc2 * 16 + q * 4]);
+            const float y0 = fmaxf(fmaf(xc[k][q].x, ga.x, gb.x), 0.f), y1 = fmaxf(fmaf(xc[k][q].y, ga.y, gb.y), 0.f);
+            const float y2 = fmaxf(fmaf(xc[k][q].z, ga.z, gb.z), 0.f), y3 = fmaxf(fmaf(xc[k][q].w, ga.w, gb.w), 0.f);
+            tc::split_pack2(y0, y1, hi[q * 2], lo[q * 2]);
+            tc::split_pack2(y2, y3, hi[q * 2 + 1], lo[q * 2 + 1]);
           }
         } else {
 #pragma unroll
           for (int c = 0; c < 8; c++) { hi[c] = 0u; lo[c] = 0u; }
         }
-        uint8_t* d0 = dst + (size_t)uc * 16;
+        uint8_t* d0 = dst + (size_t)uc[k] * 16;
         *reinterpret_cast<uint4*>(d0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<uint4*>(d0 + CG) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
         *reinterpret_cast<uint4*>(d0 + Cfg::A_PREC_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         *reinterpret_cast<uint4*>(d0 + Cfg::A_PREC_BYTES + CG) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
       }
-      if (ck == KPT - 1) {
-        tc::fence_async_smem();
-        tc::mbar_arrive(&full[b]);
-        cnt++;
-      }
+      tc::fence_async_smem();
+      tc::mbar_arrive(&full[b]);
+      cnt++;
     }
   } else if (warp == TC_MMA_WARP) {
     if (lane == 0) {

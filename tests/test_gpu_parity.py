@@ -92,11 +92,20 @@ def test_map_crop_bit_exact():
     ang = torch.rand(26, generator=gen) * 6.28318
     pose_un = torch.cat([O.unnorm_state(pos_n), torch.cat([extra, torch.cos(ang)[:, None], torch.sin(ang)[:, None]], 1)], 0).contiguous()
     mapix = torch.cat([mapix, torch.randint(0, 2, (26,), generator=gen)])
+    from strive_b200 import _cabi
+    # poses near the map border / rotated off-map and a NaN pose exercise the (0,0) rule and the exact-rounding slow path
+    pose_un[30] = torch.tensor([2.0, 318.0, 0.6, -0.8])
+    pose_un[31] = torch.tensor([float('nan'), 100.0, 1.0, 0.0])
     ref = O.map_crop(raster, dx, pose_un, mapix)
-    got = env.crop_poses(pose_un.to(dev), mapix.to(dev)).cpu()
-    nbad = int((ref != got).sum())
-    diag('map_crop: %d poses, mismatching pixels = %d of %d' % (pose_un.size(0), nbad, ref.numel()))
-    assert nbad == 0
+    for name, flag in (('exact-division arithmetic', False), ('tensor-core gather arithmetic (fp32 fast path + float64 tie path)', True)):
+        _cabi.set_mapenc_impl(flag)
+        try:
+            got = env.crop_poses(pose_un.to(dev), mapix.to(dev)).cpu()
+        finally:
+            _cabi.set_mapenc_impl(True)
+        nbad = int((ref != got).sum())
+        diag('map_crop [%s]: %d poses, mismatching pixels = %d of %d' % (name, pose_un.size(0), nbad, ref.numel()))
+        assert nbad == 0
     assert np.array_equal(got[:6].long().sum(dim=3).numpy(), g['crop_rowsum'])
 
 
