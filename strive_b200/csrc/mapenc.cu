@@ -51,9 +51,11 @@ __device__ __forceinline__ int round_div_exact_ref(float g, double dx, double in
 }
 __device__ __forceinline__ void crop_pixel_fast(const CropFrame& f, float l, float w, int H, int W, long long& xo, long long& yo) {
   int xp = 0, yp = 0;
-  if (isfinite(f.px) && isfinite(f.py) && isfinite(f.hc) && isfinite(f.hs)) {
-    const float gx = __fadd_rn(__fsub_rn(__fmul_rn(l, f.hc), __fmul_rn(w, f.hs)), f.px);
-    const float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, f.hs), __fmul_rn(w, f.hc)), f.py);
+  {
+    float gx = __fadd_rn(__fsub_rn(__fmul_rn(l, f.hc), __fmul_rn(w, f.hs)), f.px);
+    float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, f.hs), __fmul_rn(w, f.hc)), f.py);
+    if (isnan(gx)) gx = 0.f;
+    if (isnan(gy)) gy = 0.f;
     const double inv0 = 1.0 / f.dx0, inv1 = 1.0 / f.dx1;
     const float qx = gx * (float)inv0, qy = gy * (float)inv1;
     const float rx = rintf(qx), ry = rintf(qy);

@@ -114,8 +114,6 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(StriveMap map, con
       const float inv0f = (float)inv0, inv1f = (float)inv1;
       const uint8_t* base = map.packed + (size_t)m * map.H * map.W;
       const int H = map.H, W = map.W;
-      // a NaN coordinate can only come from a non-finite pose (the linspace tables are finite): then every sample is (0,0) (:251)
-      const bool finite_pose = isfinite(px) && isfinite(py) && isfinite(hc) && isfinite(hs);
       // separable part of gen_car_coords (:232-233), each product rounded on its own exactly as torch does:
       //   x = (l*hcos - w*hsin) + px ,  y = (l*hsin + w*hcos) + py
       float2* rowt = s_rowt[b];   // [r] = (l*hc, l*hs)
@@ -146,10 +144,12 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(StriveMap map, con
           if (r < ymax && c < xmax) {
             int xp = 0, yp = 0;
             bool slow = false;
-            if (finite_pose) {
+            {
               const float2 rt = rowt[r], ct = colt[c];
-              const float gx = __fadd_rn(__fsub_rn(rt.x, ct.x), px);
-              const float gy = __fadd_rn(__fadd_rn(rt.y, ct.y), py);
+              float gx = __fadd_rn(__fsub_rn(rt.x, ct.x), px);
+              float gy = __fadd_rn(__fadd_rn(rt.y, ct.y), py);
+              if (isnan(gx)) gx = 0.f;     // xys[torch.isnan(xys)] = 0.0, per coordinate (:251)
+              if (isnan(gy)) gy = 0.f;
               // fp32 quotient is within 0.002 px of the float64 one for |q| < 6e4: accept unless it is near a .5 tie
               const float qx = gx * inv0f, qy = gy * inv1f;
               const float rx = rintf(qx), ry = rintf(qy);
@@ -186,8 +186,10 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(StriveMap map, con
         const int i = s_queue[b][k];
         const int r = i / T1_PW, c = i - r * T1_PW;
         const float2 rt = rowt[r], ct = colt[c];
-        const float gx = __fadd_rn(__fsub_rn(rt.x, ct.x), px);
-        const float gy = __fadd_rn(__fadd_rn(rt.y, ct.y), py);
+        float gx = __fadd_rn(__fsub_rn(rt.x, ct.x), px);
+        float gy = __fadd_rn(__fadd_rn(rt.y, ct.y), py);
+        if (isnan(gx)) gx = 0.f;
+        if (isnan(gy)) gy = 0.f;
         int xp = round_div_exact(gx, dx0, inv0), yp = round_div_exact(gy, dx1, inv1);
         if ((unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }
         *reinterpret_cast<uint2*>(dst + (size_t)i * 8) = s_lut[__ldg(base + (size_t)((unsigned)yp * (unsigned)W + (unsigned)xp)) & 15u];

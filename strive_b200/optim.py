@@ -192,7 +192,7 @@ def run_init_optim(cur_z, init_traj, traj_vis, lr, loss_weights, model, scene_gr
 
 def run_adv_gen_optim(cur_z, lr, loss_weights, model, scene_graph, map_env, map_idx, num_iters, embed_info, planner_name,
                       tgt_prior_distrib, other_prior_distrib, feasibility_time, feasibility_infront_min, planner=None,
-                      planner_viz_out=None, attack_agt_idx=None, future_len=None, veh_coll_buffer=0.1, log=None):
+                      planner_viz_out=None, attack_agt_idx=None, future_len=None, veh_coll_buffer=0.1, log=None, debug=None):
     """reference adv_gen_optim.py:39-211, planner replay mode (planner_name == 'ego').
 
     The reference decodes twice per iteration with identical forward values (once with other_z detached for the target's
@@ -232,6 +232,8 @@ def run_adv_gen_optim(cur_z, lr, loss_weights, model, scene_graph, map_env, map_
         g_a, g_o = torch.autograd.grad(ld_a['loss'], [z_all, other_z])               # adjoint sweep 2 + direct latent terms
         tgt_z.grad = g_t[ego_mask]
         other_z.grad = g_a[~ego_mask] + g_o
+        if debug is not None and it == 0:
+            debug.update(g_tgt=tgt_z.grad.detach().clone(), g_other=other_z.grad.detach().clone())
         if log is not None:
             d = {'tgt_match_' + k: float(torch.mean(v)) for k, v in ld_t.items()}
             d.update({'adv_' + k: float(torch.mean(v)) for k, v in ld_a.items() if not k.startswith('_')})
@@ -249,7 +251,7 @@ def run_adv_gen_optim(cur_z, lr, loss_weights, model, scene_graph, map_env, map_
 
 
 def run_find_solution_optim(cur_z, final_result_traj, future_len, lr, loss_weights, model, scene_graph, map_env, map_idx,
-                            num_iters, embed_info, tgt_prior_distrib, other_prior_distrib, log=None):
+                            num_iters, embed_info, tgt_prior_distrib, other_prior_distrib, log=None, debug=None):
     """reference sol_optim.py:19-123: the target (node 0 of every scene) avoids collisions (AvoidCollLoss, single_veh_idx=0,
     rollout of `future_len`) while the others keep matching the adversarial result (TgtMatchingLoss over model.FT steps).
     One rollout of max(future_len, FT) steps + two adjoint sweeps replaces the reference's two decodes (:73-77); the
@@ -280,6 +282,8 @@ def run_find_solution_optim(cur_z, final_result_traj, future_len, lr, loss_weigh
         g_o = torch.autograd.grad(ld_o['loss'], z_all)[0]
         tgt_z.grad = g_t[tgt_mask] + g_td
         other_z.grad = g_o[~tgt_mask]
+        if debug is not None and it == 0:
+            debug.update(g_tgt=tgt_z.grad.detach().clone(), g_other=other_z.grad.detach().clone())
         if log is not None:
             d = {'tgt_' + k: float(torch.mean(v)) for k, v in ld_t.items() if not k.startswith('_')}
             d.update({'other_' + k: float(torch.mean(v)) for k, v in ld_o.items()})

@@ -467,20 +467,23 @@ def test_adv_loop_one_rollout_two_adjoints_equals_reference_two_decodes():
     graph.future_gt = fg.to(dev)
     model.FT = FT
     embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev)}
-    logs = []
+    logs, dbg = [], {}
     try:
         z, traj, out, min_agt, min_t = run_adv_gen_optim(sc['z'].to(dev), 0.05, ADV_W, model, graph, env, sc['map_idx'].to(dev), 2, embed, 'ego',
                                                           (sc['prior_mu'][ego].to(dev), sc['prior_var'][ego].to(dev)),
                                                           (sc['prior_mu'][~ego].to(dev), sc['prior_var'][~ego].to(dev)), 1, -0.5,
-                                                          future_len=FT, veh_coll_buffer=0.1, log=lambda it, d: logs.append(d))
+                                                          future_len=FT, veh_coll_buffer=0.1, log=lambda it, d: logs.append(d), debug=dbg)
     finally:
         model.FT = 20
     l0 = logs[0]['tgt_match_loss'] + logs[0]['adv_loss']
     dz = (z.cpu() - z_ref).abs()
-    diag('adv loop: loss0 gpu %.4f oracle %.4f | z after 2 iters: max diff %.3e, frac>1e-3 %.4f | traj %s' % (
-        l0, rec[0]['loss'], dz.max().item(), float((dz > 1e-3).float().mean()), tuple(traj.shape)))
+    e_t = (dbg['g_tgt'].cpu() - rec[0]['g_tgt']).abs().max().item() / rec[0]['g_tgt'].abs().max().item()
+    e_o = (dbg['g_other'].cpu() - rec[0]['g_other']).abs().max().item() / rec[0]['g_other'].abs().max().item()
+    diag('adv loop: loss0 gpu %.4f oracle %.4f | iter-0 grads rel err tgt %.2e other %.2e | z after 2 iters: max diff %.3e | traj %s' % (
+        l0, rec[0]['loss'], e_t, e_o, dz.max().item(), tuple(traj.shape)))
     assert abs(l0 - rec[0]['loss']) < 1e-4 * abs(rec[0]['loss'])
-    assert dz.max().item() <= 2 * 0.05 * 2 + 1e-4 and float((dz > 1e-3).float().mean()) < 0.05
+    assert e_t < 2e-3 and e_o < 2e-3          # forward differs by ~1e-5 (pixel flips), see the teacher-forced test for the strict check
+    assert dz.max().item() <= 2 * 0.05 * 2 + 1e-4   # Adam's sign-like first steps: an element whose gradient is at noise level may flip
 
 
 def test_solution_loop_vs_oracle():
@@ -502,19 +505,22 @@ def test_solution_loop_vs_oracle():
     graph = to_graph(sc, dev)
     model.FT = FTm
     embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev)}
-    logs = []
+    logs, dbg = [], {}
     try:
         z, sol_traj, out = run_find_solution_optim(sc['z'].to(dev), adv_traj.unsqueeze(1).to(dev), FTs, 0.05, wfull, model, graph, env,
                                                    sc['map_idx'].to(dev), 2, embed,
                                                    (sc['prior_mu'][ego].to(dev), sc['prior_var'][ego].to(dev)),
                                                    (sc['prior_mu'][~ego].to(dev), sc['prior_var'][~ego].to(dev)),
-                                                   log=lambda it, d: logs.append(d))
+                                                   log=lambda it, d: logs.append(d), debug=dbg)
     finally:
         model.FT = 20
     l0 = logs[0]['tgt_loss'] + logs[0]['other_loss']
     dz = (z[:, 0].cpu() - z_ref).abs()
-    diag('sol loop: loss0 gpu %.5f oracle %.5f | z after 2 iters: max diff %.3e, frac>1e-3 %.4f' % (
-        l0, rec[0]['loss'], dz.max().item(), float((dz > 1e-3).float().mean())))
+    e_t = (dbg['g_tgt'].cpu() - rec[0]['g_tgt']).abs().max().item() / max(rec[0]['g_tgt'].abs().max().item(), 1e-6)
+    e_o = (dbg['g_other'].cpu() - rec[0]['g_other']).abs().max().item() / max(rec[0]['g_other'].abs().max().item(), 1e-6)
+    diag('sol loop: loss0 gpu %.5f oracle %.5f | iter-0 grads rel err tgt %.2e (max %.2e) other %.2e | z after 2 iters: max diff %.3e' % (
+        l0, rec[0]['loss'], e_t, rec[0]['g_tgt'].abs().max().item(), e_o, dz.max().item()))
     assert abs(l0 - rec[0]['loss']) < 1e-3 * max(1.0, abs(rec[0]['loss']))
-    assert dz.max().item() <= 2 * 0.05 * 2 + 1e-4 and float((dz > 1e-3).float().mean()) < 0.05
+    assert e_t < 2e-3 and e_o < 2e-3
+    assert dz.max().item() <= 2 * 0.05 * 2 + 1e-4
     assert tuple(z.shape) == (NA, 1, 32) and tuple(sol_traj.shape) == (NA, FTm, 4)
