@@ -40,35 +40,10 @@ __device__ __forceinline__ void crop_pixel(const CropFrame& f, float l, float w,
   if (yp < 0 || yp >= H || xp < 0 || xp >= W) { xp = 0; yp = 0; }   // :260-262
 }
 
-// the tensor-core encoder's sampling arithmetic (mapenc_tc.cu): fp32 quotient accepted unless it is near a rounding tie,
-// exact float64 reciprocal/division path otherwise.  Exposed through strive_map_crop so the bit-exactness test covers it.
-__device__ __forceinline__ int round_div_exact_ref(float g, double dx, double inv) {
-  const double gd = (double)g;
-  const double q = gd * inv;
-  int r = __double2int_rn(q);
-  if (fabs(q - (double)r) > 0.499999) r = __double2int_rn(gd / dx);
-  return r;
-}
-__device__ __forceinline__ void crop_pixel_fast(const CropFrame& f, float l, float w, int H, int W, long long& xo, long long& yo) {
-  int xp = 0, yp = 0;
-  {
-    float gx = __fadd_rn(__fsub_rn(__fmul_rn(l, f.hc), __fmul_rn(w, f.hs)), f.px);
-    float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, f.hs), __fmul_rn(w, f.hc)), f.py);
-    if (isnan(gx)) gx = 0.f;
-    if (isnan(gy)) gy = 0.f;
-    const double inv0 = 1.0 / f.dx0, inv1 = 1.0 / f.dx1;
-    const float qx = gx * (float)inv0, qy = gy * (float)inv1;
-    const float rx = rintf(qx), ry = rintf(qy);
-    const bool slow = !(fabsf(qx - rx) < 0.49f && fabsf(qy - ry) < 0.49f && fabsf(qx) < 6e4f && fabsf(qy) < 6e4f);
-    xp = (int)rx; yp = (int)ry;
-    if (slow) { xp = round_div_exact_ref(gx, f.dx0, inv0); yp = round_div_exact_ref(gy, f.dx1, inv1); }
-    if ((unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }
-  }
-  xo = xp; yo = yp;
-}
+int tc_crop_pack_unpacked(const StriveMap* map, const float* pose, const int32_t* map_of, int n, uint8_t* out, cudaStream_t stream);
 
 __global__ void map_crop_kernel(StriveMap map, const float* __restrict__ pose, const int32_t* __restrict__ map_of, int n,
-                                uint8_t* __restrict__ out, int fast) {
+                                uint8_t* __restrict__ out) {
   const int crop = blockIdx.y;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over 256*256
   if (crop >= n || idx >= CROP * CROP) return;
@@ -79,8 +54,7 @@ __global__ void map_crop_kernel(StriveMap map, const float* __restrict__ pose, c
   f.dx0 = map.dx[m * 2 + 0]; f.dx1 = map.dx[m * 2 + 1];
   f.base = map.raster + (size_t)m * map.C * map.H * map.W;
   long long xp, yp;
-  if (fast) crop_pixel_fast(f, map.lin_l[iy], map.lin_w[ix], map.H, map.W, xp, yp);
-  else crop_pixel(f, map.lin_l[iy], map.lin_w[ix], map.H, map.W, xp, yp);
+  crop_pixel(f, map.lin_l[iy], map.lin_w[ix], map.H, map.W, xp, yp);
   for (int c = 0; c < map.C; c++)
     out[(((size_t)crop * map.C + c) * CROP + iy) * CROP + ix] = f.base[((size_t)c * map.H + yp) * map.W + xp];
 }
@@ -88,8 +62,10 @@ __global__ void map_crop_kernel(StriveMap map, const float* __restrict__ pose, c
 extern "C" int strive_map_crop(const StriveMap* map, const float* pose_un, const int32_t* map_of, int32_t n,
                                uint8_t* out_crop, void* stream) {
   STRIVE_CHECK(map && pose_un && map_of && out_crop && n > 0, STRIVE_EINVAL, "strive_map_crop: bad arguments");
+  // impl 1: the production crop_pack kernel of the tensor-core encoder (unpacked); impl 0: straight float64-division restatement
+  if (g_mapenc_impl == 1 && map->packed != nullptr) return tc_crop_pack_unpacked(map, pose_un, map_of, n, out_crop, (cudaStream_t)stream);
   dim3 grid((CROP * CROP + 255) / 256, n);
-  KPROF("map_crop", (cudaStream_t)stream, map_crop_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*map, pose_un, map_of, n, out_crop, g_mapenc_impl));
+  KPROF("map_crop", (cudaStream_t)stream, map_crop_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*map, pose_un, map_of, n, out_crop));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
@@ -362,7 +338,7 @@ extern "C" int strive_mapenc_set_impl(int impl) {
   return 0;
 }
 int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_of, const uint8_t* wpack, const float* bias, float* out,
-                    double* out_stats, int n, cudaStream_t stream);
+                    double* out_stats, uint8_t* packed_crop, int n, cudaStream_t stream);
 int tc_launch_conv2(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
                     float* out, double* out_stats, int n, cudaStream_t stream);
 int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
@@ -381,7 +357,7 @@ extern "C" int64_t strive_mapenc_workspace_bytes(int32_t n) {
   const size_t c = (size_t)(n < MAPENC_CHUNK ? n : MAPENC_CHUNK);
   size_t fl = 0;
   for (int i = 0; i < 6; i++) fl += ((kActFloats[i] * c + 63) & ~(size_t)63);
-  return (int64_t)(fl * 4 + 6 * c * 2 * 8 + 256);
+  return (int64_t)(fl * 4 + 6 * c * 2 * 8 + c * 65536 + 512);
 }
 
 extern "C" int strive_mapenc_fwd(const StriveModel* m, const StriveMap* map, const float* pose_un, const int32_t* map_of,
@@ -400,6 +376,8 @@ extern "C" int strive_mapenc_fwd(const StriveModel* m, const StriveMap* map, con
     workspace = (void*)p;
   }
   double* stats = (double*)workspace;   // [6][c][2]
+  uint8_t* packed_crop = (uint8_t*)(stats + 6 * c * 2);   // [c][256][256] bit-packed crops (tensor-core path)
+  packed_crop = (uint8_t*)(((uintptr_t)packed_crop + 255) & ~(uintptr_t)255);
   const float* const* sg = m->seg;
   for (int start = 0; start < n; start += MAPENC_CHUNK) {
     const int cn = (n - start) < MAPENC_CHUNK ? (n - start) : MAPENC_CHUNK;
@@ -411,7 +389,7 @@ extern "C" int strive_mapenc_fwd(const StriveModel* m, const StriveMap* map, con
     int rc;
     if (g_mapenc_impl == 1 && m->tc_blob != nullptr) {
       // tensor-core path (mapenc_tc.cu): conv1..conv4 on tcgen05, activations NHWC fp32
-      rc = tc_launch_conv1(map, pose, mo, m->tc_blob + m->tc_off[0], sg[S_CB0], act[0], st[0], cn, stream);
+      rc = tc_launch_conv1(map, pose, mo, m->tc_blob + m->tc_off[0], sg[S_CB0], act[0], st[0], packed_crop, cn, stream);
       if (rc) return rc;
       rc = tc_launch_conv2(act[0], st[0], sg[S_GG0], sg[S_GB0], m->tc_blob + m->tc_off[1], sg[S_CB1], act[1], st[1], cn, stream);
       if (rc) return rc;

@@ -64,8 +64,66 @@ __device__ __forceinline__ int round_div_exact(float g, double dx, double inv) {
   return r;
 }
 
-__global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(StriveMap map, const float* __restrict__ pose,
-                                                              const int32_t* __restrict__ map_of, const uint8_t* __restrict__ wpack,
+
+// ------------------------------------------------------------------------------------------------------
+// crop_pack: the rotated nearest-neighbour crop itself (exact get_map_obs arithmetic), written ONCE per crop as
+// [256][256] bytes with bit c = layer c (64 KB per crop instead of the reference's 256 KB uint8 + 4 MB of int64 indices).
+// A plain elementwise kernel: thousands of resident warps hide the gather latency; conv1 then only expands bytes.
+// Block = 4 crop rows (1024 samples); samples within 0.49 of a rounding tie are resolved exactly after the fast pass.
+// ------------------------------------------------------------------------------------------------------
+#define CP_ROWS 4
+__global__ void __launch_bounds__(256) crop_pack_kernel(StriveMap map, const float* __restrict__ pose, const int32_t* __restrict__ map_of,
+                                                        uint8_t* __restrict__ packed_crop, int n) {
+  __shared__ unsigned short s_q[CP_ROWS * 256];
+  __shared__ int s_nq;
+  const int crop = blockIdx.y, row0 = blockIdx.x * CP_ROWS, tid = threadIdx.x;
+  if (tid == 0) s_nq = 0;
+  const int m = map_of[crop];
+  const float px = pose[crop * 4 + 0], py = pose[crop * 4 + 1], hc = pose[crop * 4 + 2], hs = pose[crop * 4 + 3];
+  const double dx0 = map.dx[m * 2 + 0], dx1 = map.dx[m * 2 + 1];
+  const double inv0 = 1.0 / dx0, inv1 = 1.0 / dx1;
+  const float inv0f = (float)inv0, inv1f = (float)inv1;
+  const uint8_t* base = map.packed + (size_t)m * map.H * map.W;
+  const int H = map.H, W = map.W;
+  const float w = __ldg(map.lin_w + tid);
+  const float whs = __fmul_rn(w, hs), whc = __fmul_rn(w, hc);     // gen_car_coords (:232-233), every product rounded on its own
+  uint8_t* dst = packed_crop + ((size_t)crop * 256 + row0) * 256 + tid;
+  __syncthreads();
+  unsigned off[CP_ROWS];
+#pragma unroll
+  for (int r = 0; r < CP_ROWS; r++) {
+    const float l = __ldg(map.lin_l + row0 + r);
+    float gx = __fadd_rn(__fsub_rn(__fmul_rn(l, hc), whs), px);
+    float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, hs), whc), py);
+    if (isnan(gx)) gx = 0.f;     // xys[torch.isnan(xys)] = 0.0 (:251)
+    if (isnan(gy)) gy = 0.f;
+    // the fp32 quotient is within 0.002 px of the float64 one for |q| < 6e4: accept unless it is near a .5 tie
+    const float qx = gx * inv0f, qy = gy * inv1f;
+    const float rx = rintf(qx), ry = rintf(qy);
+    const bool slow = !(fabsf(qx - rx) < 0.49f && fabsf(qy - ry) < 0.49f && fabsf(qx) < 6e4f && fabsf(qy) < 6e4f);
+    int xp = (int)rx, yp = (int)ry;
+    if (slow) s_q[atomicAdd(&s_nq, 1)] = (unsigned short)(r * 256 + tid);
+    if ((unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }     // :260-262
+    off[r] = slow ? 0xffffffffu : (unsigned)yp * (unsigned)W + (unsigned)xp;
+  }
+#pragma unroll
+  for (int r = 0; r < CP_ROWS; r++)
+    if (off[r] != 0xffffffffu) dst[r * 256] = __ldg(base + off[r]) & 15u;
+  __syncthreads();
+  for (int k = tid; k < s_nq; k += 256) {
+    const int r = s_q[k] >> 8, c = s_q[k] & 255;
+    const float l = __ldg(map.lin_l + row0 + r), wc = __ldg(map.lin_w + c);
+    float gx = __fadd_rn(__fsub_rn(__fmul_rn(l, hc), __fmul_rn(wc, hs)), px);
+    float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, hs), __fmul_rn(wc, hc)), py);
+    if (isnan(gx)) gx = 0.f;
+    if (isnan(gy)) gy = 0.f;
+    int xp = round_div_exact(gx, dx0, inv0), yp = round_div_exact(gy, dx1, inv1);
+    if ((unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }
+    packed_crop[((size_t)crop * 256 + row0 + r) * 256 + c] = __ldg(base + (size_t)((unsigned)yp * (unsigned)W + (unsigned)xp)) & 15u;
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __restrict__ packed_crop, const uint8_t* __restrict__ wpack,
                                                               const float* __restrict__ bias, float* __restrict__ out,
                                                               double* __restrict__ out_stats, int n) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -75,9 +133,6 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(StriveMap map, con
   __shared__ uint32_t tmem_base;
   __shared__ float s_bias[16];
   __shared__ uint2 s_lut[16];   // 4 layer bits -> 4 x bf16 {0,1}
-  __shared__ float2 s_rowt[T1_NBUF][T1_PH + 3], s_colt[T1_NBUF][T1_PW + 2];
-  __shared__ unsigned short s_queue[T1_NBUF][T1_QMAX];
-  __shared__ int s_qn[T1_NBUF];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < 16) {
     const uint32_t one = 0x3F80u;
@@ -107,92 +162,21 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(StriveMap map, con
       const int b = cnt % T1_NBUF;
       tc::mbar_wait(&empty[b], ((cnt / T1_NBUF) & 1) ^ 1);
       uint8_t* dst = sP + (size_t)b * T1_PATCH_BYTES;
-      const int m = map_of[crop];
-      const float px = pose[crop * 4 + 0], py = pose[crop * 4 + 1], hc = pose[crop * 4 + 2], hs = pose[crop * 4 + 3];
-      const double dx0 = map.dx[m * 2 + 0], dx1 = map.dx[m * 2 + 1];
-      const double inv0 = 1.0 / dx0, inv1 = 1.0 / dx1;
-      const float inv0f = (float)inv0, inv1f = (float)inv1;
-      const uint8_t* base = map.packed + (size_t)m * map.H * map.W;
-      const int H = map.H, W = map.W;
-      // separable part of gen_car_coords (:232-233), each product rounded on its own exactly as torch does:
-      //   x = (l*hcos - w*hsin) + px ,  y = (l*hsin + w*hcos) + py
-      float2* rowt = s_rowt[b];   // [r] = (l*hc, l*hs)
-      float2* colt = s_colt[b];   // [c] = (w*hs, w*hc)
-      int* qn = &s_qn[b];
-      if (tid < T1_PH) {
-        const int iy = oy0 * 2 + tid;
-        const float l = (iy < 256) ? __ldg(map.lin_l + iy) : 0.f;
-        rowt[tid] = make_float2(__fmul_rn(l, hc), __fmul_rn(l, hs));
-      } else if (tid >= 128 && tid < 128 + T1_PW) {
-        const int c = tid - 128, ix = ox0 * 2 + c;
-        const float w = (ix < 256) ? __ldg(map.lin_w + ix) : 0.f;
-        colt[c] = make_float2(__fmul_rn(w, hs), __fmul_rn(w, hc));
-      }
-      if (tid == 0) *qn = 0;
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
+      const uint8_t* src = packed_crop + (size_t)crop * 65536 + (size_t)(oy0 * 2) * 256 + ox0 * 2;
       constexpr int NPX = T1_PH * T1_PW;
       constexpr int NPT = (NPX + TC_PROD_THREADS - 1) / TC_PROD_THREADS;     // 14 samples per thread
       const int ymax = 256 - oy0 * 2, xmax = 256 - ox0 * 2;   // rows/cols of the tile inside the 256x256 crop
-      // phase A: all coordinates (independent ALU chains), phase B: all raster loads in flight, phase C: expand + store
-      unsigned off[NPT];          // byte offset into the packed raster; 0xffffffff = emit zeros (outside crop or deferred)
+      unsigned bits[NPT];
 #pragma unroll
       for (int k = 0; k < NPT; k++) {
         const int i = tid + k * TC_PROD_THREADS;
-        off[k] = 0xffffffffu;
-        if (i < NPX) {
-          const int r = i / T1_PW, c = i - r * T1_PW;
-          if (r < ymax && c < xmax) {
-            int xp = 0, yp = 0;
-            bool slow = false;
-            {
-              const float2 rt = rowt[r], ct = colt[c];
-              float gx = __fadd_rn(__fsub_rn(rt.x, ct.x), px);
-              float gy = __fadd_rn(__fadd_rn(rt.y, ct.y), py);
-              if (isnan(gx)) gx = 0.f;     // xys[torch.isnan(xys)] = 0.0, per coordinate (:251)
-              if (isnan(gy)) gy = 0.f;
-              // fp32 quotient is within 0.002 px of the float64 one for |q| < 6e4: accept unless it is near a .5 tie
-              const float qx = gx * inv0f, qy = gy * inv1f;
-              const float rx = rintf(qx), ry = rintf(qy);
-              slow = !(fabsf(qx - rx) < 0.49f && fabsf(qy - ry) < 0.49f && fabsf(qx) < 6e4f && fabsf(qy) < 6e4f);
-              xp = (int)rx; yp = (int)ry;
-              if (slow) {
-                const int q = atomicAdd(qn, 1);
-                if (q < T1_QMAX) {
-                  s_queue[b][q] = (unsigned short)i;
-                } else {     // queue full: resolve exactly right here
-                  xp = round_div_exact(gx, dx0, inv0);
-                  yp = round_div_exact(gy, dx1, inv1);
-                  slow = false;
-                }
-              }
-              if ((unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }     // :260-262
-            }
-            if (!slow) off[k] = (unsigned)yp * (unsigned)W + (unsigned)xp;
-          }
-        }
+        const int r = i / T1_PW, c = i - r * T1_PW;
+        bits[k] = (i < NPX && r < ymax && c < xmax) ? (unsigned)__ldg(src + r * 256 + c) : 16u;
       }
-      unsigned bits[NPT];
-#pragma unroll
-      for (int k = 0; k < NPT; k++) bits[k] = (off[k] != 0xffffffffu) ? (unsigned)__ldg(base + off[k]) : 16u;
 #pragma unroll
       for (int k = 0; k < NPT; k++) {
         const int i = tid + k * TC_PROD_THREADS;
         if (i < NPX) *reinterpret_cast<uint2*>(dst + (size_t)i * 8) = (bits[k] < 16u) ? s_lut[bits[k] & 15u] : make_uint2(0u, 0u);
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
-      // exact float64 path for the few samples near a rounding tie (or far outside the map)
-      const int nq = min(*qn, T1_QMAX);
-      for (int k = tid; k < nq; k += TC_PROD_THREADS) {
-        const int i = s_queue[b][k];
-        const int r = i / T1_PW, c = i - r * T1_PW;
-        const float2 rt = rowt[r], ct = colt[c];
-        float gx = __fadd_rn(__fsub_rn(rt.x, ct.x), px);
-        float gy = __fadd_rn(__fadd_rn(rt.y, ct.y), py);
-        if (isnan(gx)) gx = 0.f;
-        if (isnan(gy)) gy = 0.f;
-        int xp = round_div_exact(gx, dx0, inv0), yp = round_div_exact(gy, dx1, inv1);
-        if ((unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }
-        *reinterpret_cast<uint2*>(dst + (size_t)i * 8) = s_lut[__ldg(base + (size_t)((unsigned)yp * (unsigned)W + (unsigned)xp)) & 15u];
       }
       tc::fence_async_smem();
       tc::mbar_arrive(&full[b]);
@@ -702,8 +686,30 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------------
+// test hook (strive_map_crop): the production crop_pack kernel, unpacked to the reference's (N,4,256,256) uint8 layout
+__global__ void crop_unpack_kernel(const uint8_t* __restrict__ packed_crop, uint8_t* __restrict__ out, int n, int C) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * 65536) return;
+  const size_t crop = i >> 16, pix = i & 65535;
+  const unsigned b = packed_crop[i];
+  for (int c = 0; c < C; c++) out[(crop * C + c) * 65536 + pix] = (b >> c) & 1u;
+}
+int tc_crop_pack_unpacked(const StriveMap* map, const float* pose, const int32_t* map_of, int n, uint8_t* out, cudaStream_t stream) {
+  STRIVE_CHECK(map->packed != nullptr && map->C <= 4, STRIVE_EINVAL, "crop_pack needs StriveMap.packed and <= 4 layers");
+  uint8_t* tmp = nullptr;
+  STRIVE_CUDA(cudaMallocAsync((void**)&tmp, (size_t)n * 65536, stream));
+  dim3 gp(256 / CP_ROWS, n);
+  KPROF("crop_pack", stream, crop_pack_kernel<<<gp, 256, 0, stream>>>(*map, pose, map_of, tmp, n));
+  STRIVE_LAUNCH_CHECK();
+  const size_t tot = (size_t)n * 65536;
+  crop_unpack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(tmp, out, n, map->C);
+  STRIVE_LAUNCH_CHECK();
+  STRIVE_CUDA(cudaFreeAsync(tmp, stream));
+  return 0;
+}
+
 int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_of, const uint8_t* wpack, const float* bias, float* out,
-                    double* out_stats, int n, cudaStream_t stream) {
+                    double* out_stats, uint8_t* packed_crop, int n, cudaStream_t stream) {
   static bool attr = false;
   const size_t smem = T1_WBYTES + T1_NBUF * T1_PATCH_BYTES;
   if (!attr) {
@@ -711,9 +717,12 @@ int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_
     attr = true;
   }
   STRIVE_CHECK(map->packed != nullptr, STRIVE_EINVAL, "tensor-core map encoder needs StriveMap.packed");
+  dim3 gp(256 / CP_ROWS, n);
+  KPROF("crop_pack", stream, crop_pack_kernel<<<gp, 256, 0, stream>>>(*map, pose, map_of, packed_crop, n));
+  STRIVE_LAUNCH_CHECK();
   const int items = n * T1_SUPER * T1_SUPER;
   const int grid = items < num_sms() * 2 ? items : num_sms() * 2;
-  KPROF("tc_conv1", stream, tc_conv1_kernel<<<grid, TC_THREADS, smem, stream>>>(*map, pose, map_of, wpack, bias, out, out_stats, n));
+  KPROF("tc_conv1", stream, tc_conv1_kernel<<<grid, TC_THREADS, smem, stream>>>(packed_crop, wpack, bias, out, out_stats, n));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
