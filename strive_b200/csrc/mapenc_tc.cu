@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
   __shared__ uint32_t tmem_base;
   __shared__ float s_bias[16];
   __shared__ uint2 s_lut[16];   // 4 layer bits -> 4 x bf16 {0,1}
+  __shared__ __align__(16) float s_stage[4][32 * 20];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < 16) {
     const uint32_t one = 0x3F80u;
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
       tc::mbar_wait(&acc_full[a], (cnt >> 1) & 1);
       tc::tc_fence_after();
       float s1 = 0.f, s2 = 0.f;
+      float* stg = s_stage[q];                 // [32 px][16 ch] per warp, padded rows of 20 floats (conflict-free float4 access)
 #pragma unroll 1
       for (int sub = 0; sub < 8; sub++) {
         const int sy = sub >> 2, sx = sub & 3;
@@ -236,16 +238,27 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
           tc::mbar_arrive(&acc_empty[a]);
         }
         const int oy = oy0 + sy * 16 + oyl, ox = ox0 + sx * 8 + oxl;
-        if (oy < 125 && ox < 125) {
-          float* o = out + (((size_t)crop * 125 + oy) * 125 + ox) * 16;
+        const bool ok = oy < 125 && ox < 125;
 #pragma unroll
-          for (int c = 0; c < 16; c++) {
-            v[c] += s_bias[c];
+        for (int c = 0; c < 16; c++) {
+          v[c] += s_bias[c];
+          if (ok) {
             s1 += v[c];
             s2 = fmaf(v[c], v[c], s2);
           }
+        }
+        __syncwarp();
 #pragma unroll
-          for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(stg + lane * 20 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        __syncwarp();
+        // 4 lanes per pixel (64 B), 8 pixels of an output row = 512 contiguous bytes per 32 lanes
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int e = lane + 32 * j;           // float4 index inside the 32 x 16 block
+          const int pl = e >> 2, ch = (e & 3) * 4;
+          const int oyy = oy0 + sy * 16 + (q * 4 + (pl >> 3)), oxx = ox0 + sx * 8 + (pl & 7);
+          if (oyy < 125 && oxx < 125)
+            *reinterpret_cast<float4*>(out + (((size_t)crop * 125 + oyy) * 125 + oxx) * 16 + ch) = *reinterpret_cast<const float4*>(stg + pl * 20 + ch);
         }
       }
       s1 = warp_sum(s1);
@@ -300,6 +313,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
   __shared__ uint32_t tmem_base;
   __shared__ float s_gam[CIN], s_bet[CIN], s_bias[32];
   __shared__ __align__(16) float s_ga[CIN], s_gb[CIN];
+  __shared__ __align__(16) float s_stage[4][32 * 36];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunk = blockIdx.y;
   {
@@ -470,21 +484,35 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
       tc::tc_fence_before();
       tc::mbar_arrive(&acc_empty[a]);
       const int oy = ty0 + (m >> 3), ox = tx0 + (m & 7);
+      const bool ok = oy < HOUT && ox < HOUT;
       float s1 = 0.f, s2 = 0.f;
-      if (oy < HOUT && ox < HOUT) {
-        float* o = out + (((size_t)crop * HOUT + oy) * HOUT + ox) * COUT + nchunk * 32;
 #pragma unroll
-        for (int c = 0; c < 16; c++) {
-          v0[c] += s_bias[c];
-          v1[c] += s_bias[16 + c];
+      for (int c = 0; c < 16; c++) {
+        v0[c] += s_bias[c];
+        v1[c] += s_bias[16 + c];
+        if (ok) {
           s1 += v0[c] + v1[c];
           s2 = fmaf(v0[c], v0[c], s2);
           s2 = fmaf(v1[c], v1[c], s2);
         }
+      }
+      float* stg = s_stage[q];                 // [32 px][32 ch] per warp, rows padded to 36 floats
+      __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v0[c], v0[c + 1], v0[c + 2], v0[c + 3]);
+      for (int c = 0; c < 16; c += 4) {
+        *reinterpret_cast<float4*>(stg + lane * 36 + c) = make_float4(v0[c], v0[c + 1], v0[c + 2], v0[c + 3]);
+        *reinterpret_cast<float4*>(stg + lane * 36 + 16 + c) = make_float4(v1[c], v1[c + 1], v1[c + 2], v1[c + 3]);
+      }
+      __syncwarp();
+      // 8 lanes per pixel (128 B of this channel chunk): full 128-byte lines per 8 lanes
 #pragma unroll
-        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(o + 16 + c) = make_float4(v1[c], v1[c + 1], v1[c + 2], v1[c + 3]);
+      for (int j = 0; j < 8; j++) {
+        const int e = lane + 32 * j;
+        const int pl = e >> 3, ch = (e & 7) * 4;
+        const int oyy = ty0 + q * 4 + (pl >> 3), oxx = tx0 + (pl & 7);
+        if (oyy < HOUT && oxx < HOUT)
+          *reinterpret_cast<float4*>(out + (((size_t)crop * HOUT + oyy) * HOUT + oxx) * COUT + nchunk * 32 + ch) =
+              *reinterpret_cast<const float4*>(stg + pl * 36 + ch);
       }
       s1 = warp_sum(s1);
       s2 = warp_sum(s2);
@@ -526,12 +554,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
                                                              float* __restrict__ out, double* __restrict__ out_stats, int n) {
   using Cfg = Tc3Cfg<CIN, KS, HIN, HOUT, COUT, FINAL>;
   constexpr int PIX = Cfg::PIX, NCH = Cfg::NCH, NBUF = Cfg::NBUF;
-  static_assert(CIN % 64 == 0 && COUT % 16 == 0 && 2 * COUT <= 512, "tc_gemm tiling");
+  static_assert(CIN % 64 == 0 && COUT % 32 == 0 && 2 * COUT <= 512, "tc_gemm tiling");
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
   __shared__ float s_gam[CIN], s_bet[CIN], s_bias[COUT];
   __shared__ float s_mean[2][128], s_rstd[2][128];
+  __shared__ __align__(16) float s_stage[4][32 * 36];
   __shared__ int s_off[2][128];     // element offset of the row's (2oy, 2ox) input pixel, -1 = row beyond the batch
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < CIN; i += TC_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
@@ -648,24 +677,40 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
       tc::mbar_wait(&acc_full[a], (it >> 1) & 1);
       tc::tc_fence_after();
       float s1 = 0.f, s2 = 0.f;
+      float* stg = s_stage[q];
+      const long long gm0 = (long long)tile * 128 + q * 32;     // first row of this warp
 #pragma unroll 1
-      for (int h = 0; h < COUT / 16; h++) {
-        float v[16];
-        tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * COUT + h * 16, v);
-        if (h == COUT / 16 - 1) {
+      for (int h = 0; h < COUT / 32; h++) {
+        float v0[16], v1[16];
+        tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * COUT + h * 32, v0);
+        tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * COUT + h * 32 + 16, v1);
+        if (h == COUT / 32 - 1) {
           tc::tc_fence_before();
           tc::mbar_arrive(&acc_empty[a]);
         }
-        if (valid) {
-          float* o = out + (size_t)gm * COUT + h * 16;
 #pragma unroll
-          for (int c = 0; c < 16; c++) {
-            v[c] += s_bias[h * 16 + c];
-            s1 += v[c];
-            s2 = fmaf(v[c], v[c], s2);
+        for (int c = 0; c < 16; c++) {
+          v0[c] += s_bias[h * 32 + c];
+          v1[c] += s_bias[h * 32 + 16 + c];
+          if (valid) {
+            s1 += v0[c] + v1[c];
+            s2 = fmaf(v0[c], v0[c], s2);
+            s2 = fmaf(v1[c], v1[c], s2);
           }
+        }
+        __syncwarp();
 #pragma unroll
-          for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(o + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        for (int c = 0; c < 16; c += 4) {
+          *reinterpret_cast<float4*>(stg + lane * 36 + c) = make_float4(v0[c], v0[c + 1], v0[c + 2], v0[c + 3]);
+          *reinterpret_cast<float4*>(stg + lane * 36 + 16 + c) = make_float4(v1[c], v1[c + 1], v1[c + 2], v1[c + 3]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int e = lane + 32 * j;
+          const int rl = e >> 3, ch = (e & 7) * 4;
+          if (gm0 + rl < rows_total)
+            *reinterpret_cast<float4*>(out + (size_t)(gm0 + rl) * COUT + h * 32 + ch) = *reinterpret_cast<const float4*>(stg + rl * 36 + ch);
         }
       }
       if (!FINAL && valid) {
