@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
       tc::mbar_arrive(&full[b]);
     }
   } else if (warp == TC_MMA_WARP) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = tc::idesc_bf16_f32(128, 16);
       const uint32_t wbase = tc::smem_u32(sW);
       int cnt = 0;
@@ -192,27 +192,30 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
         tc::mbar_wait(&acc_empty[a], ((cnt >> 1) & 1) ^ 1);
         tc::mbar_wait(&full[b], (cnt / T1_NBUF) & 1);
         tc::tc_fence_after();
+        if (tc::elect_one()) {
         const uint32_t pbase = tc::smem_u32(sP + (size_t)b * T1_PATCH_BYTES);
+        const uint32_t a_hi = tc::desc_hi(2 * T1_PW * 8), b_hi = tc::desc_hi(128);
+        const uint32_t b_lo0 = tc::desc_lo(wbase, 256);
 #pragma unroll 1
         for (int sub = 0; sub < 8; sub++) {
           const int sy = sub >> 2, sx = sub & 3;
-          const uint32_t abase = pbase + ((sy * 32) * T1_PW + sx * 16) * 8;
+          const uint32_t a_lo0 = tc::desc_lo(pbase + ((sy * 32) * T1_PW + sx * 16) * 8, 16);
           const uint32_t d = tm + a * 128 + sub * 16;
-          uint32_t acc = 0;
-#pragma unroll 1
+#pragma unroll
           for (int ky = 0; ky < 7; ky++) {
 #pragma unroll
             for (int kq = 0; kq < 2; kq++) {
-              const uint64_t ad = tc::smem_desc(abase + (ky * T1_PW + 4 * kq) * 8, 16, 2 * T1_PW * 8);
-              const uint32_t wb = wbase + ((ky * 2 + kq) * 2) * 512;
-              tc::mma_bf16(d, ad, tc::smem_desc(wb, 256, 128), idesc, acc);
-              tc::mma_bf16(d, ad, tc::smem_desc(wb + 512, 256, 128), idesc, 1);
-              acc = 1;
+              const uint64_t ad = tc::desc_make(a_lo0 + (((ky * T1_PW + 4 * kq) * 8) >> 4), a_hi);
+              const uint32_t wl = b_lo0 + ((((ky * 2 + kq) * 2) * 512) >> 4);
+              tc::mma_bf16(d, ad, tc::desc_make(wl, b_hi), idesc, (ky | kq) ? 1u : 0u);
+              tc::mma_bf16(d, ad, tc::desc_make(wl + (512 >> 4), b_hi), idesc, 1u);
             }
           }
         }
         tc::mma_commit(&empty[b]);
         tc::mma_commit(&acc_full[a]);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
       cnt++;
     }
   } else if (warp == TC_MMA_WARP) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = tc::idesc_bf16_f32(128, 32);
       constexpr uint32_t LBO_A = PH * 2 * PQ * 16, SBO_A = 64 * PQ;
       int cnt = 0, it = 0;
@@ -443,28 +446,29 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
           const int b = cnt % NBUF;
           tc::mbar_wait(&full[b], (cnt / NBUF) & 1);
           tc::tc_fence_after();
-          const uint32_t abase = tc::smem_u32(sA + (size_t)b * Cfg::A_BYTES);
-          const uint32_t wbase = tc::smem_u32(sW) + c2 * TAPS * 2048;
-          uint32_t acc = (c2 > 0) ? 1u : 0u;
-#pragma unroll 1
+          if (tc::elect_one()) {
+          const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(sA + (size_t)b * Cfg::A_BYTES), LBO_A);
+          const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(sW) + c2 * TAPS * 2048, 512);
+          const uint32_t a_hi = tc::desc_hi(SBO_A), b_hi = tc::desc_hi(128);
+#pragma unroll
           for (int ky = 0; ky < KS; ky++) {
 #pragma unroll
             for (int kx = 0; kx < KS; kx++) {
               const int tap = ky * KS + kx;
-              const uint32_t aoff = ((ky * 2 + (kx & 1)) * PQ + (kx >> 1)) * 16;
-              const uint64_t ah = tc::smem_desc(abase + aoff, LBO_A, SBO_A);
-              const uint64_t al = tc::smem_desc(abase + Cfg::A_PREC_BYTES + aoff, LBO_A, SBO_A);
-              const uint64_t bh = tc::smem_desc(wbase + tap * 2048, 512, 128);
-              const uint64_t bl = tc::smem_desc(wbase + tap * 2048 + 1024, 512, 128);
-              tc::mma_bf16(d, ah, bh, idesc, acc);
-              tc::mma_bf16(d, al, bh, idesc, 1);
-              tc::mma_bf16(d, ah, bl, idesc, 1);
-              acc = 1;
+              const uint32_t al0 = a_lo0 + ((((ky * 2 + (kx & 1)) * PQ + (kx >> 1)) * 16) >> 4);
+              const uint32_t bl0 = b_lo0 + ((tap * 2048) >> 4);
+              const uint64_t ah = tc::desc_make(al0, a_hi), al = tc::desc_make(al0 + (Cfg::A_PREC_BYTES >> 4), a_hi);
+              const uint64_t bh = tc::desc_make(bl0, b_hi), bl = tc::desc_make(bl0 + (1024 >> 4), b_hi);
+              tc::mma_bf16(d, ah, bh, idesc, (tap > 0 || c2 > 0) ? 1u : 0u);
+              tc::mma_bf16(d, al, bh, idesc, 1u);
+              tc::mma_bf16(d, ah, bl, idesc, 1u);
             }
           }
           tc::mma_commit(&empty[b]);
+          if (c2 == C2 - 1) tc::mma_commit(&acc_full[a]);
+          }
+          __syncwarp();
         }
-        tc::mma_commit(&acc_full[a]);
       }
     }
   } else {
@@ -635,7 +639,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
       }
     }
   } else if (warp == TC_MMA_WARP) {
-    if (lane == 0) {
+    {
       const uint32_t idesc = tc::idesc_bf16_f32(128, COUT);
       constexpr uint32_t LBO_W = (COUT / 8) * 128;
       int cnt = 0, it = 0;
@@ -648,23 +652,25 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
           const int b = cnt % NBUF;
           tc::mbar_wait(&full[b], (cnt / NBUF) & 1);
           tc::tc_fence_after();
+          if (tc::elect_one()) {
           const uint32_t abase = tc::smem_u32(smem + (size_t)b * Cfg::STAGE);
-          const uint32_t wbase = abase + 2 * Cfg::A_PREC;
-          uint32_t acc = (kc > 0) ? 1u : 0u;
+          const uint32_t a_lo0 = tc::desc_lo(abase, 2048), b_lo0 = tc::desc_lo(abase + 2 * Cfg::A_PREC, LBO_W);
+          const uint32_t a_hi = tc::desc_hi(128), b_hi = tc::desc_hi(128);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            const uint64_t ah = tc::smem_desc(abase + j * 2 * 2048, 2048, 128);
-            const uint64_t al = tc::smem_desc(abase + Cfg::A_PREC + j * 2 * 2048, 2048, 128);
-            const uint64_t bh = tc::smem_desc(wbase + j * 2 * LBO_W, LBO_W, 128);
-            const uint64_t bl = tc::smem_desc(wbase + Cfg::W_PREC + j * 2 * LBO_W, LBO_W, 128);
-            tc::mma_bf16(d, ah, bh, idesc, acc);
-            tc::mma_bf16(d, al, bh, idesc, 1);
-            tc::mma_bf16(d, ah, bl, idesc, 1);
-            acc = 1;
+            const uint64_t ah = tc::desc_make(a_lo0 + ((j * 2 * 2048) >> 4), a_hi);
+            const uint64_t al = tc::desc_make(a_lo0 + ((Cfg::A_PREC + j * 2 * 2048) >> 4), a_hi);
+            const uint64_t bh = tc::desc_make(b_lo0 + ((j * 2 * LBO_W) >> 4), b_hi);
+            const uint64_t bl = tc::desc_make(b_lo0 + ((Cfg::W_PREC + j * 2 * LBO_W) >> 4), b_hi);
+            tc::mma_bf16(d, ah, bh, idesc, (j > 0 || kc > 0) ? 1u : 0u);
+            tc::mma_bf16(d, al, bh, idesc, 1u);
+            tc::mma_bf16(d, ah, bl, idesc, 1u);
           }
           tc::mma_commit(&empty[b]);
+          if (kc == NCH - 1) tc::mma_commit(&acc_full[a]);
+          }
+          __syncwarp();
         }
-        tc::mma_commit(&acc_full[a]);
       }
     }
   } else {

@@ -35,6 +35,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// one lane of a CONVERGED warp (the compiler treats the guarded region as single-threaded/uniform: no per-instruction election)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t"
+      "}\n"
+      : "=r"(pred)::"memory");
+  return pred != 0;
+}
+
 // ---- proxies / fences --------------------------------------------------------------------------------------
 // generic-proxy shared-memory writes (st.shared) -> visible to the async proxy (tensor-core descriptor reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -62,6 +76,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;   // descriptor version 1 (Blackwell)
   return d;                 // base_offset = 0, lbo_mode = 0, layout_type = 0 (SWIZZLE_NONE)
 }
+
+// Descriptor words for the MMA issue loops: the 64-bit descriptor is {lo, hi} with lo = addr>>4 | (LBO>>4)<<16 and
+// hi = SBO>>4 | version<<14; stepping through taps / K slices only adds a constant to `lo` (addresses < 256 KB never carry
+// into the LBO field), so the single issuing thread spends ~1 integer add per operand per MMA.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc_make(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 // Instruction descriptor for kind::f16: BF16 x BF16 -> FP32, A and B K-major, dense.
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
