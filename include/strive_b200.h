@@ -45,6 +45,10 @@ int64_t strive_profile_report(char* buf, int64_t cap);
 /* ---- tcgen05 primitive self-test (tests only): A (128,32), B (32,32), X0/X1 (144,8) fp32 (rounded to bf16 inside);
  * D0 = A B^T, D1[m] = [X0[m+1] | X1[m+3]] B[:, :16]^T, both (128,32) fp32. */
 int strive_tc_selftest(const float* A, const float* B, const float* X0, const float* X1, float* D0, float* D1, void* stream);
+/* Pipeline diagnostics of the tensor-core convolutions: out32 = [4 kernels conv1..conv4][8] SM-cycle counters summed over
+ * CTAs since the last reset ([0] producers blocked on a ring slot, [1] producer total, [2] MMA warp starved, [3] MMA warp
+ * blocked on an accumulator, [4] MMA total, [5] epilogue idle, [6] epilogue total, [7] CTAs).  No reference counterpart. */
+int strive_tc_trace(unsigned long long* out32, int reset);
 
 /* ---- model weights -------------------------------------------------------------------------------------
  * Replaces: torch state_dict of decoder_net.*, decoder_memory.*, map_conv.*, map_feature.* loaded by

@@ -19,6 +19,8 @@ mapix = torch.zeros(N, dtype=torch.int32, device=dev)
 for _ in range(REPS):
     f = model.encode_map_poses(pose, mapix, env)
 torch.cuda.synchronize()
+from strive_b200 import _cabi
+_cabi.tc_trace(True)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(REPS):
@@ -26,3 +28,9 @@ for _ in range(REPS):
 e1.record()
 torch.cuda.synchronize()
 print('mapenc: %d crops, %.3f ms per call, %.3f us per crop, feat checksum %.6f' % (N, e0.elapsed_time(e1) / REPS, 1000 * e0.elapsed_time(e1) / REPS / N, float(f.double().sum())))
+tr = _cabi.tc_trace(True)
+for k, name in enumerate(['conv1', 'conv2', 'conv3', 'conv4']):
+    t = tr[k]
+    ct = max(t[7], 1)
+    print('%s per CTA-launch kcycles: producer wait-empty %.0f / total %.0f | mma wait-full %.0f wait-acc %.0f / total %.0f | epi wait %.0f / total %.0f (CTAs %d)' % (
+        name, t[0] / ct / 1e3, t[1] / ct / 1e3, t[2] / ct / 1e3, t[3] / ct / 1e3, t[4] / ct / 1e3, t[5] / ct / 1e3, t[6] / ct / 1e3, t[7]))

@@ -43,7 +43,7 @@ class StriveLossCfg(C.Structure):
                 ('circ_cx', C.c_void_p), ('lw_un', C.c_void_p)]
 
 
-EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl',
+EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_tc_trace', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl',
            'strive_mapenc_workspace_bytes', 'strive_mapenc_fwd', 'strive_map_crop', 'strive_decode_tape_bytes',
            'strive_decode_fwd', 'strive_decode_bwd', 'strive_decode_tape_read', 'strive_loss_workspace_bytes',
            'strive_loss_fwd_bwd', 'strive_adam_step']
@@ -85,6 +85,7 @@ def lib():
     L.strive_struct_layout.argtypes = [C.POINTER(i64), C.c_int]
     L.strive_profile_enable.argtypes = [C.c_int]
     L.strive_tc_selftest.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.strive_tc_trace.argtypes = [vp, C.c_int]
     L.strive_profile_report.argtypes = [C.c_char_p, i64]
     L.strive_profile_report.restype = i64
     if L.strive_abi_version() != 1:
@@ -124,6 +125,14 @@ def _verify_layout(L):
             StriveLossCfg.attack_mask.offset, StriveLossCfg.lw_un.offset]
     if n != len(mine) or list(buf[:n]) != mine:
         raise RuntimeError('strive_b200: ctypes struct layout %s does not match the library %s' % (mine, list(buf[:max(n, 0)])))
+
+
+def tc_trace(reset=True):
+    """[4][8] cycle counters of the tensor-core conv pipelines (see include/strive_b200.h: strive_tc_trace)."""
+    buf = (C.c_uint64 * 32)()
+    if lib().strive_tc_trace(C.cast(buf, C.c_void_p), int(bool(reset))) != 0:
+        raise RuntimeError('strive_tc_trace failed')
+    return [[int(buf[k * 8 + j]) for j in range(8)] for k in range(4)]
 
 
 def profile_enable(on):

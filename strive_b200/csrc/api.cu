@@ -96,7 +96,7 @@ extern "C" int strive_model_create(const float* blob, int64_t blob_floats, const
 
 extern "C" void strive_model_destroy(StriveModel* m) { delete m; }
 
-// tensor-core weight blob: [conv1 14336 B][conv2 51200 B][conv3 2 x 102400 B][conv4 2 x 73728 B][conv5][conv6][fc]  (layouts in mapenc_tc.cu)
+// tensor-core weight blob: [conv1 14336 B][conv2 51200 B][conv3 2 x 102400 B][conv4 147456 B][conv5][conv6][fc]  (layouts in mapenc_tc.cu)
 static const int64_t kTcBytes[7] = {7 * 2 * 2 * 512, 1 * (1 * 25 * 2 * 1024), 2 * (2 * 25 * 2 * 1024), 2 * (4 * 9 * 2 * 1024),
                                     9 * 2 * 128 * 64 * 2, 18 * 2 * 128 * 64 * 2, 8 * 2 * 64 * 64 * 2};
 extern "C" int64_t strive_model_tc_bytes(void) {
@@ -109,6 +109,14 @@ extern "C" int strive_model_set_tc_weights(StriveModel* m, const void* blob, int
   STRIVE_CHECK(blob != nullptr && bytes == strive_model_tc_bytes(), STRIVE_ESIZE, "tc weight blob has %lld bytes, expected %lld", (long long)bytes,
                (long long)strive_model_tc_bytes());
   STRIVE_CHECK(((uintptr_t)blob & 15) == 0, STRIVE_EINVAL, "tc weight blob must be 16-byte aligned");
+  // conv1..conv4 biases travel as kernel arguments (constant bank): keep host copies (one-time synchronous copy)
+  static const int kBiasSeg[4] = {S_CB0, S_CB1, S_CB2, S_CB3};
+  static const int kBiasN[4] = {16, 32, 64, 64};
+  for (int l = 0; l < 4; l++) {
+    STRIVE_CHECK(m->seg_size[kBiasSeg[l]] == kBiasN[l], STRIVE_ESIZE, "conv%d bias has %lld entries", l + 1, (long long)m->seg_size[kBiasSeg[l]]);
+    for (int i = 0; i < 64; i++) m->h_cbias[l][i] = 0.f;
+    STRIVE_CUDA(cudaMemcpy(m->h_cbias[l], m->seg[kBiasSeg[l]], sizeof(float) * kBiasN[l], cudaMemcpyDeviceToHost));
+  }
   m->tc_blob = (const uint8_t*)blob;
   int64_t off = 0;
   for (int i = 0; i < 7; i++) { m->tc_off[i] = off; off += kTcBytes[i]; }

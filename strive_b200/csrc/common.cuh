@@ -99,6 +99,7 @@ struct StriveModel {
   int u0_rows;    // rows of U0_T  (= 64+64+NC rounded up to 4)
   const uint8_t* tc_blob;   // bf16 hi/lo conv weights in UMMA canonical layout (strive_model_set_tc_weights) or null
   int64_t tc_off[7];        // byte offsets of conv1..conv6, fc inside tc_blob
+  float h_cbias[4][64];     // host copies of the conv1..conv4 biases (kernel arguments of the tensor-core convolutions)
 };
 
 __host__ __device__ inline int round_up4(int x) { return (x + 3) & ~3; }

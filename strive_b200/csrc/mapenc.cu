@@ -389,13 +389,13 @@ extern "C" int strive_mapenc_fwd(const StriveModel* m, const StriveMap* map, con
     int rc;
     if (g_mapenc_impl == 1 && m->tc_blob != nullptr) {
       // tensor-core path (mapenc_tc.cu): conv1..conv4 on tcgen05, activations NHWC fp32
-      rc = tc_launch_conv1(map, pose, mo, m->tc_blob + m->tc_off[0], sg[S_CB0], act[0], st[0], packed_crop, cn, stream);
+      rc = tc_launch_conv1(map, pose, mo, m->tc_blob + m->tc_off[0], m->h_cbias[0], act[0], st[0], packed_crop, cn, stream);
       if (rc) return rc;
-      rc = tc_launch_conv2(act[0], st[0], sg[S_GG0], sg[S_GB0], m->tc_blob + m->tc_off[1], sg[S_CB1], act[1], st[1], cn, stream);
+      rc = tc_launch_conv2(act[0], st[0], sg[S_GG0], sg[S_GB0], m->tc_blob + m->tc_off[1], m->h_cbias[1], act[1], st[1], cn, stream);
       if (rc) return rc;
-      rc = tc_launch_conv3(act[1], st[1], sg[S_GG1], sg[S_GB1], m->tc_blob + m->tc_off[2], sg[S_CB2], act[2], st[2], cn, stream);
+      rc = tc_launch_conv3(act[1], st[1], sg[S_GG1], sg[S_GB1], m->tc_blob + m->tc_off[2], m->h_cbias[2], act[2], st[2], cn, stream);
       if (rc) return rc;
-      rc = tc_launch_conv4(act[2], st[2], sg[S_GG2], sg[S_GB2], m->tc_blob + m->tc_off[3], sg[S_CB3], act[3], st[3], cn, stream);
+      rc = tc_launch_conv4(act[2], st[2], sg[S_GG2], sg[S_GB2], m->tc_blob + m->tc_off[3], m->h_cbias[3], act[3], st[3], cn, stream);
       if (rc) return rc;
       rc = tc_launch_conv5(act[3], st[3], sg[S_GG3], sg[S_GB3], m->tc_blob + m->tc_off[4], sg[S_CB4], act[4], st[4], cn, stream);
       if (rc) return rc;

@@ -5,8 +5,9 @@
 // Two TMEM accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1; all hand-offs are mbarriers.
 //
 // Numerics: bf16 operand SPLITTING with fp32 accumulation in TMEM.  x = hi + lo (hi = bf16(x), lo = bf16(x - hi)).
-//   conv1: the input is the binary crop (exact in bf16); weights are split -> 2 MMAs per K step (error 2^-17 relative).
-//   conv2..fc: activations and weights both split -> hi*hi + lo*hi + hi*lo (3 MMAs, dropped lo*lo term 2^-18).
+//   conv1: the input is the binary crop (exact in bf16); weights are split, [W_hi | W_lo] stacked along N -> 1 MMA per K step.
+//   conv2..4: activations and weights both split -> A_hi*[W_hi | W_lo] + A_lo*W_hi (2 MMAs, dropped lo*lo term 2^-18).
+//   conv5..fc: hi*hi + lo*hi + hi*lo as 3 MMAs.
 // Measured against the fp64 oracle: 1.4e-5 abs on O(1) features (tests allow 1e-4), at 1/3 of the dense bf16 tensor rate.
 //
 // Operand addressing ("shifted window", conv1..conv4): the input tile is written to shared memory ONCE, columns
@@ -20,6 +21,23 @@
 #define TC_EPI_WARP0 12
 #define TC_THREADS 512
 #define TC_PROD_THREADS (TC_NPROD * 32)
+
+// Pipeline diagnostics (strive_tc_trace): per kernel, cycles each role spent blocked on its mbarriers, summed over CTAs.
+//   [0] producer: waiting for a free ring slot   [1] producer: loop total
+//   [2] MMA: waiting for a filled slot           [3] MMA: waiting for a free accumulator   [4] MMA: loop total
+//   [5] epilogue: waiting for an accumulator     [6] epilogue: loop total                  [7] CTAs
+__device__ unsigned long long g_tc_trace[4][8];
+#define TRACE_T() clock64()
+__device__ __forceinline__ void trace_add(int k, int slot, long long v) { atomicAdd(&g_tc_trace[k][slot], (unsigned long long)v); }
+
+extern "C" int strive_tc_trace(unsigned long long* out32, int reset) {
+  if (out32 && cudaMemcpyFromSymbol(out32, g_tc_trace, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[32] = {0};
+    if (cudaMemcpyToSymbol(g_tc_trace, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -50,7 +68,7 @@ __device__ __forceinline__ void gn_stats(const double* __restrict__ st, int crop
 #define T1_WBYTES (7 * 2 * 2 * 512)
 #define T1_PATCH_BYTES (T1_PH * T1_PW * 8)
 #define T1_SUPER 4   // 4 x 4 super-tiles of 32 x 32 outputs cover 125 x 125
-#define T1_NBUF 2
+#define T1_NBUF 3
 #define T1_QMAX 1024   // deferred exact-rounding samples per tile (about 4 % of 4830 are near a tie); overflow is handled inline
 
 // round-half-even(g / dx) exactly as torch.round(float64 quotient) (reference datasets/nuscenes_utils.py:254-255): multiply by
@@ -123,46 +141,56 @@ __global__ void __launch_bounds__(256) crop_pack_kernel(StriveMap map, const flo
   }
 }
 
+// Bias passed BY VALUE (constant bank): the epilogue adds it as an immediate-constant operand, no shared-memory traffic.
+struct BiasArg {
+  float b[64];
+};
+
+// 4 layer bits -> 4 x bf16 {0.0, 1.0} (0x3F80), arithmetic instead of a shared-memory table: the MMA operand fetch
+// saturates the shared-memory pipe, every other LDS/STS in these kernels waits behind it.
+__device__ __forceinline__ uint2 expand_bits4(unsigned b) {
+  return make_uint2((b & 1u) * 0x3F80u + (b & 2u) * 0x1FC00000u, ((b >> 2) & 1u) * 0x3F80u + ((b >> 2) & 2u) * 0x1FC00000u);
+}
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __restrict__ packed_crop, const uint8_t* __restrict__ wpack,
-                                                              const float* __restrict__ bias, float* __restrict__ out,
-                                                              double* __restrict__ out_stats, int n) {
+                                                              const BiasArg bias, float* __restrict__ out, double* __restrict__ out_stats, int n) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sP = smem + T1_WBYTES;
   __shared__ __align__(8) uint64_t full[T1_NBUF], empty[T1_NBUF], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
-  __shared__ float s_bias[16];
-  __shared__ uint2 s_lut[16];   // 4 layer bits -> 4 x bf16 {0,1}
-  __shared__ __align__(16) float s_stage[4][32 * 20];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid < 16) {
-    const uint32_t one = 0x3F80u;
-    s_lut[tid] = make_uint2(((tid & 1) ? one : 0u) | ((tid & 2) ? (one << 16) : 0u), ((tid & 4) ? one : 0u) | ((tid & 8) ? (one << 16) : 0u));
-  }
   for (int i = tid; i < T1_WBYTES / 16; i += TC_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(reinterpret_cast<const int4*>(wpack) + i);
-  if (tid < 16) s_bias[tid] = bias[tid];
   if (tid == 0) {
     for (int b = 0; b < T1_NBUF; b++) { tc::mbar_init(&full[b], TC_PROD_THREADS); tc::mbar_init(&empty[b], 1); }
     for (int a = 0; a < 2; a++) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 128); }
     tc::fence_mbar_init();
   }
-  if (warp == TC_MMA_WARP) tc::tmem_alloc(&tmem_base, 256);
+  if (warp == TC_MMA_WARP) tc::tmem_alloc(&tmem_base, 512);     // 2 accumulator sets x 8 sub-tiles x 32 columns: one CTA per SM
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tm = tmem_base;
   const int items = n * T1_SUPER * T1_SUPER;
+  // contiguous item range per CTA: the 16 super-tiles of a crop stay on one SM (L1/L2 locality, one statistics flush per crop)
+  const int item_lo = (int)(((long long)items * blockIdx.x) / gridDim.x);
+  const int item_hi = (int)(((long long)items * (blockIdx.x + 1)) / gridDim.x);
 
   if (warp < TC_NPROD) {
-    // ---------------- producers: gather the crop tile (exact get_map_obs arithmetic) ----------------
+    // ---------------- producers: expand the bit-packed crop tile to bf16 [row][col][4 ch] ----------------
     int cnt = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, cnt++) {
+    long long tw = 0, t_start = TRACE_T();
+    for (int item = item_lo; item < item_hi; item++, cnt++) {
       const int crop = item / (T1_SUPER * T1_SUPER), st = item % (T1_SUPER * T1_SUPER);
       const int oy0 = (st / T1_SUPER) * 32, ox0 = (st % T1_SUPER) * 32;
       const int b = cnt % T1_NBUF;
-      tc::mbar_wait(&empty[b], ((cnt / T1_NBUF) & 1) ^ 1);
-      uint8_t* dst = sP + (size_t)b * T1_PATCH_BYTES;
       const uint8_t* src = packed_crop + (size_t)crop * 65536 + (size_t)(oy0 * 2) * 256 + ox0 * 2;
       constexpr int NPX = T1_PH * T1_PW;
       constexpr int NPT = (NPX + TC_PROD_THREADS - 1) / TC_PROD_THREADS;     // 14 samples per thread
@@ -172,122 +200,147 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
       for (int k = 0; k < NPT; k++) {
         const int i = tid + k * TC_PROD_THREADS;
         const int r = i / T1_PW, c = i - r * T1_PW;
-        bits[k] = (i < NPX && r < ymax && c < xmax) ? (unsigned)__ldg(src + r * 256 + c) : 16u;
+        bits[k] = (i < NPX && r < ymax && c < xmax) ? (unsigned)__ldg(src + r * 256 + c) : 0u;     // zero padding outside the crop
       }
+      const long long tq = TRACE_T();
+      tc::mbar_wait(&empty[b], ((cnt / T1_NBUF) & 1) ^ 1);
+      tw += TRACE_T() - tq;
+      uint8_t* dst = sP + (size_t)b * T1_PATCH_BYTES;
 #pragma unroll
       for (int k = 0; k < NPT; k++) {
         const int i = tid + k * TC_PROD_THREADS;
-        if (i < NPX) *reinterpret_cast<uint2*>(dst + (size_t)i * 8) = (bits[k] < 16u) ? s_lut[bits[k] & 15u] : make_uint2(0u, 0u);
+        if (i < NPX) *reinterpret_cast<uint2*>(dst + (size_t)i * 8) = expand_bits4(bits[k]);
       }
       tc::fence_async_smem();
       tc::mbar_arrive(&full[b]);
     }
+    if (tid == 0) { trace_add(0, 0, tw); trace_add(0, 1, TRACE_T() - t_start); trace_add(0, 7, 1); }
   } else if (warp == TC_MMA_WARP) {
-    {
-      const uint32_t idesc = tc::idesc_bf16_f32(128, 16);
-      const uint32_t wbase = tc::smem_u32(sW);
-      int cnt = 0;
-      for (int item = blockIdx.x; item < items; item += gridDim.x, cnt++) {
-        const int b = cnt % T1_NBUF, a = cnt & 1;
-        tc::mbar_wait(&acc_empty[a], ((cnt >> 1) & 1) ^ 1);
-        tc::mbar_wait(&full[b], (cnt / T1_NBUF) & 1);
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
+    // One MMA per K step: B = [W_hi | W_lo] stacked along N (32 rows) so the A tile is fetched once for both halves
+    // (SS-mode MMA time = (4096 + 32 N) / 128 cycles: the A fetch dominates at small N).
+    const uint32_t idesc = tc::idesc_bf16_f32(128, 32);
+    const uint32_t wbase = tc::smem_u32(sW);
+    int cnt = 0;
+    long long twf = 0, twa = 0, t_start = TRACE_T();
+    for (int item = item_lo; item < item_hi; item++, cnt++) {
+      const int b = cnt % T1_NBUF, a = cnt & 1;
+      const long long tq0 = TRACE_T();
+      tc::mbar_wait(&acc_empty[a], ((cnt >> 1) & 1) ^ 1);
+      const long long tq1 = TRACE_T();
+      tc::mbar_wait(&full[b], (cnt / T1_NBUF) & 1);
+      twa += tq1 - tq0;
+      twf += TRACE_T() - tq1;
+      tc::tc_fence_after();
+      if (tc::elect_one()) {
         const uint32_t pbase = tc::smem_u32(sP + (size_t)b * T1_PATCH_BYTES);
         const uint32_t a_hi = tc::desc_hi(2 * T1_PW * 8), b_hi = tc::desc_hi(128);
-        const uint32_t b_lo0 = tc::desc_lo(wbase, 256);
+        const uint32_t b_lo0 = tc::desc_lo(wbase, 512);
 #pragma unroll 1
         for (int sub = 0; sub < 8; sub++) {
           const int sy = sub >> 2, sx = sub & 3;
           const uint32_t a_lo0 = tc::desc_lo(pbase + ((sy * 32) * T1_PW + sx * 16) * 8, 16);
-          const uint32_t d = tm + a * 128 + sub * 16;
+          const uint32_t d = tm + a * 256 + sub * 32;
 #pragma unroll
           for (int ky = 0; ky < 7; ky++) {
 #pragma unroll
             for (int kq = 0; kq < 2; kq++) {
               const uint64_t ad = tc::desc_make(a_lo0 + (((ky * T1_PW + 4 * kq) * 8) >> 4), a_hi);
-              const uint32_t wl = b_lo0 + ((((ky * 2 + kq) * 2) * 512) >> 4);
-              tc::mma_bf16(d, ad, tc::desc_make(wl, b_hi), idesc, (ky | kq) ? 1u : 0u);
-              tc::mma_bf16(d, ad, tc::desc_make(wl + (512 >> 4), b_hi), idesc, 1u);
+              const uint64_t bd = tc::desc_make(b_lo0 + (((ky * 2 + kq) * 1024) >> 4), b_hi);
+              tc::mma_bf16(d, ad, bd, idesc, (ky | kq) ? 1u : 0u);
             }
           }
         }
         tc::mma_commit(&empty[b]);
         tc::mma_commit(&acc_full[a]);
-        }
-        __syncwarp();
       }
+      __syncwarp();
     }
+    if (lane == 0) { trace_add(0, 2, twf); trace_add(0, 3, twa); trace_add(0, 4, TRACE_T() - t_start); }
   } else {
-    // ---------------- epilogue: warp q reads TMEM lanes 32q..32q+31 of all 8 sub-tiles ----------------
+    // ---------------- epilogue: warp q reads TMEM lanes 32q..32q+31 of all 8 sub-tiles; registers -> global directly ----------------
     const int q = warp - TC_EPI_WARP0;
     const int m = q * 32 + lane, oyl = m >> 3, oxl = m & 7;
-    int cnt = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x, cnt++) {
+    int cnt = 0, cur_crop = -1;
+    double d1 = 0.0, d2 = 0.0;
+    long long twe = 0, t_start = TRACE_T();
+    for (int item = item_lo; item < item_hi; item++, cnt++) {
       const int crop = item / (T1_SUPER * T1_SUPER), st = item % (T1_SUPER * T1_SUPER);
       const int oy0 = (st / T1_SUPER) * 32, ox0 = (st % T1_SUPER) * 32;
       const int a = cnt & 1;
+      if (crop != cur_crop) {
+        if (cur_crop >= 0) {
+          d1 = warp_sum_f64(d1);
+          d2 = warp_sum_f64(d2);
+          if (lane == 0) {
+            atomicAdd(out_stats + (size_t)cur_crop * 2, d1);
+            atomicAdd(out_stats + (size_t)cur_crop * 2 + 1, d2);
+          }
+        }
+        cur_crop = crop;
+        d1 = 0.0;
+        d2 = 0.0;
+      }
+      const long long tq = TRACE_T();
       tc::mbar_wait(&acc_full[a], (cnt >> 1) & 1);
+      twe += TRACE_T() - tq;
       tc::tc_fence_after();
       float s1 = 0.f, s2 = 0.f;
-      float* stg = s_stage[q];                 // [32 px][16 ch] per warp, padded rows of 20 floats (conflict-free float4 access)
 #pragma unroll 1
       for (int sub = 0; sub < 8; sub++) {
         const int sy = sub >> 2, sx = sub & 3;
-        float v[16];
-        tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * 128 + sub * 16, v);
+        float vh[16], vl[16];
+        tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * 256 + sub * 32, vh);
+        tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * 256 + sub * 32 + 16, vl);
         if (sub == 7) {
           tc::tc_fence_before();
           tc::mbar_arrive(&acc_empty[a]);
         }
         const int oy = oy0 + sy * 16 + oyl, ox = ox0 + sx * 8 + oxl;
-        const bool ok = oy < 125 && ox < 125;
+        if (oy < 125 && ox < 125) {
+          float* dst = out + (((size_t)crop * 125 + oy) * 125 + ox) * 16;
 #pragma unroll
-        for (int c = 0; c < 16; c++) {
-          v[c] += s_bias[c];
-          if (ok) {
-            s1 += v[c];
-            s2 = fmaf(v[c], v[c], s2);
+          for (int c = 0; c < 16; c++) {
+            vh[c] = (vh[c] + vl[c]) + bias.b[c];
+            s1 += vh[c];
+            s2 = fmaf(vh[c], vh[c], s2);
           }
-        }
-        __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(stg + lane * 20 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-        __syncwarp();
-        // 4 lanes per pixel (64 B), 8 pixels of an output row = 512 contiguous bytes per 32 lanes
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int e = lane + 32 * j;           // float4 index inside the 32 x 16 block
-          const int pl = e >> 2, ch = (e & 3) * 4;
-          const int oyy = oy0 + sy * 16 + (q * 4 + (pl >> 3)), oxx = ox0 + sx * 8 + (pl & 7);
-          if (oyy < 125 && oxx < 125)
-            *reinterpret_cast<float4*>(out + (((size_t)crop * 125 + oyy) * 125 + oxx) * 16 + ch) = *reinterpret_cast<const float4*>(stg + pl * 20 + ch);
+          for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(vh[c], vh[c + 1], vh[c + 2], vh[c + 3]);
         }
       }
-      s1 = warp_sum(s1);
-      s2 = warp_sum(s2);
+      d1 += (double)s1;
+      d2 += (double)s2;
+    }
+    if (cur_crop >= 0) {
+      d1 = warp_sum_f64(d1);
+      d2 = warp_sum_f64(d2);
       if (lane == 0) {
-        atomicAdd(out_stats + (size_t)crop * 2, (double)s1);
-        atomicAdd(out_stats + (size_t)crop * 2 + 1, (double)s2);
+        atomicAdd(out_stats + (size_t)cur_crop * 2, d1);
+        atomicAdd(out_stats + (size_t)cur_crop * 2 + 1, d2);
       }
     }
+    if (q == 0 && lane == 0) { trace_add(0, 5, twe); trace_add(0, 6, TRACE_T() - t_start); }
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == TC_MMA_WARP) {
     __syncwarp();
-    tc::tmem_dealloc(tm, 256);
+    tc::tmem_dealloc(tm, 512);
   }
 }
 
 // ======================================================================================================
-// conv2..4: stride-2 kxk conv, CIN multiple of 16, output-channel chunks of N=32 (blockIdx.y), NHWC fp32 in/out.
+// conv2..4: stride-2 kxk conv, CIN multiple of 16, NCH output channels per CTA (blockIdx.y chunks), NHWC fp32 in/out.
 // CTA tile = 16 x 8 outputs (M = 128).  Weights of the chunk stay resident in shared memory; the input tile is staged
-// per 16-channel chunk into an NBUF-deep ring.
+// per 16-channel chunk into an NBUF-deep ring.  Per filter tap and 16 channels TWO MMAs:
+//     D[:, 0:2NCH]  += A_hi * [W_hi | W_lo]^T      (N = 2 NCH: hi and lo weights stacked along N, A_hi fetched once)
+//     D[:, 0:NCH]   += A_lo * W_hi^T               (N = NCH)
+// and the epilogue adds the two column halves.  Measured SS-mode cost of one M=128,K=16 MMA is (4096 + 32 N) / 128 cycles
+// (scripts/mma_bench.cu): the A-tile fetch dominates, so stacking N is worth 27 % over three N = NCH MMAs.
 // ======================================================================================================
-template <int CIN, int KS, int HIN, int HOUT, int COUT, int NBUF>
+template <int CIN, int KS, int HIN, int HOUT, int COUT, int NCH_, int NBUF>
 struct TcCfg {
-  static constexpr int N = 32;
+  static constexpr int NCH = NCH_;
   static constexpr int C2 = CIN / 16;
   static constexpr int TAPS = KS * KS;
   static constexpr int PH = 30 + KS;
@@ -295,42 +348,43 @@ struct TcCfg {
   static constexpr int PQ = 8 + (KS - 1) / 2;
   static constexpr int A_PREC_BYTES = 2 * PH * 2 * PQ * 16;
   static constexpr int A_BYTES = 2 * A_PREC_BYTES;
-  static constexpr int W_BYTES = C2 * TAPS * 2 * 1024;
+  static constexpr int TAP_BYTES = 64 * NCH;                 // [khalf 2][prec 2][NCH rows][8 k] bf16
+  static constexpr int W_BYTES = C2 * TAPS * TAP_BYTES;
   static constexpr int TILES_Y = (HOUT + 15) / 16;
   static constexpr int TILES_X = (HOUT + 7) / 8;
   static constexpr int TILES = TILES_Y * TILES_X;
+  static constexpr int TMEM_COLS = 4 * NCH;                  // 2 accumulator sets x (hi part | lo part)
   static constexpr size_t SMEM = (size_t)W_BYTES + (size_t)NBUF * A_BYTES;
 };
 
-template <int CIN, int KS, int HIN, int HOUT, int COUT, int NBUF>
+template <int CIN, int KS, int HIN, int HOUT, int COUT, int NCH, int NBUF>
 __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
                                                              const float* __restrict__ gam, const float* __restrict__ bet,
-                                                             const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
+                                                             const uint8_t* __restrict__ wpack, const BiasArg bias,
                                                              float* __restrict__ out, double* __restrict__ out_stats, int n) {
-  using Cfg = TcCfg<CIN, KS, HIN, HOUT, COUT, NBUF>;
+  using Cfg = TcCfg<CIN, KS, HIN, HOUT, COUT, NCH, NBUF>;
   constexpr int PH = Cfg::PH, PW = Cfg::PW, PQ = Cfg::PQ, C2 = Cfg::C2, TAPS = Cfg::TAPS;
+  constexpr int TK = CIN == 16 ? 1 : (CIN == 32 ? 2 : 3);
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem;
   uint8_t* sA = smem + Cfg::W_BYTES;
   __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
-  __shared__ float s_gam[CIN], s_bet[CIN], s_bias[32];
+  __shared__ float s_gam[CIN], s_bet[CIN];
   __shared__ __align__(16) float s_ga[CIN], s_gb[CIN];
-  __shared__ __align__(16) float s_stage[4][32 * 36];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nchunk = blockIdx.y;
+  const int nchunk = (COUT == NCH) ? 0 : (int)blockIdx.y;
   {
     const int4* src = reinterpret_cast<const int4*>(wpack + (size_t)nchunk * Cfg::W_BYTES);
     for (int i = tid; i < Cfg::W_BYTES / 16; i += TC_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(src + i);
   }
   for (int i = tid; i < CIN; i += TC_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
-  if (tid < 32) s_bias[tid] = bias[nchunk * 32 + tid];
   if (tid == 0) {
     for (int b = 0; b < NBUF; b++) { tc::mbar_init(&full[b], TC_PROD_THREADS); tc::mbar_init(&empty[b], 1); }
     for (int a = 0; a < 2; a++) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 128); }
     tc::fence_mbar_init();
   }
-  if (warp == TC_MMA_WARP) tc::tmem_alloc(&tmem_base, 64);
+  if (warp == TC_MMA_WARP) tc::tmem_alloc(&tmem_base, Cfg::TMEM_COLS);
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
@@ -342,53 +396,60 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
   const int item_hi = (int)(((long long)items * (blockIdx.x + 1)) / gridDim.x);
 
   if (warp < TC_NPROD) {
-    // ---------------- producers: one pixel (16 channels) per step, the next pixel's global loads always in flight ----------------
-    constexpr int NPIX = PH * PW;
-    constexpr int KPT = (NPIX + TC_PROD_THREADS - 1) / TC_PROD_THREADS;
+    // ---------------- producers ----------------
+    // Work item = 4 channels of one input pixel (one float4).  Thread t owns items t, t + 352, ...: its channel quad
+    // q = t & 3 is fixed (so its GroupNorm affine lives in 8 registers) and the (row, col) of each of its items inside
+    // the input patch never changes: global and shared offsets are computed once.  A warp reads 512 contiguous bytes per
+    // load and writes 16 distinct 8-byte bank slots per half-warp (conflict-free).
+    constexpr int NPIX = PH * PW, NITEM = NPIX * 4;
+    constexpr int KI = (NITEM + TC_PROD_THREADS - 1) / TC_PROD_THREADS;
     constexpr int CG = PH * 2 * PQ * 16;
-    // the loads of the NEXT chunk (KPT pixels x 64 B per thread) are always in flight while the current one is transformed
-    auto load_chunk = [&](int item, int c2, float4 (&x)[KPT][4], bool (&ok)[KPT], int (&u)[KPT]) {
+    const int q4 = (tid & 3) * 4;
+    int rc[KI], soff[KI];
+#pragma unroll
+    for (int k = 0; k < KI; k++) {
+      const int i = tid + k * TC_PROD_THREADS;
+      rc[k] = -1;
+      soff[k] = 0;
+      if (i < NITEM) {
+        const int p = i >> 2, qq = i & 3;
+        const int row = p / PW, col = p - row * PW;
+        rc[k] = (row << 8) | col;
+        soff[k] = ((row * 2 + (col & 1)) * PQ + (col >> 1)) * 16 + (qq & 1) * 8 + (qq >> 1) * CG;
+      }
+    }
+    auto load_chunk = [&](int item, int c2, float4 (&x)[KI], unsigned& okmask) {
       const int crop = item / Cfg::TILES, tile = item - crop * Cfg::TILES;
       const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
+      const int rows_valid = HIN - 2 * ty0, cols_valid = HIN - 2 * tx0;
+      const float* base = in + ((size_t)(crop * HIN + 2 * ty0) * HIN + 2 * tx0) * CIN + c2 * 16 + q4;
+      okmask = 0u;
 #pragma unroll
-      for (int k = 0; k < KPT; k++) {
-        const int p = tid + k * TC_PROD_THREADS;
-        ok[k] = false;
-        u[k] = -1;
-        if (p < NPIX) {
-          const int row = p / PW, col = p - row * PW;
-          const int iy = 2 * ty0 + row, ix = 2 * tx0 + col;
-          u[k] = (row * 2 + (col & 1)) * PQ + (col >> 1);
-          if (iy < HIN && ix < HIN) {
-            ok[k] = true;
-            const float4* s4 = reinterpret_cast<const float4*>(in + ((size_t)(crop * HIN + iy) * HIN + ix) * CIN + c2 * 16);
-#pragma unroll
-            for (int q = 0; q < 4; q++) x[k][q] = __ldg(s4 + q);
-          }
+      for (int k = 0; k < KI; k++) {
+        const int row = rc[k] >> 8, col = rc[k] & 255;
+        if (rc[k] >= 0 && row < rows_valid && col < cols_valid) {
+          okmask |= 1u << k;
+          x[k] = __ldg(reinterpret_cast<const float4*>(base + (row * HIN + col) * CIN));
         }
       }
     };
     int item = item_lo, c2 = 0, cnt = 0, cur_crop = -1;
-    float4 xn[KPT][4];
-    bool okn[KPT];
-    int un[KPT];
-    if (item < item_hi) load_chunk(item, c2, xn, okn, un);
+    long long tw = 0, t_start = TRACE_T();
+    float4 xn[KI];
+    unsigned okn = 0u;
+    float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+    if (item < item_hi) load_chunk(item, c2, xn, okn);
     while (item < item_hi) {
-      float4 xc[KPT][4];
-      bool okc[KPT];
-      int uc[KPT];
+      float4 xc[KI];
 #pragma unroll
-      for (int k = 0; k < KPT; k++) {
-#pragma unroll
-        for (int q = 0; q < 4; q++) xc[k][q] = xn[k][q];
-        okc[k] = okn[k];
-        uc[k] = un[k];
-      }
+      for (int k = 0; k < KI; k++) xc[k] = xn[k];
+      const unsigned okc = okn;
       const int ci = item, cc2 = c2;
       if (++c2 == C2) { c2 = 0; item++; }
-      if (item < item_hi) load_chunk(item, c2, xn, okn, un);
+      if (item < item_hi) load_chunk(item, c2, xn, okn);
       const int crop = ci / Cfg::TILES;
-      if (crop != cur_crop) {
+      const bool new_crop = crop != cur_crop;
+      if (new_crop) {
         // GroupNorm affine of this crop, shared by all producers:  y = relu(x * ga + gb) == relu((x - mean) * rstd * gamma + beta)
         cur_crop = crop;
         asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
@@ -401,54 +462,54 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
         }
         asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
       }
+      if (C2 > 1 || new_crop) {
+        ga = *reinterpret_cast<const float4*>(&s_ga[cc2 * 16 + q4]);
+        gb = *reinterpret_cast<const float4*>(&s_gb[cc2 * 16 + q4]);
+      }
       const int b = cnt % NBUF;
+      const long long tq = TRACE_T();
       tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
+      tw += TRACE_T() - tq;
       uint8_t* dst = sA + (size_t)b * Cfg::A_BYTES;
 #pragma unroll
-      for (int k = 0; k < KPT; k++) {
-        if (uc[k] < 0) continue;
-        uint32_t hi[8], lo[8];
-        if (okc[k]) {
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            const float4 ga = *reinterpret_cast<const float4*>(&s_ga[cc2 * 16 + q * 4]);
-            const float4 gb = *reinterpret_cast<const float4*>(&s_gb[cc2 * 16 + q * 4]);
-            const float y0 = fmaxf(fmaf(xc[k][q].x, ga.x, gb.x), 0.f), y1 = fmaxf(fmaf(xc[k][q].y, ga.y, gb.y), 0.f);
-            const float y2 = fmaxf(fmaf(xc[k][q].z, ga.z, gb.z), 0.f), y3 = fmaxf(fmaf(xc[k][q].w, ga.w, gb.w), 0.f);
-            tc::split_pack2(y0, y1, hi[q * 2], lo[q * 2]);
-            tc::split_pack2(y2, y3, hi[q * 2 + 1], lo[q * 2 + 1]);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; c++) { hi[c] = 0u; lo[c] = 0u; }
+      for (int k = 0; k < KI; k++) {
+        if (rc[k] < 0) continue;
+        uint2 hi = make_uint2(0u, 0u), lo = hi;
+        if ((okc >> k) & 1u) {
+          const float y0 = fmaxf(fmaf(xc[k].x, ga.x, gb.x), 0.f), y1 = fmaxf(fmaf(xc[k].y, ga.y, gb.y), 0.f);
+          const float y2 = fmaxf(fmaf(xc[k].z, ga.z, gb.z), 0.f), y3 = fmaxf(fmaf(xc[k].w, ga.w, gb.w), 0.f);
+          tc::split_pack2(y0, y1, hi.x, lo.x);
+          tc::split_pack2(y2, y3, hi.y, lo.y);
         }
-        uint8_t* d0 = dst + (size_t)uc[k] * 16;
-        *reinterpret_cast<uint4*>(d0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(d0 + CG) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-        *reinterpret_cast<uint4*>(d0 + Cfg::A_PREC_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(d0 + Cfg::A_PREC_BYTES + CG) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        *reinterpret_cast<uint2*>(dst + soff[k]) = hi;
+        *reinterpret_cast<uint2*>(dst + Cfg::A_PREC_BYTES + soff[k]) = lo;
       }
       tc::fence_async_smem();
       tc::mbar_arrive(&full[b]);
       cnt++;
     }
+    if (tid == 0) { trace_add(TK, 0, tw); trace_add(TK, 1, TRACE_T() - t_start); trace_add(TK, 7, 1); }
   } else if (warp == TC_MMA_WARP) {
-    {
-      const uint32_t idesc = tc::idesc_bf16_f32(128, 32);
-      constexpr uint32_t LBO_A = PH * 2 * PQ * 16, SBO_A = 64 * PQ;
-      int cnt = 0, it = 0;
-      for (int item = item_lo; item < item_hi; item++, it++) {
-        const int a = it & 1;
-        tc::mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
-        const uint32_t d = tm + a * 32;
+    const uint32_t idesc1 = tc::idesc_bf16_f32(128, 2 * NCH), idesc2 = tc::idesc_bf16_f32(128, NCH);
+    constexpr uint32_t LBO_A = PH * 2 * PQ * 16, SBO_A = 64 * PQ, LBO_B = 32 * NCH;
+    int cnt = 0, it = 0;
+    long long twf = 0, twa = 0, t_start = TRACE_T();
+    for (int item = item_lo; item < item_hi; item++, it++) {
+      const int a = it & 1;
+      const long long tq0 = TRACE_T();
+      tc::mbar_wait(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+      twa += TRACE_T() - tq0;
+      const uint32_t d = tm + a * (2 * NCH);
 #pragma unroll 1
-        for (int c2 = 0; c2 < C2; c2++, cnt++) {
-          const int b = cnt % NBUF;
-          tc::mbar_wait(&full[b], (cnt / NBUF) & 1);
-          tc::tc_fence_after();
-          if (tc::elect_one()) {
+      for (int c2 = 0; c2 < C2; c2++, cnt++) {
+        const int b = cnt % NBUF;
+        const long long tq1 = TRACE_T();
+        tc::mbar_wait(&full[b], (cnt / NBUF) & 1);
+        twf += TRACE_T() - tq1;
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
           const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(sA + (size_t)b * Cfg::A_BYTES), LBO_A);
-          const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(sW) + c2 * TAPS * 2048, 512);
+          const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(sW) + c2 * TAPS * Cfg::TAP_BYTES, LBO_B);
           const uint32_t a_hi = tc::desc_hi(SBO_A), b_hi = tc::desc_hi(128);
 #pragma unroll
           for (int ky = 0; ky < KS; ky++) {
@@ -456,81 +517,91 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
             for (int kx = 0; kx < KS; kx++) {
               const int tap = ky * KS + kx;
               const uint32_t al0 = a_lo0 + ((((ky * 2 + (kx & 1)) * PQ + (kx >> 1)) * 16) >> 4);
-              const uint32_t bl0 = b_lo0 + ((tap * 2048) >> 4);
               const uint64_t ah = tc::desc_make(al0, a_hi), al = tc::desc_make(al0 + (Cfg::A_PREC_BYTES >> 4), a_hi);
-              const uint64_t bh = tc::desc_make(bl0, b_hi), bl = tc::desc_make(bl0 + (1024 >> 4), b_hi);
-              tc::mma_bf16(d, ah, bh, idesc, (tap > 0 || c2 > 0) ? 1u : 0u);
-              tc::mma_bf16(d, al, bh, idesc, 1u);
-              tc::mma_bf16(d, ah, bl, idesc, 1u);
+              const uint64_t bd = tc::desc_make(b_lo0 + ((tap * Cfg::TAP_BYTES) >> 4), b_hi);
+              tc::mma_bf16(d, ah, bd, idesc1, (tap > 0 || c2 > 0) ? 1u : 0u);
+              tc::mma_bf16(d, al, bd, idesc2, 1u);
             }
           }
           tc::mma_commit(&empty[b]);
           if (c2 == C2 - 1) tc::mma_commit(&acc_full[a]);
-          }
-          __syncwarp();
         }
+        __syncwarp();
       }
     }
+    if (lane == 0) { trace_add(TK, 2, twf); trace_add(TK, 3, twa); trace_add(TK, 4, TRACE_T() - t_start); }
   } else {
-    // ---------------- epilogue ----------------
+    // ---------------- epilogue: TMEM -> registers -> (+bias) -> global, no shared memory ----------------
     const int q = warp - TC_EPI_WARP0;
     const int m = q * 32 + lane;
-    int it = 0;
+    int it = 0, cur_crop = -1;
+    double d1 = 0.0, d2 = 0.0;
+    long long twe = 0, t_start = TRACE_T();
     for (int item = item_lo; item < item_hi; item++, it++) {
       const int crop = item / Cfg::TILES, tile = item % Cfg::TILES;
       const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
       const int a = it & 1;
+      if (crop != cur_crop) {
+        if (cur_crop >= 0) {
+          d1 = warp_sum_f64(d1);
+          d2 = warp_sum_f64(d2);
+          if (lane == 0) {
+            atomicAdd(out_stats + (size_t)cur_crop * 2, d1);
+            atomicAdd(out_stats + (size_t)cur_crop * 2 + 1, d2);
+          }
+        }
+        cur_crop = crop;
+        d1 = 0.0;
+        d2 = 0.0;
+      }
+      const long long tq = TRACE_T();
       tc::mbar_wait(&acc_full[a], (it >> 1) & 1);
+      twe += TRACE_T() - tq;
       tc::tc_fence_after();
-      float v0[16], v1[16];
-      tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * 32, v0);
-      tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * 32 + 16, v1);
-      tc::tc_fence_before();
-      tc::mbar_arrive(&acc_empty[a]);
       const int oy = ty0 + (m >> 3), ox = tx0 + (m & 7);
       const bool ok = oy < HOUT && ox < HOUT;
+      float* dst = out + (((size_t)crop * HOUT + oy) * HOUT + ox) * COUT + nchunk * NCH;
+      const uint32_t tbase = tm + ((uint32_t)(q * 32) << 16) + a * (2 * NCH);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 16; c++) {
-        v0[c] += s_bias[c];
-        v1[c] += s_bias[16 + c];
+      for (int h = 0; h < NCH / 16; h++) {
+        float vh[16], vl[16];
+        tc::tmem_ld16(tbase + h * 16, vh);
+        tc::tmem_ld16(tbase + NCH + h * 16, vl);
+        if (h == NCH / 16 - 1) {
+          tc::tc_fence_before();
+          tc::mbar_arrive(&acc_empty[a]);
+        }
         if (ok) {
-          s1 += v0[c] + v1[c];
-          s2 = fmaf(v0[c], v0[c], s2);
-          s2 = fmaf(v1[c], v1[c], s2);
+#pragma unroll
+          for (int c = 0; c < 16; c++) {
+            const float bv = (COUT == NCH) ? bias.b[h * 16 + c] : bias.b[nchunk * NCH + h * 16 + c];
+            vh[c] = (vh[c] + vl[c]) + bv;
+            s1 += vh[c];
+            s2 = fmaf(vh[c], vh[c], s2);
+          }
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(dst + h * 16 + c) = make_float4(vh[c], vh[c + 1], vh[c + 2], vh[c + 3]);
         }
       }
-      float* stg = s_stage[q];                 // [32 px][32 ch] per warp, rows padded to 36 floats
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < 16; c += 4) {
-        *reinterpret_cast<float4*>(stg + lane * 36 + c) = make_float4(v0[c], v0[c + 1], v0[c + 2], v0[c + 3]);
-        *reinterpret_cast<float4*>(stg + lane * 36 + 16 + c) = make_float4(v1[c], v1[c + 1], v1[c + 2], v1[c + 3]);
-      }
-      __syncwarp();
-      // 8 lanes per pixel (128 B of this channel chunk): full 128-byte lines per 8 lanes
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int e = lane + 32 * j;
-        const int pl = e >> 3, ch = (e & 7) * 4;
-        const int oyy = ty0 + q * 4 + (pl >> 3), oxx = tx0 + (pl & 7);
-        if (oyy < HOUT && oxx < HOUT)
-          *reinterpret_cast<float4*>(out + (((size_t)crop * HOUT + oyy) * HOUT + oxx) * COUT + nchunk * 32 + ch) =
-              *reinterpret_cast<const float4*>(stg + pl * 36 + ch);
-      }
-      s1 = warp_sum(s1);
-      s2 = warp_sum(s2);
+      d1 += (double)s1;
+      d2 += (double)s2;
+    }
+    if (cur_crop >= 0) {
+      d1 = warp_sum_f64(d1);
+      d2 = warp_sum_f64(d2);
       if (lane == 0) {
-        atomicAdd(out_stats + (size_t)crop * 2, (double)s1);
-        atomicAdd(out_stats + (size_t)crop * 2 + 1, (double)s2);
+        atomicAdd(out_stats + (size_t)cur_crop * 2, d1);
+        atomicAdd(out_stats + (size_t)cur_crop * 2 + 1, d2);
       }
     }
+    if (q == 0 && lane == 0) { trace_add(TK, 5, twe); trace_add(TK, 6, TRACE_T() - t_start); }
   }
   tc::tc_fence_before();
   __syncthreads();
   if (warp == TC_MMA_WARP) {
     __syncwarp();
-    tc::tmem_dealloc(tm, 64);
+    tc::tmem_dealloc(tm, Cfg::TMEM_COLS);
   }
 }
 
@@ -759,7 +830,13 @@ int tc_crop_pack_unpacked(const StriveMap* map, const float* pose, const int32_t
   return 0;
 }
 
-int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_of, const uint8_t* wpack, const float* bias, float* out,
+static BiasArg make_bias(const float* h_bias, int nb) {
+  BiasArg b;
+  for (int i = 0; i < 64; i++) b.b[i] = i < nb ? h_bias[i] : 0.f;
+  return b;
+}
+
+int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_of, const uint8_t* wpack, const float* h_bias, float* out,
                     double* out_stats, uint8_t* packed_crop, int n, cudaStream_t stream) {
   static bool attr = false;
   const size_t smem = T1_WBYTES + T1_NBUF * T1_PATCH_BYTES;
@@ -772,45 +849,47 @@ int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_
   KPROF("crop_pack", stream, crop_pack_kernel<<<gp, 256, 0, stream>>>(*map, pose, map_of, packed_crop, n));
   STRIVE_LAUNCH_CHECK();
   const int items = n * T1_SUPER * T1_SUPER;
-  const int grid = items < num_sms() * 2 ? items : num_sms() * 2;
+  const int grid = items < num_sms() ? items : num_sms();     // the kernel owns all 512 TMEM columns: one CTA per SM
+  const BiasArg bias = make_bias(h_bias, 16);
   KPROF("tc_conv1", stream, tc_conv1_kernel<<<grid, TC_THREADS, smem, stream>>>(packed_crop, wpack, bias, out, out_stats, n));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
 
-template <int CIN, int KS, int HIN, int HOUT, int COUT, int NBUF>
+template <int CIN, int KS, int HIN, int HOUT, int COUT, int NCH, int NBUF>
 static int tc_launch(const char* name, const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack,
-                     const float* bias, float* out, double* out_stats, int n, cudaStream_t stream) {
-  using Cfg = TcCfg<CIN, KS, HIN, HOUT, COUT, NBUF>;
-  static_assert(COUT % 32 == 0 && CIN % 16 == 0, "tc conv tiling");
-  static_assert(Cfg::SMEM <= 226 * 1024, "tc conv shared memory");
-  auto kern = tc_conv_kernel<CIN, KS, HIN, HOUT, COUT, NBUF>;
+                     const float* h_bias, float* out, double* out_stats, int n, cudaStream_t stream) {
+  using Cfg = TcCfg<CIN, KS, HIN, HOUT, COUT, NCH, NBUF>;
+  static_assert(COUT % NCH == 0 && (NCH == 32 || NCH == 64) && CIN % 16 == 0, "tc conv tiling");
+  static_assert(Cfg::SMEM <= 225 * 1024, "tc conv shared memory");
+  auto kern = tc_conv_kernel<CIN, KS, HIN, HOUT, COUT, NCH, NBUF>;
   static bool attr = false;
   if (!attr) {
     STRIVE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     attr = true;
   }
   const int items = n * Cfg::TILES;
-  int gx = num_sms() / (COUT / 32);
+  int gx = num_sms() / (COUT / NCH);
   if (gx < 1) gx = 1;
   if (gx > items) gx = items;
-  dim3 grid(gx, COUT / 32);
+  dim3 grid(gx, COUT / NCH);
+  const BiasArg bias = make_bias(h_bias, COUT);
   KPROF(name, stream, kern<<<grid, TC_THREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
 
-int tc_launch_conv2(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+int tc_launch_conv2(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* h_bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {
-  return tc_launch<16, 5, 125, 61, 32, 3>("tc_conv2", in, in_stats, gam, bet, wpack, bias, out, out_stats, n, stream);
+  return tc_launch<16, 5, 125, 61, 32, 32, 3>("tc_conv2", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
 }
-int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* h_bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {
-  return tc_launch<32, 5, 61, 29, 64, 2>("tc_conv3", in, in_stats, gam, bet, wpack, bias, out, out_stats, n, stream);
+  return tc_launch<32, 5, 61, 29, 64, 32, 2>("tc_conv3", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
 }
-int tc_launch_conv4(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+int tc_launch_conv4(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* h_bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {
-  return tc_launch<64, 3, 29, 14, 64, 3>("tc_conv4", in, in_stats, gam, bet, wpack, bias, out, out_stats, n, stream);
+  return tc_launch<64, 3, 29, 14, 64, 64, 2>("tc_conv4", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
 }
 
 template <int CIN, int KS, int HIN, int HOUT, int COUT, bool FINAL>

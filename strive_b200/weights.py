@@ -100,9 +100,11 @@ def _bytes(t):
 
 
 def pack_tc_weights(sd):
-    """bf16 hi/lo split conv1..conv4 weights in the tcgen05 K-major no-swizzle operand layout (csrc/mapenc_tc.cu).
-    conv1: [ky 7][kq 2][prec 2][khalf 2][ngroup 2][r 8][k 8], k = (kx_l % 2) * 4 + c, taps kx = 4 kq + kx_l (kx = 7 is zero);
-    conv2..4: [nchunk][c2][tap][prec 2][khalf 2][ngroup 4][r 8][k 8], n = 32 nchunk + 8 ngroup + r, c = 16 c2 + 8 khalf + k."""
+    """bf16 hi/lo split conv1..conv4 weights in the tcgen05 K-major no-swizzle operand layout (csrc/mapenc_tc.cu).  The hi and
+    lo halves are STACKED ALONG N (rows n' = prec * NCH + n), so one MMA multiplies an A tile with both:
+    conv1: [ky 7][kq 2][khalf 2][prec 2][ngroup 2][r 8][k 8], k = (kx_l % 2) * 4 + c, taps kx = 4 kq + kx_l (kx = 7 is zero);
+    conv2..4: [nchunk][c2][tap][khalf 2][prec 2][ngroup NCH/8][r 8][k 8], n = NCH nchunk + 8 ngroup + r, c = 16 c2 + 8 khalf + k,
+    NCH = 32 output channels per CTA for conv2 / conv3 and 64 for conv4."""
     g = lambda k: sd[k].detach().to(torch.float32).cpu()
     out = []
     w = g('map_conv.0.weight')                                              # (16,4,7,7)
@@ -111,16 +113,16 @@ def pack_tc_weights(sd):
     for p in _split(w):
         t = p.reshape(2, 8, 4, 7, 2, 2, 2)                                  # (ngroup, r, c, ky, kq, khalf, kxh)
         parts.append(t.permute(3, 4, 5, 0, 1, 6, 2))                        # (ky, kq, khalf, ngroup, r, kxh, c)
-    t = torch.stack(parts, dim=2)                                           # (ky, kq, prec, khalf, ngroup, r, kxh, c)
+    t = torch.stack(parts, dim=3)                                           # (ky, kq, khalf, prec, ngroup, r, kxh, c)
     out.append(_bytes(t))
-    for li, ks in ((1, 5), (2, 5), (3, 3)):
+    for li, ks, nch in ((1, 5, 32), (2, 5, 32), (3, 3, 64)):
         w = g('map_conv.%d.weight' % (3 * li))                              # (Cout, Cin, ks, ks)
         cout, cin = w.size(0), w.size(1)
         parts = []
         for p in _split(w):
-            t = p.reshape(cout // 32, 4, 8, cin // 16, 2, 8, ks * ks)       # (nchunk, ngroup, r, c2, khalf, k, tap)
+            t = p.reshape(cout // nch, nch // 8, 8, cin // 16, 2, 8, ks * ks)  # (nchunk, ngroup, r, c2, khalf, k, tap)
             parts.append(t.permute(0, 3, 6, 4, 1, 2, 5))                    # (nchunk, c2, tap, khalf, ngroup, r, k)
-        t = torch.stack(parts, dim=3)                                       # (nchunk, c2, tap, prec, khalf, ngroup, r, k)
+        t = torch.stack(parts, dim=4)                                       # (nchunk, c2, tap, khalf, prec, ngroup, r, k)
         out.append(_bytes(t))
     # conv5 / conv6 / fc as GEMMs with K = tap * Cin + c in 64-wide chunks: [kchunk][prec][kg 8][ng Cout/8][r 8][kk 8]
     def gemm_pack(wk):                                                      # wk (Cout, K)
