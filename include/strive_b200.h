@@ -49,6 +49,9 @@ int strive_tc_selftest(const float* A, const float* B, const float* X0, const fl
  * CTAs since the last reset ([0] producers blocked on a ring slot, [1] producer total, [2] MMA warp starved, [3] MMA warp
  * blocked on an accumulator, [4] MMA total, [5] epilogue idle, [6] epilogue total, [7] CTAs).  No reference counterpart. */
 int strive_tc_trace(unsigned long long* out32, int reset);
+/* Timing experiments only: bit0/1/2/3 disable the epilogue stores / producer shared stores / producer global loads / MMAs of
+ * conv2..conv4 (results become garbage).  0 = normal operation. */
+int strive_tc_debug(int flags);
 
 /* ---- model weights -------------------------------------------------------------------------------------
  * Replaces: torch state_dict of decoder_net.*, decoder_memory.*, map_conv.*, map_feature.* loaded by

@@ -10,7 +10,7 @@ struct Case {
   int N, sbo_a, lbo_a, a_step, nacc, b_step;
 };
 
-template <int N, int SBO_A, int LBO_A, int A_STEP, int NACC, int B_STEP>
+template <int N, int SBO_A, int LBO_A, int A_STEP, int NACC, int B_STEP, int N2 = 0, int PATTERN = 0>
 __global__ void __launch_bounds__(128) bench(int iters, long long* out) {
   constexpr Case c = {N, SBO_A, LBO_A, A_STEP, NACC, B_STEP};
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(128) bench(int iters, long long* out) {
   if (tid < 32) {
     if (tc::elect_one()) {
       const uint32_t idesc = tc::idesc_bf16_f32(128, c.N);
+      const uint32_t idesc2 = tc::idesc_bf16_f32(128, N2 ? N2 : N);
       const uint32_t a0 = tc::desc_lo(tc::smem_u32(smem), c.lbo_a), ah = tc::desc_hi(c.sbo_a);
       const uint32_t b0 = tc::desc_lo(tc::smem_u32(smem) + 128 * 1024, 128 * (c.N / 8)), bh = tc::desc_hi(128);
       long long t0 = clock64();
@@ -40,7 +41,9 @@ __global__ void __launch_bounds__(128) bench(int iters, long long* out) {
         for (int u = 0; u < 16; u++) {
           const uint32_t al = a0 + ((u * c.a_step) >> 4);
           const uint32_t bl = b0 + (((u % 8) * c.b_step) >> 4);
-          tc::mma_bf16(tm + (u % c.nacc) * c.N, tc::desc_make(al, ah), tc::desc_make(bl, bh), idesc, 1u);
+          // PATTERN 0: alternate N / N2 every MMA;  PATTERN 1: 8 x N then 8 x N2
+          const bool second = N2 != 0 && (PATTERN == 0 ? (u & 1) : (u >= 8));
+          tc::mma_bf16(tm + (u % c.nacc) * c.N, tc::desc_make(al, ah), tc::desc_make(bl, bh), second ? idesc2 : idesc, 1u);
         }
       }
       long long t1 = clock64();
@@ -58,16 +61,17 @@ __global__ void __launch_bounds__(128) bench(int iters, long long* out) {
 }
 
 
-template <int N, int SBO_A, int LBO_A, int A_STEP, int NACC, int B_STEP>
+template <int N, int SBO_A, int LBO_A, int A_STEP, int NACC, int B_STEP, int N2 = 0, int PATTERN = 0>
 void run(long long* d) {
   const int iters = 4096;
-  auto k = bench<N, SBO_A, LBO_A, A_STEP, NACC, B_STEP>;
+  auto k = bench<N, SBO_A, LBO_A, A_STEP, NACC, B_STEP, N2, PATTERN>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   for (int grid : {1, 148}) {
     k<<<grid, 128, 200 * 1024>>>(iters, d);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[2];
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    if (N2) printf("[N2=%d pattern=%d: expected %.1f] ", N2, PATTERN, ((4096.0 + 32 * N) / 128 + (4096.0 + 32 * N2) / 128) / 2);
     printf("N=%3d sbo=%5d lbo=%5d a_step=%4d b_step=%4d nacc=%d grid=%3d : issue %.1f cyc/MMA, complete %.1f cyc/MMA (math floor %d) %s\n", N, SBO_A, LBO_A, A_STEP,
            B_STEP, NACC, grid, (double)h[0] / iters, (double)h[1] / iters, N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
   }
@@ -94,5 +98,10 @@ int main() {
   run<64, 320, 11200, 160, 1, 2048>(d);
   run<96, 320, 11200, 160, 1, 2048>(d);
   run<128, 320, 11200, 160, 1, 2048>(d);
+  // mixed-N sequences (conv2..4 issue N=64 and N=32 MMAs into the same accumulator)
+  run<64, 320, 11200, 160, 1, 2048, 32, 0>(d);
+  run<64, 320, 11200, 160, 1, 2048, 32, 1>(d);
+  run<128, 320, 11200, 160, 1, 2048, 64, 0>(d);
+  run<128, 320, 11200, 160, 1, 2048, 64, 1>(d);
   return 0;
 }

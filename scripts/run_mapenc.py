@@ -20,6 +20,7 @@ for _ in range(REPS):
     f = model.encode_map_poses(pose, mapix, env)
 torch.cuda.synchronize()
 from strive_b200 import _cabi
+_cabi.lib().strive_tc_debug(int(os.environ.get('DBG', '0')))
 _cabi.tc_trace(True)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()

@@ -43,7 +43,7 @@ class StriveLossCfg(C.Structure):
                 ('circ_cx', C.c_void_p), ('lw_un', C.c_void_p)]
 
 
-EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_tc_trace', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl',
+EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_tc_trace', 'strive_tc_debug', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl',
            'strive_mapenc_workspace_bytes', 'strive_mapenc_fwd', 'strive_map_crop', 'strive_decode_tape_bytes',
            'strive_decode_fwd', 'strive_decode_bwd', 'strive_decode_tape_read', 'strive_loss_workspace_bytes',
            'strive_loss_fwd_bwd', 'strive_adam_step']
@@ -86,6 +86,7 @@ def lib():
     L.strive_profile_enable.argtypes = [C.c_int]
     L.strive_tc_selftest.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.strive_tc_trace.argtypes = [vp, C.c_int]
+    L.strive_tc_debug.argtypes = [C.c_int]
     L.strive_profile_report.argtypes = [C.c_char_p, i64]
     L.strive_profile_report.restype = i64
     if L.strive_abi_version() != 1:

@@ -39,6 +39,14 @@ extern "C" int strive_tc_trace(unsigned long long* out32, int reset) {
   return 0;
 }
 
+// Timing experiments only (strive_tc_debug): bit0 epilogue skips its global stores, bit1 producers skip their shared
+// stores, bit2 producers skip their global loads, bit3 the MMA warp issues no MMAs.  Results are garbage when set.
+static int g_tc_dbg = 0;
+extern "C" int strive_tc_debug(int flags) {
+  g_tc_dbg = flags;
+  return 0;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {
@@ -297,15 +305,18 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
         }
         const int oy = oy0 + sy * 16 + oyl, ox = ox0 + sx * 8 + oxl;
         if (oy < 125 && ox < 125) {
-          float* dst = out + (((size_t)crop * 125 + oy) * 125 + ox) * 16;
 #pragma unroll
           for (int c = 0; c < 16; c++) {
             vh[c] = (vh[c] + vl[c]) + bias.b[c];
             s1 += vh[c];
             s2 = fmaf(vh[c], vh[c], s2);
           }
+          // channel-blocked activations [crop][C/8][H][W][8]: a lane stores 32 contiguous bytes per block, a warp 4 rows x 256 B
 #pragma unroll
-          for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(vh[c], vh[c + 1], vh[c + 2], vh[c + 3]);
+          for (int j = 0; j < 2; j++) {
+            float* dst = out + ((((size_t)crop * 2 + j) * 125 + oy) * 125 + ox) * 8;
+            tc::stg256(dst, vh[j * 8], vh[j * 8 + 1], vh[j * 8 + 2], vh[j * 8 + 3], vh[j * 8 + 4], vh[j * 8 + 5], vh[j * 8 + 6], vh[j * 8 + 7]);
+          }
         }
       }
       d1 += (double)s1;
@@ -338,6 +349,12 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
 // and the epilogue adds the two column halves.  Measured SS-mode cost of one M=128,K=16 MMA is (4096 + 32 N) / 128 cycles
 // (scripts/mma_bench.cu): the A-tile fetch dominates, so stacking N is worth 27 % over three N = NCH MMAs.
 // ======================================================================================================
+// (24-warp CTAs with 19 producer warps were measured SLOWER: the producers are bound by shared-memory store issue, not latency)
+#define T2_NPROD 11
+#define T2_MMA_WARP 11
+#define T2_EPI_WARP0 12
+#define T2_THREADS 512
+#define T2_PROD_THREADS (T2_NPROD * 32)
 template <int CIN, int KS, int HIN, int HOUT, int COUT, int NCH_, int NBUF>
 struct TcCfg {
   static constexpr int NCH = NCH_;
@@ -354,14 +371,16 @@ struct TcCfg {
   static constexpr int TILES_X = (HOUT + 7) / 8;
   static constexpr int TILES = TILES_Y * TILES_X;
   static constexpr int TMEM_COLS = 4 * NCH;                  // 2 accumulator sets x (hi part | lo part)
+  static constexpr int DUMP_OFF = (2 * PQ - 1) * 16;         // last slot of the odd-column plane of patch row 0: never written by a real
+                                                             // pixel (PW is odd) nor read by a tap window -> dump slot for the idle work items
   static constexpr size_t SMEM = (size_t)W_BYTES + (size_t)NBUF * A_BYTES;
 };
 
-template <int CIN, int KS, int HIN, int HOUT, int COUT, int NCH, int NBUF>
-__global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
+template <int CIN, int KS, int HIN, int HOUT, int COUT, int NCH, int NBUF, bool OUT_BLK>
+__global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
                                                              const float* __restrict__ gam, const float* __restrict__ bet,
                                                              const uint8_t* __restrict__ wpack, const BiasArg bias,
-                                                             float* __restrict__ out, double* __restrict__ out_stats, int n) {
+                                                             float* __restrict__ out, double* __restrict__ out_stats, int n, int dbg) {
   using Cfg = TcCfg<CIN, KS, HIN, HOUT, COUT, NCH, NBUF>;
   constexpr int PH = Cfg::PH, PW = Cfg::PW, PQ = Cfg::PQ, C2 = Cfg::C2, TAPS = Cfg::TAPS;
   constexpr int TK = CIN == 16 ? 1 : (CIN == 32 ? 2 : 3);
@@ -376,15 +395,15 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
   const int nchunk = (COUT == NCH) ? 0 : (int)blockIdx.y;
   {
     const int4* src = reinterpret_cast<const int4*>(wpack + (size_t)nchunk * Cfg::W_BYTES);
-    for (int i = tid; i < Cfg::W_BYTES / 16; i += TC_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(src + i);
+    for (int i = tid; i < Cfg::W_BYTES / 16; i += T2_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(src + i);
   }
-  for (int i = tid; i < CIN; i += TC_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
+  for (int i = tid; i < CIN; i += T2_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
   if (tid == 0) {
-    for (int b = 0; b < NBUF; b++) { tc::mbar_init(&full[b], TC_PROD_THREADS); tc::mbar_init(&empty[b], 1); }
+    for (int b = 0; b < NBUF; b++) { tc::mbar_init(&full[b], T2_PROD_THREADS); tc::mbar_init(&empty[b], 1); }
     for (int a = 0; a < 2; a++) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 128); }
     tc::fence_mbar_init();
   }
-  if (warp == TC_MMA_WARP) tc::tmem_alloc(&tmem_base, Cfg::TMEM_COLS);
+  if (warp == T2_MMA_WARP) tc::tmem_alloc(&tmem_base, Cfg::TMEM_COLS);
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
@@ -395,54 +414,59 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
   const int item_lo = (int)(((long long)items * blockIdx.x) / gridDim.x);
   const int item_hi = (int)(((long long)items * (blockIdx.x + 1)) / gridDim.x);
 
-  if (warp < TC_NPROD) {
+  if (warp < T2_NPROD) {
     // ---------------- producers ----------------
-    // Work item = 4 channels of one input pixel (one float4).  Thread t owns items t, t + 352, ...: its channel quad
-    // q = t & 3 is fixed (so its GroupNorm affine lives in 8 registers) and the (row, col) of each of its items inside
-    // the input patch never changes: global and shared offsets are computed once.  A warp reads 512 contiguous bytes per
-    // load and writes 16 distinct 8-byte bank slots per half-warp (conflict-free).
-    constexpr int NPIX = PH * PW, NITEM = NPIX * 4;
-    constexpr int KI = (NITEM + TC_PROD_THREADS - 1) / TC_PROD_THREADS;
+    // Work item = 8 channels (one channel block, 32 bytes) of one input pixel; activations are channel-blocked
+    // [crop][C/8][H][W][8].  Thread t owns items t, t + 352, ...: its block half (t & 1) is fixed, so its GroupNorm affine
+    // lives in 16 registers, and the (row, col) of each of its items inside the input patch never changes: global and
+    // shared offsets are computed once.  A warp reads two 512-byte runs per 256-bit load and writes one 16-byte operand row
+    // per item (8 distinct 16-byte bank groups per quarter-warp: conflict-free).
+    constexpr int NPIX = PH * PW, NITEM = NPIX * 2;
+    constexpr int KI = (NITEM + T2_PROD_THREADS - 1) / T2_PROD_THREADS;
     constexpr int CG = PH * 2 * PQ * 16;
-    const int q4 = (tid & 3) * 4;
+    const int half = tid & 1;
     int rc[KI], soff[KI];
 #pragma unroll
     for (int k = 0; k < KI; k++) {
-      const int i = tid + k * TC_PROD_THREADS;
+      const int i = tid + k * T2_PROD_THREADS;
       rc[k] = -1;
-      soff[k] = 0;
+      soff[k] = Cfg::DUMP_OFF;
       if (i < NITEM) {
-        const int p = i >> 2, qq = i & 3;
+        const int p = i >> 1;
         const int row = p / PW, col = p - row * PW;
         rc[k] = (row << 8) | col;
-        soff[k] = ((row * 2 + (col & 1)) * PQ + (col >> 1)) * 16 + (qq & 1) * 8 + (qq >> 1) * CG;
+        soff[k] = ((row * 2 + (col & 1)) * PQ + (col >> 1)) * 16 + half * CG;
       }
     }
-    auto load_chunk = [&](int item, int c2, float4 (&x)[KI], unsigned& okmask) {
+    auto load_chunk = [&](int item, int c2, float (&x)[KI][8], unsigned& okmask) {
       const int crop = item / Cfg::TILES, tile = item - crop * Cfg::TILES;
       const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
       const int rows_valid = HIN - 2 * ty0, cols_valid = HIN - 2 * tx0;
-      const float* base = in + ((size_t)(crop * HIN + 2 * ty0) * HIN + 2 * tx0) * CIN + c2 * 16 + q4;
+      const float* base = in + ((((size_t)crop * (CIN / 8) + c2 * 2 + half) * HIN + 2 * ty0) * HIN + 2 * tx0) * 8;
       okmask = 0u;
 #pragma unroll
       for (int k = 0; k < KI; k++) {
         const int row = rc[k] >> 8, col = rc[k] & 255;
         if (rc[k] >= 0 && row < rows_valid && col < cols_valid) {
           okmask |= 1u << k;
-          x[k] = __ldg(reinterpret_cast<const float4*>(base + (row * HIN + col) * CIN));
+          if (!(dbg & 4)) tc::ldg256(base + (row * HIN + col) * 8, x[k]);
         }
       }
     };
     int item = item_lo, c2 = 0, cnt = 0, cur_crop = -1;
     long long tw = 0, t_start = TRACE_T();
-    float4 xn[KI];
+    float xn[KI][8];
     unsigned okn = 0u;
-    float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga;
+    float ga[8], gb[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { ga[j] = 0.f; gb[j] = 0.f; }
     if (item < item_hi) load_chunk(item, c2, xn, okn);
     while (item < item_hi) {
-      float4 xc[KI];
+      float xc[KI][8];
 #pragma unroll
-      for (int k = 0; k < KI; k++) xc[k] = xn[k];
+      for (int k = 0; k < KI; k++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) xc[k][j] = xn[k][j];
       const unsigned okc = okn;
       const int ci = item, cc2 = c2;
       if (++c2 == C2) { c2 = 0; item++; }
@@ -452,7 +476,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
       if (new_crop) {
         // GroupNorm affine of this crop, shared by all producers:  y = relu(x * ga + gb) == relu((x - mean) * rstd * gamma + beta)
         cur_crop = crop;
-        asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(T2_PROD_THREADS) : "memory");
         if (tid < CIN) {
           float mean, rstd;
           gn_stats(in_stats, crop, (double)CIN * HIN * HIN, mean, rstd);
@@ -460,36 +484,48 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
           s_ga[tid] = g;
           s_gb[tid] = fmaf(-mean, g, s_bet[tid]);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD_THREADS) : "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(T2_PROD_THREADS) : "memory");
       }
       if (C2 > 1 || new_crop) {
-        ga = *reinterpret_cast<const float4*>(&s_ga[cc2 * 16 + q4]);
-        gb = *reinterpret_cast<const float4*>(&s_gb[cc2 * 16 + q4]);
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+          const float4 a4 = *reinterpret_cast<const float4*>(&s_ga[cc2 * 16 + half * 8 + j]);
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_gb[cc2 * 16 + half * 8 + j]);
+          ga[j] = a4.x; ga[j + 1] = a4.y; ga[j + 2] = a4.z; ga[j + 3] = a4.w;
+          gb[j] = b4.x; gb[j + 1] = b4.y; gb[j + 2] = b4.z; gb[j + 3] = b4.w;
+        }
       }
       const int b = cnt % NBUF;
       const long long tq = TRACE_T();
       tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
       tw += TRACE_T() - tq;
       uint8_t* dst = sA + (size_t)b * Cfg::A_BYTES;
+      // transform everything first, then store everything: a store's source registers stay locked until the (congested)
+      // shared-memory pipe has read them, so interleaving would serialise the arithmetic behind the stores
+      uint4 hi[KI], lo[KI];
 #pragma unroll
       for (int k = 0; k < KI; k++) {
-        if (rc[k] < 0) continue;
-        uint2 hi = make_uint2(0u, 0u), lo = hi;
-        if ((okc >> k) & 1u) {
-          const float y0 = fmaxf(fmaf(xc[k].x, ga.x, gb.x), 0.f), y1 = fmaxf(fmaf(xc[k].y, ga.y, gb.y), 0.f);
-          const float y2 = fmaxf(fmaf(xc[k].z, ga.z, gb.z), 0.f), y3 = fmaxf(fmaf(xc[k].w, ga.w, gb.w), 0.f);
-          tc::split_pack2(y0, y1, hi.x, lo.x);
-          tc::split_pack2(y2, y3, hi.y, lo.y);
-        }
-        *reinterpret_cast<uint2*>(dst + soff[k]) = hi;
-        *reinterpret_cast<uint2*>(dst + Cfg::A_PREC_BYTES + soff[k]) = lo;
+        const bool okk = (okc >> k) & 1u;
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) y[j] = okk ? fmaxf(fmaf(xc[k][j], ga[j], gb[j]), 0.f) : 0.f;
+        tc::split_pack2(y[0], y[1], hi[k].x, lo[k].x);
+        tc::split_pack2(y[2], y[3], hi[k].y, lo[k].y);
+        tc::split_pack2(y[4], y[5], hi[k].z, lo[k].z);
+        tc::split_pack2(y[6], y[7], hi[k].w, lo[k].w);
+      }
+      if (!(dbg & 2))
+#pragma unroll
+      for (int k = 0; k < KI; k++) {
+        *reinterpret_cast<uint4*>(dst + soff[k]) = hi[k];                            // items beyond the patch land in the dump slot
+        *reinterpret_cast<uint4*>(dst + Cfg::A_PREC_BYTES + soff[k]) = lo[k];
       }
       tc::fence_async_smem();
       tc::mbar_arrive(&full[b]);
       cnt++;
     }
     if (tid == 0) { trace_add(TK, 0, tw); trace_add(TK, 1, TRACE_T() - t_start); trace_add(TK, 7, 1); }
-  } else if (warp == TC_MMA_WARP) {
+  } else if (warp == T2_MMA_WARP) {
     const uint32_t idesc1 = tc::idesc_bf16_f32(128, 2 * NCH), idesc2 = tc::idesc_bf16_f32(128, NCH);
     constexpr uint32_t LBO_A = PH * 2 * PQ * 16, SBO_A = 64 * PQ, LBO_B = 32 * NCH;
     int cnt = 0, it = 0;
@@ -519,8 +555,10 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
               const uint32_t al0 = a_lo0 + ((((ky * 2 + (kx & 1)) * PQ + (kx >> 1)) * 16) >> 4);
               const uint64_t ah = tc::desc_make(al0, a_hi), al = tc::desc_make(al0 + (Cfg::A_PREC_BYTES >> 4), a_hi);
               const uint64_t bd = tc::desc_make(b_lo0 + ((tap * Cfg::TAP_BYTES) >> 4), b_hi);
-              tc::mma_bf16(d, ah, bd, idesc1, (tap > 0 || c2 > 0) ? 1u : 0u);
-              tc::mma_bf16(d, al, bd, idesc2, 1u);
+              if (!(dbg & 8)) {
+                tc::mma_bf16(d, ah, bd, idesc1, (tap > 0 || c2 > 0) ? 1u : 0u);
+                tc::mma_bf16(d, al, bd, idesc2, 1u);
+              }
             }
           }
           tc::mma_commit(&empty[b]);
@@ -532,7 +570,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
     if (lane == 0) { trace_add(TK, 2, twf); trace_add(TK, 3, twa); trace_add(TK, 4, TRACE_T() - t_start); }
   } else {
     // ---------------- epilogue: TMEM -> registers -> (+bias) -> global, no shared memory ----------------
-    const int q = warp - TC_EPI_WARP0;
+    const int q = warp - T2_EPI_WARP0;
     const int m = q * 32 + lane;
     int it = 0, cur_crop = -1;
     double d1 = 0.0, d2 = 0.0;
@@ -560,7 +598,6 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
       tc::tc_fence_after();
       const int oy = ty0 + (m >> 3), ox = tx0 + (m & 7);
       const bool ok = oy < HOUT && ox < HOUT;
-      float* dst = out + (((size_t)crop * HOUT + oy) * HOUT + ox) * COUT + nchunk * NCH;
       const uint32_t tbase = tm + ((uint32_t)(q * 32) << 16) + a * (2 * NCH);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -580,8 +617,17 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
             s1 += vh[c];
             s2 = fmaf(vh[c], vh[c], s2);
           }
+          if (!(dbg & 1)) {
 #pragma unroll
-          for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(dst + h * 16 + c) = make_float4(vh[c], vh[c + 1], vh[c + 2], vh[c + 3]);
+            for (int j = 0; j < 2; j++) {
+              const int ch0 = nchunk * NCH + h * 16 + j * 8;
+              // OUT_BLK: channel-blocked [crop][C/8][H][W][8] (a warp stores 4 rows x 256 contiguous bytes per instruction);
+              // otherwise plain NHWC for the GEMM-style conv5 kernel
+              float* dst = OUT_BLK ? out + ((((size_t)crop * (COUT / 8) + (ch0 >> 3)) * HOUT + oy) * HOUT + ox) * 8
+                                   : out + (((size_t)crop * HOUT + oy) * HOUT + ox) * COUT + ch0;
+              tc::stg256(dst, vh[j * 8], vh[j * 8 + 1], vh[j * 8 + 2], vh[j * 8 + 3], vh[j * 8 + 4], vh[j * 8 + 5], vh[j * 8 + 6], vh[j * 8 + 7]);
+            }
+          }
         }
       }
       d1 += (double)s1;
@@ -599,7 +645,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const float* __rest
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == TC_MMA_WARP) {
+  if (warp == T2_MMA_WARP) {
     __syncwarp();
     tc::tmem_dealloc(tm, Cfg::TMEM_COLS);
   }
@@ -856,13 +902,13 @@ int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_
   return 0;
 }
 
-template <int CIN, int KS, int HIN, int HOUT, int COUT, int NCH, int NBUF>
+template <int CIN, int KS, int HIN, int HOUT, int COUT, int NCH, int NBUF, bool OUT_BLK>
 static int tc_launch(const char* name, const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack,
                      const float* h_bias, float* out, double* out_stats, int n, cudaStream_t stream) {
   using Cfg = TcCfg<CIN, KS, HIN, HOUT, COUT, NCH, NBUF>;
   static_assert(COUT % NCH == 0 && (NCH == 32 || NCH == 64) && CIN % 16 == 0, "tc conv tiling");
   static_assert(Cfg::SMEM <= 225 * 1024, "tc conv shared memory");
-  auto kern = tc_conv_kernel<CIN, KS, HIN, HOUT, COUT, NCH, NBUF>;
+  auto kern = tc_conv_kernel<CIN, KS, HIN, HOUT, COUT, NCH, NBUF, OUT_BLK>;
   static bool attr = false;
   if (!attr) {
     STRIVE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -874,22 +920,22 @@ static int tc_launch(const char* name, const float* in, const double* in_stats, 
   if (gx > items) gx = items;
   dim3 grid(gx, COUT / NCH);
   const BiasArg bias = make_bias(h_bias, COUT);
-  KPROF(name, stream, kern<<<grid, TC_THREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
+  KPROF(name, stream, kern<<<grid, T2_THREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n, g_tc_dbg));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
 
 int tc_launch_conv2(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* h_bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {
-  return tc_launch<16, 5, 125, 61, 32, 32, 3>("tc_conv2", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
+  return tc_launch<16, 5, 125, 61, 32, 32, 3, true>("tc_conv2", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
 }
 int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* h_bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {
-  return tc_launch<32, 5, 61, 29, 64, 32, 2>("tc_conv3", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
+  return tc_launch<32, 5, 61, 29, 64, 32, 2, true>("tc_conv3", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
 }
 int tc_launch_conv4(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* h_bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {
-  return tc_launch<64, 3, 29, 14, 64, 64, 2>("tc_conv4", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
+  return tc_launch<64, 3, 29, 14, 64, 64, 2, false>("tc_conv4", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
 }
 
 template <int CIN, int KS, int HIN, int HOUT, int COUT, bool FINAL>

@@ -49,6 +49,21 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// L2 prefetch of a contiguous global range (16-byte aligned, size multiple of 16): no register or shared-memory destination
+__device__ __forceinline__ void prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256), pointer 32-byte aligned
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h) : "memory");
+}
+
 // ---- proxies / fences --------------------------------------------------------------------------------------
 // generic-proxy shared-memory writes (st.shared) -> visible to the async proxy (tensor-core descriptor reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
