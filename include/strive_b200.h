@@ -90,7 +90,8 @@ typedef struct StriveMap {
   int32_t M, C, H, W;
   const float* lin_l;          /* (256) torch.linspace(bounds[0], bounds[2], 256) float32, nuscenes_utils.py:219 */
   const float* lin_w;          /* (256) torch.linspace(bounds[1], bounds[3], 256) float32, nuscenes_utils.py:220 */
-  const uint8_t* packed;       /* (M,H,W) uint8: bit c = (raster[m,c,y,x] != 0); the raster must be binary (nuScenes get_map_mask) */
+  const uint8_t* packed;       /* (M,H,packed_pitch) uint8: bit c = (raster[m,c,y,x] != 0); the raster must be binary (nuScenes get_map_mask) */
+  int32_t packed_pitch;        /* bytes per row of `packed`: >= W, a multiple of 16 (rows are staged with 16-byte cp.async), base 16-byte aligned */
 } StriveMap;
 
 /* ---- map encoder ---------------------------------------------------------------------------------------

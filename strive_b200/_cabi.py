@@ -25,7 +25,7 @@ class StriveScene(C.Structure):
 
 class StriveMap(C.Structure):
     _fields_ = [('raster', C.c_void_p), ('dx', C.c_void_p), ('M', C.c_int32), ('C', C.c_int32), ('H', C.c_int32),
-                ('W', C.c_int32), ('lin_l', C.c_void_p), ('lin_w', C.c_void_p), ('packed', C.c_void_p)]
+                ('W', C.c_int32), ('lin_l', C.c_void_p), ('lin_w', C.c_void_p), ('packed', C.c_void_p), ('packed_pitch', C.c_int32)]
 
 
 class StriveLossCfg(C.Structure):

@@ -94,58 +94,165 @@ __device__ __forceinline__ int round_div_exact(float g, double dx, double inv) {
 // ------------------------------------------------------------------------------------------------------
 // crop_pack: the rotated nearest-neighbour crop itself (exact get_map_obs arithmetic), written ONCE per crop as
 // [256][256] bytes with bit c = layer c (64 KB per crop instead of the reference's 256 KB uint8 + 4 MB of int64 indices).
-// A plain elementwise kernel: thousands of resident warps hide the gather latency; conv1 then only expands bytes.
-// Block = 4 crop rows (1024 samples); samples within 0.49 of a rounding tie are resolved exactly after the fast pass.
+// Block = one 64 x 64 tile of crop pixels.  Its footprint in the raster is a rotated square of ~77 px: the bounding box
+// (<= 116 x 116 px at 4 px/m) is first copied into shared memory with coalesced 32-bit loads, then every sample is a
+// shared-memory byte read (a direct byte gather costs ~20 L1 sectors per warp instruction: the v2 kernel sat at 92 % of
+// the L1 throughput).  Two block-uniform code paths with identical pixel-index arithmetic:
+//   CLEAN   : pose finite, |q| < 5e4, the whole footprint inside the raster and staged -> no NaN / range / bounds tests
+//   generic : everything else (NaN poses, crops over the map border, footprints that do not fit) reads global memory
+// Samples within 0.49 of a rounding tie are resolved exactly (float64 quotient) after the fast pass.
+// A thread owns 4 consecutive pixels of 4 rows -> 32-bit stores.
 // ------------------------------------------------------------------------------------------------------
-#define CP_ROWS 4
-__global__ void __launch_bounds__(256) crop_pack_kernel(StriveMap map, const float* __restrict__ pose, const int32_t* __restrict__ map_of,
+#define CP_TILE 64
+#define CP_BOX_BYTES 18432
+template <bool CLEAN>
+__device__ __forceinline__ void crop_pack_rows(const uint8_t* __restrict__ s_box, const uint8_t* __restrict__ base, const float* __restrict__ lin_l,
+                                               int H, int W, int P, int bx0, int by0, int bw, int bh, int pitch, float px, float py, float hc,
+                                               float hs, float inv0f, float inv1f, float thr, const float (&whs)[4], const float (&whc)[4],
+                                               int row0, int rg, int c4, unsigned short* s_q, int* s_nq, uint8_t* dst_tile) {
+  unsigned mask = 0u;     // bit 4j + k: sample (row j, pixel k) of this thread needs the exact path
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int r = rg + 16 * j;
+    const float l = __ldg(lin_l + row0 + r);
+    const float lhc = __fmul_rn(l, hc), lhs = __fmul_rn(l, hs);     // gen_car_coords (:232-233), every product rounded on its own
+    uint32_t word = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float gx = __fadd_rn(__fsub_rn(lhc, whs[k]), px);
+      float gy = __fadd_rn(__fadd_rn(lhs, whc[k]), py);
+      if (!CLEAN) {
+        if (isnan(gx)) gx = 0.f;     // xys[torch.isnan(xys)] = 0.0 (:251)
+        if (isnan(gy)) gy = 0.f;
+      }
+      // |fp32 quotient - float64 quotient| <= |q| 2^-23: accept the fp32 rounding unless it is that close to a .5 tie (thr)
+      const float qx = gx * inv0f, qy = gy * inv1f;
+      float rx, ry;
+      int xp, yp;
+      if (CLEAN) {
+        // |q| < 5e4 here: q + 1.5 * 2^23 rounds to the nearest integer (ties to even, like rintf) and carries it in its low
+        // mantissa bits -- FADD/IADD instead of the quarter-rate FRND + F2I
+        const float mx = __fadd_rn(qx, 12582912.f), my = __fadd_rn(qy, 12582912.f);
+        rx = __fsub_rn(mx, 12582912.f); ry = __fsub_rn(my, 12582912.f);
+        xp = __float_as_int(mx) - 0x4B400000; yp = __float_as_int(my) - 0x4B400000;
+      } else {
+        rx = rintf(qx); ry = rintf(qy);
+        xp = (int)rx; yp = (int)ry;
+      }
+      bool slow = !(fabsf(qx - rx) < thr && fabsf(qy - ry) < thr);
+      if (!CLEAN) slow = slow || !(fabsf(qx) < 6e4f && fabsf(qy) < 6e4f);
+      mask |= slow ? (1u << (4 * j + k)) : 0u;
+      unsigned v;
+      if (CLEAN) {
+        v = s_box[(yp - by0) * pitch + (xp - bx0)];     // always inside the staged box (a tie sample is overwritten below)
+      } else {
+        if (slow || (unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }     // :260-262
+        const unsigned ux = (unsigned)(xp - bx0), uy = (unsigned)(yp - by0);
+        v = (ux < (unsigned)bw && uy < (unsigned)bh) ? (unsigned)s_box[uy * pitch + ux]
+                                                     : (unsigned)__ldg(base + (size_t)((unsigned)yp * (unsigned)P + (unsigned)xp));
+      }
+      word |= (v & 15u) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(dst_tile + r * 256 + c4) = word;
+  }
+  if (mask) {
+    int at = atomicAdd(s_nq, __popc(mask));
+    while (mask) {
+      const int bit = __ffs(mask) - 1;
+      mask &= mask - 1;
+      s_q[at++] = (unsigned short)((rg + 16 * (bit >> 2)) * CP_TILE + c4 + (bit & 3));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 5) crop_pack_kernel(StriveMap map, const float* __restrict__ pose, const int32_t* __restrict__ map_of,
                                                         uint8_t* __restrict__ packed_crop, int n) {
-  __shared__ unsigned short s_q[CP_ROWS * 256];
+  __shared__ __align__(16) uint8_t s_box[CP_BOX_BYTES];
+  __shared__ unsigned short s_q[CP_TILE * CP_TILE];
   __shared__ int s_nq;
-  const int crop = blockIdx.y, row0 = blockIdx.x * CP_ROWS, tid = threadIdx.x;
-  if (tid == 0) s_nq = 0;
+  __shared__ int s_geo[6];     // bx0, by0, bw, bh, pitch, clean
+  __shared__ float s_thr;
+  const int crop = blockIdx.y, tid = threadIdx.x;
+  const int row0 = (blockIdx.x >> 2) * CP_TILE, col0 = (blockIdx.x & 3) * CP_TILE;
   const int m = map_of[crop];
   const float px = pose[crop * 4 + 0], py = pose[crop * 4 + 1], hc = pose[crop * 4 + 2], hs = pose[crop * 4 + 3];
   const double dx0 = map.dx[m * 2 + 0], dx1 = map.dx[m * 2 + 1];
   const double inv0 = 1.0 / dx0, inv1 = 1.0 / dx1;
   const float inv0f = (float)inv0, inv1f = (float)inv1;
-  const uint8_t* base = map.packed + (size_t)m * map.H * map.W;
-  const int H = map.H, W = map.W;
-  const float w = __ldg(map.lin_w + tid);
-  const float whs = __fmul_rn(w, hs), whc = __fmul_rn(w, hc);     // gen_car_coords (:232-233), every product rounded on its own
-  uint8_t* dst = packed_crop + ((size_t)crop * 256 + row0) * 256 + tid;
-  __syncthreads();
-  unsigned off[CP_ROWS];
+  const int H = map.H, W = map.W, P = map.packed_pitch;
+  const uint8_t* base = map.packed + (size_t)m * H * P;
+  if (tid == 0) {
+    // bounding box of the tile in raster pixels from its 4 corners (+-2 px: the footprint is their convex hull up to rounding)
+    s_nq = 0;
+    int bx0 = 0, by0 = 0, bw = 0, bh = 0, pitch = 4, clean = 0;
+    const float l0 = __ldg(map.lin_l + row0), l1 = __ldg(map.lin_l + row0 + CP_TILE - 1);
+    const float w0 = __ldg(map.lin_w + col0), w1 = __ldg(map.lin_w + col0 + CP_TILE - 1);
+    float xmin = 3e38f, xmax = -3e38f, ymin = 3e38f, ymax = -3e38f;
+    bool finite = true;
 #pragma unroll
-  for (int r = 0; r < CP_ROWS; r++) {
-    const float l = __ldg(map.lin_l + row0 + r);
-    float gx = __fadd_rn(__fsub_rn(__fmul_rn(l, hc), whs), px);
-    float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, hs), whc), py);
-    if (isnan(gx)) gx = 0.f;     // xys[torch.isnan(xys)] = 0.0 (:251)
-    if (isnan(gy)) gy = 0.f;
-    // the fp32 quotient is within 0.002 px of the float64 one for |q| < 6e4: accept unless it is near a .5 tie
-    const float qx = gx * inv0f, qy = gy * inv1f;
-    const float rx = rintf(qx), ry = rintf(qy);
-    const bool slow = !(fabsf(qx - rx) < 0.49f && fabsf(qy - ry) < 0.49f && fabsf(qx) < 6e4f && fabsf(qy) < 6e4f);
-    int xp = (int)rx, yp = (int)ry;
-    if (slow) s_q[atomicAdd(&s_nq, 1)] = (unsigned short)(r * 256 + tid);
-    if ((unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }     // :260-262
-    off[r] = slow ? 0xffffffffu : (unsigned)yp * (unsigned)W + (unsigned)xp;
+    for (int k = 0; k < 4; k++) {
+      const float l = (k & 1) ? l1 : l0, w = (k & 2) ? w1 : w0;
+      const float qx = (l * hc - w * hs + px) * inv0f, qy = (l * hs + w * hc + py) * inv1f;
+      finite = finite && fabsf(qx) < 5e4f && fabsf(qy) < 5e4f;     // false for NaN too
+      xmin = fminf(xmin, qx); xmax = fmaxf(xmax, qx); ymin = fminf(ymin, qy); ymax = fmaxf(ymax, qy);
+    }
+    // every |term| of gx, gy finite and small: no intermediate can overflow or become NaN in the sample arithmetic
+    finite = finite && fabsf(px) < 1e6f && fabsf(py) < 1e6f && fabsf(hc) < 1e3f && fabsf(hs) < 1e3f;
+    if (finite) {
+      const int fx0 = (int)floorf(xmin) - 2, fx1 = (int)ceilf(xmax) + 2, fy0 = (int)floorf(ymin) - 2, fy1 = (int)ceilf(ymax) + 2;
+      int x0 = max(fx0 & ~15, 0), y0 = max(fy0, 0), x1 = min(fx1, W - 1), y1 = min(fy1, H - 1);
+      if (x1 >= x0 && y1 >= y0) {
+        const int chunks = (x1 - x0 + 16) >> 4;          // 16-byte chunks; x0 and the row pitch P are multiples of 16: a row segment never leaves its row
+        const int pc = chunks | 1;                        // odd chunk pitch spreads rows over the banks
+        if (chunks <= 16 && (y1 - y0 + 1) * pc * 16 <= CP_BOX_BYTES) {
+          bx0 = x0; by0 = y0; bw = chunks * 16; bh = y1 - y0 + 1; pitch = pc * 16;
+          clean = (fx0 >= 0 && fy0 >= 0 && fx1 <= W - 1 && fy1 <= H - 1) ? 1 : 0;
+        }
+      }
+    }
+    s_geo[0] = bx0; s_geo[1] = by0; s_geo[2] = bw; s_geo[3] = bh; s_geo[4] = pitch; s_geo[5] = clean;
+    // tie margin: 4e-7 |q| (> 3x the fp32 quotient error bound) when |q| is known, else the 0.01 that covers |q| < 6e4
+    const float qabs = fmaxf(fmaxf(fabsf(xmin), fabsf(xmax)), fmaxf(fabsf(ymin), fabsf(ymax)));
+    s_thr = clean ? 0.5f - fmaxf(qabs * 4e-7f + 1e-5f, 1e-4f) : 0.49f;
   }
-#pragma unroll
-  for (int r = 0; r < CP_ROWS; r++)
-    if (off[r] != 0xffffffffu) dst[r * 256] = __ldg(base + off[r]) & 15u;
   __syncthreads();
+  const int bx0 = s_geo[0], by0 = s_geo[1], bw = s_geo[2], bh = s_geo[3], pitch = s_geo[4];
+  const bool clean = s_geo[5] != 0;
+  const float thr = s_thr;
+  {
+    // a warp copies 2 box rows per step (16 lanes x 16 bytes each); cp.async keeps every load of the box in flight at once
+    // (a register-staged loop serialised ~14 L2 round trips per warp and cost half of the kernel's instructions)
+    const int lane = tid & 31, ch = lane & 15;
+    if (ch * 16 < bw) {
+      const uint8_t* src = base + (size_t)by0 * P + bx0 + ch * 16;
+      const uint32_t sdst = tc::smem_u32(s_box) + ch * 16;
+      for (int r = (tid >> 5) * 2 + (lane >> 4); r < bh; r += 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst + (uint32_t)(r * pitch)), "l"(src + (size_t)r * P) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const int rg = tid >> 4, c4 = (tid & 15) * 4;
+  const float4 w4 = __ldg(reinterpret_cast<const float4*>(map.lin_w + col0 + c4));
+  const float whs[4] = {__fmul_rn(w4.x, hs), __fmul_rn(w4.y, hs), __fmul_rn(w4.z, hs), __fmul_rn(w4.w, hs)};
+  const float whc[4] = {__fmul_rn(w4.x, hc), __fmul_rn(w4.y, hc), __fmul_rn(w4.z, hc), __fmul_rn(w4.w, hc)};
+  uint8_t* dst_tile = packed_crop + ((size_t)crop * 256 + row0) * 256 + col0;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (clean)
+    crop_pack_rows<true>(s_box, base, map.lin_l, H, W, P, bx0, by0, bw, bh, pitch, px, py, hc, hs, inv0f, inv1f, thr, whs, whc, row0, rg, c4, s_q, &s_nq, dst_tile);
+  else
+    crop_pack_rows<false>(s_box, base, map.lin_l, H, W, P, bx0, by0, bw, bh, pitch, px, py, hc, hs, inv0f, inv1f, thr, whs, whc, row0, rg, c4, s_q, &s_nq, dst_tile);
+  __syncthreads();     // also orders the word stores above before the byte patches below (same block)
   for (int k = tid; k < s_nq; k += 256) {
-    const int r = s_q[k] >> 8, c = s_q[k] & 255;
-    const float l = __ldg(map.lin_l + row0 + r), wc = __ldg(map.lin_w + c);
-    float gx = __fadd_rn(__fsub_rn(__fmul_rn(l, hc), __fmul_rn(wc, hs)), px);
-    float gy = __fadd_rn(__fadd_rn(__fmul_rn(l, hs), __fmul_rn(wc, hc)), py);
+    const int rr = s_q[k] >> 6, cc = s_q[k] & 63;
+    const float ll = __ldg(map.lin_l + row0 + rr), wc = __ldg(map.lin_w + col0 + cc);
+    float gx = __fadd_rn(__fsub_rn(__fmul_rn(ll, hc), __fmul_rn(wc, hs)), px);
+    float gy = __fadd_rn(__fadd_rn(__fmul_rn(ll, hs), __fmul_rn(wc, hc)), py);
     if (isnan(gx)) gx = 0.f;
     if (isnan(gy)) gy = 0.f;
     int xp = round_div_exact(gx, dx0, inv0), yp = round_div_exact(gy, dx1, inv1);
     if ((unsigned)yp >= (unsigned)H || (unsigned)xp >= (unsigned)W) { xp = 0; yp = 0; }
-    packed_crop[((size_t)crop * 256 + row0 + r) * 256 + c] = __ldg(base + (size_t)((unsigned)yp * (unsigned)W + (unsigned)xp)) & 15u;
+    dst_tile[rr * 256 + cc] = __ldg(base + (size_t)((unsigned)yp * (unsigned)P + (unsigned)xp)) & 15u;
   }
 }
 
@@ -864,9 +971,10 @@ __global__ void crop_unpack_kernel(const uint8_t* __restrict__ packed_crop, uint
 }
 int tc_crop_pack_unpacked(const StriveMap* map, const float* pose, const int32_t* map_of, int n, uint8_t* out, cudaStream_t stream) {
   STRIVE_CHECK(map->packed != nullptr && map->C <= 4, STRIVE_EINVAL, "crop_pack needs StriveMap.packed and <= 4 layers");
+  STRIVE_CHECK(map->packed_pitch >= map->W && (map->packed_pitch & 15) == 0 && ((uintptr_t)map->packed & 15) == 0, STRIVE_EINVAL, "StriveMap.packed_pitch must be >= W and a multiple of 16, packed 16-byte aligned");
   uint8_t* tmp = nullptr;
   STRIVE_CUDA(cudaMallocAsync((void**)&tmp, (size_t)n * 65536, stream));
-  dim3 gp(256 / CP_ROWS, n);
+  dim3 gp(16, n);
   KPROF("crop_pack", stream, crop_pack_kernel<<<gp, 256, 0, stream>>>(*map, pose, map_of, tmp, n));
   STRIVE_LAUNCH_CHECK();
   const size_t tot = (size_t)n * 65536;
@@ -891,7 +999,8 @@ int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_
     attr = true;
   }
   STRIVE_CHECK(map->packed != nullptr, STRIVE_EINVAL, "tensor-core map encoder needs StriveMap.packed");
-  dim3 gp(256 / CP_ROWS, n);
+  STRIVE_CHECK(map->packed_pitch >= map->W && (map->packed_pitch & 15) == 0 && ((uintptr_t)map->packed & 15) == 0, STRIVE_EINVAL, "StriveMap.packed_pitch must be >= W and a multiple of 16, packed 16-byte aligned");
+  dim3 gp(16, n);
   KPROF("crop_pack", stream, crop_pack_kernel<<<gp, 256, 0, stream>>>(*map, pose, map_of, packed_crop, n));
   STRIVE_LAUNCH_CHECK();
   const int items = n * T1_SUPER * T1_SUPER;

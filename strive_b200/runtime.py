@@ -70,11 +70,13 @@ class MapEnv(object):
         if int(self.nusc_raster.max()) > 1:
             raise RuntimeError('strive_b200: the map raster must be binary (0/1 layers as produced by get_map_mask, map_env.py:106-118)')
         # one byte per pixel, bit c = layer c: the crop gather then touches 1 byte instead of C scattered bytes
-        self._packed = torch.zeros((M, H, Wd), dtype=torch.uint8, device=self.device)
+        # rows padded to a multiple of 16 bytes: crop_pack stages raster rows with 16-byte cp.async
+        Wp = (Wd + 15) // 16 * 16
+        self._packed = torch.zeros((M, H, Wp), dtype=torch.uint8, device=self.device)
         for c in range(min(Cc, 8)):
-            self._packed |= (self.nusc_raster[:, c] << c)
+            self._packed[:, :, :Wd] |= (self.nusc_raster[:, c] << c)
         self.cstruct = _cabi.StriveMap(_cabi.dptr(self.nusc_raster), _cabi.dptr(self.nusc_dx), M, Cc, H, Wd,
-                                       _cabi.dptr(self._lin_l), _cabi.dptr(self._lin_w), _cabi.dptr(self._packed))
+                                       _cabi.dptr(self._lin_l), _cabi.dptr(self._lin_w), _cabi.dptr(self._packed), Wp)
 
     def crop_poses(self, pose_un, mapixes):
         """(N,4) unnormalised poses -> (N,C,256,256) uint8 (reference get_map_obs, nuscenes_utils.py:236-264)."""

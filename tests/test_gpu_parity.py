@@ -109,6 +109,40 @@ def test_map_crop_bit_exact():
     assert np.array_equal(got[:6].long().sum(dim=3).numpy(), g['crop_rowsum'])
 
 
+def test_map_crop_bit_exact_odd_raster_and_extreme_poses():
+    """Raster whose width is not a multiple of 16 (padded row pitch of the packed copy), anisotropic float64 resolution,
+    poses on every border, far outside the map, +-inf / NaN / huge: the staged (shared-memory) and direct (global) sample
+    paths of crop_pack must both reproduce get_map_obs bit for bit."""
+    import strive_b200
+    dev, _, _ = ctx()
+    raster, dx, _ = world()
+    H2, W2 = 1203, 1270 - 3
+    r2 = raster[:, :, :H2, :W2].contiguous()
+    dx2 = torch.tensor([[0.25, 0.2], [0.3, 0.25]], dtype=torch.float64)
+    env2 = strive_b200.MapEnv(r2, dx2, device=dev)
+    gen = torch.Generator().manual_seed(9)
+    n = 40
+    xy = torch.rand(n, 2, generator=gen) * 280.0 + 5.0
+    ang = torch.rand(n, generator=gen) * 6.28318
+    pose = torch.cat([xy, torch.cos(ang)[:, None], torch.sin(ang)[:, None]], 1)
+    pose[0] = torch.tensor([0.0, 0.0, 1.0, 0.0])
+    pose[1] = torch.tensor([W2 * 0.25, H2 * 0.2, -1.0, 0.0])
+    pose[2] = torch.tensor([-500.0, 40.0, 0.0, 1.0])
+    pose[3] = torch.tensor([1e7, -1e7, 0.6, 0.8])
+    pose[4] = torch.tensor([float('inf'), 10.0, 1.0, 0.0])
+    pose[5] = torch.tensor([50.0, 60.0, float('nan'), 0.5])
+    pose[6] = torch.tensor([3.0e9, 3.0e9, 1.0, 0.0])
+    pose[7] = torch.tensor([100.0, 100.0, 0.0, 0.0])          # degenerate heading: every sample lands on one pixel
+    pose[8] = torch.tensor([100.125, 100.1, 1.0, 0.0])        # axis aligned: many exact .5 ties in the quotient
+    pose[9] = torch.tensor([W2 * 0.25 - 20.0, 30.0, 0.70710678, 0.70710678])
+    mapix = torch.randint(0, 2, (n,), generator=gen)
+    ref = O.map_crop(r2, dx2, pose, mapix)
+    got = env2.crop_poses(pose.to(dev), mapix.to(dev)).cpu()
+    nbad = int((ref != got).sum())
+    diag('map_crop [odd raster %dx%d, anisotropic dx, extreme poses]: %d poses, mismatching pixels = %d of %d' % (H2, W2, n, nbad, ref.numel()))
+    assert nbad == 0
+
+
 def test_map_encoder_feature():
     dev, model, env = ctx()
     raster, dx, sd = world()
