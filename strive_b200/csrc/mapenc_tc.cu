@@ -759,6 +759,341 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __rest
 }
 
 // ======================================================================================================
+// conv3 (32 -> 64, k5 s2): all 64 output channels in ONE CTA, so the MMAs run at N = 128 ([W_hi | W_lo] stacked, the SS-mode
+// rate reaches the math floor at N >= 128: scripts/mma_bench2.cu) and every input tile is staged once instead of once per
+// 32-channel chunk.  The hi/lo weights of both 16-channel K chunks are 204.8 KB -- more than shared memory -- so only ONE
+// chunk (102.4 KB) is resident and the K chunks are the OUTER loop over a pair of tiles whose accumulators wait in TMEM:
+//     pair p:  (t0, c) (t1, c)   [weights -> chunk 1-c]   (t0, 1-c) (t1, 1-c)        c = p & 1
+// so the weights are swapped once per pair and the next pair starts with the chunk that is already resident.  The swap is
+// two cp.async.bulk halves (taps 0-12 / 13-24), each issued by the loader warp as soon as the MMAs that read the old half
+// have completed (tcgen05.commit -> w_free[h]), i.e. the first half streams in while the tensor core still works on taps
+// 13-24.  4 accumulators of 128 columns = all 512 TMEM columns: the epilogue of pair p overlaps the MMAs of pair p + 1.
+// Roles: warps 0-9 producers, warp 10 weight loader, warp 11 MMA issuer, warps 12-15 epilogue.
+// ======================================================================================================
+#define T3_NPROD 10
+#define T3_PROD_THREADS (T3_NPROD * 32)
+#define T3_LOAD_WARP 10
+#define T3_NBUF 2
+#define T3_WCHUNK (25 * 4096)
+#define T3_H0_TAPS 13
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc),
+               "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
+                                                              const float* __restrict__ gam, const float* __restrict__ bet,
+                                                              const uint8_t* __restrict__ wpack, const BiasArg bias,
+                                                              float* __restrict__ out, double* __restrict__ out_stats, int n) {
+  using Cfg = TcCfg<32, 5, 61, 29, 64, 64, T3_NBUF>;
+  constexpr int CIN = 32, KS = 5, HIN = 61, HOUT = 29, COUT = 64, NCH = 64, NBUF = T3_NBUF;
+  constexpr int PH = Cfg::PH, PW = Cfg::PW, PQ = Cfg::PQ, TAPS = Cfg::TAPS;
+  static_assert(Cfg::TAP_BYTES == 4096 && Cfg::C2 == 2, "conv3 weight chunk layout");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + T3_WCHUNK;
+  __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF], acc_full[4], acc_empty[4], w_full[2], w_free[2];
+  __shared__ uint32_t tmem_base;
+  __shared__ float s_gam[CIN], s_bet[CIN];
+  __shared__ __align__(16) float s_ga[CIN], s_gb[CIN];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    const int4* src = reinterpret_cast<const int4*>(wpack);     // K chunk 0 is resident first
+    for (int i = tid; i < T3_WCHUNK / 16; i += T2_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(src + i);
+  }
+  for (int i = tid; i < CIN; i += T2_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; b++) { tc::mbar_init(&full[b], T3_PROD_THREADS); tc::mbar_init(&empty[b], 1); }
+    for (int a = 0; a < 4; a++) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 128); }
+    for (int h = 0; h < 2; h++) { tc::mbar_init(&w_full[h], 1); tc::mbar_init(&w_free[h], 1); }
+    tc::fence_mbar_init();
+  }
+  if (warp == T2_MMA_WARP) tc::tmem_alloc(&tmem_base, 512);
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm = tmem_base;
+  const int items = n * Cfg::TILES;
+  const int item_lo = (int)(((long long)items * blockIdx.x) / gridDim.x);
+  const int item_hi = (int)(((long long)items * (blockIdx.x + 1)) / gridDim.x);
+  const int npairs = (item_hi - item_lo + 1) >> 1;
+
+  if (warp < T3_NPROD) {
+    // ---------------- producers: same work items as tc_conv_kernel (8 channels of one input pixel), 320 threads ----------------
+    constexpr int NPIX = PH * PW, NITEM = NPIX * 2;
+    constexpr int KI = (NITEM + T3_PROD_THREADS - 1) / T3_PROD_THREADS;
+    constexpr int CG = PH * 2 * PQ * 16;
+    const int half = tid & 1;
+    int rc[KI], soff[KI];
+#pragma unroll
+    for (int k = 0; k < KI; k++) {
+      const int i = tid + k * T3_PROD_THREADS;
+      rc[k] = -1;
+      soff[k] = Cfg::DUMP_OFF;
+      if (i < NITEM) {
+        const int p = i >> 1;
+        const int row = p / PW, col = p - row * PW;
+        rc[k] = (row << 8) | col;
+        soff[k] = ((row * 2 + (col & 1)) * PQ + (col >> 1)) * 16 + half * CG;
+      }
+    }
+    int cur_crop = -1;
+    long long tw = 0, t_start = TRACE_T();
+    const int njobs = 2 * (item_hi - item_lo);
+    // job j of this CTA -> (tile, K chunk): pairs of tiles, K chunk outer (see the header comment)
+    auto decode = [&](int j, int& item, int& c2) {
+      const int p = j >> 2, r = j & 3;
+      const int np = min(2, item_hi - (item_lo + 2 * p));
+      const int s2 = np == 2 ? (r >> 1) : r, i2 = np == 2 ? (r & 1) : 0;
+      item = item_lo + 2 * p + i2;
+      c2 = (p & 1) ^ s2;
+    };
+    auto job_base = [&](int item, int c2, int& rows_valid, int& cols_valid) -> const float* {
+      const int crop = item / Cfg::TILES, tile = item - crop * Cfg::TILES;
+      const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
+      rows_valid = HIN - 2 * ty0;
+      cols_valid = HIN - 2 * tx0;
+      return in + ((((size_t)crop * (CIN / 8) + c2 * 2 + half) * HIN + 2 * ty0) * HIN + 2 * tx0) * 8;
+    };
+    for (int cnt = 0; cnt < njobs; cnt++) {
+      int item, c2;
+      decode(cnt, item, c2);
+      const int crop = item / Cfg::TILES;
+      {
+        {
+          int rows_valid, cols_valid;
+          const float* base = job_base(item, c2, rows_valid, cols_valid);
+          float x[KI][8];
+          unsigned ok = 0u;
+#pragma unroll
+          for (int k = 0; k < KI; k++) {
+            const int row = rc[k] >> 8, col = rc[k] & 255;
+            if (rc[k] >= 0 && row < rows_valid && col < cols_valid) {
+              ok |= 1u << k;
+              tc::ldg256(base + (row * HIN + col) * 8, x[k]);
+            }
+          }
+          if (cnt + 1 < njobs) {
+            // pull the next job's input towards L2 (no registers, no scoreboard: fence.proxy.async below waits for every
+            // outstanding register load, so a register prefetch would serialise behind it)
+            int nitem, nc2, nrv, ncv;
+            decode(cnt + 1, nitem, nc2);
+            const float* nbase = job_base(nitem, nc2, nrv, ncv);
+#pragma unroll
+            for (int k = 0; k < KI; k++) {
+              const int row = rc[k] >> 8, col = rc[k] & 255;
+              if (rc[k] >= 0 && row < nrv && col < ncv) asm volatile("prefetch.global.L2 [%0];" ::"l"(nbase + (row * HIN + col) * 8));
+            }
+          }
+          if (crop != cur_crop) {
+            cur_crop = crop;
+            asm volatile("bar.sync 1, %0;" ::"n"(T3_PROD_THREADS) : "memory");
+            if (tid < CIN) {
+              float mean, rstd;
+              gn_stats(in_stats, crop, (double)CIN * HIN * HIN, mean, rstd);
+              const float g = rstd * s_gam[tid];
+              s_ga[tid] = g;
+              s_gb[tid] = fmaf(-mean, g, s_bet[tid]);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(T3_PROD_THREADS) : "memory");
+          }
+          float ga[8], gb[8];
+#pragma unroll
+          for (int j = 0; j < 8; j += 4) {
+            const float4 a4 = *reinterpret_cast<const float4*>(&s_ga[c2 * 16 + half * 8 + j]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&s_gb[c2 * 16 + half * 8 + j]);
+            ga[j] = a4.x; ga[j + 1] = a4.y; ga[j + 2] = a4.z; ga[j + 3] = a4.w;
+            gb[j] = b4.x; gb[j + 1] = b4.y; gb[j + 2] = b4.z; gb[j + 3] = b4.w;
+          }
+          const int b = cnt % NBUF;
+          const long long tq = TRACE_T();
+          tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
+          tw += TRACE_T() - tq;
+          uint8_t* dst = sA + (size_t)b * Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < KI; k++) {
+            const bool okk = (ok >> k) & 1u;
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) y[j] = okk ? fmaxf(fmaf(x[k][j], ga[j], gb[j]), 0.f) : 0.f;
+            uint4 hi, lo;
+            tc::split_pack2(y[0], y[1], hi.x, lo.x);
+            tc::split_pack2(y[2], y[3], hi.y, lo.y);
+            tc::split_pack2(y[4], y[5], hi.z, lo.z);
+            tc::split_pack2(y[6], y[7], hi.w, lo.w);
+            *reinterpret_cast<uint4*>(dst + soff[k]) = hi;                            // items beyond the patch land in the dump slot
+            *reinterpret_cast<uint4*>(dst + Cfg::A_PREC_BYTES + soff[k]) = lo;
+          }
+          tc::fence_async_smem();
+          tc::mbar_arrive(&full[b]);
+        }
+      }
+    }
+    if (tid == 0) { trace_add(2, 0, tw); trace_add(2, 1, TRACE_T() - t_start); trace_add(2, 7, 1); }
+  } else if (warp == T3_LOAD_WARP) {
+    // ---------------- weight loader: one swap per pair, two halves, each as soon as its old contents are dead ----------------
+    if (tc::elect_one()) {
+      for (int p = 0; p < npairs; p++) {
+        const uint8_t* src = wpack + (size_t)(1 - (p & 1)) * T3_WCHUNK;
+        tc::mbar_wait(&w_free[0], p & 1);
+        mbar_expect_tx(&w_full[0], T3_H0_TAPS * 4096);
+        for (int t = 0; t < T3_H0_TAPS; t++) bulk_g2s(sW + t * 4096, src + t * 4096, 4096, &w_full[0]);
+        tc::mbar_wait(&w_free[1], p & 1);
+        mbar_expect_tx(&w_full[1], (TAPS - T3_H0_TAPS) * 4096);
+        for (int t = T3_H0_TAPS; t < TAPS; t++) bulk_g2s(sW + t * 4096, src + t * 4096, 4096, &w_full[1]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == T2_MMA_WARP) {
+    const uint32_t idesc1 = tc::idesc_bf16_f32(128, 2 * NCH), idesc2 = tc::idesc_bf16_f32(128, NCH);
+    constexpr uint32_t LBO_A = PH * 2 * PQ * 16, SBO_A = 64 * PQ, LBO_B = 32 * NCH;
+    int cnt = 0;
+    long long twf = 0, twa = 0, t_start = TRACE_T();
+    for (int p = 0; p < npairs; p++) {
+      const int np = min(2, item_hi - (item_lo + 2 * p));
+      for (int s2 = 0; s2 < 2; s2++) {
+        for (int i2 = 0; i2 < np; i2++, cnt++) {
+          const int k = (p & 1) * 2 + i2;
+          const uint32_t d = tm + k * (2 * NCH);
+          if (s2 == 0) {
+            const long long tq0 = TRACE_T();
+            tc::mbar_wait(&acc_empty[k], ((p >> 1) & 1) ^ 1);
+            twa += TRACE_T() - tq0;
+          }
+          const int b = cnt % NBUF;
+          const long long tq1 = TRACE_T();
+          tc::mbar_wait(&full[b], (cnt / NBUF) & 1);
+          twf += TRACE_T() - tq1;
+          const bool after_swap = (s2 == 1 && i2 == 0), before_swap = (s2 == 0 && i2 == np - 1);
+          if (after_swap) tc::mbar_wait(&w_full[0], p & 1);
+          tc::tc_fence_after();
+          const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(sA + (size_t)b * Cfg::A_BYTES), LBO_A);
+          const uint32_t b_lo0 = tc::desc_lo(tc::smem_u32(sW), LBO_B);
+          const uint32_t a_hi = tc::desc_hi(SBO_A), b_hi = tc::desc_hi(128);
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < T3_H0_TAPS; tap++) {
+              const int ky = tap / KS, kx = tap % KS;
+              const uint32_t al0 = a_lo0 + ((((ky * 2 + (kx & 1)) * PQ + (kx >> 1)) * 16) >> 4);
+              const uint64_t ah = tc::desc_make(al0, a_hi), al = tc::desc_make(al0 + (Cfg::A_PREC_BYTES >> 4), a_hi);
+              const uint64_t bd = tc::desc_make(b_lo0 + ((tap * Cfg::TAP_BYTES) >> 4), b_hi);
+              tc::mma_bf16(d, ah, bd, idesc1, (tap > 0 || s2 > 0) ? 1u : 0u);
+              tc::mma_bf16(d, al, bd, idesc2, 1u);
+            }
+            if (before_swap) tc::mma_commit(&w_free[0]);
+          }
+          __syncwarp();
+          if (after_swap) {
+            tc::mbar_wait(&w_full[1], p & 1);
+            tc::tc_fence_after();
+          }
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int tap = T3_H0_TAPS; tap < TAPS; tap++) {
+              const int ky = tap / KS, kx = tap % KS;
+              const uint32_t al0 = a_lo0 + ((((ky * 2 + (kx & 1)) * PQ + (kx >> 1)) * 16) >> 4);
+              const uint64_t ah = tc::desc_make(al0, a_hi), al = tc::desc_make(al0 + (Cfg::A_PREC_BYTES >> 4), a_hi);
+              const uint64_t bd = tc::desc_make(b_lo0 + ((tap * Cfg::TAP_BYTES) >> 4), b_hi);
+              tc::mma_bf16(d, ah, bd, idesc1, 1u);
+              tc::mma_bf16(d, al, bd, idesc2, 1u);
+            }
+            if (before_swap) tc::mma_commit(&w_free[1]);
+            tc::mma_commit(&empty[b]);
+            if (s2 == 1) tc::mma_commit(&acc_full[k]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    if (lane == 0) { trace_add(2, 2, twf); trace_add(2, 3, twa); trace_add(2, 4, TRACE_T() - t_start); }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> (+bias) -> global (channel-blocked), fp64 GroupNorm statistics ----------------
+    const int q = warp - T2_EPI_WARP0;
+    const int m = q * 32 + lane;
+    int cur_crop = -1;
+    double d1 = 0.0, d2 = 0.0;
+    long long twe = 0, t_start = TRACE_T();
+    for (int p = 0; p < npairs; p++) {
+      const int np = min(2, item_hi - (item_lo + 2 * p));
+      for (int i2 = 0; i2 < np; i2++) {
+        const int item = item_lo + 2 * p + i2;
+        const int crop = item / Cfg::TILES, tile = item % Cfg::TILES;
+        const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
+        const int k = (p & 1) * 2 + i2;
+        if (crop != cur_crop) {
+          if (cur_crop >= 0) {
+            d1 = warp_sum_f64(d1);
+            d2 = warp_sum_f64(d2);
+            if (lane == 0) {
+              atomicAdd(out_stats + (size_t)cur_crop * 2, d1);
+              atomicAdd(out_stats + (size_t)cur_crop * 2 + 1, d2);
+            }
+          }
+          cur_crop = crop;
+          d1 = 0.0;
+          d2 = 0.0;
+        }
+        const long long tq = TRACE_T();
+        tc::mbar_wait(&acc_full[k], (p >> 1) & 1);
+        twe += TRACE_T() - tq;
+        tc::tc_fence_after();
+        const int oy = ty0 + (m >> 3), ox = tx0 + (m & 7);
+        const bool ok = oy < HOUT && ox < HOUT;
+        const uint32_t tbase = tm + ((uint32_t)(q * 32) << 16) + k * (2 * NCH);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int h = 0; h < NCH / 16; h++) {
+          float vh[16], vl[16];
+          tc::tmem_ld16(tbase + h * 16, vh);
+          tc::tmem_ld16(tbase + NCH + h * 16, vl);
+          if (h == NCH / 16 - 1) {
+            tc::tc_fence_before();
+            tc::mbar_arrive(&acc_empty[k]);
+          }
+          if (ok) {
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+              vh[c] = (vh[c] + vl[c]) + bias.b[h * 16 + c];
+              s1 += vh[c];
+              s2 = fmaf(vh[c], vh[c], s2);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const int ch0 = h * 16 + j * 8;
+              float* dst = out + ((((size_t)crop * (COUT / 8) + (ch0 >> 3)) * HOUT + oy) * HOUT + ox) * 8;
+              tc::stg256(dst, vh[j * 8], vh[j * 8 + 1], vh[j * 8 + 2], vh[j * 8 + 3], vh[j * 8 + 4], vh[j * 8 + 5], vh[j * 8 + 6], vh[j * 8 + 7]);
+            }
+          }
+        }
+        d1 += (double)s1;
+        d2 += (double)s2;
+      }
+    }
+    if (cur_crop >= 0) {
+      d1 = warp_sum_f64(d1);
+      d2 = warp_sum_f64(d2);
+      if (lane == 0) {
+        atomicAdd(out_stats + (size_t)cur_crop * 2, d1);
+        atomicAdd(out_stats + (size_t)cur_crop * 2 + 1, d2);
+      }
+    }
+    if (q == 0 && lane == 0) { trace_add(2, 5, twe); trace_add(2, 6, TRACE_T() - t_start); }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == T2_MMA_WARP) {
+    __syncwarp();
+    tc::tmem_dealloc(tm, 512);
+  }
+}
+
+// ======================================================================================================
 // conv5 / conv6 / fc: small spatial extent (6x6, 2x2, 1x1 outputs) -> rows of many crops are packed into M = 128 tiles and
 // the A operand is gathered explicitly (im2col rows written straight into the canonical K-major layout, 64-wide K chunks).
 // GEMM:  out[m][n] = sum_k relu(GN(in))[row m, tap(k), c(k)] * W[n][k],   k = tap * CIN + c,  NHWC in/out.
@@ -1040,7 +1375,21 @@ int tc_launch_conv2(const float* in, const double* in_stats, const float* gam, c
 }
 int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* h_bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {
-  return tc_launch<32, 5, 61, 29, 64, 32, 2, true>("tc_conv3", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
+  using Cfg = TcCfg<32, 5, 61, 29, 64, 64, T3_NBUF>;
+  constexpr size_t SMEM = (size_t)T3_WCHUNK + (size_t)T3_NBUF * Cfg::A_BYTES;
+  static_assert(SMEM <= 225 * 1024, "conv3 shared memory");
+  static bool attr = false;
+  if (!attr) {
+    STRIVE_CUDA(cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    attr = true;
+  }
+  const int items = n * Cfg::TILES;
+  int gx = num_sms();
+  if (gx > (items + 1) / 2) gx = (items + 1) / 2;
+  const BiasArg bias = make_bias(h_bias, 64);
+  KPROF("tc_conv3", stream, tc_conv3_kernel<<<gx, T2_THREADS, SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
+  STRIVE_LAUNCH_CHECK();
+  return 0;
 }
 int tc_launch_conv4(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* h_bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {

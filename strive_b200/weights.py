@@ -104,7 +104,7 @@ def pack_tc_weights(sd):
     lo halves are STACKED ALONG N (rows n' = prec * NCH + n), so one MMA multiplies an A tile with both:
     conv1: [ky 7][kq 2][khalf 2][prec 2][ngroup 2][r 8][k 8], k = (kx_l % 2) * 4 + c, taps kx = 4 kq + kx_l (kx = 7 is zero);
     conv2..4: [nchunk][c2][tap][khalf 2][prec 2][ngroup NCH/8][r 8][k 8], n = NCH nchunk + 8 ngroup + r, c = 16 c2 + 8 khalf + k,
-    NCH = 32 output channels per CTA for conv2 / conv3 and 64 for conv4."""
+    NCH = 32 output channels per CTA for conv2 and 64 for conv3 / conv4."""
     g = lambda k: sd[k].detach().to(torch.float32).cpu()
     out = []
     w = g('map_conv.0.weight')                                              # (16,4,7,7)
@@ -115,7 +115,7 @@ def pack_tc_weights(sd):
         parts.append(t.permute(3, 4, 5, 0, 1, 6, 2))                        # (ky, kq, khalf, ngroup, r, kxh, c)
     t = torch.stack(parts, dim=3)                                           # (ky, kq, khalf, prec, ngroup, r, kxh, c)
     out.append(_bytes(t))
-    for li, ks, nch in ((1, 5, 32), (2, 5, 32), (3, 3, 64)):
+    for li, ks, nch in ((1, 5, 32), (2, 5, 64), (3, 3, 64)):
         w = g('map_conv.%d.weight' % (3 * li))                              # (Cout, Cin, ks, ks)
         cout, cin = w.size(0), w.size(1)
         parts = []
