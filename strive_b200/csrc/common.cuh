@@ -140,12 +140,16 @@ __device__ __forceinline__ void stvec(float* p, const float (&w)[V]) {
 // acc[r][v] += sum_k xs[r*ldx + k] * Wm[k*OUT + lane*V + v],  V = OUT/32.   red % 4 == 0, ldx % 4 == 0.
 // Wm is a global [red][OUT] matrix (coalesced across lanes, L1/L2 resident); xs is per-warp shared memory
 // (broadcast reads).  R rows share every weight load.
+#ifndef WG_UNROLL
+#define WG_UNROLL 4
+#endif
+constexpr int kWgUnroll = WG_UNROLL;   // k-steps of 4 in flight per warp in the GEMV loops (weight loads are L2-latency bound)
 template <int OUT, int R>
 __device__ __forceinline__ void warp_gemm(const float* __restrict__ Wm, int red, const float* xs, int ldx,
                                           float (&acc)[R][OUT / 32], int lane) {
   constexpr int V = OUT / 32;
   const float* wp = Wm + lane * V;
-#pragma unroll 2
+#pragma unroll kWgUnroll
   for (int k = 0; k < red; k += 4) {
     float w[4][V];
 #pragma unroll
@@ -170,7 +174,7 @@ template <int R>
 __device__ __forceinline__ void warp_gemm_gru(const float* __restrict__ Wm, int red, const float* xs, int ldx,
                                               float (&acc)[R][6], int lane) {
   const float* wp = Wm + lane * 2;
-#pragma unroll 2
+#pragma unroll kWgUnroll
   for (int k = 0; k < red; k += 4) {
     float w[4][6];
 #pragma unroll

@@ -114,8 +114,14 @@ struct StepArgs {
   Tape tp;
 };
 
-#define NODE_R 4
+// rows per warp of the node-level kernels: measured on B200 at NA = 2048 (scripts/prof_step.py): R=4/unroll 2: 9.5 ms of node-level
+// kernels per iteration, R=2/unroll 4: 7.8 ms (the GEMV loops are bound by the L2 latency of the weight stream, not by FMAs)
+#ifndef NODE_R
+#define NODE_R 2
+#endif
+#ifndef NODE_WARPS
 #define NODE_WARPS 4
+#endif
 #define EDGE_R 8
 #define EDGE_WARPS 4
 #define LDA 172   // >= 168, multiple of 4
@@ -501,7 +507,7 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) post_fwd_kernel(ModelDev M, S
 // ------------------------------------------------------------------------------------------------------
 // GRU memory: one step of nn.GRU(4,64,3) (traffic_model.py:152-156, 686-688)
 // ------------------------------------------------------------------------------------------------------
-#define GRU_R 4
+#define GRU_R NODE_R
 // per-warp shared: xin [R][68], h [3][R][68], gate stash for backward [3][R][4][64]
 #define LDG 68
 
