@@ -96,8 +96,8 @@ extern "C" int strive_model_create(const float* blob, int64_t blob_floats, const
 
 extern "C" void strive_model_destroy(StriveModel* m) { delete m; }
 
-// tensor-core weight blob: [conv1 14336 B][conv2 51200 B][conv3 2 x 102400 B][conv4 147456 B][conv5][conv6][fc]  (layouts in mapenc_tc.cu)
-static const int64_t kTcBytes[7] = {7 * 2 * 2 * 512, 1 * (1 * 25 * 2 * 1024), 2 * (2 * 25 * 2 * 1024), 2 * (4 * 9 * 2 * 1024),
+// tensor-core weight blob: [conv1 10752 B int8 digit planes + 16 fp32 scales][conv2 51200 B][conv3 2 x 102400 B][conv4 147456 B][conv5][conv6][fc]  (layouts in mapenc_tc.cu)
+static const int64_t kTcBytes[7] = {7 * 2 * 48 * 16 + 64, 1 * (1 * 25 * 2 * 1024), 2 * (2 * 25 * 2 * 1024), 2 * (4 * 9 * 2 * 1024),
                                     9 * 2 * 128 * 64 * 2, 18 * 2 * 128 * 64 * 2, 8 * 2 * 64 * 64 * 2};
 extern "C" int64_t strive_model_tc_bytes(void) {
   int64_t t = 0;

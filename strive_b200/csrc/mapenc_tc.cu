@@ -67,17 +67,38 @@ __device__ __forceinline__ void gn_stats(const double* __restrict__ st, int crop
 }
 
 // ======================================================================================================
-// conv1: 4 -> 16, k7 s2, input gathered from the packed binary raster.  CTA tile = 32x32 outputs = 8 MMA sub-tiles
-// (16 rows x 8 cols each, own TMEM accumulator).  A tile: [row][col][4 ch] bf16 (8 B / pixel); one K=16 MMA = 4 taps
-// (kx..kx+3) x 4 channels at fixed ky.
+// conv1: 4 -> 16, k7 s2 on the INTEGER tensor path (tcgen05.mma kind::i8, s32 accumulators).
+// The input is the binary crop -- exact as int8 {0,1}.  Each output channel's weights are written in 31-bit fixed point
+//     w[o][k] ~= sc[o] * q[o][k],   q = round(w / max|w[o]| * 127 * 2^16) = sum_d digit_d 256^d,  digit_d in [-128, 127]
+// and the three digit planes are stacked along N (rows n = 16 d + o), so ONE MMA (K = 32 = 8 taps x 4 channels) multiplies
+// a pixel window with all of them; the s32 accumulators are exact and the epilogue recombines
+//     out = sc[o] * float(acc2 * 65536 + acc1 * 256 + acc0) + bias        (exact int32, one conversion, one fma)
+// |w - sc q| <= 2^-24 max|w[o]| (the fp32 half-ulp of the largest weight); summed over <= 196 active taps that is ~1e-8 on O(0.1)
+// outputs, ten times below the rounding noise of the reference's own fp32 accumulation.  Three planes, not four: the
+// epilogue is bound by the TMEM read bandwidth (64 B/clk: 4 planes = 131 KB per item took longer than the MMAs).  Against the bf16 hi/lo version
+// this halves the operand bytes per tap (int8, K = 32 per instruction) -- the kernel is bound by the 128 B/clk shared-memory
+// operand fetch (profiles/r01_ncu_full_v2_encoder.txt), so bytes are time.
+// CTA item = 16 x 32 outputs = 4 sub-tiles (M = 128 rows = 16 output rows x 8 output columns of ONE column parity).
+// Operand rows must be 16 bytes apart and a pixel is 4 bytes, so consecutive rows are 4 input pixels = 2 output columns
+// apart: even output columns read the patch as stored, odd ones read a second copy shifted by 2 pixels.
 // ======================================================================================================
-#define T1_PH 69
-#define T1_PW 70
-#define T1_WBYTES (7 * 2 * 2 * 512)
-#define T1_PATCH_BYTES (T1_PH * T1_PW * 8)
-#define T1_SUPER 4   // 4 x 4 super-tiles of 32 x 32 outputs cover 125 x 125
-#define T1_NBUF 3
-#define T1_QMAX 1024   // deferred exact-rounding samples per tile (about 4 % of 4830 are near a tie); overflow is handled inline
+#define T1_ROWS 37                    // input rows of an item: 2 * 16 + 5
+#define T1_COLS 72                    // input columns 0..68 are needed (+ the zero-weight 8th tap), padded to a multiple of 4
+#define T1_ROWB (T1_COLS * 4)         // 288 bytes per patch row
+#define T1_COPY (T1_ROWS * T1_ROWB)   // 10656 bytes
+#define T1_PATCH_BYTES (2 * T1_COPY)
+#define T1_NP 48                      // N = 3 digit planes x 16 channels
+#define T1_WBYTES (7 * 2 * T1_NP * 16)   // [ky][khalf][n = 16 d + o][16 k-bytes]; 16 fp32 scales follow in global memory
+#define T1_RB 8                       // 8 row blocks x 4 column blocks of 16 x 32 outputs cover 125 x 125
+#define T1_CB 4
+#define T1_NBUF 4
+// roles: warps 0-5 producers (the patch is 666 32-bit loads), warp 6 MMA issuer, warps 8-15 epilogue (two per TMEM lane quarter:
+// recombining four digit planes is ~10 instructions per output, the epilogue -- not the tensor core -- was the bottleneck with 4 warps)
+#define T1_NPROD 6
+#define T1_PROD_THREADS (T1_NPROD * 32)
+#define T1_NGRP 3
+#define T1_MMA_WARP 6
+#define T1_EPI_WARP0 8
 
 // round-half-even(g / dx) exactly as torch.round(float64 quotient) (reference datasets/nuscenes_utils.py:254-255): multiply by
 // the reciprocal; only when the product lands within 1e-6 of a .5 boundary (where the two could round differently) divide.
@@ -261,16 +282,45 @@ struct BiasArg {
   float b[64];
 };
 
-// 4 layer bits -> 4 x bf16 {0.0, 1.0} (0x3F80), arithmetic instead of a shared-memory table: the MMA operand fetch
-// saturates the shared-memory pipe, every other LDS/STS in these kernels waits behind it.
-__device__ __forceinline__ uint2 expand_bits4(unsigned b) {
-  return make_uint2((b & 1u) * 0x3F80u + (b & 2u) * 0x1FC00000u, ((b >> 2) & 1u) * 0x3F80u + ((b >> 2) & 2u) * 0x1FC00000u);
-}
-
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor of kind::i8: s8 x s8 -> s32, A and B K-major, dense, no saturation
+__host__ __device__ constexpr uint32_t idesc_s8_s32(int M, int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld16i(uint32_t taddr, int (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld48i(uint32_t taddr, int (&v)[48]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47])
+               : "r"(taddr + 32)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __restrict__ packed_crop, const uint8_t* __restrict__ wpack,
@@ -282,58 +332,75 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < T1_WBYTES / 16; i += TC_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(reinterpret_cast<const int4*>(wpack) + i);
+  // the patch columns that no item writes (copy 1, columns 70-71) are never read; zero everything once anyway
+  for (int i = tid; i < T1_NBUF * T1_PATCH_BYTES / 16; i += TC_THREADS) reinterpret_cast<int4*>(sP)[i] = make_int4(0, 0, 0, 0);
   if (tid == 0) {
-    for (int b = 0; b < T1_NBUF; b++) { tc::mbar_init(&full[b], TC_PROD_THREADS); tc::mbar_init(&empty[b], 1); }
-    for (int a = 0; a < 2; a++) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 128); }
+    for (int b = 0; b < T1_NBUF; b++) { tc::mbar_init(&full[b], T1_PROD_THREADS / T1_NGRP); tc::mbar_init(&empty[b], 1); }
+    for (int a = 0; a < 2; a++) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], 256); }
     tc::fence_mbar_init();
   }
-  if (warp == TC_MMA_WARP) tc::tmem_alloc(&tmem_base, 512);     // 2 accumulator sets x 8 sub-tiles x 32 columns: one CTA per SM
+  if (warp == T1_MMA_WARP) tc::tmem_alloc(&tmem_base, 512);     // 2 accumulator sets (256 columns apart) x 4 sub-tiles x 48 columns
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tm = tmem_base;
-  const int items = n * T1_SUPER * T1_SUPER;
-  // contiguous item range per CTA: the 16 super-tiles of a crop stay on one SM (L1/L2 locality, one statistics flush per crop)
+  constexpr int IPC = T1_RB * T1_CB;     // items per crop
+  const int items = n * IPC;
+  // contiguous item range per CTA: the items of a crop stay on one SM (L1/L2 locality, one statistics flush per crop)
   const int item_lo = (int)(((long long)items * blockIdx.x) / gridDim.x);
   const int item_hi = (int)(((long long)items * (blockIdx.x + 1)) / gridDim.x);
 
-  if (warp < TC_NPROD) {
-    // ---------------- producers: expand the bit-packed crop tile to bf16 [row][col][4 ch] ----------------
-    int cnt = 0;
+  if (warp < T1_NPROD) {
+    // ---------------- producers: 4 packed pixels (one 32-bit load) -> 4 x int8x4, written to both patch copies ----------------
+    // Three groups of two warps take the items round-robin: an item is "load 666 words, wait, expand, store, fence" -- a pure
+    // latency chain (fence.proxy.async waits for every outstanding load, so there is no prefetching across the fence) -- and
+    // three chains in flight hide it.
+    constexpr int QPR = T1_COLS / 4, NQ = T1_ROWS * QPR;                      // 18 quads per row, 666 per item
+    constexpr int GT = T1_PROD_THREADS / T1_NGRP;                             // 64 threads per group
+    constexpr int QPT = (NQ + GT - 1) / GT;                                   // 11
+    const int grp = tid / GT, gt = tid % GT;
     long long tw = 0, t_start = TRACE_T();
-    for (int item = item_lo; item < item_hi; item++, cnt++) {
-      const int crop = item / (T1_SUPER * T1_SUPER), st = item % (T1_SUPER * T1_SUPER);
-      const int oy0 = (st / T1_SUPER) * 32, ox0 = (st % T1_SUPER) * 32;
+    for (int cnt = grp; item_lo + cnt < item_hi; cnt += T1_NGRP) {
+      const int item = item_lo + cnt;
+      const int crop = item / IPC, st = item % IPC;
+      const int row0 = (st / T1_CB) * 32, col0 = (st % T1_CB) * 64;          // first input row / column of the item
       const int b = cnt % T1_NBUF;
-      const uint8_t* src = packed_crop + (size_t)crop * 65536 + (size_t)(oy0 * 2) * 256 + ox0 * 2;
-      constexpr int NPX = T1_PH * T1_PW;
-      constexpr int NPT = (NPX + TC_PROD_THREADS - 1) / TC_PROD_THREADS;     // 14 samples per thread
-      const int ymax = 256 - oy0 * 2, xmax = 256 - ox0 * 2;   // rows/cols of the tile inside the 256x256 crop
-      unsigned bits[NPT];
+      const uint8_t* src = packed_crop + (size_t)crop * 65536 + (size_t)row0 * 256 + col0;
+      uint32_t wv[QPT];
 #pragma unroll
-      for (int k = 0; k < NPT; k++) {
-        const int i = tid + k * TC_PROD_THREADS;
-        const int r = i / T1_PW, c = i - r * T1_PW;
-        bits[k] = (i < NPX && r < ymax && c < xmax) ? (unsigned)__ldg(src + r * 256 + c) : 0u;     // zero padding outside the crop
+      for (int k = 0; k < QPT; k++) {
+        const int i = gt + k * GT, r = i / QPR, c = i - r * QPR;
+        const bool ok = i < NQ && row0 + r < 256 && col0 + 4 * c < 256;          // zero padding outside the crop
+        wv[k] = ok ? __ldg(reinterpret_cast<const uint32_t*>(src + r * 256 + 4 * c)) : 0u;
       }
       const long long tq = TRACE_T();
       tc::mbar_wait(&empty[b], ((cnt / T1_NBUF) & 1) ^ 1);
       tw += TRACE_T() - tq;
       uint8_t* dst = sP + (size_t)b * T1_PATCH_BYTES;
 #pragma unroll
-      for (int k = 0; k < NPT; k++) {
-        const int i = tid + k * TC_PROD_THREADS;
-        if (i < NPX) *reinterpret_cast<uint2*>(dst + (size_t)i * 8) = expand_bits4(bits[k]);
+      for (int k = 0; k < QPT; k++) {
+        const int i = gt + k * GT, r = i / QPR, c = i - r * QPR;
+        if (i < NQ) {
+          uint32_t e[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const uint32_t v = (wv[k] >> (8 * j)) & 15u;     // bit c = layer c  ->  byte c = 0 / 1
+            e[j] = (v & 1u) | ((v & 2u) << 7) | ((v & 4u) << 14) | ((v & 8u) << 21);
+          }
+          uint8_t* d0 = dst + r * T1_ROWB + c * 16;
+          *reinterpret_cast<uint4*>(d0) = make_uint4(e[0], e[1], e[2], e[3]);
+          uint8_t* d1 = d0 + T1_COPY;                        // copy 1 column c holds pixel c + 2
+          if (c > 0) *reinterpret_cast<uint2*>(d1 - 8) = make_uint2(e[0], e[1]);
+          *reinterpret_cast<uint2*>(d1) = make_uint2(e[2], e[3]);
+        }
       }
       tc::fence_async_smem();
       tc::mbar_arrive(&full[b]);
     }
     if (tid == 0) { trace_add(0, 0, tw); trace_add(0, 1, TRACE_T() - t_start); trace_add(0, 7, 1); }
-  } else if (warp == TC_MMA_WARP) {
-    // One MMA per K step: B = [W_hi | W_lo] stacked along N (32 rows) so the A tile is fetched once for both halves
-    // (SS-mode MMA time = (4096 + 32 N) / 128 cycles: the A fetch dominates at small N).
-    const uint32_t idesc = tc::idesc_bf16_f32(128, 32);
+  } else if (warp == T1_MMA_WARP) {
+    const uint32_t idesc = idesc_s8_s32(128, T1_NP);
     const uint32_t wbase = tc::smem_u32(sW);
     int cnt = 0;
     long long twf = 0, twa = 0, t_start = TRACE_T();
@@ -348,21 +415,18 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
       tc::tc_fence_after();
       if (tc::elect_one()) {
         const uint32_t pbase = tc::smem_u32(sP + (size_t)b * T1_PATCH_BYTES);
-        const uint32_t a_hi = tc::desc_hi(2 * T1_PW * 8), b_hi = tc::desc_hi(128);
-        const uint32_t b_lo0 = tc::desc_lo(wbase, 512);
-#pragma unroll 1
-        for (int sub = 0; sub < 8; sub++) {
-          const int sy = sub >> 2, sx = sub & 3;
-          const uint32_t a_lo0 = tc::desc_lo(pbase + ((sy * 32) * T1_PW + sx * 16) * 8, 16);
-          const uint32_t d = tm + a * 256 + sub * 32;
+        const uint32_t a_hi = tc::desc_hi(2 * T1_ROWB), b_hi = tc::desc_hi(128);
+        const uint32_t b_lo0 = tc::desc_lo(wbase, T1_NP * 16);
+#pragma unroll
+        for (int sub = 0; sub < 4; sub++) {
+          const int xb = sub >> 1, par = sub & 1;
+          const uint32_t a_lo0 = tc::desc_lo(pbase + par * T1_COPY + xb * 128, 16);
+          const uint32_t d = tm + a * 256 + sub * T1_NP;
 #pragma unroll
           for (int ky = 0; ky < 7; ky++) {
-#pragma unroll
-            for (int kq = 0; kq < 2; kq++) {
-              const uint64_t ad = tc::desc_make(a_lo0 + (((ky * T1_PW + 4 * kq) * 8) >> 4), a_hi);
-              const uint64_t bd = tc::desc_make(b_lo0 + (((ky * 2 + kq) * 1024) >> 4), b_hi);
-              tc::mma_bf16(d, ad, bd, idesc, (ky | kq) ? 1u : 0u);
-            }
+            const uint64_t ad = tc::desc_make(a_lo0 + ((ky * T1_ROWB) >> 4), a_hi);
+            const uint64_t bd = tc::desc_make(b_lo0 + ((ky * 2 * T1_NP * 16) >> 4), b_hi);
+            mma_i8(d, ad, bd, idesc, ky ? 1u : 0u);
           }
         }
         tc::mma_commit(&empty[b]);
@@ -371,16 +435,19 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
       __syncwarp();
     }
     if (lane == 0) { trace_add(0, 2, twf); trace_add(0, 3, twa); trace_add(0, 4, TRACE_T() - t_start); }
-  } else {
-    // ---------------- epilogue: warp q reads TMEM lanes 32q..32q+31 of all 8 sub-tiles; registers -> global directly ----------------
-    const int q = warp - TC_EPI_WARP0;
-    const int m = q * 32 + lane, oyl = m >> 3, oxl = m & 7;
+  } else if (warp >= T1_EPI_WARP0) {
+    // ---------------- epilogue: warp (q, half) reads TMEM lanes 32q..32q+31 of sub-tiles 2 half, 2 half + 1 ----------------
+    const int q = warp & 3, half = (warp - T1_EPI_WARP0) >> 2;
+    const int m = q * 32 + lane, oyl = m >> 3, jx = m & 7;
+    float sc[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) sc[c] = __ldg(reinterpret_cast<const float*>(wpack + T1_WBYTES) + c);
     int cnt = 0, cur_crop = -1;
     double d1 = 0.0, d2 = 0.0;
     long long twe = 0, t_start = TRACE_T();
     for (int item = item_lo; item < item_hi; item++, cnt++) {
-      const int crop = item / (T1_SUPER * T1_SUPER), st = item % (T1_SUPER * T1_SUPER);
-      const int oy0 = (st / T1_SUPER) * 32, ox0 = (st % T1_SUPER) * 32;
+      const int crop = item / IPC, st = item % IPC;
+      const int oy0 = (st / T1_CB) * 16, ox0 = (st % T1_CB) * 32;
       const int a = cnt & 1;
       if (crop != cur_crop) {
         if (cur_crop >= 0) {
@@ -401,28 +468,33 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
       tc::tc_fence_after();
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-      for (int sub = 0; sub < 8; sub++) {
-        const int sy = sub >> 2, sx = sub & 3;
-        float vh[16], vl[16];
-        tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * 256 + sub * 32, vh);
-        tc::tmem_ld16(tm + ((uint32_t)(q * 32) << 16) + a * 256 + sub * 32 + 16, vl);
-        if (sub == 7) {
+      for (int par = 0; par < 2; par++) {
+        const int sub = half * 2 + par;     // xb = half
+        const uint32_t tb = tm + ((uint32_t)(q * 32) << 16) + a * 256 + sub * T1_NP;
+        int acc[48];
+        tmem_ld48i(tb, acc);
+        if (par == 1) {
           tc::tc_fence_before();
           tc::mbar_arrive(&acc_empty[a]);
         }
-        const int oy = oy0 + sy * 16 + oyl, ox = ox0 + sx * 8 + oxl;
+        const int oy = oy0 + oyl, ox = ox0 + half * 16 + 2 * jx + par;
         if (oy < 125 && ox < 125) {
+          float v[16];
 #pragma unroll
           for (int c = 0; c < 16; c++) {
-            vh[c] = (vh[c] + vl[c]) + bias.b[c];
-            s1 += vh[c];
-            s2 = fmaf(vh[c], vh[c], s2);
+            // |acc_d| <= 196 * 128: the three planes recombine exactly in int32 (|t| < 1.64e9 < 2^31); ONE conversion rounds the
+            // exact integer to fp32 (I2F runs on the XU pipe: 16 per output pixel, far below its rate; the magic-number
+            // conversions of the separate planes cost 3x the issue slots and the epilogue is issue-bound)
+            const int t = (acc[32 + c] * 256 + acc[16 + c]) * 256 + acc[c];
+            v[c] = fmaf(__int2float_rn(t), sc[c], bias.b[c]);
+            s1 += v[c];
+            s2 = fmaf(v[c], v[c], s2);
           }
-          // channel-blocked activations [crop][C/8][H][W][8]: a lane stores 32 contiguous bytes per block, a warp 4 rows x 256 B
+          // channel-blocked activations [crop][C/8][H][W][8]: a lane stores 32 contiguous bytes per block
 #pragma unroll
           for (int j = 0; j < 2; j++) {
             float* dst = out + ((((size_t)crop * 2 + j) * 125 + oy) * 125 + ox) * 8;
-            tc::stg256(dst, vh[j * 8], vh[j * 8 + 1], vh[j * 8 + 2], vh[j * 8 + 3], vh[j * 8 + 4], vh[j * 8 + 5], vh[j * 8 + 6], vh[j * 8 + 7]);
+            tc::stg256(dst, v[j * 8], v[j * 8 + 1], v[j * 8 + 2], v[j * 8 + 3], v[j * 8 + 4], v[j * 8 + 5], v[j * 8 + 6], v[j * 8 + 7]);
           }
         }
       }
@@ -437,11 +509,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
         atomicAdd(out_stats + (size_t)cur_crop * 2 + 1, d2);
       }
     }
-    if (q == 0 && lane == 0) { trace_add(0, 5, twe); trace_add(0, 6, TRACE_T() - t_start); }
+    if (warp == T1_EPI_WARP0 && lane == 0) { trace_add(0, 5, twe); trace_add(0, 6, TRACE_T() - t_start); }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == TC_MMA_WARP) {
+  if (warp == T1_MMA_WARP) {
     __syncwarp();
     tc::tmem_dealloc(tm, 512);
   }
@@ -1338,7 +1410,7 @@ int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_
   dim3 gp(16, n);
   KPROF("crop_pack", stream, crop_pack_kernel<<<gp, 256, 0, stream>>>(*map, pose, map_of, packed_crop, n));
   STRIVE_LAUNCH_CHECK();
-  const int items = n * T1_SUPER * T1_SUPER;
+  const int items = n * T1_RB * T1_CB;
   const int grid = items < num_sms() ? items : num_sms();     // the kernel owns all 512 TMEM columns: one CTA per SM
   const BiasArg bias = make_bias(h_bias, 16);
   KPROF("tc_conv1", stream, tc_conv1_kernel<<<grid, TC_THREADS, smem, stream>>>(packed_crop, wpack, bias, out, out_stats, n));

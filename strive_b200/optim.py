@@ -295,3 +295,39 @@ def run_find_solution_optim(cur_z, final_result_traj, future_len, lr, loss_weigh
     sol_traj = sol['future_pred'].clone().detach()
     sol_traj[~tgt_mask] = nrm.normalize(other_match)[:, :sol_traj.size(1)]
     return cur_z.unsqueeze(1), sol_traj, sol
+
+
+# ----------------------------------------------------------------------------------------------------------
+# multi-GPU: one process per GPU, whole loss-normalisation groups per rank, no collective inside the loop
+# ----------------------------------------------------------------------------------------------------------
+class _DictGraph(object):
+    pass
+
+
+def refine_sharded(model, scene, map_env, loss_weights, iters, lr, FT, group_scene_ptr, veh_coll_buffer=0.2, dst=0):
+    """Refines the latents of a whole batch across the ranks of the default process group.
+
+    scene: dict of CPU tensors (ptr, past, lw, sem, map_idx, z, map_feat, past_feat, prior_mu, prior_var) describing the FULL
+    batch, identical on every rank; group_scene_ptr: scene offsets of the loss-normalisation groups (the batches the reference
+    driver would have formed).  Every rank runs a device-resident RefineLoop on the groups `shard.partition_groups` gives it;
+    rank `dst` returns the refined (NA,32) latents in batch order (CPU), the other ranks return None."""
+    import torch.distributed as dist
+    from . import shard
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    costs = shard.group_costs(scene['ptr'], group_scene_ptr, FT)
+    mine = shard.partition_groups(costs, world)[rank]
+    sub, lgptr, agent_index = shard.shard_scenes(scene, group_scene_ptr, mine)
+    NA = int(scene['ptr'][-1])
+    if agent_index.numel() == 0:
+        return shard.gather_rows(torch.zeros((0, scene['z'].size(1)), dtype=scene['z'].dtype), agent_index, NA, dst=dst)
+    dev = map_env.device
+    g = _DictGraph()
+    for k in ('past', 'lw', 'sem', 'ptr', 'batch', 'edge_index'):
+        setattr(g, k, sub[k].to(dev))
+    embed = {'map_feat': sub['map_feat'].to(dev), 'past_feat': sub['past_feat'].to(dev),
+             'prior_out': (sub['prior_mu'].to(dev), sub['prior_var'].to(dev))}
+    loop = RefineLoop(model, g, sub['map_idx'].to(dev), map_env, embed, sub['z'].to(dev), loss_weights, lr, FT,
+                      veh_coll_buffer=veh_coll_buffer, group_scene_ptr=lgptr)
+    z = loop.run(iters)
+    return shard.gather_rows(z, agent_index, NA, dst=dst)

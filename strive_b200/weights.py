@@ -99,22 +99,47 @@ def _bytes(t):
     return t.contiguous().view(torch.int16).reshape(-1).view(torch.uint8)
 
 
+CONV1_F = 127 * 65536      # fixed-point scale of the conv1 weights: the top digit of max|w| is exactly 127
+
+
+def conv1_fixed_point(w):
+    """(16,4,7,7) float32 -> (digits int64 (3,16,4,7,7) in [-128,127], scale float32 (16)):  w ~= scale[o] * sum_d digits[d] 256^d,
+    q = round(w / max|w[o]| * 127 * 2^16) in balanced base-256 digits, |w - scale q| <= 2^-24 max|w[o]| (+ the fp32 rounding of
+    scale = max|w[o]| / (127 * 2^16), a common factor of the channel).  The sums over the 196 binary inputs of one digit plane
+    stay below 2^15, so the kernel epilogue recombines the planes exactly in fp32 arithmetic."""
+    w64 = w.to(torch.float64)
+    s = w64.abs().reshape(w.size(0), -1).max(dim=1).values
+    s = torch.where(s > 0, s, torch.ones_like(s))
+    q = torch.round(w64 / s.view(-1, 1, 1, 1) * float(CONV1_F)).to(torch.int64)
+    digits = []
+    for i in range(3):
+        d = ((q + 128) % 256) - 128 if i < 2 else q
+        digits.append(d)
+        q = (q - d) // 256
+    assert int(q.abs().max()) == 0 and int(digits[2].abs().max()) <= 127
+    return torch.stack(digits), (s / float(CONV1_F)).to(torch.float32)
+
+
+def pack_conv1_fixed_point(w):
+    """conv1 operand B of tcgen05.mma kind::i8: [ky 7][khalf 2][n = 16 d + o][k = 4 kx_l + c] int8, taps kx = 4 khalf + kx_l
+    (kx = 7 is a zero pad), followed by the 16 fp32 scales."""
+    digits, scale = conv1_fixed_point(w)                                        # (3,16,4,7,7)
+    dg = torch.cat([digits, torch.zeros(3, 16, 4, 7, 1, dtype=torch.int64)], dim=4)   # pad kx to 8
+    t = dg.reshape(3, 16, 4, 7, 2, 4)                                           # (d, o, c, ky, khalf, kxl)
+    t = t.permute(3, 4, 0, 1, 5, 2).contiguous()                                # (ky, khalf, d, o, kxl, c)
+    b = t.to(torch.int8).reshape(-1).view(torch.uint8)
+    return torch.cat([b, scale.contiguous().view(torch.uint8).reshape(-1)])
+
+
 def pack_tc_weights(sd):
-    """bf16 hi/lo split conv1..conv4 weights in the tcgen05 K-major no-swizzle operand layout (csrc/mapenc_tc.cu).  The hi and
-    lo halves are STACKED ALONG N (rows n' = prec * NCH + n), so one MMA multiplies an A tile with both:
-    conv1: [ky 7][kq 2][khalf 2][prec 2][ngroup 2][r 8][k 8], k = (kx_l % 2) * 4 + c, taps kx = 4 kq + kx_l (kx = 7 is zero);
-    conv2..4: [nchunk][c2][tap][khalf 2][prec 2][ngroup NCH/8][r 8][k 8], n = NCH nchunk + 8 ngroup + r, c = 16 c2 + 8 khalf + k,
+    """Map-encoder weights in the tcgen05 K-major no-swizzle operand layout (csrc/mapenc_tc.cu).
+    conv1: int8 digit planes of a 31-bit fixed-point representation (pack_conv1_fixed_point).
+    conv2..fc: bf16 hi/lo split, the hi and lo halves STACKED ALONG N (rows n' = prec * NCH + n), so one MMA multiplies an A tile
+    with both;  conv2..4: [nchunk][c2][tap][khalf 2][prec 2][ngroup NCH/8][r 8][k 8], n = NCH nchunk + 8 ngroup + r, c = 16 c2 + 8 khalf + k,
     NCH = 32 output channels per CTA for conv2 and 64 for conv3 / conv4."""
     g = lambda k: sd[k].detach().to(torch.float32).cpu()
     out = []
-    w = g('map_conv.0.weight')                                              # (16,4,7,7)
-    w = torch.cat([w, torch.zeros(16, 4, 7, 1)], dim=3)                     # pad kx to 8
-    parts = []
-    for p in _split(w):
-        t = p.reshape(2, 8, 4, 7, 2, 2, 2)                                  # (ngroup, r, c, ky, kq, khalf, kxh)
-        parts.append(t.permute(3, 4, 5, 0, 1, 6, 2))                        # (ky, kq, khalf, ngroup, r, kxh, c)
-    t = torch.stack(parts, dim=3)                                           # (ky, kq, khalf, prec, ngroup, r, kxh, c)
-    out.append(_bytes(t))
+    out.append(pack_conv1_fixed_point(g('map_conv.0.weight')))
     for li, ks, nch in ((1, 5, 32), (2, 5, 64), (3, 3, 64)):
         w = g('map_conv.%d.weight' % (3 * li))                              # (Cout, Cin, ks, ks)
         cout, cin = w.size(0), w.size(1)

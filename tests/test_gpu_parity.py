@@ -558,3 +558,33 @@ def test_solution_loop_vs_oracle():
     assert e_t < 3e-2 and e_o < 3e-2      # 6-step BPTT after ~1e-5 forward noise (pixel flips); strict check = teacher-forced test
     assert dz.max().item() <= 2 * 0.05 * 2 + 1e-4
     assert tuple(z.shape) == (NA, 1, 32) and tuple(sol_traj.shape) == (NA, FTm, 4)
+
+
+def test_refine_sharded_single_rank_equals_fused_loop():
+    """optim.refine_sharded (the multi-GPU driver entry; world size 1 here) = shard -> RefineLoop -> gather: identical to
+    running RefineLoop on the whole batch with the same loss groups, and groups are independent of their neighbours."""
+    from strive_b200 import optim, synth, shard
+    dev, model, env = ctx()
+    FT = 4
+    sc = synth.make_scenes(31, [3, 2, 4, 1, 2, 3], map_extent_m=EXTENT, M=2, FT=FT, collide_frac=1.0, offroad_frac=1.0)
+    gptr = [0, 2, 3, 5, 6]
+    z_all = optim.refine_sharded(model, sc, env, REFINE_W, 3, 0.05, FT, gptr)
+    g = to_graph(sc, dev)
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev),
+             'prior_out': (sc['prior_mu'].to(dev), sc['prior_var'].to(dev))}
+    loop = optim.RefineLoop(model, g, sc['map_idx'].to(dev), env, embed, sc['z'].to(dev), REFINE_W, 0.05, FT, veh_coll_buffer=0.2,
+                            group_scene_ptr=gptr)
+    z_ref = loop.run(3).cpu()
+    d_all = (z_all - z_ref).abs().max().item()
+    # a rank that owns only groups {1, 3} must reproduce exactly those rows
+    sub, lgptr, idx = shard.shard_scenes(sc, gptr, [1, 3])
+    g2 = to_graph(sub, dev)
+    embed2 = {'map_feat': sub['map_feat'].to(dev), 'past_feat': sub['past_feat'].to(dev),
+              'prior_out': (sub['prior_mu'].to(dev), sub['prior_var'].to(dev))}
+    loop2 = optim.RefineLoop(model, g2, sub['map_idx'].to(dev), env, embed2, sub['z'].to(dev), REFINE_W, 0.05, FT, veh_coll_buffer=0.2,
+                             group_scene_ptr=lgptr)
+    d_sub = (loop2.run(3).cpu() - z_ref[idx]).abs().max().item()
+    diag('refine_sharded: |z_sharded - z_fused| = %.3e, rank-subset rows vs full batch rows = %.3e, moved %.3e' % (
+        d_all, d_sub, (z_ref - sc['z']).abs().max().item()))
+    # (floating-point atomics in the loss reductions make two runs agree to rounding, not bitwise)
+    assert d_all < 1e-6 and d_sub < 1e-5
