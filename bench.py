@@ -32,6 +32,14 @@ WORK = dict(scenes=64, agents=32, FT=20, group=4, raster=4096)
 CNN_MAC = {'conv1_gather': 49.0e6, 'conv2': 47.63e6, 'conv3': 43.06e6, 'conv4': 7.23e6, 'conv5': 2.65e6, 'conv6': 0.59e6, 'fc': 0.03e6,
            'tc_conv1': 49.0e6, 'tc_conv2': 47.63e6, 'tc_conv3': 43.06e6, 'tc_conv4': 7.23e6, 'tc_conv5': 2.65e6, 'tc_conv6': 0.59e6, 'tc_fc': 0.03e6}
 MAPENC_CHUNK = 2048
+# per-launch (2048 crops) DRAM traffic of the encoder kernels from ONE `ncu --set full` capture: dram__bytes_read.sum + dram__bytes_write.sum
+# (profiles/r01_ncu_full_v2_encoder.txt; conv3 / conv1 re-captured after their rewrites: profiles/r01_ncu_full_v3_encoder.txt)
+NCU_TRAFFIC_BYTES = {'tc_conv2': 2.067361e9 + 0.946168e9, 'tc_conv3': 0.978821e9 + 0.421498e9, 'tc_conv1': 0.135026e9 + 1.993950e9}
+# shared-memory operand bytes one launch moves (tcgen05 SS-mode operand fetch + producer stores), the resource that actually binds
+# these kernels: conv2 per 128-pixel tile = 25 taps x (4096 A_hi + 2048 B + 4096 A_lo + 1024 B) + 42.6 KB staged input
+SMEM_BYTES_PER_CROP = {'tc_conv2': 32 * (25 * (4096 + 2048 + 4096 + 1024) + 665 * 16 * 4),
+                       'tc_conv3': 8 * 2 * (25 * (4096 + 4096 + 4096 + 2048) + 665 * 16 * 4 + 25600),
+                       'tc_conv1': 32 * (28 * (4096 + 1536) + 21312)}
 
 
 def measured_peaks():
@@ -312,10 +320,22 @@ def run_gpu(args):
         crops_total = NA * (FT - 1) * prof_steps
         flops = 2.0 * CNN_MAC[top[0]] * crops_total
         achieved = flops / (tms / 1000.0) / 1e12
+        avg_s = tms / launches / 1000.0
+        crops_per_launch = crops_total / launches
+        traffic = NCU_TRAFFIC_BYTES.get(top[0])
         roof = {'kernel': top[0], 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / peaks['bf16_sustained'], 'traffic': None, 'peak_source': peaks['source'] + ' bf16 sustained (cuBLAS 8192^3)',
+                'frac': achieved / peaks['bf16_sustained'], 'traffic': traffic, 'peak_source': peaks['source'] + ' bf16 sustained (cuBLAS 8192^3)',
                 'share_of_step': tms / tot, 'avg_launch_ms': tms / launches,
-                'note': 'algorithmic FLOPs = 2*MAC*crops (the bf16 hi/lo split issues 2-3x that many tensor MACs), vs dense bf16 peak'}
+                'note': 'algorithmic FLOPs = 2*MAC*crops per launch (the bf16 hi/lo split issues 3x that many tensor MACs: ceiling of this '
+                        'precision choice = 1/3 of the dense peak), vs dense bf16 peak; traffic = ncu dram bytes per 2048-crop launch'}
+        if traffic is not None:
+            roof['hbm'] = {'achieved_gbs': traffic * (crops_per_launch / MAPENC_CHUNK) / avg_s / 1e9, 'peak_gbs': peaks['hbm_gbs'],
+                           'frac': traffic * (crops_per_launch / MAPENC_CHUNK) / avg_s / 1e9 / peaks['hbm_gbs']}
+        if top[0] in SMEM_BYTES_PER_CROP:
+            sm_peak = 148 * 128.0 * (clocks.get('sm_mhz') or 1965.0) * 1e6      # 128 B/clk/SM operand fetch (scripts/mma_bench2.cu)
+            sm_ach = SMEM_BYTES_PER_CROP[top[0]] * crops_per_launch / avg_s
+            roof['smem_operand'] = {'achieved_tbs': sm_ach / 1e12, 'peak_tbs': sm_peak / 1e12, 'frac': sm_ach / sm_peak,
+                                    'note': 'SS-mode tcgen05 operand fetch + staging stores vs 128 B/clk/SM: the binding resource'}
     enc = sum(prof[k][1] for k in CNN_MAC if k in prof)
     shares = {k: round(v[1] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
 

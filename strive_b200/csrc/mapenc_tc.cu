@@ -1232,26 +1232,44 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
 #pragma unroll 1
       for (int kc = 0; kc < NCH; kc++, cnt++) {
         const int b = cnt % NBUF;
-        tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
         uint8_t* sA = smem + (size_t)b * Cfg::STAGE;
         uint8_t* sWt = sA + 2 * Cfg::A_PREC;
-        {
-          const int4* src = reinterpret_cast<const int4*>(wpack + (size_t)kc * 2 * Cfg::W_PREC);
-          for (int i = tid; i < 2 * Cfg::W_PREC / 16; i += TC_PROD_THREADS) reinterpret_cast<int4*>(sWt)[i] = __ldg(src + i);
-        }
         const int k0 = kc * 64;
         const int tap = k0 / CIN, c0 = k0 % CIN;
         const int ky = tap / KS, kx = tap % KS;
-        for (int idx = tid; idx < 128 * 8; idx += TC_PROD_THREADS) {
+        // every global load of the chunk is issued before anything waits on one (the old load -> use loops paid ~9 L2 round
+        // trips per chunk and made these kernels 10x slower than their MMAs): the im2col rows go to registers now, the weight
+        // chunk goes through cp.async once the ring slot is free
+        constexpr int NIT = (128 * 8 + TC_PROD_THREADS - 1) / TC_PROD_THREADS;     // 3 (row, 8-channel group) items per thread
+        float4 t0[NIT], t1[NIT];
+        int offs[NIT];
+#pragma unroll
+        for (int j = 0; j < NIT; j++) {
+          const int idx = tid + j * TC_PROD_THREADS;
+          offs[j] = idx < 128 * 8 ? s_off[tpar][idx & 127] : -2;
+          if (offs[j] >= 0) {
+            const float* src = in + (size_t)offs[j] + (ky * HIN + kx) * CIN + c0 + (idx >> 7) * 8;
+            t0[j] = __ldg(reinterpret_cast<const float4*>(src));
+            t1[j] = __ldg(reinterpret_cast<const float4*>(src + 4));
+          }
+        }
+        tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
+        {
+          const uint8_t* src = wpack + (size_t)kc * 2 * Cfg::W_PREC;
+          const uint32_t dstw = tc::smem_u32(sWt);
+          for (int i = tid; i < 2 * Cfg::W_PREC / 16; i += TC_PROD_THREADS)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstw + (uint32_t)i * 16u), "l"(src + (size_t)i * 16) : "memory");
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+#pragma unroll
+        for (int j = 0; j < NIT; j++) {
+          const int idx = tid + j * TC_PROD_THREADS;
+          if (offs[j] == -2) continue;
           const int m = idx & 127, kg = idx >> 7;
           uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
-          const int off = s_off[tpar][m];
-          if (off >= 0) {
+          if (offs[j] >= 0) {
             const float mean = s_mean[tpar][m], rstd = s_rstd[tpar][m];
-            const float* src = in + (size_t)off + (ky * HIN + kx) * CIN + c0 + kg * 8;
-            const float4 t0 = __ldg(reinterpret_cast<const float4*>(src));
-            const float4 t1 = __ldg(reinterpret_cast<const float4*>(src + 4));
-            const float x[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+            const float x[8] = {t0[j].x, t0[j].y, t0[j].z, t0[j].w, t1[j].x, t1[j].y, t1[j].z, t1[j].w};
 #pragma unroll
             for (int c = 0; c < 8; c += 2) {
               const int ch = c0 + kg * 8 + c;
@@ -1265,6 +1283,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
           *reinterpret_cast<uint4*>(sA + (size_t)unit * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(sA + Cfg::A_PREC + (size_t)unit * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         tc::fence_async_smem();
         tc::mbar_arrive(&full[b]);
       }
