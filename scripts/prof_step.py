@@ -33,3 +33,5 @@ torch.cuda.synchronize()
 rep = _cabi.profile_report()
 tot = sum(v[1] for v in rep.values())
 print('  ' + '  '.join('%s %.2f' % (k, v[1]) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:18]) + '  | total %.2f ms' % tot)
+print('  per launch (us): ' + '  '.join('%s %.1f' % (k, 1000 * rep[k][1] / rep[k][0]) for k in
+                                        ('node_fwd', 'edge_fwd', 'post_fwd', 'gru_fwd', 'gru_bwd', 'post_bwd', 'edge_bwd', 'node_bwd') if k in rep))

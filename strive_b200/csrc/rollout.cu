@@ -16,6 +16,7 @@
 // Backward recomputes edge/node activations from the tape (node-level tensors only) instead of storing
 // per-edge activations (E x 320 floats per step would be 4 GB at BASELINE config 5).
 #include "common.cuh"
+#include "wpipe.cuh"
 
 // ------------------------------------------------------------------------------------------------------
 // tape layout (floats unless noted), all [t][agent][...]
@@ -114,14 +115,16 @@ struct StepArgs {
   Tape tp;
 };
 
-// rows per warp of the node-level kernels: measured on B200 at NA = 2048 (scripts/prof_step.py): R=4/unroll 2: 9.5 ms of node-level
-// kernels per iteration, R=2/unroll 4: 7.8 ms (the GEMV loops are bound by the L2 latency of the weight stream, not by FMAs)
+// node-level kernels: NODE_WARPS consumer warps x NODE_R rows each + one producer warp that streams the weights through
+// shared memory (wpipe.cuh).  History, measured on B200 at NA = 2048 (scripts/prof_step.py) with per-warp weight reads from
+// L1/L2: R=4/unroll 2: 9.5 ms of node-level kernels per iteration, R=2/unroll 4: 7.8 ms (L2-latency bound, 0.3 % of the FMA peak).
 #ifndef NODE_R
-#define NODE_R 2
+#define NODE_R 4
 #endif
 #ifndef NODE_WARPS
 #define NODE_WARPS 4
 #endif
+#define NODE_THREADS ((NODE_WARPS + 1) * 32)
 #define EDGE_R 8
 #define EDGE_WARPS 4
 #define LDA 172   // >= 168, multiple of 4
@@ -132,21 +135,34 @@ struct StepArgs {
 // ------------------------------------------------------------------------------------------------------
 template <int R>
 __device__ __forceinline__ void stage_node_feat(float* bufA, const StepArgs& a, const int (&row)[R], int lane, int in0_rows) {
+  // every global load of the R rows is issued before the first shared-memory store waits on one (a load -> store loop
+  // serialises 6 L2 round trips per row: 22 % of node_fwd's cycles in the ncu stall profile)
   const int NA = a.NA, NC = a.NC;
   const float* pf = a.tp.pastfeat + (size_t)a.t * NA * 64;
   const float* mf = a.tp.mapfeat + (size_t)a.t * NA * 64;
+  float4 head[R];
+  float tail[R][2];
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int ag = row[r];
-    for (int k = lane; k < in0_rows; k += 32) {
-      float v;
-      if (k < 64) v = pf[(size_t)ag * 64 + k];
-      else if (k < 128) v = mf[(size_t)ag * 64 + k - 64];
-      else if (k < 128 + NC) v = a.sem[(size_t)ag * NC + k - 128];
-      else if (k < 128 + NC + ZDIM) v = a.z[(size_t)ag * ZDIM + k - 128 - NC];
-      else if (k < 128 + NC + ZDIM + 2) v = a.lw[(size_t)ag * 2 + k - 128 - NC - ZDIM];
-      else v = 0.f;
-      bufA[r * LDA + k] = v;
+    head[r] = __ldg(reinterpret_cast<const float4*>((lane < 16 ? pf : mf) + (size_t)ag * 64 + (lane & 15) * 4));
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int k = 128 + h * 32 + lane;
+      float v = 0.f;
+      if (k < 128 + NC) v = __ldg(a.sem + (size_t)ag * NC + k - 128);
+      else if (k < 128 + NC + ZDIM) v = __ldg(a.z + (size_t)ag * ZDIM + k - 128 - NC);
+      else if (k < 128 + NC + ZDIM + 2) v = __ldg(a.lw + (size_t)ag * 2 + k - 128 - NC - ZDIM);
+      tail[r][h] = v;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    *reinterpret_cast<float4*>(bufA + r * LDA + lane * 4) = head[r];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int k = 128 + h * 32 + lane;
+      if (k < in0_rows) bufA[r * LDA + k] = tail[r][h];
     }
   }
 }
@@ -154,43 +170,90 @@ __device__ __forceinline__ void stage_node_feat(float* bufA, const StepArgs& a, 
 // forward of mlp_in on R staged rows. Leaves h2 (post LN/ReLU of layer 2) in bufA (ld LDA) and, if keep, the
 // pre-LN activations a1 in pre1 and a2 in pre2 (ld LDH). Returns x in xacc.
 template <int R>
-__device__ __forceinline__ void mlp_in_fwd(const ModelDev& M, float* bufA, float* bufB, float* pre1, float* pre2,
+__device__ __forceinline__ void mlp_in_fwd(const ModelDev& M, WPipe& wp, float* bufA, float* bufB, float* pre1, float* pre2,
                                            float (&xacc)[R][2], int lane) {
   float acc[R][4];
   init_bias<4, R>(acc, M.seg[S_IN0_B], lane);
-  warp_gemm<128, R>(M.seg[S_IN0_T], M.in0_rows, bufA, LDA, acc, lane);
+  pipe_gemm<128, R>(wp, M.in0_rows, bufA, LDA, acc, lane);
   __syncwarp();
   ln_relu_store<R>(acc, M.seg[S_IN_LN1_G], M.seg[S_IN_LN1_B], bufB, LDH, pre1, LDH, lane);
   __syncwarp();
   init_bias<4, R>(acc, M.seg[S_IN3_B], lane);
-  warp_gemm<128, R>(M.seg[S_IN3_T], 128, bufB, LDH, acc, lane);
+  pipe_gemm<128, R>(wp, 128, bufB, LDH, acc, lane);
   __syncwarp();
   ln_relu_store<R>(acc, M.seg[S_IN_LN4_G], M.seg[S_IN_LN4_B], bufA, LDA, pre2, LDH, lane);
   __syncwarp();
   init_bias<2, R>(xacc, M.seg[S_IN6_B], lane);
-  warp_gemm<64, R>(M.seg[S_IN6_T], 128, bufA, LDA, xacc, lane);
+  pipe_gemm<64, R>(wp, 128, bufA, LDA, xacc, lane);
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(NODE_WARPS * 32) node_fwd_kernel(ModelDev M, StepArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* bufA = smem + warp * (NODE_R * (LDA + LDH));
-  float* bufB = bufA + NODE_R * LDA;
-  const int NA = a.NA;
-  int row[NODE_R];
-  bool valid[NODE_R];
-  const int base = (blockIdx.x * NODE_WARPS + warp) * NODE_R;
-  if (base >= NA) return;
+// small parameter vectors -> L1 (called by every consumer warp while its inputs are in flight)
+__device__ __forceinline__ void prefetch_mlp_in_params(const ModelDev& M, int lane) {
+  wp_prefetch_l1(M.seg[S_IN0_B], 128, lane); wp_prefetch_l1(M.seg[S_IN_LN1_G], 128, lane); wp_prefetch_l1(M.seg[S_IN_LN1_B], 128, lane);
+  wp_prefetch_l1(M.seg[S_IN3_B], 128, lane); wp_prefetch_l1(M.seg[S_IN_LN4_G], 128, lane); wp_prefetch_l1(M.seg[S_IN_LN4_B], 128, lane);
+  wp_prefetch_l1(M.seg[S_IN6_B], 64, lane);
+}
+__device__ __forceinline__ void prefetch_post_params(const ModelDev& M, int lane) {
+  wp_prefetch_l1(M.seg[S_U0_B], 128, lane); wp_prefetch_l1(M.seg[S_U_LN1_G], 128, lane); wp_prefetch_l1(M.seg[S_U_LN1_B], 128, lane);
+  wp_prefetch_l1(M.seg[S_U3_B], 64, lane); wp_prefetch_l1(M.seg[S_O0_B], 128, lane); wp_prefetch_l1(M.seg[S_O_LN1_G], 128, lane);
+  wp_prefetch_l1(M.seg[S_O_LN1_B], 128, lane); wp_prefetch_l1(M.seg[S_O3_B], 128, lane); wp_prefetch_l1(M.seg[S_O_LN4_G], 128, lane);
+  wp_prefetch_l1(M.seg[S_O_LN4_B], 128, lane); wp_prefetch_l1(M.seg[S_O6_N], 256, lane); wp_prefetch_l1(M.seg[S_O6_B], 2, lane);
+}
+__device__ __forceinline__ void prefetch_gru_params(const ModelDev& M, int lane) {
 #pragma unroll
-  for (int r = 0; r < NODE_R; r++) {
+  for (int l = 0; l < 3; l++) {
+    wp_prefetch_l1(M.seg[S_GBI0 + l * 6], 192, lane);
+    wp_prefetch_l1(M.seg[S_GBH0 + l * 6], 192, lane);
+  }
+  wp_prefetch_l1(M.seg[S_GI_T0], 4 * 192, lane);
+  wp_prefetch_l1(M.seg[S_GI_N0], 4 * 192, lane);
+}
+
+// producer-side schedules: the matrices each kernel's consumers multiply by, in consumption order
+__device__ __forceinline__ void produce_mlp_in(const ModelDev& M, WPipe& wp) {
+  wp_produce(wp, M.seg[S_IN0_T], M.in0_rows, 128);
+  wp_produce(wp, M.seg[S_IN3_T], 128, 128);
+  wp_produce(wp, M.seg[S_IN6_T], 128, 64);
+}
+
+// rows of this consumer warp (clamped: warps past the end of the batch still step through the weight ring)
+template <int R>
+__device__ __forceinline__ void node_rows(int warp, int NA, int& base, int (&row)[R], bool (&valid)[R]) {
+  base = (blockIdx.x * NODE_WARPS + warp) * R;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
     valid[r] = (base + r) < NA;
     row[r] = valid[r] ? base + r : NA - 1;
   }
+}
+
+__global__ void __launch_bounds__(NODE_THREADS, 2) node_fwd_kernel(ModelDev M, StepArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WPipe wp = wp_init(smem, NODE_WARPS);
+  if (warp == NODE_WARPS) {
+    if (lane == 0) {
+      produce_mlp_in(M, wp);
+      wp_produce(wp, M.seg[S_E0_T_XI], 64, 128);
+      wp_produce(wp, M.seg[S_E0_T_XJ], 64, 128);
+    }
+    return;
+  }
+  float* bufA = smem + WP_SMEM_FLOATS + warp * (NODE_R * (LDA + LDH));
+  float* bufB = bufA + NODE_R * LDA;
+  const int NA = a.NA;
+  int row[NODE_R], base;
+  bool valid[NODE_R];
+  node_rows<NODE_R>(warp, NA, base, row, valid);
+  prefetch_mlp_in_params(M, lane);
+  wp_prefetch_l1(M.seg[S_E0_B], 128, lane);
+  wp_prefetch_l1(M.seg[S_E0_T_SEMI], a.NC * 128, lane);
+  wp_prefetch_l1(M.seg[S_E0_T_SEMJ], a.NC * 128, lane);
   stage_node_feat<NODE_R>(bufA, a, row, lane, M.in0_rows);
   __syncwarp();
   float xacc[NODE_R][2];
-  mlp_in_fwd<NODE_R>(M, bufA, bufB, nullptr, nullptr, xacc, lane);
+  mlp_in_fwd<NODE_R>(M, wp, bufA, bufB, nullptr, nullptr, xacc, lane);
   // x -> tape + shared (bufB as [R][LDH], first 64 cols)
   float* xg = a.tp.x + (size_t)a.t * NA * 64;
 #pragma unroll
@@ -202,7 +265,7 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) node_fwd_kernel(ModelDev M, S
   // P = W_xi x + W_semi sem + b ; Q = W_xj x + W_semj sem
   float acc[NODE_R][4];
   init_bias<4, NODE_R>(acc, M.seg[S_E0_B], lane);
-  warp_gemm<128, NODE_R>(M.seg[S_E0_T_XI], 64, bufB, LDH, acc, lane);
+  pipe_gemm<128, NODE_R>(wp, 64, bufB, LDH, acc, lane);
   for (int c = 0; c < a.NC; c++) {
     float w[4];
     ldvec<4>(w, M.seg[S_E0_T_SEMI] + c * 128 + lane * 4);
@@ -218,7 +281,7 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) node_fwd_kernel(ModelDev M, S
   for (int r = 0; r < NODE_R; r++)
     if (valid[r]) stvec<4>(Pg + (size_t)row[r] * 128 + lane * 4, acc[r]);
   init_zero<4, NODE_R>(acc);
-  warp_gemm<128, NODE_R>(M.seg[S_E0_T_XJ], 64, bufB, LDH, acc, lane);
+  pipe_gemm<128, NODE_R>(wp, 64, bufB, LDH, acc, lane);
   for (int c = 0; c < a.NC; c++) {
     float w[4];
     ldvec<4>(w, M.seg[S_E0_T_SEMJ] + c * 128 + lane * 4);
@@ -369,44 +432,45 @@ __device__ __forceinline__ void stage_update_in(float* bufA, const StepArgs& a, 
   const int NA = a.NA, NC = a.NC;
   const float* xg = a.tp.x + (size_t)a.t * NA * 64;
   const float* ag = a.tp.aggr + (size_t)a.t * NA * 64;
+  float4 head[R];
+  float tail[R];
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int agn = row[r];
-    for (int k = lane; k < u0_rows; k += 32) {
-      float v;
-      if (k < 64) v = xg[(size_t)agn * 64 + k];
-      else if (k < 128) v = ag[(size_t)agn * 64 + k - 64];
-      else if (k < 128 + NC) v = a.sem[(size_t)agn * NC + k - 128];
-      else v = 0.f;
-      bufA[r * LDA + k] = v;
-    }
+    head[r] = __ldg(reinterpret_cast<const float4*>((lane < 16 ? xg : ag) + (size_t)agn * 64 + (lane & 15) * 4));
+    tail[r] = (lane < NC) ? __ldg(a.sem + (size_t)agn * NC + lane) : 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    *reinterpret_cast<float4*>(bufA + r * LDA + lane * 4) = head[r];
+    if (128 + lane < u0_rows) bufA[r * LDA + 128 + lane] = tail[r];
   }
 }
 
 // update_mlp + mlp_out forward on R staged rows; returns o (2 per row, replicated in every lane).
 // If keep: preU (a_u), pre1 (a_1), pre2 (a_2) pre-LN activations (ld LDH) are kept for the backward pass.
 template <int R>
-__device__ __forceinline__ void post_mlps_fwd(const ModelDev& M, float* bufA, float* bufB, float* preU, float* pre1,
+__device__ __forceinline__ void post_mlps_fwd(const ModelDev& M, WPipe& wp, float* bufA, float* bufB, float* preU, float* pre1,
                                               float* pre2, float (&o)[R][2], int lane) {
   float acc[R][4];
   init_bias<4, R>(acc, M.seg[S_U0_B], lane);
-  warp_gemm<128, R>(M.seg[S_U0_T], M.u0_rows, bufA, LDA, acc, lane);
+  pipe_gemm<128, R>(wp, M.u0_rows, bufA, LDA, acc, lane);
   __syncwarp();
   ln_relu_store<R>(acc, M.seg[S_U_LN1_G], M.seg[S_U_LN1_B], bufB, LDH, preU, LDH, lane);
   __syncwarp();
   float xu[R][2];
   init_bias<2, R>(xu, M.seg[S_U3_B], lane);
-  warp_gemm<64, R>(M.seg[S_U3_T], 128, bufB, LDH, xu, lane);
+  pipe_gemm<64, R>(wp, 128, bufB, LDH, xu, lane);
   __syncwarp();
   store_rows<2, R>(xu, bufA, LDA, lane);
   __syncwarp();
   init_bias<4, R>(acc, M.seg[S_O0_B], lane);
-  warp_gemm<128, R>(M.seg[S_O0_T], 64, bufA, LDA, acc, lane);
+  pipe_gemm<128, R>(wp, 64, bufA, LDA, acc, lane);
   __syncwarp();
   ln_relu_store<R>(acc, M.seg[S_O_LN1_G], M.seg[S_O_LN1_B], bufB, LDH, pre1, LDH, lane);
   __syncwarp();
   init_bias<4, R>(acc, M.seg[S_O3_B], lane);
-  warp_gemm<128, R>(M.seg[S_O3_T], 128, bufB, LDH, acc, lane);
+  pipe_gemm<128, R>(wp, 128, bufB, LDH, acc, lane);
   __syncwarp();
   ln_relu_store<R>(acc, M.seg[S_O_LN4_G], M.seg[S_O_LN4_B], bufA, LDA, pre2, LDH, lane);
   __syncwarp();
@@ -422,6 +486,13 @@ __device__ __forceinline__ void post_mlps_fwd(const ModelDev& M, float* bufA, fl
     o[r][0] = warp_sum(p0) + b0;
     o[r][1] = warp_sum(p1) + b1;
   }
+}
+
+__device__ __forceinline__ void produce_post_mlps(const ModelDev& M, WPipe& wp) {
+  wp_produce(wp, M.seg[S_U0_T], M.u0_rows, 128);
+  wp_produce(wp, M.seg[S_U3_T], 128, 64);
+  wp_produce(wp, M.seg[S_O0_T], 64, 128);
+  wp_produce(wp, M.seg[S_O3_T], 128, 128);
 }
 
 struct BikeFwd {
@@ -449,21 +520,25 @@ __device__ __forceinline__ void bicycle_fwd(const float prev[6], float o0, float
   for (int k = 0; k < 6; k++) cur[k] = (out[k] - kStateMean[k]) / kStateStd[k];
 }
 
-__global__ void __launch_bounds__(NODE_WARPS * 32) post_fwd_kernel(ModelDev M, StepArgs a) {
+__global__ void __launch_bounds__(NODE_THREADS, 2) post_fwd_kernel(ModelDev M, StepArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* bufA = smem + warp * (NODE_R * (LDA + LDH));
+  WPipe wp = wp_init(smem, NODE_WARPS);
+  if (warp == NODE_WARPS) {
+    if (lane == 0) produce_post_mlps(M, wp);
+    return;
+  }
+  float* bufA = smem + WP_SMEM_FLOATS + warp * (NODE_R * (LDA + LDH));
   float* bufB = bufA + NODE_R * LDA;
   const int NA = a.NA, t = a.t, FT = a.FT;
-  int row[NODE_R];
-  const int base = (blockIdx.x * NODE_WARPS + warp) * NODE_R;
-  if (base >= NA) return;
-#pragma unroll
-  for (int r = 0; r < NODE_R; r++) row[r] = (base + r) < NA ? base + r : NA - 1;
+  int row[NODE_R], base;
+  bool valid[NODE_R];
+  node_rows<NODE_R>(warp, NA, base, row, valid);
+  prefetch_post_params(M, lane);
   stage_update_in<NODE_R>(bufA, a, row, lane, M.u0_rows);
   __syncwarp();
   float o[NODE_R][2];
-  post_mlps_fwd<NODE_R>(M, bufA, bufB, nullptr, nullptr, nullptr, o, lane);
+  post_mlps_fwd<NODE_R>(M, wp, bufA, bufB, nullptr, nullptr, nullptr, o, lane);
   float my_o0 = 0.f, my_o1 = 0.f;
 #pragma unroll
   for (int r = 0; r < NODE_R; r++)
@@ -511,8 +586,30 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) post_fwd_kernel(ModelDev M, S
 // per-warp shared: xin [R][68], h [3][R][68], gate stash for backward [3][R][4][64]
 #define LDG 68
 
+// hidden state [3][64] and local-frame delta [4] of R rows -> shared (all loads in flight before the first store)
 template <int R>
-__device__ __forceinline__ void gru_layer_fwd(const ModelDev& M, int l, const float* xin, const float* loc /*[R][4] if l==0*/,
+__device__ __forceinline__ void stage_gru_in(float* hbuf, float* locs, const float* __restrict__ memg, const float* __restrict__ locg,
+                                             const int (&row)[R], int lane) {
+  float4 h0[R], h1[R];
+  float lc[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const float4* src = reinterpret_cast<const float4*>(memg + (size_t)row[r] * 192);
+    h0[r] = __ldg(src + lane);
+    h1[r] = (lane < 16) ? __ldg(src + 32 + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+    lc[r] = (lane < 4) ? __ldg(locg + (size_t)row[r] * 4 + lane) : 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    // float4 index q = k/4 of mem[row][k]: layer q>>4, offset (q&15)*4
+    *reinterpret_cast<float4*>(hbuf + ((lane >> 4) * R + r) * LDG + (lane & 15) * 4) = h0[r];
+    if (lane < 16) *reinterpret_cast<float4*>(hbuf + (2 * R + r) * LDG + lane * 4) = h1[r];
+    if (lane < 4) locs[r * 4 + lane] = lc[r];
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void gru_layer_fwd(const ModelDev& M, WPipe& wp, int l, const float* xin, const float* loc /*[R][4] if l==0*/,
                                               const float* hprev, float (&hnew)[R][2], float* stash /*[R][4][64] or null*/,
                                               int lane) {
   const int so = l * 6;
@@ -548,9 +645,9 @@ __device__ __forceinline__ void gru_layer_fwd(const ModelDev& M, int l, const fl
       }
     }
   } else {
-    warp_gemm_gru<R>(M.seg[S_GI_T0 + so], 64, xin, LDG, gi, lane);
+    pipe_gemm_gru<R>(wp, 64, xin, LDG, gi, lane);
   }
-  warp_gemm_gru<R>(M.seg[S_GH_T0 + so], 64, hprev, LDG, gh, lane);
+  pipe_gemm_gru<R>(wp, 64, hprev, LDG, gh, lane);
 #pragma unroll
   for (int r = 0; r < R; r++) {
 #pragma unroll
@@ -568,31 +665,39 @@ __device__ __forceinline__ void gru_layer_fwd(const ModelDev& M, int l, const fl
   }
 }
 
-__global__ void __launch_bounds__(NODE_WARPS * 32) gru_fwd_kernel(ModelDev M, StepArgs a) {
+// forward weight order of the GRU: layer 0 has no input-side GEMM (its 4-wide input is applied from L1)
+__device__ __forceinline__ void produce_gru_fwd(const ModelDev& M, WPipe& wp) {
+  wp_produce(wp, M.seg[S_GH_T0], 64, 192);
+  wp_produce(wp, M.seg[S_GI_T1], 64, 192);
+  wp_produce(wp, M.seg[S_GH_T1], 64, 192);
+  wp_produce(wp, M.seg[S_GI_T2], 64, 192);
+  wp_produce(wp, M.seg[S_GH_T2], 64, 192);
+}
+
+__global__ void __launch_bounds__(NODE_THREADS, 2) gru_fwd_kernel(ModelDev M, StepArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* xin = smem + warp * (GRU_R * LDG * 4 + GRU_R * 4);
+  WPipe wp = wp_init(smem, NODE_WARPS);
+  if (warp == NODE_WARPS) {
+    if (lane == 0) produce_gru_fwd(M, wp);
+    return;
+  }
+  float* xin = smem + WP_SMEM_FLOATS + warp * (GRU_R * LDG * 4 + GRU_R * 4);
   float* hbuf = xin + GRU_R * LDG;          // [3][R][LDG]
   float* locs = hbuf + 3 * GRU_R * LDG;     // [R][4]
   const int NA = a.NA, t = a.t;
-  const int base = (blockIdx.x * NODE_WARPS + warp) * GRU_R;
-  if (base >= NA) return;
-  int row[GRU_R];
+  int row[GRU_R], base;
   bool valid[GRU_R];
-#pragma unroll
-  for (int r = 0; r < GRU_R; r++) { valid[r] = base + r < NA; row[r] = valid[r] ? base + r : NA - 1; }
+  node_rows<GRU_R>(warp, NA, base, row, valid);
+  prefetch_gru_params(M, lane);
   const float* memg = a.tp.mem + (size_t)t * NA * 192;
-#pragma unroll
-  for (int r = 0; r < GRU_R; r++) {
-    for (int k = lane; k < 192; k += 32) hbuf[((k >> 6) * GRU_R + r) * LDG + (k & 63)] = memg[(size_t)row[r] * 192 + k];
-    if (lane < 4) locs[r * 4 + lane] = a.tp.loc[((size_t)t * NA + row[r]) * 4 + lane];
-  }
+  stage_gru_in<GRU_R>(hbuf, locs, memg, a.tp.loc + (size_t)t * NA * 4, row, lane);
   __syncwarp();
   float* memn = a.tp.mem + (size_t)(t + 1) * NA * 192;
   float* pfn = a.tp.pastfeat + (size_t)(t + 1) * NA * 64;
   for (int l = 0; l < 3; l++) {
     float hnew[GRU_R][2];
-    gru_layer_fwd<GRU_R>(M, l, xin, locs, hbuf + l * GRU_R * LDG, hnew, nullptr, lane);
+    gru_layer_fwd<GRU_R>(M, wp, l, xin, locs, hbuf + l * GRU_R * LDG, hnew, nullptr, lane);
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < GRU_R; r++) {
@@ -612,35 +717,41 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) gru_fwd_kernel(ModelDev M, St
 
 // GRU backward. In: g_mem (grad wrt mem_{t+1}), g_pf (grad wrt past_feat_{t+1} = top output). Out: g_mem <- grad wrt
 // mem_t, d_loc. (Not launched for t = FT-1: no GRU step there.)
-__global__ void __launch_bounds__(NODE_WARPS * 32) gru_bwd_kernel(ModelDev M, StepArgs a) {
+__global__ void __launch_bounds__(NODE_THREADS, 2) gru_bwd_kernel(ModelDev M, StepArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WPipe wp = wp_init(smem, NODE_WARPS);
+  if (warp == NODE_WARPS) {
+    if (lane == 0) {
+      produce_gru_fwd(M, wp);
+      wp_produce(wp, M.seg[S_GI_N2], 192, 64);
+      wp_produce(wp, M.seg[S_GH_N2], 192, 64);
+      wp_produce(wp, M.seg[S_GI_N1], 192, 64);
+      wp_produce(wp, M.seg[S_GH_N1], 192, 64);
+      wp_produce(wp, M.seg[S_GH_N0], 192, 64);
+    }
+    return;
+  }
   // per-warp: xin[3][R][LDG] (inputs of layers 1,2 = new h of layers 0,1; slot 0 unused), h[3][R][LDG], loc[R][4],
   //           stash[3][R][4][64], dg [R][196]
   constexpr int PER_WARP = 6 * GRU_R * LDG + GRU_R * 4 + 3 * GRU_R * 256 + GRU_R * 196;
-  float* xin = smem + warp * PER_WARP;
+  float* xin = smem + WP_SMEM_FLOATS + warp * PER_WARP;
   float* hbuf = xin + 3 * GRU_R * LDG;
   float* locs = hbuf + 3 * GRU_R * LDG;
   float* stash = locs + GRU_R * 4;
   float* dgb = stash + 3 * GRU_R * 256;   // [R][196] gate grads staged for the native GEMMs
   const int NA = a.NA, t = a.t;
-  const int base = (blockIdx.x * NODE_WARPS + warp) * GRU_R;
-  if (base >= NA) return;
-  int row[GRU_R];
+  int row[GRU_R], base;
   bool valid[GRU_R];
-#pragma unroll
-  for (int r = 0; r < GRU_R; r++) { valid[r] = base + r < NA; row[r] = valid[r] ? base + r : NA - 1; }
+  node_rows<GRU_R>(warp, NA, base, row, valid);
+  prefetch_gru_params(M, lane);
   const float* memg = a.tp.mem + (size_t)t * NA * 192;
-#pragma unroll
-  for (int r = 0; r < GRU_R; r++) {
-    for (int k = lane; k < 192; k += 32) hbuf[((k >> 6) * GRU_R + r) * LDG + (k & 63)] = memg[(size_t)row[r] * 192 + k];
-    if (lane < 4) locs[r * 4 + lane] = a.tp.loc[((size_t)t * NA + row[r]) * 4 + lane];
-  }
+  stage_gru_in<GRU_R>(hbuf, locs, memg, a.tp.loc + (size_t)t * NA * 4, row, lane);
   __syncwarp();
   // recompute forward, stash gates
   for (int l = 0; l < 3; l++) {
     float hnew[GRU_R][2];
-    gru_layer_fwd<GRU_R>(M, l, xin + l * GRU_R * LDG, locs, hbuf + l * GRU_R * LDG, hnew, stash + l * GRU_R * 256, lane);
+    gru_layer_fwd<GRU_R>(M, wp, l, xin + l * GRU_R * LDG, locs, hbuf + l * GRU_R * LDG, hnew, stash + l * GRU_R * 256, lane);
     __syncwarp();
     if (l < 2) {
 #pragma unroll
@@ -694,7 +805,7 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) gru_bwd_kernel(ModelDev M, St
     if (l > 0) {
       float dx[GRU_R][2];
       init_zero<2, GRU_R>(dx);
-      warp_gemm<64, GRU_R>(M.seg[S_GI_N0 + so], 192, dgb, 196, dx, lane);
+      pipe_gemm<64, GRU_R>(wp, 192, dgb, 196, dx, lane);
 #pragma unroll
       for (int r = 0; r < GRU_R; r++) { dx_next[r][0] = dx[r][0]; dx_next[r][1] = dx[r][1]; }
     } else {
@@ -719,7 +830,7 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) gru_bwd_kernel(ModelDev M, St
       for (int e = 0; e < 2; e++) dgb[r * 196 + 128 + lane * 2 + e] = stash[((size_t)l * GRU_R + r) * 256 + 192 + lane * 2 + e];
     }
     __syncwarp();
-    warp_gemm<64, GRU_R>(M.seg[S_GH_N0 + so], 192, dgb, 196, dhp, lane);
+    pipe_gemm<64, GRU_R>(wp, 192, dgb, 196, dhp, lane);
     __syncwarp();
 #pragma unroll
     for (int r = 0; r < GRU_R; r++)
@@ -734,26 +845,36 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) gru_bwd_kernel(ModelDev M, St
 
 // post backward: (d_traj[t], g_prev, g_pos, d_loc) -> bicycle/transform adjoint -> mlp_out/update_mlp adjoint
 // outputs: g_prev <- grad wrt prev_state_t, d_xupd, d_aggr; zeroes g_pos and dQ rows for the edge phase.
-__global__ void __launch_bounds__(NODE_WARPS * 32) post_bwd_kernel(ModelDev M, StepArgs a, int has_gru) {
+__global__ void __launch_bounds__(NODE_THREADS, 2) post_bwd_kernel(ModelDev M, StepArgs a, int has_gru) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WPipe wp = wp_init(smem, NODE_WARPS);
+  if (warp == NODE_WARPS) {
+    if (lane == 0) {
+      produce_post_mlps(M, wp);
+      wp_produce(wp, M.seg[S_O3_N], 128, 128);
+      wp_produce(wp, M.seg[S_O0_N], 128, 64);
+      wp_produce(wp, M.seg[S_U3_N], 64, 128);
+      wp_produce(wp, M.seg[S_U0_N_X], 128, 64);
+      wp_produce(wp, M.seg[S_U0_N_AGGR], 128, 64);
+    }
+    return;
+  }
   constexpr int PER_WARP = NODE_R * (LDA + LDH) + 3 * NODE_R * LDH;
-  float* bufA = smem + warp * PER_WARP;
+  float* bufA = smem + WP_SMEM_FLOATS + warp * PER_WARP;
   float* bufB = bufA + NODE_R * LDA;
   float* preU = bufB + NODE_R * LDH;
   float* pre1 = preU + NODE_R * LDH;
   float* pre2 = pre1 + NODE_R * LDH;
   const int NA = a.NA, t = a.t, FT = a.FT;
-  const int base = (blockIdx.x * NODE_WARPS + warp) * NODE_R;
-  if (base >= NA) return;
-  int row[NODE_R];
+  int row[NODE_R], base;
   bool valid[NODE_R];
-#pragma unroll
-  for (int r = 0; r < NODE_R; r++) { valid[r] = base + r < NA; row[r] = valid[r] ? base + r : NA - 1; }
+  node_rows<NODE_R>(warp, NA, base, row, valid);
+  prefetch_post_params(M, lane);
   stage_update_in<NODE_R>(bufA, a, row, lane, M.u0_rows);
   __syncwarp();
   float o[NODE_R][2];
-  post_mlps_fwd<NODE_R>(M, bufA, bufB, preU, pre1, pre2, o, lane);
+  post_mlps_fwd<NODE_R>(M, wp, bufA, bufB, preU, pre1, pre2, o, lane);
   // scalar adjoint: lane r handles row r, then d_o is broadcast to the warp
   float my_o0 = 0.f, my_o1 = 0.f;
 #pragma unroll
@@ -857,20 +978,20 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) post_bwd_kernel(ModelDev M, S
   store_rows<4, NODE_R>(dh, bufB, LDH, lane);
   __syncwarp();
   init_zero<4, NODE_R>(dh);
-  warp_gemm<128, NODE_R>(M.seg[S_O3_N], 128, bufB, LDH, dh, lane);
+  pipe_gemm<128, NODE_R>(wp, 128, bufB, LDH, dh, lane);
   ln_relu_bwd<NODE_R>(dh, pre1, LDH, M.seg[S_O_LN1_G], M.seg[S_O_LN1_B], lane);
   __syncwarp();
   store_rows<4, NODE_R>(dh, bufB, LDH, lane);
   __syncwarp();
   float dxu[NODE_R][2];
   init_zero<2, NODE_R>(dxu);
-  warp_gemm<64, NODE_R>(M.seg[S_O0_N], 128, bufB, LDH, dxu, lane);
+  pipe_gemm<64, NODE_R>(wp, 128, bufB, LDH, dxu, lane);
   __syncwarp();
   // update_mlp backward
   store_rows<2, NODE_R>(dxu, bufA, LDA, lane);
   __syncwarp();
   init_zero<4, NODE_R>(dh);
-  warp_gemm<128, NODE_R>(M.seg[S_U3_N], 64, bufA, LDA, dh, lane);
+  pipe_gemm<128, NODE_R>(wp, 64, bufA, LDA, dh, lane);
   ln_relu_bwd<NODE_R>(dh, preU, LDH, M.seg[S_U_LN1_G], M.seg[S_U_LN1_B], lane);
   __syncwarp();
   store_rows<4, NODE_R>(dh, bufB, LDH, lane);
@@ -878,8 +999,8 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) post_bwd_kernel(ModelDev M, S
   float dxx[NODE_R][2], dag[NODE_R][2];
   init_zero<2, NODE_R>(dxx);
   init_zero<2, NODE_R>(dag);
-  warp_gemm<64, NODE_R>(M.seg[S_U0_N_X], 128, bufB, LDH, dxx, lane);
-  warp_gemm<64, NODE_R>(M.seg[S_U0_N_AGGR], 128, bufB, LDH, dag, lane);
+  pipe_gemm<64, NODE_R>(wp, 128, bufB, LDH, dxx, lane);
+  pipe_gemm<64, NODE_R>(wp, 128, bufB, LDH, dag, lane);
 #pragma unroll
   for (int r = 0; r < NODE_R; r++) {
     if (valid[r]) {
@@ -995,25 +1116,36 @@ __global__ void __launch_bounds__(EDGE_WARPS * 32) edge_bwd_kernel(ModelDev M, S
 }
 
 // node backward: d_x = d_xupd + dP.W_xi + dQ.W_xj ; back through mlp_in; d_z += ; g_pf <- grad wrt past_feat_t
-__global__ void __launch_bounds__(NODE_WARPS * 32) node_bwd_kernel(ModelDev M, StepArgs a) {
+__global__ void __launch_bounds__(NODE_THREADS, 2) node_bwd_kernel(ModelDev M, StepArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  WPipe wp = wp_init(smem, NODE_WARPS);
+  if (warp == NODE_WARPS) {
+    if (lane == 0) {
+      produce_mlp_in(M, wp);
+      wp_produce(wp, M.seg[S_E0_N_XI], 128, 64);
+      wp_produce(wp, M.seg[S_E0_N_XJ], 128, 64);
+      wp_produce(wp, M.seg[S_IN6_N], 64, 128);
+      wp_produce(wp, M.seg[S_IN3_N], 128, 128);
+      wp_produce(wp, M.seg[S_IN0_N_PF], 128, 64);
+      wp_produce(wp, M.seg[S_IN0_N_Z], 128, 32);
+    }
+    return;
+  }
   constexpr int PER_WARP = NODE_R * (LDA + LDH) + 2 * NODE_R * LDH;
-  float* bufA = smem + warp * PER_WARP;
+  float* bufA = smem + WP_SMEM_FLOATS + warp * PER_WARP;
   float* bufB = bufA + NODE_R * LDA;
   float* pre1 = bufB + NODE_R * LDH;
   float* pre2 = pre1 + NODE_R * LDH;
   const int NA = a.NA;
-  const int base = (blockIdx.x * NODE_WARPS + warp) * NODE_R;
-  if (base >= NA) return;
-  int row[NODE_R];
+  int row[NODE_R], base;
   bool valid[NODE_R];
-#pragma unroll
-  for (int r = 0; r < NODE_R; r++) { valid[r] = base + r < NA; row[r] = valid[r] ? base + r : NA - 1; }
+  node_rows<NODE_R>(warp, NA, base, row, valid);
+  prefetch_mlp_in_params(M, lane);
   stage_node_feat<NODE_R>(bufA, a, row, lane, M.in0_rows);
   __syncwarp();
   float xacc[NODE_R][2];
-  mlp_in_fwd<NODE_R>(M, bufA, bufB, pre1, pre2, xacc, lane);
+  mlp_in_fwd<NODE_R>(M, wp, bufA, bufB, pre1, pre2, xacc, lane);
   // d_x
   float dx[NODE_R][2];
 #pragma unroll
@@ -1023,25 +1155,25 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) node_bwd_kernel(ModelDev M, S
     *reinterpret_cast<float4*>(bufB + r * LDH + lane * 4) = *reinterpret_cast<const float4*>(a.tp.dP + (size_t)row[r] * 128 + lane * 4);
   }
   __syncwarp();
-  warp_gemm<64, NODE_R>(M.seg[S_E0_N_XI], 128, bufB, LDH, dx, lane);
+  pipe_gemm<64, NODE_R>(wp, 128, bufB, LDH, dx, lane);
   __syncwarp();
 #pragma unroll
   for (int r = 0; r < NODE_R; r++)
     *reinterpret_cast<float4*>(bufB + r * LDH + lane * 4) = *reinterpret_cast<const float4*>(a.tp.dQ + (size_t)row[r] * 128 + lane * 4);
   __syncwarp();
-  warp_gemm<64, NODE_R>(M.seg[S_E0_N_XJ], 128, bufB, LDH, dx, lane);
+  pipe_gemm<64, NODE_R>(wp, 128, bufB, LDH, dx, lane);
   __syncwarp();
   store_rows<2, NODE_R>(dx, bufA, LDA, lane);
   __syncwarp();
   float dh[NODE_R][4];
   init_zero<4, NODE_R>(dh);
-  warp_gemm<128, NODE_R>(M.seg[S_IN6_N], 64, bufA, LDA, dh, lane);
+  pipe_gemm<128, NODE_R>(wp, 64, bufA, LDA, dh, lane);
   ln_relu_bwd<NODE_R>(dh, pre2, LDH, M.seg[S_IN_LN4_G], M.seg[S_IN_LN4_B], lane);
   __syncwarp();
   store_rows<4, NODE_R>(dh, bufB, LDH, lane);
   __syncwarp();
   init_zero<4, NODE_R>(dh);
-  warp_gemm<128, NODE_R>(M.seg[S_IN3_N], 128, bufB, LDH, dh, lane);
+  pipe_gemm<128, NODE_R>(wp, 128, bufB, LDH, dh, lane);
   ln_relu_bwd<NODE_R>(dh, pre1, LDH, M.seg[S_IN_LN1_G], M.seg[S_IN_LN1_B], lane);
   __syncwarp();
   store_rows<4, NODE_R>(dh, bufB, LDH, lane);
@@ -1049,8 +1181,8 @@ __global__ void __launch_bounds__(NODE_WARPS * 32) node_bwd_kernel(ModelDev M, S
   float dpf[NODE_R][2], dz[NODE_R][1];
   init_zero<2, NODE_R>(dpf);
   init_zero<1, NODE_R>(dz);
-  warp_gemm<64, NODE_R>(M.seg[S_IN0_N_PF], 128, bufB, LDH, dpf, lane);
-  warp_gemm<32, NODE_R>(M.seg[S_IN0_N_Z], 128, bufB, LDH, dz, lane);
+  pipe_gemm<64, NODE_R>(wp, 128, bufB, LDH, dpf, lane);
+  pipe_gemm<32, NODE_R>(wp, 128, bufB, LDH, dz, lane);
 #pragma unroll
   for (int r = 0; r < NODE_R; r++) {
     if (valid[r]) {
@@ -1093,18 +1225,22 @@ static ModelDev model_dev(const StriveModel* m) {
   return d;
 }
 
-static const size_t SM_NODE = NODE_WARPS * NODE_R * (LDA + LDH) * 4;
+static const size_t SM_PIPE = WP_SMEM_FLOATS * 4;
+static const size_t SM_NODE = SM_PIPE + NODE_WARPS * NODE_R * (LDA + LDH) * 4;
 static const size_t SM_EDGE_F = EDGE_WARPS * 2 * EDGE_R * LDH * 4;
 static const size_t SM_EDGE_B = EDGE_WARPS * 4 * EDGE_R * LDH * 4;
-static const size_t SM_GRU_F = NODE_WARPS * (GRU_R * LDG * 4 + GRU_R * 4) * 4;
-static const size_t SM_GRU_B = NODE_WARPS * (6 * GRU_R * LDG + GRU_R * 4 + 3 * GRU_R * 256 + GRU_R * 196) * 4;
-static const size_t SM_POST_B = NODE_WARPS * (NODE_R * (LDA + LDH) + 3 * NODE_R * LDH) * 4;
-static const size_t SM_NODE_B = NODE_WARPS * (NODE_R * (LDA + LDH) + 2 * NODE_R * LDH) * 4;
+static const size_t SM_GRU_F = SM_PIPE + NODE_WARPS * (GRU_R * LDG * 4 + GRU_R * 4) * 4;
+static const size_t SM_GRU_B = SM_PIPE + NODE_WARPS * (6 * GRU_R * LDG + GRU_R * 4 + 3 * GRU_R * 256 + GRU_R * 196) * 4;
+static const size_t SM_POST_B = SM_PIPE + NODE_WARPS * (NODE_R * (LDA + LDH) + 3 * NODE_R * LDH) * 4;
+static const size_t SM_NODE_B = SM_PIPE + NODE_WARPS * (NODE_R * (LDA + LDH) + 2 * NODE_R * LDH) * 4;
 
 static int set_smem_attrs() {
   static bool done = false;
   if (done) return 0;
   STRIVE_CUDA(cudaFuncSetAttribute(edge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_EDGE_B));
+  STRIVE_CUDA(cudaFuncSetAttribute(node_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE));
+  STRIVE_CUDA(cudaFuncSetAttribute(post_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE));
+  STRIVE_CUDA(cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GRU_F));
   STRIVE_CUDA(cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GRU_B));
   STRIVE_CUDA(cudaFuncSetAttribute(post_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_POST_B));
   STRIVE_CUDA(cudaFuncSetAttribute(node_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE_B));
@@ -1142,14 +1278,14 @@ extern "C" int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, co
   const int node_blocks = (NA + NODE_WARPS * NODE_R - 1) / (NODE_WARPS * NODE_R);
   for (int t = 0; t < ft; t++) {
     a.t = t;
-    KPROF("node_fwd", stream, node_fwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_NODE, stream>>>(M, a));
+    KPROF("node_fwd", stream, node_fwd_kernel<<<node_blocks, NODE_THREADS, SM_NODE, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();
     KPROF("edge_fwd", stream, edge_fwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_F, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();
-    KPROF("post_fwd", stream, post_fwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_NODE, stream>>>(M, a));
+    KPROF("post_fwd", stream, post_fwd_kernel<<<node_blocks, NODE_THREADS, SM_NODE, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();
     if (t + 1 < ft) {
-      KPROF("gru_fwd", stream, gru_fwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_GRU_F, stream>>>(M, a));
+      KPROF("gru_fwd", stream, gru_fwd_kernel<<<node_blocks, NODE_THREADS, SM_GRU_F, stream>>>(M, a));
       STRIVE_LAUNCH_CHECK();
       rc = strive_mapenc_fwd(m, map, a.tp.pose, a.tp.map_of, NA, a.tp.mapfeat + (size_t)(t + 1) * NA * 64, a.tp.mapenc_ws,
                              a.tp.mapenc_ws_bytes, stream_);
@@ -1186,14 +1322,14 @@ extern "C" int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, in
     a.t = t;
     const int has_gru = (t + 1 < ft) ? 1 : 0;
     if (has_gru) {
-      KPROF("gru_bwd", stream, gru_bwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_GRU_B, stream>>>(M, a));
+      KPROF("gru_bwd", stream, gru_bwd_kernel<<<node_blocks, NODE_THREADS, SM_GRU_B, stream>>>(M, a));
       STRIVE_LAUNCH_CHECK();
     }
-    KPROF("post_bwd", stream, post_bwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_POST_B, stream>>>(M, a, has_gru));
+    KPROF("post_bwd", stream, post_bwd_kernel<<<node_blocks, NODE_THREADS, SM_POST_B, stream>>>(M, a, has_gru));
     STRIVE_LAUNCH_CHECK();
     KPROF("edge_bwd", stream, edge_bwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_B, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();
-    KPROF("node_bwd", stream, node_bwd_kernel<<<node_blocks, NODE_WARPS * 32, SM_NODE_B, stream>>>(M, a));
+    KPROF("node_bwd", stream, node_bwd_kernel<<<node_blocks, NODE_THREADS, SM_NODE_B, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();
   }
   return 0;

@@ -587,4 +587,4 @@ def test_refine_sharded_single_rank_equals_fused_loop():
     diag('refine_sharded: |z_sharded - z_fused| = %.3e, rank-subset rows vs full batch rows = %.3e, moved %.3e' % (
         d_all, d_sub, (z_ref - sc['z']).abs().max().item()))
     # (floating-point atomics in the loss reductions make two runs agree to rounding, not bitwise)
-    assert d_all < 1e-6 and d_sub < 1e-5
+    assert d_all < 1e-5 and d_sub < 1e-5
