@@ -292,8 +292,11 @@ def run_gpu(args):
         api_step()
     barrier()
     e0.record()
+    wall = []
     for _ in range(e2e_steps):
+        t0 = time.perf_counter()
         api_step()
+        wall.append(round(1000.0 * (time.perf_counter() - t0), 2))
     e1.record()
     torch.cuda.synchronize()
     ms_e = e0.elapsed_time(e1)
@@ -355,7 +358,7 @@ def run_gpu(args):
                               loop.tape_bytes / 1e6, _cabi.lib().strive_mapenc_workspace_bytes(NA) / 1e6),
                           'loss_after_timed_steps': loss_now},
                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
-                       'ms_per_step': ms_e / e2e_steps,
+                       'ms_per_step': ms_e / e2e_steps, 'host_ms_each_step': wall,
                        'api': 'TrafficModel.decode_embedding + losses.AvoidCollLoss + torch.optim.Adam, inputs from pinned host memory every step'},
                'gpu_launches': loop.launches_per_iter * args.steps,
                'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
