@@ -185,6 +185,27 @@ int strive_loss_fwd_bwd(const StriveLossCfg* cfg, const StriveScene* sc, const S
 int strive_adam_step(float* z, const float* g_a, const float* g_b, float* exp_avg, float* exp_avg_sq,
                      int64_t n, int32_t step_count, float lr, float beta1, float beta2, float eps, void* stream);
 
+/* ---- success / plausibility checks around the loop (all inputs UNNORMALISED, device) -----
+ * strive_on_layer_frac: nutils.check_on_layer, src/datasets/nuscenes_utils.py:266-298 (used by compute_coll_rate_env,
+ *   src/losses/traffic_model.py:366-419): fraction of an L x W footprint grid of each car (cars_un (n,4), lw_un (n,2)) that
+ *   reads non-zero in raster layer `layer` of map map_of[i]; L, W and the two torch.linspace(-1,1,.) tables are the
+ *   batch-global values the reference derives on the host (:278-282); a car with a NaN state gets 1.0
+ *   (traffic_model.py:400-408: NaN frames never count as collisions).
+ * strive_line_layer: nutils.check_line_layer, nuscenes_utils.py:300-333 (determine_feasibility_nusc,
+ *   src/utils/scenario_gen.py:91-99): hit[i] = 1 iff one of the num_samples points torch.linspace(0,1,.) (lin01) along
+ *   start_un[i] -> end_un[i] reads 0 in `layer`.  Negative pixel indices wrap as torch indexing does; indices that would
+ *   raise IndexError in the reference are counted in *oob_count (device int) and skipped.
+ * strive_veh_iou_hits: the polygon test of check_single_veh_coll / check_pairwise_veh_coll, src/losses/adv_gen_nusc.py:517-623
+ *   (shapely intersection / union of nutils.get_corners rectangles, nuscenes_utils.py:416-428):
+ *   hit[(i*nb + j)*T + t] = IoU(rect(traj_a[i,t], lw_a[i]), rect(traj_b[j,t], lw_b[j])) > iou_thresh, 0 if either state has a
+ *   NaN; iou_out (same shape, float) optional. */
+int strive_on_layer_frac(const StriveMap* map, int32_t layer, const float* cars_un, const float* lw_un, const int32_t* map_of,
+                         const float* lin_l, const float* lin_w, int32_t L, int32_t W, int32_t n, float* frac_out, void* stream);
+int strive_line_layer(const StriveMap* map, int32_t layer, const float* start_un, const float* end_un, const int32_t* map_of,
+                      const float* lin01, int32_t num_samples, int32_t n, uint8_t* hit_out, int32_t* oob_count, void* stream);
+int strive_veh_iou_hits(const float* traj_a_un, const float* lw_a_un, int32_t na, const float* traj_b_un, const float* lw_b_un,
+                        int32_t nb, int32_t T, double iou_thresh, uint8_t* hit_out, float* iou_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

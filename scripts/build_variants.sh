@@ -8,7 +8,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 while [ $# -ge 2 ]; do
   name=$1; defs=$2; shift 2
   ( nvcc $FLAGS $defs -c strive_b200/csrc/rollout.cu -o build/variants/rollout_$name.o &&
-    nvcc -shared -gencode arch=compute_100a,code=sm_100a -o build/variants/lib_$name.so build/api.o build/mapenc.o build/variants/rollout_$name.o build/loss.o build/tc_selftest.o build/mapenc_tc.o &&
+    nvcc -shared -gencode arch=compute_100a,code=sm_100a -o build/variants/lib_$name.so build/api.o build/mapenc.o build/variants/rollout_$name.o build/loss.o build/tc_selftest.o build/mapenc_tc.o build/metrics.o &&
     echo built $name ) &
 done
 wait

@@ -314,19 +314,46 @@ class TrafficModel(nn.Module):
     def rsample(self, mean, var):
         return mean + torch.randn_like(mean) * torch.sqrt(var)
 
+    def _replicated(self, scene_graph, map_idx, NS):
+        """NS copies of the scene batch laid end to end (copy s owns agents [s*NA, (s+1)*NA)): scenes are independent in the
+        model, so the reference's (NA, NS, ...) sample axis (traffic_model.py:352-353) is just more scenes for the kernels."""
+        key = (id(scene_graph), int(scene_graph.past.data_ptr()), int(scene_graph.ptr.data_ptr()), int(map_idx.data_ptr()), int(NS))
+        rep = self._rep_cache.get(key) if hasattr(self, '_rep_cache') else None
+        if rep is None:
+            class _G(object):
+                pass
+            g = _G()
+            NA = scene_graph.past.size(0)
+            ptr = scene_graph.ptr.detach().to(torch.int64)
+            S = ptr.numel() - 1
+            off = (torch.arange(NS, device=ptr.device, dtype=torch.int64) * NA).view(NS, 1)
+            g.ptr = torch.cat([(ptr[:-1].view(1, S) + off).reshape(-1), torch.tensor([NS * NA], device=ptr.device, dtype=torch.int64)])
+            g.past = scene_graph.past.detach().repeat(NS, 1, 1)
+            g.lw = scene_graph.lw.detach().repeat(NS, 1)
+            g.sem = scene_graph.sem.detach().repeat(NS, 1)
+            g.batch = torch.repeat_interleave(torch.arange(NS * S, device=ptr.device), (g.ptr[1:] - g.ptr[:-1]))
+            rep = (g, map_idx.detach().repeat(NS))
+            if not hasattr(self, '_rep_cache') or len(self._rep_cache) > 4:
+                self._rep_cache = {}
+            self._rep_cache[key] = rep
+        return rep
+
     def sample_batched(self, scene_graph, map_idx, map_env, num_samples, include_mean=False, nfuture=None):
-        """reference :319-370; the NS rollouts are independent, so they run as NS kernel rollouts (no grad)."""
+        """reference :319-370.  The NS sampled rollouts run as ONE kernel rollout over NS x NA agents (no grad)."""
         NA = scene_graph.past.size(0)
+        NS = int(num_samples)
         emb = self.embed(scene_graph, map_idx, map_env)
         mu, var = emb['prior_out']
-        z = self.rsample(mu.unsqueeze(0).expand(num_samples, NA, -1), var.unsqueeze(0).expand(num_samples, NA, -1))
+        z = self.rsample(mu.unsqueeze(0).expand(NS, NA, -1), var.unsqueeze(0).expand(NS, NA, -1))
         if include_mean:
             z[-1] = mu
-        futs = []
+        g_rep, midx_rep = self._replicated(scene_graph, map_idx, NS)
+        emb_rep = {'map_feat': emb['map_feat'].detach().repeat(NS, 1), 'past_feat': emb['past_feat'].detach().repeat(NS, 1)}
         with torch.no_grad():
-            for s in range(num_samples):
-                futs.append(self.decode_embedding(z[s].contiguous(), emb, scene_graph, map_idx, map_env, nfuture=nfuture)['future_pred'])
+            fut = self.decode_embedding(z.reshape(NS * NA, -1).contiguous(), emb_rep, g_rep, midx_rep, map_env, nfuture=nfuture)['future_pred']
+        FT = fut.size(1)
+        fut = fut.view(NS, NA, FT, 4).transpose(0, 1).contiguous()
         dist = torch.distributions.Normal(mu.unsqueeze(0), torch.sqrt(var).unsqueeze(0))
-        return {'prior_out': (mu, var), 'z_samp': z.transpose(0, 1), 'future_pred': torch.stack(futs, 1),
+        return {'prior_out': (mu, var), 'z_samp': z.transpose(0, 1), 'future_pred': fut,
                 'z_logprob': dist.log_prob(z).sum(-1).transpose(0, 1),
                 'z_mdist': torch.norm((z - mu.unsqueeze(0)) / torch.sqrt(var).unsqueeze(0), dim=-1).transpose(0, 1)}

@@ -43,3 +43,27 @@ def scene_for(g, **kw):
     args = dict(map_extent_m=EXTENT, M=2, FT=int(g['FT']), collide_frac=1.0, offroad_frac=1.0)
     args.update(kw)
     return synth.make_scenes(int(g['seed']), sizes, **args)
+
+
+def metric_inputs():
+    """Seeded inputs of the success / plausibility checks (tests/golden/metrics.npz holds the reference's outputs for them):
+    two scenes on the golden world, NS sampled futures per agent = constant-velocity rollouts with per-sample heading / speed
+    noise, a few NaN frames, some agents steered off the road."""
+    from strive_b200.traffic_model import MeanStdNormalizer, STATE_MEAN, STATE_STD, ATT_MEAN, ATT_STD
+    sc = synth.make_scenes(41, [5, 3], map_extent_m=EXTENT, M=2, FT=8, collide_frac=1.0, offroad_frac=1.0)
+    NA, NS, FT = sc['past'].size(0), 4, 8
+    g = torch.Generator().manual_seed(77)
+    nrm = MeanStdNormalizer(torch.tensor(STATE_MEAN), torch.tensor(STATE_STD))
+    att = MeanStdNormalizer(torch.tensor(ATT_MEAN), torch.tensor(ATT_STD))
+    last = nrm.unnormalize(sc['past'][:, -1, :])                      # (NA,6) x,y,hx,hy,s,hdot
+    h0 = torch.atan2(last[:, 3], last[:, 2]).view(NA, 1, 1)
+    h = h0 + 0.5 * (torch.rand(NA, NS, 1, generator=g) - 0.5) + 0.05 * torch.arange(FT).view(1, 1, FT) * (torch.rand(NA, NS, 1, generator=g) - 0.5)
+    spd = (last[:, 4].view(NA, 1, 1) * (0.5 + torch.rand(NA, NS, 1, generator=g))).expand(NA, NS, FT)
+    step = 0.5 * spd
+    x = last[:, 0].view(NA, 1, 1) + torch.cumsum(step * torch.cos(h), dim=2)
+    y = last[:, 1].view(NA, 1, 1) + torch.cumsum(step * torch.sin(h), dim=2)
+    fut_un = torch.stack([x, y, torch.cos(h), torch.sin(h)], dim=3)
+    fut_un[1, 2, 3:] = float('nan')
+    fut_un[6, 0, 0] = float('nan')
+    samples = nrm.normalize(fut_un)
+    return dict(sc=sc, samples=samples, nrm=nrm, att=att, NA=NA, NS=NS, FT=FT)

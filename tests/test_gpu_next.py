@@ -1,0 +1,134 @@
+"""GPU tests of the SURVEY 8(f) "next" rows built so far: the callers either side of the latent loop."""
+import numpy as np
+import pytest
+import torch
+
+from tests.common import scene_for, golden
+from tests.test_gpu_parity import ctx, to_graph, diag
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sample_batched_is_one_rollout_over_ns_copies():
+    """sample_batched (traffic_model.py:319-370): the NS x NA batched rollout equals decoding every sample on its own
+    (bitwise on the first step; to the encoder's batch-position re-association, amplified per step, afterwards),
+    include_mean puts the prior mean last, shapes / log-prob / Mahalanobis outputs follow the reference."""
+    dev, model, env = ctx()
+    g = golden('decode_small')
+    sc = scene_for(g)
+    FT, NS = 5, 6
+    graph = to_graph(sc, dev)
+    midx = sc['map_idx'].to(dev)
+    torch.manual_seed(7)
+    out = model.sample_batched(graph, midx, env, NS, include_mean=True, nfuture=FT)
+    NA = sc['z'].size(0)
+    mu, var = out['prior_out']
+    assert tuple(out['future_pred'].shape) == (NA, NS, FT, 4) and tuple(out['z_samp'].shape) == (NA, NS, 32)
+    assert tuple(out['z_logprob'].shape) == (NA, NS) and tuple(out['z_mdist'].shape) == (NA, NS)
+    assert torch.equal(out['z_samp'][:, -1], mu)
+    assert float(out['z_mdist'][:, -1].abs().max()) == 0.0
+    ref_lp = torch.distributions.Normal(mu, var.sqrt()).log_prob(out['z_samp'][:, 2]).sum(-1)
+    assert torch.allclose(out['z_logprob'][:, 2], ref_lp, atol=1e-4)
+    emb = model.embed(graph, midx, env)
+    d = torch.zeros(FT)
+    with torch.no_grad():
+        for s in range(NS):
+            one = model.decode_embedding(out['z_samp'][:, s].contiguous(), emb, graph, midx, env, nfuture=FT)['future_pred']
+            d = torch.maximum(d, (one - out['future_pred'][:, s]).abs().amax(dim=(0, 2)).cpu())
+    diag('sample_batched: NS=%d batched vs per-sample decode, max |diff| per step %s' % (NS, ' '.join('%.1e' % v for v in d.tolist())))
+    assert d[0].item() == 0.0 and d[1].item() < 2e-5 and d.max().item() < 2e-3
+    assert bool(torch.isfinite(out['future_pred']).all())
+
+
+def _metric_ctx():
+    from tests.common import metric_inputs
+    dev, model, env = ctx()
+    return dev, env, metric_inputs(), golden('metrics')
+
+
+def test_on_layer_and_env_collision_rate_bit_exact_vs_reference():
+    """check_on_layer / compute_coll_rate_env (integer pixel work): bit exact against the unmodified reference's outputs."""
+    from strive_b200 import metrics
+    dev, env, mi, g = _metric_ctx()
+    sc, nrm, att = mi['sc'], mi['nrm'], mi['att']
+    NA, NS, FT = mi['NA'], mi['NS'], mi['FT']
+    un = nrm.unnormalize(mi['samples'])
+    cars = un[:, 0].reshape(NA * FT, 4)
+    lw = att.unnormalize(sc['lw']).view(NA, 1, 2).expand(NA, FT, 2).reshape(NA * FT, 2)
+    mix = sc['map_idx'][sc['batch']].view(NA, 1).expand(NA, FT).reshape(NA * FT)
+    ok = ~torch.isnan(cars.sum(-1))
+    f0 = metrics.check_on_layer(env, 0, cars[ok].to(dev), lw[ok].to(dev), mix[ok].to(dev)).cpu().numpy()
+    f2 = metrics.check_on_layer(env, 2, cars[ok].to(dev), lw[ok].to(dev), mix[ok].to(dev)).cpu().numpy()
+    assert np.array_equal(f0, g['on_layer_frac']) and np.array_equal(f2, g['on_layer_frac_l2'])
+    graph = to_graph(sc, dev)
+    cd = metrics.compute_coll_rate_env(graph, sc['map_idx'].to(dev), mi['samples'].to(dev), env, nrm, att)
+    assert np.array_equal(cd['did_collide'].cpu().numpy(), g['env_did_collide'])
+    assert cd['num_coll_map'] == float(g['env_num_coll']) and cd['num_traj_map'] == float(NA * NS)
+    ce = metrics.compute_coll_rate_env(graph, sc['map_idx'].to(dev), {'future_pred': mi['samples'].to(dev)}, env, nrm, att, ego_only=True)
+    assert tuple(ce['did_collide'].shape) == (2, NS)
+    diag('on_layer / coll_rate_env: %d fractions and %d collision flags bit-exact vs the reference (%d collide)' % (
+        f0.size, g['env_did_collide'].size, int(g['env_did_collide'].sum())))
+
+
+def test_line_layer_and_feasibility_vs_reference():
+    from strive_b200 import metrics
+    dev, env, mi, g = _metric_ctx()
+    sc, nrm = mi['sc'], mi['nrm']
+    mix_a = sc['map_idx'][sc['batch']]
+    hit = metrics.check_line_layer(env, 0, torch.from_numpy(g['line_start']).to(dev), torch.from_numpy(g['line_end']).to(dev), mix_a.to(dev))
+    assert np.array_equal(hit.cpu().numpy(), g['line_hit'])
+    n0 = int(sc['ptr'][1])
+    s0 = mi['samples'][:n0].clone()
+    s0[torch.isnan(s0)] = 0.0
+    for name, kw in (('feas_a', dict(feasibility_time=0, feasibility_vel=0.0, feasibility_infront_min=None, check_non_drivable_separation=True)),
+                     ('feas_b', dict(feasibility_time=2, feasibility_vel=1.0, feasibility_infront_min=-0.5, check_non_drivable_separation=True)),
+                     ('feas_c', dict(feasibility_time=1, feasibility_vel=0.5, feasibility_infront_min=0.0, check_non_drivable_separation=False))):
+        f, ts, dist = metrics.determine_feasibility_nusc(s0.clone().to(dev), nrm, 10.0, map_env=env, map_idx=sc['map_idx'][0:1].to(dev), **kw)
+        assert np.array_equal(f.cpu().numpy(), g[name + '_feasible'])
+        assert np.array_equal(ts.cpu().numpy(), g[name + '_step'])
+        assert np.allclose(dist.cpu().numpy(), g[name + '_dist'], rtol=1e-6, atol=1e-5)
+    assert metrics.determine_feasibility_nusc(s0[:1].to(dev), nrm, 10.0, map_env=env, map_idx=sc['map_idx'][0:1].to(dev)) == (None, None, None)
+    with pytest.raises(RuntimeError):
+        far = torch.tensor([[1.0e5, 1.0e5]], device=dev)
+        metrics.check_line_layer(env, 0, torch.zeros(1, 2, device=dev) + 100.0, far, torch.zeros(1, dtype=torch.long, device=dev))
+
+
+def test_vehicle_iou_checks_vs_oracle():
+    """check_single_veh_coll / check_pairwise_veh_coll against the CPU restatement on seeded rectangles incl. touching,
+    nested, NaN and heading-flipped cases (shapely is absent: the oracle's polygon arithmetic is pinned by closed-form cases)."""
+    from strive_b200 import metrics
+    from oracle import metrics_oracle as MO
+    dev, env, mi, g = _metric_ctx()
+    rng = np.random.RandomState(3)
+    N, T = 24, 10
+    xy = rng.uniform(0.0, 14.0, size=(N, 1, 2)) + np.cumsum(rng.uniform(-0.8, 0.8, size=(N, T, 2)), axis=1)
+    ang = rng.uniform(-np.pi, np.pi, size=(N, 1)) + np.cumsum(rng.uniform(-0.2, 0.2, size=(N, T)), axis=1)
+    traj = np.concatenate([xy, np.cos(ang)[..., None], np.sin(ang)[..., None]], axis=2).astype(np.float32)
+    lw = np.stack([rng.uniform(3.5, 6.0, N), rng.uniform(1.6, 2.4, N)], axis=1).astype(np.float32)
+    traj[3, 4:] = np.nan
+    traj[7] = traj[2]                       # identical boxes -> IoU 1
+    traj[9, :, 2:] = -traj[2, :, 2:]; traj[9, :, :2] = traj[2, :, :2]     # same place, heading flipped
+    tt, ll = torch.from_numpy(traj), torch.from_numpy(lw)
+    # raw IoU values
+    hit, iou = metrics._iou_hits(tt.to(dev), ll.to(dev), tt.to(dev), ll.to(dev), want_iou=True)
+    ref = np.zeros((N, N, T))
+    for i in range(N):
+        for j in range(N):
+            for t in range(T):
+                if np.isnan(traj[i, t]).any() or np.isnan(traj[j, t]).any():
+                    continue
+                ref[i, j, t] = MO.rect_iou(MO.get_corners(traj[i, t], lw[i]), MO.get_corners(traj[j, t], lw[j]))
+    err = np.abs(iou.cpu().numpy() - ref).max()
+    edge = np.abs(ref - MO.VEH_COLL_THRESH) < 1e-5
+    assert err < 2e-5                       # float32 corner arithmetic (cosf/sinf vs numpy), float64 clipping
+    assert np.array_equal(hit.cpu().numpy().astype(bool)[~edge], (ref > MO.VEH_COLL_THRESH)[~edge])
+    # reference-shaped entry points
+    coll, when = metrics.check_single_veh_coll(tt[0].to(dev), ll[0].to(dev), tt[1:].to(dev), ll[1:].to(dev))
+    rc, rw = MO.check_single_veh_coll(traj[0], lw[0], traj[1:], lw[1:])
+    assert coll.dtype == bool and np.array_equal(coll, rc) and np.array_equal(when, rw)
+    pw = metrics.check_pairwise_veh_coll(tt.to(dev), ll.to(dev))
+    rp = MO.check_pairwise_veh_coll(traj, lw)
+    assert np.array_equal(pw['did_collide'], rp['did_collide']) and pw['num_coll_veh'] == rp['num_coll_veh'] and pw['num_traj_veh'] == float(N)
+    diag('veh IoU: %d rectangle pairs, max |IoU - oracle| %.2e, %d hits; single: %d collide; pairwise: %d flagged' % (
+        N * N * T, err, int((ref > MO.VEH_COLL_THRESH).sum()), int(rc.sum()), int(rp['num_coll_veh'])))
+    assert int(rc.sum()) > 0 and 0 < int(rp['num_coll_veh']) < N

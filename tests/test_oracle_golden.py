@@ -95,3 +95,74 @@ def test_loss_modules():
     ls['loss'].backward()
     assert abs(float(ls['loss']) - float(g['sol_loss'])) < 1e-4 * abs(float(g['sol_loss']))
     assert np.abs(futs.grad.numpy() - g['sol_d_fut']).max() < 1e-4
+
+
+# ----------------------------------------------------------------------------------------------------------
+# success / plausibility checks: oracle/metrics_oracle.py against the unmodified reference
+# ----------------------------------------------------------------------------------------------------------
+def _metric_case():
+    from tests.common import metric_inputs
+    mi = metric_inputs()
+    g = golden('metrics')
+    raster, dx, _ = world()
+    return mi, g, raster, dx
+
+
+def test_metrics_oracle_raster_checks_match_reference():
+    from oracle import metrics_oracle as MO
+    mi, g, raster, dx = _metric_case()
+    sc, nrm, att = mi['sc'], mi['nrm'], mi['att']
+    NA, NS, FT = mi['NA'], mi['NS'], mi['FT']
+    un = nrm.unnormalize(mi['samples'])
+    cars = un[:, 0].reshape(NA * FT, 4)
+    lw_un = att.unnormalize(sc['lw'])
+    lw = lw_un.view(NA, 1, 2).expand(NA, FT, 2).reshape(NA * FT, 2)
+    mix_a = sc['map_idx'][sc['batch']]
+    mix = mix_a.view(NA, 1).expand(NA, FT).reshape(NA * FT)
+    ok = ~torch.isnan(cars.sum(-1))
+    assert np.array_equal(MO.check_on_layer(raster[:, 0], dx, cars[ok], lw[ok], mix[ok]).numpy(), g['on_layer_frac'])
+    assert np.array_equal(MO.check_on_layer(raster[:, 2], dx, cars[ok], lw[ok], mix[ok]).numpy(), g['on_layer_frac_l2'])
+    assert np.array_equal(MO.compute_coll_rate_env(sc['lw'], mix_a, un, lw_un, raster, dx).numpy(), g['env_did_collide'])
+    assert 0 < int(g['env_did_collide'].sum()) < NA * NS
+    hit = MO.check_line_layer(raster[:, 0], dx, torch.from_numpy(g['line_start']), torch.from_numpy(g['line_end']), mix_a)
+    assert np.array_equal(hit.numpy(), g['line_hit'])
+
+
+def test_metrics_oracle_feasibility_matches_reference():
+    from oracle import metrics_oracle as MO
+    mi, g, raster, dx = _metric_case()
+    sc, nrm = mi['sc'], mi['nrm']
+    n0 = int(sc['ptr'][1])
+    s0 = mi['samples'][:n0].clone()
+    s0[torch.isnan(s0)] = 0.0
+    for name, (ft, fv, fi, sep) in (('feas_a', (0, 0.0, None, True)), ('feas_b', (2, 1.0, -0.5, True)), ('feas_c', (1, 0.5, 0.0, False))):
+        f, ts, dist = MO.determine_feasibility(nrm.unnormalize(s0.clone()), 10.0, ft, fv, fi, sep, raster[:, 0], dx, sc['map_idx'][0:1])
+        assert np.array_equal(f.numpy(), g[name + '_feasible'])
+        assert np.array_equal(ts.numpy(), g[name + '_step'])
+        assert np.allclose(dist.numpy(), g[name + '_dist'], rtol=0, atol=0)
+
+
+def test_rect_iou_closed_form_cases():
+    """Known answers anchoring the polygon arithmetic that the reference delegates to shapely (absent: parity unpinned)."""
+    from oracle import metrics_oracle as MO
+
+    def rect(x, y, ang, l, w):
+        return MO.get_corners(np.array([x, y, np.cos(ang), np.sin(ang)], dtype=np.float32), np.array([l, w], dtype=np.float32))
+    assert abs(MO.rect_iou(rect(0, 0, 0, 4, 2), rect(0, 0, 0, 4, 2)) - 1.0) < 1e-12
+    assert abs(MO.rect_iou(rect(0, 0, 0, 2, 1), rect(1, 0, 0, 2, 1)) - 1.0 / 3.0) < 1e-6
+    assert MO.rect_iou(rect(0, 0, 0, 2, 1), rect(5, 0, 0.3, 2, 1)) == 0.0
+    assert abs(MO.rect_iou(rect(0, 0, 0, 2, 2), rect(0, 0, np.pi / 4, np.sqrt(2.0), np.sqrt(2.0))) - 0.5) < 1e-6
+    assert abs(MO.rect_iou(rect(0, 0, 0, 4, 1), rect(0, 0, np.pi / 2, 4, 1)) - 1.0 / 7.0) < 1e-6
+    assert abs(MO.rect_iou(rect(3, -2, 1.1, 4.5, 2), rect(3, -2, 1.1 + np.pi, 4.5, 2)) - 1.0) < 1e-5      # same box, heading flipped
+    # loop semantics: first colliding step; NaN frames skipped; pairwise flags only the earlier agent of a pair, once
+    T = 4
+    tgt = np.array([[t * 1.0, 0.0, 1.0, 0.0] for t in range(T)], dtype=np.float32)
+    others = np.stack([np.array([[3.0, 0.0, 1.0, 0.0]] * T, dtype=np.float32),
+                       np.array([[0.0, 9.0, 1.0, 0.0]] * T, dtype=np.float32),
+                       np.array([[0.0, 0.5, 1.0, 0.0]] * T, dtype=np.float32)])
+    others[2, 0] = np.nan
+    lw = np.array([[2.0, 1.0]] * 3, dtype=np.float32)
+    coll, when = MO.check_single_veh_coll(tgt, np.array([2.0, 1.0], dtype=np.float32), others, lw)
+    assert coll.tolist() == [True, False, True] and when.tolist() == [2, T, 1]
+    pw = MO.check_pairwise_veh_coll(np.concatenate([tgt[None], others]), np.array([[2.0, 1.0]] * 4, dtype=np.float32))
+    assert pw['did_collide'].tolist() == [True, False, False, False] and pw['num_coll_veh'] == 1.0 and pw['num_traj_veh'] == 4.0
