@@ -67,6 +67,13 @@ int64_t strive_model_tc_bytes(void);
 int strive_model_set_tc_weights(StriveModel* m, const void* blob, int64_t bytes);
 /* 1 = tensor-core map encoder (default), 0 = fp32 SIMT kernels (A/B verification only) */
 int strive_mapenc_set_impl(int impl);
+/* Edge MLP of the decoder GNN (interaction_net.py:139-184) on the warp-level tensor path: the library packs the edge-MLP
+ * matrices of the weight blob into mma.sync fragment order inside `buf` (device, 16-byte aligned,
+ * strive_model_edge_frag_bytes() bytes, owned by the caller for the lifetime of the model).  Without it -- or with
+ * strive_edge_set_impl(0) -- the fp32 SIMT edge kernels run (A/B verification). */
+int64_t strive_model_edge_frag_bytes(void);
+int strive_model_set_edge_frags(StriveModel* m, void* buf, int64_t bytes, void* stream);
+int strive_edge_set_impl(int impl);
 
 /* ---- scene description (all device) --------------------------------------------------------------------
  * Mirrors the torch_geometric Batch the drivers build (src/datasets/nuscenes_dataset.py:609-687): edges are

@@ -7,6 +7,8 @@ from strive_b200 import _cabi
 if os.environ.get('STRIVE_LIB'):
     _cabi.LIB_PATH = os.environ['STRIVE_LIB']
 import strive_b200
+if os.environ.get('EDGE_IMPL'):
+    _cabi.set_edge_impl(int(os.environ['EDGE_IMPL']) != 0)
 import bench
 from strive_b200.optim import RefineLoop
 dev = torch.device('cuda:0')

@@ -88,6 +88,7 @@ extern "C" int strive_model_create(const float* blob, int64_t blob_floats, const
   }
   m->nc = num_classes;
   m->tc_blob = nullptr;
+  m->edge_frags = nullptr;
   m->in0_rows = round_up4(64 + 64 + num_classes + ZDIM + 2);
   m->u0_rows = round_up4(64 + 64 + num_classes);
   *out = m;

@@ -100,6 +100,7 @@ struct StriveModel {
   const uint8_t* tc_blob;   // bf16 hi/lo conv weights in UMMA canonical layout (strive_model_set_tc_weights) or null
   int64_t tc_off[7];        // byte offsets of conv1..conv6, fc inside tc_blob
   float h_cbias[4][64];     // host copies of the conv1..conv4 biases (kernel arguments of the tensor-core convolutions)
+  const uint8_t* edge_frags; // mma.sync weight fragment packs of the edge MLP (strive_model_set_edge_frags) or null
 };
 
 __host__ __device__ inline int round_up4(int x) { return (x + 3) & ~3; }

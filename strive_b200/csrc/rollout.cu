@@ -17,6 +17,7 @@
 // per-edge activations (E x 320 floats per step would be 4 GB at BASELINE config 5).
 #include "common.cuh"
 #include "wpipe.cuh"
+#include <cuda_bf16.h>
 
 // ------------------------------------------------------------------------------------------------------
 // tape layout (floats unless noted), all [t][agent][...]
@@ -1115,6 +1116,8 @@ __global__ void __launch_bounds__(EDGE_WARPS * 32) edge_bwd_kernel(ModelDev M, S
   }
 }
 
+#include "edge_mma.cuh"
+
 // node backward: d_x = d_xupd + dP.W_xi + dQ.W_xj ; back through mlp_in; d_z += ; g_pf <- grad wrt past_feat_t
 __global__ void __launch_bounds__(NODE_THREADS, 2) node_bwd_kernel(ModelDev M, StepArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -1234,10 +1237,56 @@ static const size_t SM_GRU_B = SM_PIPE + NODE_WARPS * (6 * GRU_R * LDG + GRU_R *
 static const size_t SM_POST_B = SM_PIPE + NODE_WARPS * (NODE_R * (LDA + LDH) + 3 * NODE_R * LDH) * 4;
 static const size_t SM_NODE_B = SM_PIPE + NODE_WARPS * (NODE_R * (LDA + LDH) + 2 * NODE_R * LDH) * 4;
 
+static int g_edge_impl = 1;   // 1 = mma.sync TF32 edge kernels (default, needs the fragment packs), 0 = fp32 SIMT kernels (A/B verification)
+extern "C" int strive_edge_set_impl(int impl) {
+  g_edge_impl = impl;
+  return 0;
+}
+
+static int em_grid(int NA) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int want = (NA + EM_WARPS - 1) / EM_WARPS;
+  return want < sms ? want : sms;
+}
+
+extern "C" int64_t strive_model_edge_frag_bytes(void) { return EM_FRAG_BYTES; }
+
+// Packs the edge-MLP matrices of the model's weight blob into mma.sync fragment order (edge_mma.cuh) inside `buf`
+// (device, 16-byte aligned, strive_model_edge_frag_bytes() bytes, owned by the caller for the lifetime of the model).
+extern "C" int strive_model_set_edge_frags(StriveModel* m, void* buf, int64_t bytes, void* stream_) {
+  STRIVE_CHECK(m != nullptr && buf != nullptr, STRIVE_EINVAL, "set_edge_frags: null argument");
+  STRIVE_CHECK(bytes == EM_FRAG_BYTES && ((uintptr_t)buf & 15) == 0, STRIVE_ESIZE, "edge fragment buffer: %lld bytes (need %d, 16-byte aligned)",
+               (long long)bytes, (int)EM_FRAG_BYTES);
+  STRIVE_CHECK(m->seg_size[S_E3_T] == 128 * 128 && m->seg_size[S_E6_T] == 128 * 64 && m->seg_size[S_E6_N] == 64 * 128 && m->seg_size[S_E3_N] == 128 * 128,
+               STRIVE_ESIZE, "edge MLP is not 128-128-64");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  uint8_t* b = (uint8_t*)buf;
+  auto pack = [&](const float* W, int K, int N, int off, bool bf16) {
+    const int n = (K / 8) * (N / 8) * 32;
+    edge_frag_pack_kernel<<<(n + 255) / 256, 256, 0, stream>>>(W, K, N, bf16 ? nullptr : (float*)(b + off), bf16 ? (uint16_t*)(b + off) : nullptr);
+  };
+  pack(m->seg[S_E3_T], 128, 128, EM_F3_OFF, false);
+  pack(m->seg[S_E6_T], 128, 64, EM_F6_OFF, false);
+  pack(m->seg[S_E3_T], 128, 128, EM_B3T_OFF, true);
+  pack(m->seg[S_E6_N], 64, 128, EM_B6N_OFF, true);
+  pack(m->seg[S_E3_N], 128, 128, EM_B3N_OFF, true);
+  STRIVE_LAUNCH_CHECK();
+  m->edge_frags = b;
+  return 0;
+}
+
 static int set_smem_attrs() {
   static bool done = false;
   if (done) return 0;
   STRIVE_CUDA(cudaFuncSetAttribute(edge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_EDGE_B));
+  STRIVE_CUDA(cudaFuncSetAttribute(edge_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_FWD_SMEM));
+  STRIVE_CUDA(cudaFuncSetAttribute(edge_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_BWD_SMEM));
   STRIVE_CUDA(cudaFuncSetAttribute(node_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE));
   STRIVE_CUDA(cudaFuncSetAttribute(post_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE));
   STRIVE_CUDA(cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GRU_F));
@@ -1280,7 +1329,11 @@ extern "C" int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, co
     a.t = t;
     KPROF("node_fwd", stream, node_fwd_kernel<<<node_blocks, NODE_THREADS, SM_NODE, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();
-    KPROF("edge_fwd", stream, edge_fwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_F, stream>>>(M, a));
+    if (g_edge_impl != 0 && m->edge_frags != nullptr) {
+      KPROF("edge_fwd", stream, edge_fwd_mma_kernel<<<em_grid(NA), EM_THREADS, EM_FWD_SMEM, stream>>>(M, a, m->edge_frags));
+    } else {
+      KPROF("edge_fwd", stream, edge_fwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_F, stream>>>(M, a));
+    }
     STRIVE_LAUNCH_CHECK();
     KPROF("post_fwd", stream, post_fwd_kernel<<<node_blocks, NODE_THREADS, SM_NODE, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();
@@ -1327,7 +1380,11 @@ extern "C" int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, in
     }
     KPROF("post_bwd", stream, post_bwd_kernel<<<node_blocks, NODE_THREADS, SM_POST_B, stream>>>(M, a, has_gru));
     STRIVE_LAUNCH_CHECK();
-    KPROF("edge_bwd", stream, edge_bwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_B, stream>>>(M, a));
+    if (g_edge_impl != 0 && m->edge_frags != nullptr) {
+      KPROF("edge_bwd", stream, edge_bwd_mma_kernel<<<em_grid(NA), EM_THREADS, EM_BWD_SMEM, stream>>>(M, a, m->edge_frags));
+    } else {
+      KPROF("edge_bwd", stream, edge_bwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_B, stream>>>(M, a));
+    }
     STRIVE_LAUNCH_CHECK();
     KPROF("node_bwd", stream, node_bwd_kernel<<<node_blocks, NODE_THREADS, SM_NODE_B, stream>>>(M, a));
     STRIVE_LAUNCH_CHECK();

@@ -38,6 +38,9 @@ class DeviceModel(object):
             raise RuntimeError('strive_b200: tensor-core weight packing size mismatch')
         self.tc_blob = tcb.to(device)
         _cabi.check(L.strive_model_set_tc_weights(h, _cabi.dptr(self.tc_blob), self.tc_blob.numel()))
+        # mma.sync fragment packs of the edge MLP, packed on the device from the blob (csrc/edge_mma.cuh)
+        self.edge_frags = torch.empty(L.strive_model_edge_frag_bytes(), dtype=torch.uint8, device=device)
+        _cabi.check(L.strive_model_set_edge_frags(h, _cabi.dptr(self.edge_frags), self.edge_frags.numel(), _cabi.stream_ptr()))
 
     def __del__(self):
         try:
