@@ -100,6 +100,10 @@ class ClockSampler(object):
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.25)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=10)      # nvidia-smi tears its driver handle down on exit: let that finish before anything is timed again
+        except Exception:
+            self.proc.kill()
         sm, mx, reasons = [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(',')]
@@ -288,7 +292,7 @@ def run_gpu(args):
         host['z'].copy_(z_host_out)
 
     e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(min(args.warmup, 2)):
+    for _ in range(max(3, min(args.warmup, 5))):
         api_step()
     barrier()
     e0.record()

@@ -6,6 +6,7 @@ nvidia-smi --query-gpu=name,driver_version,memory.total,clocks.max.sm --format=c
 echo "nproc=$(nproc)" >> gpurun_out/gpu_info.txt
 timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 900 python bench.py --steps ${BENCH_STEPS:-5} --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "${RUN_NCU:-1}" = "1" ]; then
