@@ -11,6 +11,7 @@ Workload at every N (weak scaling, scenes are independent): BASELINE.json config
 Prints ONE JSON line (rank 0).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -294,6 +295,8 @@ def run_gpu(args):
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(max(3, min(args.warmup, 5))):
         api_step()
+    gc.collect()
+    gc.disable()            # as timeit does: a generation-2 collection inside the timed region is a 30 ms outlier on a 60 ms step
     barrier()
     e0.record()
     wall = []
@@ -303,6 +306,7 @@ def run_gpu(args):
         wall.append(round(1000.0 * (time.perf_counter() - t0), 2))
     e1.record()
     torch.cuda.synchronize()
+    gc.enable()
     ms_e = e0.elapsed_time(e1)
     barrier()
     t = torch.tensor([ms_e], device=dev)
