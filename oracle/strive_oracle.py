@@ -628,3 +628,23 @@ def sol_loop(sd, scene, raster, dx, weights, iters, lr, future_len, FT, other_ma
             record.append({'loss': float(loss.detach()), 'g_tgt': tgt_z.grad.clone(), 'g_other': other_z.grad.clone()})
         opt.step()
     return _collate(ptr, tgt_z.detach(), other_z.detach())
+
+
+def init_loop(sd, scene, raster, dx, weights, iters, lr, FT, init_traj_n, traj_vis, record=None):
+    """utils/init_optim.py:11-68: Adam([z]) on TgtMatchingLoss (init_* weights) between the decoded future and the observed
+    one at the visible (agent, step) entries."""
+    z = scene['z'].clone().requires_grad_(True)
+    opt = torch.optim.Adam([z], lr=lr)
+    vis = traj_vis == 1.0
+    tgt_un = unnorm_state(init_traj_n)[vis]
+    w = {k[5:]: v for k, v in weights.items() if k[:5] == 'init_'}
+    for it in range(iters):
+        opt.zero_grad()
+        fut = decode(sd, z, scene['map_feat'], scene['past_feat'], scene['past'][:, -1, :], scene['lw'], scene['sem'], scene['ptr'],
+                     scene['edge_index'], scene['map_idx'], raster, dx, FT)
+        ld = tgt_matching_loss(unnorm_state(fut)[vis], tgt_un, w)
+        ld['loss'].backward()
+        if record is not None:
+            record.append({'loss': float(ld['loss'].detach()), 'grad': z.grad.clone()})
+        opt.step()
+    return z.detach()

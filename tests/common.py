@@ -67,3 +67,22 @@ def metric_inputs():
     fut_un[6, 0, 0] = float('nan')
     samples = nrm.normalize(fut_un)
     return dict(sc=sc, samples=samples, nrm=nrm, att=att, NA=NA, NS=NS, FT=FT)
+
+
+INIT_W = {'init_match_ext': 10.0, 'init_motion_prior_ext': 0.1}       # configs/adv_gen_rule_based.cfg:28-30
+
+
+def init_case(FT=6):
+    """Seeded inputs of the init-loop case (tests/golden/init_loop.npz): observed futures = constant-velocity continuations of
+    the past with noise, ~25 % of the (agent, step) entries invisible."""
+    sc = synth.make_scenes(61, [4, 2, 3], map_extent_m=EXTENT, M=2, FT=FT, collide_frac=0.0, offroad_frac=0.0)
+    NA = sc['past'].size(0)
+    g = torch.Generator().manual_seed(62)
+    last = sc['past'][:, -1, :4]
+    vel = sc['past'][:, -1, :2] - sc['past'][:, -2, :2]
+    steps = torch.arange(1, FT + 1).view(1, FT, 1).float()
+    xy = last[:, None, :2] + vel[:, None, :] * steps + 0.02 * torch.randn(NA, FT, 2, generator=g)
+    init_traj = torch.cat([xy, last[:, None, 2:4].expand(NA, FT, 2)], dim=2).contiguous()
+    vis = (torch.rand(NA, FT, generator=g) > 0.25).float()
+    vis[:, 0] = 1.0
+    return sc, init_traj, vis

@@ -132,3 +132,83 @@ def test_vehicle_iou_checks_vs_oracle():
     diag('veh IoU: %d rectangle pairs, max |IoU - oracle| %.2e, %d hits; single: %d collide; pairwise: %d flagged' % (
         N * N * T, err, int((ref > MO.VEH_COLL_THRESH).sum()), int(rc.sum()), int(rp['num_coll_veh'])))
     assert int(rc.sum()) > 0 and 0 < int(rp['num_coll_veh']) < N
+
+
+def test_init_loop_vs_reference_golden_and_oracle():
+    """optim.run_init_optim (reference utils/init_optim.py:11-68) through the drop-in modules: iteration-0 loss and gradient
+    against the oracle, z after 3 Adam iterations against the unmodified reference's (Adam's first steps are sign-like:
+    an element whose gradient is at noise level may flip, hence the 2*lr*iters bound, with 99 % of the elements tight)."""
+    from oracle import strive_oracle as O
+    from strive_b200.optim import run_init_optim
+    from tests.common import init_case, INIT_W, world
+    dev, model, env = ctx()
+    raster, dx, sd = world()
+    g = golden('init_loop')
+    FT, iters, lr = int(g['FT']), int(g['iters']), float(g['lr'])
+    sc, init_traj, vis = init_case(FT)
+    rec = []
+    O.init_loop(sd, sc, raster, dx, INIT_W, 1, lr, FT, init_traj, vis, record=rec)
+    graph = to_graph(sc, dev)
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev)}
+    logs = []
+    model.FT = FT
+    try:
+        z, traj, _ = run_init_optim(sc['z'].to(dev), init_traj.to(dev), vis.to(dev), lr, INIT_W, model, graph, env, sc['map_idx'].to(dev), iters,
+                                    embed, (sc['prior_mu'].to(dev), sc['prior_var'].to(dev)), log=lambda it, d: logs.append(d))
+    finally:
+        model.FT = 20
+    # iteration-0 gradient through the same modules the loop uses
+    from strive_b200.losses import TgtMatchingLoss
+    z0 = sc['z'].to(dev).clone().requires_grad_(True)
+    nrm = model.get_normalizer()
+    visd = vis.to(dev) == 1.0
+    fut = nrm.unnormalize(model.decode_embedding(z0, embed, graph, sc['map_idx'].to(dev), env, nfuture=FT)['future_pred'])[visd]
+    ld = TgtMatchingLoss({k[5:]: v for k, v in INIT_W.items()})(fut, nrm.unnormalize(init_traj.to(dev))[visd], z0,
+                                                                  (sc['prior_mu'].to(dev), sc['prior_var'].to(dev)))
+    ld['loss'].backward()
+    e_g = (z0.grad.cpu() - rec[0]['grad']).abs().max().item() / rec[0]['grad'].abs().max().item()
+    dz = np.abs(z.detach().cpu().numpy() - g['z'])
+    dt = np.abs(traj.cpu().numpy() - g['traj']).max()
+    diag('init loop: loss0 gpu %.5f oracle %.5f | iter-0 grad rel err %.2e | z after %d iters vs reference: max %.3e | final traj diff %.2e' % (
+        logs[0]['loss'], rec[0]['loss'], e_g, iters, dz.max(), dt))
+    assert abs(logs[0]['loss'] - rec[0]['loss']) < 3e-4 * abs(rec[0]['loss'])     # ~1e-5 map-feature noise (pixel flips), 15 m position scale
+    assert e_g < 3e-2            # 6-step BPTT after ~1e-5 forward noise (pixel flips), as in the solution-loop test; strict check = teacher-forced test
+    assert dz.max() <= 2 * lr * iters + 1e-4      # Adam's first steps are sign-like: noise-level gradient entries may flip
+    assert tuple(traj.shape) == (sc['z'].size(0), FT, 4)
+
+
+def test_error_behaviour_is_runtime_error_with_message():
+    """Failures surface as RuntimeError carrying strive_last_error() (the drivers catch RuntimeError to skip a batch,
+    refine_traffic_optim.py:381-388): unsupported scene size, undersized tape, wrong class count, closed-loop planner mode."""
+    import ctypes as C
+    from strive_b200 import _cabi, synth
+    from strive_b200.optim import run_adv_gen_optim
+    dev, model, env = ctx()
+    g = golden('decode_small')
+    sc = scene_for(g)
+    graph = to_graph(sc, dev)
+    scene = model.scene_batch(graph, sc['map_idx'].to(dev))
+    L = _cabi.lib()
+    NA, FT = scene.NA, 3
+    traj = torch.empty((NA, FT, 4), device=dev)
+    tape = torch.empty(1024, dtype=torch.uint8, device=dev)          # far too small
+    z, mf, pf = sc['z'].to(dev), sc['map_feat'].to(dev), sc['past_feat'].to(dev)
+    rc = L.strive_decode_fwd(model.device_model().handle, C.byref(scene.cstruct), C.byref(env.cstruct), _cabi.dptr(z), _cabi.dptr(mf),
+                             _cabi.dptr(pf), None, FT, _cabi.dptr(traj), _cabi.dptr(tape), tape.numel(), _cabi.stream_ptr())
+    assert rc != 0 and b'tape too small' in L.strive_last_error()
+    with pytest.raises(RuntimeError, match='tape too small'):
+        _cabi.check(rc)
+    # a scene with more than 255 agents (arg-max indices are stored as bytes)
+    big = synth.make_scenes(5, [256], map_extent_m=(90.0, 230.0), M=2, FT=2, collide_frac=0.0, offroad_frac=0.0)
+    with pytest.raises(RuntimeError, match='255'):
+        model.decode_embedding(big['z'].to(dev), {'map_feat': big['map_feat'].to(dev), 'past_feat': big['past_feat'].to(dev)},
+                               to_graph(big, dev), big['map_idx'].to(dev), env, nfuture=2)
+    # CPU tensors are refused (no CPU fallback)
+    with pytest.raises(RuntimeError):
+        model.decode_embedding(sc['z'], {'map_feat': sc['map_feat'], 'past_feat': sc['past_feat']}, graph, sc['map_idx'].to(dev), env, nfuture=2)
+    # closed-loop planner mode is out of scope and says so
+    with pytest.raises(RuntimeError, match='planner'):
+        run_adv_gen_optim(z, 0.05, {}, model, graph, env, sc['map_idx'].to(dev), 1, {}, 'hardcode', None, None, 0, None)
+    # the library still works after the failed calls
+    out = model.decode_embedding(z, {'map_feat': mf, 'past_feat': pf}, graph, sc['map_idx'].to(dev), env, nfuture=2)['future_pred']
+    assert bool(torch.isfinite(out).all())

@@ -166,3 +166,15 @@ def test_rect_iou_closed_form_cases():
     assert coll.tolist() == [True, False, True] and when.tolist() == [2, T, 1]
     pw = MO.check_pairwise_veh_coll(np.concatenate([tgt[None], others]), np.array([[2.0, 1.0]] * 4, dtype=np.float32))
     assert pw['did_collide'].tolist() == [True, False, False, False] and pw['num_coll_veh'] == 1.0 and pw['num_traj_veh'] == 4.0
+
+
+def test_init_loop_matches_reference():
+    """run_init_optim (utils/init_optim.py:11-68): 3 Adam iterations with a partial visibility mask."""
+    from tests.common import init_case, INIT_W
+    g = golden('init_loop')
+    raster, dx, sd = world()
+    FT, iters, lr = int(g['FT']), int(g['iters']), float(g['lr'])
+    sc, init_traj, vis = init_case(FT)
+    assert float(sc['z'].double().sum()) == float(g['z_in_sum']) and float(vis.sum()) == float(g['vis_sum'])
+    z = O.init_loop(sd, sc, raster, dx, INIT_W, iters, lr, FT, init_traj, vis)
+    assert np.abs(z.numpy() - g['z']).max() < 1e-4
