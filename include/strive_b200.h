@@ -74,6 +74,11 @@ int strive_mapenc_set_impl(int impl);
 int64_t strive_model_edge_frag_bytes(void);
 int strive_model_set_edge_frags(StriveModel* m, void* buf, int64_t bytes, void* stream);
 int strive_edge_set_impl(int impl);
+/* Programmatic dependent launch.  mask bit 0: rollout kernels (griddepcontrol.wait is their first instruction: only the launch
+ * latency overlaps), bit 1: map-encoder kernels (their prologue -- weights to shared memory, barrier init, TMEM alloc --
+ * overlaps the tail of the predecessor; the pointers to the predecessor's output pass through the wait).  Default 3;
+ * 0 = plain stream-ordered launches.  Results are identical (tests/test_gpu_fullsize.py checks run-to-run determinism). */
+int strive_set_pdl(int on);
 
 /* ---- scene description (all device) --------------------------------------------------------------------
  * Mirrors the torch_geometric Batch the drivers build (src/datasets/nuscenes_dataset.py:609-687): edges are

@@ -43,7 +43,7 @@ class StriveLossCfg(C.Structure):
                 ('circ_cx', C.c_void_p), ('lw_un', C.c_void_p)]
 
 
-EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_tc_trace', 'strive_tc_debug', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl', 'strive_model_edge_frag_bytes', 'strive_model_set_edge_frags', 'strive_edge_set_impl',
+EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_tc_trace', 'strive_tc_debug', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl', 'strive_model_edge_frag_bytes', 'strive_model_set_edge_frags', 'strive_edge_set_impl', 'strive_set_pdl',
            'strive_mapenc_workspace_bytes', 'strive_mapenc_fwd', 'strive_map_crop', 'strive_decode_tape_bytes',
            'strive_decode_fwd', 'strive_decode_bwd', 'strive_decode_tape_read', 'strive_loss_workspace_bytes',
            'strive_loss_fwd_bwd', 'strive_adam_step', 'strive_on_layer_frac', 'strive_line_layer', 'strive_veh_iou_hits']
@@ -71,6 +71,7 @@ def lib():
     L.strive_model_edge_frag_bytes.restype = i64
     L.strive_model_set_edge_frags.argtypes = [vp, vp, i64, vp]
     L.strive_edge_set_impl.argtypes = [C.c_int]
+    L.strive_set_pdl.argtypes = [C.c_int]
     L.strive_mapenc_workspace_bytes.argtypes = [i32]
     L.strive_mapenc_workspace_bytes.restype = i64
     L.strive_mapenc_fwd.argtypes = [vp, C.POINTER(StriveMap), vp, vp, i32, vp, vp, i64, vp]
@@ -98,6 +99,8 @@ def lib():
     if L.strive_abi_version() != 1:
         raise RuntimeError('strive_b200: ABI version mismatch')
     _verify_layout(L)
+    if os.environ.get('STRIVE_PDL') is not None:      # development switch: bit 0 rollout kernels, bit 1 map-encoder kernels
+        L.strive_set_pdl(int(os.environ['STRIVE_PDL']))
     _lib = L
     return L
 

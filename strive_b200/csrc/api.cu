@@ -53,6 +53,12 @@ static void seg_sizes(int nc, int64_t* sz) {
   }
 }
 
+int g_strive_pdl = 3;      // bit 0: rollout kernels, bit 1: map-encoder kernels
+extern "C" int strive_set_pdl(int on) {
+  g_strive_pdl = on;
+  return 0;
+}
+
 extern "C" int strive_model_layout(int num_classes, int64_t* seg_sizes_host, int max_segs, int* n_segs_out) {
   STRIVE_CHECK(num_classes >= 1 && num_classes <= 16, STRIVE_EINVAL, "num_classes=%d out of range", num_classes);
   STRIVE_CHECK(seg_sizes_host && n_segs_out && max_segs >= (int)S_COUNT, STRIVE_EINVAL, "layout buffer too small (%d < %d)", max_segs, (int)S_COUNT);

@@ -43,6 +43,38 @@ void strive_prof_end(cudaStream_t s);
     if (g_strive_profile_on) strive_prof_end(stream);         \
   } while (0)
 
+// ------------------------------------------------------------------------------------------------------
+// programmatic dependent launch: a kernel launched through strive_launch may start (and run its prologue: weights ->
+// shared memory, barrier init, TMEM alloc) while its predecessor in the stream drains; STRIVE_PDL_WAIT() blocks until the
+// predecessor grid has completed and its writes are visible, so everything after it is ordered exactly as a normal launch.
+// Pre-wait code only reads model weights and touches its own shared memory / TMEM.  Both instructions are no-ops in a
+// kernel that was launched without the attribute (<<<>>>, profiling mode).
+// ------------------------------------------------------------------------------------------------------
+extern int g_strive_pdl;
+#define STRIVE_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#define STRIVE_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+// wait placed after a prologue: the pointers to the predecessor's output pass THROUGH the asm, so no load from them (not
+// even a read-only ld.global.nc, which the compiler may otherwise move across a "memory" clobber) can be scheduled above it.
+// (Rollout kernels whose first loads were builtin __ldg() reads produced wrong results with the wait behind a prologue.)
+#define STRIVE_PDL_WAIT_PTRS(p, q) asm volatile("griddepcontrol.wait;" : "+l"(p), "+l"(q)::"memory")
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t strive_launch(int pdl_class, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = ((g_strive_pdl & pdl_class) != 0 && g_strive_profile_on == 0) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+#define STRIVE_CUDA_LAUNCH(kern, grid, block, smem, stream, ...) (void)strive_launch(STRIVE_PDL_CLASS, kern, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
+
 enum StriveErr { STRIVE_OK = 0, STRIVE_EINVAL = 1, STRIVE_ESIZE = 2, STRIVE_EUNSUPPORTED = 3 };
 
 // ------------------------------------------------------------------------------------------------------

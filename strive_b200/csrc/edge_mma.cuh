@@ -261,6 +261,8 @@ __device__ __forceinline__ void em_load_packs(uint8_t* dst, const uint8_t* src, 
 __device__ __forceinline__ bool em_better(float v, int ix, float bv, int bi) { return v > bv || (v == bv && ix < bi); }
 
 __global__ void __launch_bounds__(EM_THREADS, 1) edge_fwd_mma_kernel(ModelDev M, StepArgs a, const uint8_t* __restrict__ frags) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();
   extern __shared__ __align__(128) uint8_t esm[];
   __shared__ __align__(8) uint64_t bar;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -331,6 +333,8 @@ __global__ void __launch_bounds__(EM_THREADS, 1) edge_fwd_mma_kernel(ModelDev M,
 }
 
 __global__ void __launch_bounds__(EM_THREADS, 1) edge_bwd_mma_kernel(ModelDev M, StepArgs a, const uint8_t* __restrict__ frags) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();
   extern __shared__ __align__(128) uint8_t esm[];
   __shared__ __align__(8) uint64_t bar;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;

@@ -13,6 +13,7 @@
 // Operand addressing ("shifted window", conv1..conv4): the input tile is written to shared memory ONCE, columns
 // de-interleaved by parity (stride-2 conv -> consecutive output pixels are consecutive 16-byte rows of a parity plane).
 // Every filter tap is then only a different start address in the K-major no-swizzle matrix descriptor: no im2col copy.
+#define STRIVE_PDL_CLASS 2   // bit of strive_set_pdl() that enables programmatic dependent launch for this file's kernels
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -188,6 +189,8 @@ __device__ __forceinline__ void crop_pack_rows(const uint8_t* __restrict__ s_box
 
 __global__ void __launch_bounds__(256, 5) crop_pack_kernel(StriveMap map, const float* __restrict__ pose, const int32_t* __restrict__ map_of,
                                                         uint8_t* __restrict__ packed_crop, int n) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();
   __shared__ __align__(16) uint8_t s_box[CP_BOX_BYTES];
   __shared__ unsigned short s_q[CP_TILE * CP_TILE];
   __shared__ int s_nq;
@@ -341,6 +344,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
   }
   if (warp == T1_MMA_WARP) tc::tmem_alloc(&tmem_base, 512);     // 2 accumulator sets (256 columns apart) x 4 sub-tiles x 48 columns
   tc::fence_async_smem();
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT_PTRS(packed_crop, out_stats);          // prologue above: weights / GroupNorm affine (constants), barriers, TMEM; below: the previous kernel's output
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -584,6 +589,8 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __rest
   }
   if (warp == T2_MMA_WARP) tc::tmem_alloc(&tmem_base, Cfg::TMEM_COLS);
   tc::fence_async_smem();
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT_PTRS(in, in_stats);          // prologue above: weights / GroupNorm affine (constants), barriers, TMEM; below: the previous kernel's output
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -887,6 +894,8 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
   }
   if (warp == T2_MMA_WARP) tc::tmem_alloc(&tmem_base, 512);
   tc::fence_async_smem();
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT_PTRS(in, in_stats);          // prologue above: weights / GroupNorm affine (constants), barriers, TMEM; below: the previous kernel's output
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -1207,6 +1216,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
   }
   constexpr uint32_t TCOLS = 2 * COUT;   // 256 or 128: a power of two >= 32
   if (warp == TC_MMA_WARP) tc::tmem_alloc(&tmem_base, TCOLS);
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT_PTRS(in, in_stats);          // prologue above: weights / GroupNorm affine (constants), barriers, TMEM; below: the previous kernel's output
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -1401,7 +1412,7 @@ int tc_crop_pack_unpacked(const StriveMap* map, const float* pose, const int32_t
   uint8_t* tmp = nullptr;
   STRIVE_CUDA(cudaMallocAsync((void**)&tmp, (size_t)n * 65536, stream));
   dim3 gp(16, n);
-  KPROF("crop_pack", stream, crop_pack_kernel<<<gp, 256, 0, stream>>>(*map, pose, map_of, tmp, n));
+  KPROF("crop_pack", stream, STRIVE_CUDA_LAUNCH(crop_pack_kernel, gp, 256, 0, stream, *map, pose, map_of, tmp, n));
   STRIVE_LAUNCH_CHECK();
   const size_t tot = (size_t)n * 65536;
   crop_unpack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(tmp, out, n, map->C);
@@ -1427,12 +1438,12 @@ int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_
   STRIVE_CHECK(map->packed != nullptr, STRIVE_EINVAL, "tensor-core map encoder needs StriveMap.packed");
   STRIVE_CHECK(map->packed_pitch >= map->W && (map->packed_pitch & 15) == 0 && ((uintptr_t)map->packed & 15) == 0, STRIVE_EINVAL, "StriveMap.packed_pitch must be >= W and a multiple of 16, packed 16-byte aligned");
   dim3 gp(16, n);
-  KPROF("crop_pack", stream, crop_pack_kernel<<<gp, 256, 0, stream>>>(*map, pose, map_of, packed_crop, n));
+  KPROF("crop_pack", stream, STRIVE_CUDA_LAUNCH(crop_pack_kernel, gp, 256, 0, stream, *map, pose, map_of, packed_crop, n));
   STRIVE_LAUNCH_CHECK();
   const int items = n * T1_RB * T1_CB;
   const int grid = items < num_sms() ? items : num_sms();     // the kernel owns all 512 TMEM columns: one CTA per SM
   const BiasArg bias = make_bias(h_bias, 16);
-  KPROF("tc_conv1", stream, tc_conv1_kernel<<<grid, TC_THREADS, smem, stream>>>(packed_crop, wpack, bias, out, out_stats, n));
+  KPROF("tc_conv1", stream, STRIVE_CUDA_LAUNCH(tc_conv1_kernel, grid, TC_THREADS, smem, stream, packed_crop, wpack, bias, out, out_stats, n));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
@@ -1455,7 +1466,7 @@ static int tc_launch(const char* name, const float* in, const double* in_stats, 
   if (gx > items) gx = items;
   dim3 grid(gx, COUT / NCH);
   const BiasArg bias = make_bias(h_bias, COUT);
-  KPROF(name, stream, kern<<<grid, T2_THREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n, g_tc_dbg));
+  KPROF(name, stream, STRIVE_CUDA_LAUNCH(kern, grid, T2_THREADS, Cfg::SMEM, stream, in, in_stats, gam, bet, wpack, bias, out, out_stats, n, g_tc_dbg));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
@@ -1478,7 +1489,7 @@ int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, c
   int gx = num_sms();
   if (gx > (items + 1) / 2) gx = (items + 1) / 2;
   const BiasArg bias = make_bias(h_bias, 64);
-  KPROF("tc_conv3", stream, tc_conv3_kernel<<<gx, T2_THREADS, SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
+  KPROF("tc_conv3", stream, STRIVE_CUDA_LAUNCH(tc_conv3_kernel, gx, T2_THREADS, SMEM, stream, in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }
@@ -1501,7 +1512,7 @@ static int tc3_launch(const char* name, const float* in, const double* in_stats,
   const long long rows = (long long)n * Cfg::PIX;
   const int tiles = (int)((rows + 127) / 128);
   const int gx = tiles < num_sms() ? tiles : num_sms();
-  KPROF(name, stream, kern<<<gx, TC_THREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
+  KPROF(name, stream, STRIVE_CUDA_LAUNCH(kern, gx, TC_THREADS, Cfg::SMEM, stream, in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }

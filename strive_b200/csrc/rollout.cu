@@ -15,6 +15,7 @@
 //
 // Backward recomputes edge/node activations from the tape (node-level tensors only) instead of storing
 // per-edge activations (E x 320 floats per step would be 4 GB at BASELINE config 5).
+#define STRIVE_PDL_CLASS 1   // bit of strive_set_pdl() that enables programmatic dependent launch for this file's kernels
 #include "common.cuh"
 #include "wpipe.cuh"
 #include <cuda_bf16.h>
@@ -230,6 +231,8 @@ __device__ __forceinline__ void node_rows(int warp, int NA, int& base, int (&row
 }
 
 __global__ void __launch_bounds__(NODE_THREADS, 2) node_fwd_kernel(ModelDev M, StepArgs a) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();      // first instructions of the kernel: nothing (not even a hoisted read-only load) can precede them
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WPipe wp = wp_init(smem, NODE_WARPS);
@@ -354,6 +357,8 @@ __device__ __forceinline__ bool edge_ctx_init(const StepArgs& a, EdgeCtx& c) {
 }
 
 __global__ void __launch_bounds__(EDGE_WARPS * 32) edge_fwd_kernel(ModelDev M, StepArgs a) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();
   extern __shared__ __align__(16) float smem[];
   __shared__ float red_val[EDGE_WARPS][64];
   __shared__ int red_idx[EDGE_WARPS][64];
@@ -522,6 +527,8 @@ __device__ __forceinline__ void bicycle_fwd(const float prev[6], float o0, float
 }
 
 __global__ void __launch_bounds__(NODE_THREADS, 2) post_fwd_kernel(ModelDev M, StepArgs a) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();      // first instructions of the kernel: nothing (not even a hoisted read-only load) can precede them
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WPipe wp = wp_init(smem, NODE_WARPS);
@@ -676,6 +683,8 @@ __device__ __forceinline__ void produce_gru_fwd(const ModelDev& M, WPipe& wp) {
 }
 
 __global__ void __launch_bounds__(NODE_THREADS, 2) gru_fwd_kernel(ModelDev M, StepArgs a) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();      // first instructions of the kernel: nothing (not even a hoisted read-only load) can precede them
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WPipe wp = wp_init(smem, NODE_WARPS);
@@ -719,6 +728,8 @@ __global__ void __launch_bounds__(NODE_THREADS, 2) gru_fwd_kernel(ModelDev M, St
 // GRU backward. In: g_mem (grad wrt mem_{t+1}), g_pf (grad wrt past_feat_{t+1} = top output). Out: g_mem <- grad wrt
 // mem_t, d_loc. (Not launched for t = FT-1: no GRU step there.)
 __global__ void __launch_bounds__(NODE_THREADS, 2) gru_bwd_kernel(ModelDev M, StepArgs a) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();      // first instructions of the kernel: nothing (not even a hoisted read-only load) can precede them
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WPipe wp = wp_init(smem, NODE_WARPS);
@@ -847,6 +858,8 @@ __global__ void __launch_bounds__(NODE_THREADS, 2) gru_bwd_kernel(ModelDev M, St
 // post backward: (d_traj[t], g_prev, g_pos, d_loc) -> bicycle/transform adjoint -> mlp_out/update_mlp adjoint
 // outputs: g_prev <- grad wrt prev_state_t, d_xupd, d_aggr; zeroes g_pos and dQ rows for the edge phase.
 __global__ void __launch_bounds__(NODE_THREADS, 2) post_bwd_kernel(ModelDev M, StepArgs a, int has_gru) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();      // first instructions of the kernel: nothing (not even a hoisted read-only load) can precede them
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WPipe wp = wp_init(smem, NODE_WARPS);
@@ -1014,6 +1027,8 @@ __global__ void __launch_bounds__(NODE_THREADS, 2) post_bwd_kernel(ModelDev M, S
 // edge backward: recompute the edge MLP per chunk, route d_aggr to the arg-max edges, back through the MLP.
 // dP_i written (exclusive), dQ_j / g_pos_j accumulated atomically, g_pos_i accumulated atomically.
 __global__ void __launch_bounds__(EDGE_WARPS * 32) edge_bwd_kernel(ModelDev M, StepArgs a) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();
   extern __shared__ __align__(16) float smem[];
   __shared__ float red_dp[EDGE_WARPS][128];
   __shared__ float red_pos[EDGE_WARPS][4];
@@ -1120,6 +1135,8 @@ __global__ void __launch_bounds__(EDGE_WARPS * 32) edge_bwd_kernel(ModelDev M, S
 
 // node backward: d_x = d_xupd + dP.W_xi + dQ.W_xj ; back through mlp_in; d_z += ; g_pf <- grad wrt past_feat_t
 __global__ void __launch_bounds__(NODE_THREADS, 2) node_bwd_kernel(ModelDev M, StepArgs a) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();      // first instructions of the kernel: nothing (not even a hoisted read-only load) can precede them
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   WPipe wp = wp_init(smem, NODE_WARPS);
@@ -1200,6 +1217,8 @@ __global__ void __launch_bounds__(NODE_THREADS, 2) node_bwd_kernel(ModelDev M, S
 // ------------------------------------------------------------------------------------------------------
 __global__ void init_tape_kernel(StepArgs a, const float* past_last, const float* map_feat0, const float* past_feat0,
                                  const int32_t* map_idx) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();
   const int NA = a.NA;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NA * 64) return;
@@ -1322,23 +1341,23 @@ extern "C" int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, co
   a.ptr = sc->ptr; a.scene_of = sc->scene_of; a.lw = sc->lw; a.sem = sc->sem; a.z = z; a.ext = ext_future;
   a.traj = traj_out; a.d_traj = nullptr; a.d_z = nullptr;
   ModelDev M = model_dev(m);
-  KPROF("init_tape", stream, init_tape_kernel<<<(NA * 64 + 255) / 256, 256, 0, stream>>>(a, sc->past_last, map_feat0, past_feat0, sc->map_idx));
+  KPROF("init_tape", stream, STRIVE_CUDA_LAUNCH(init_tape_kernel, (NA * 64 + 255) / 256, 256, 0, stream, a, sc->past_last, map_feat0, past_feat0, sc->map_idx));
   STRIVE_LAUNCH_CHECK();
   const int node_blocks = (NA + NODE_WARPS * NODE_R - 1) / (NODE_WARPS * NODE_R);
   for (int t = 0; t < ft; t++) {
     a.t = t;
-    KPROF("node_fwd", stream, node_fwd_kernel<<<node_blocks, NODE_THREADS, SM_NODE, stream>>>(M, a));
+    KPROF("node_fwd", stream, STRIVE_CUDA_LAUNCH(node_fwd_kernel, node_blocks, NODE_THREADS, SM_NODE, stream, M, a));
     STRIVE_LAUNCH_CHECK();
     if (g_edge_impl != 0 && m->edge_frags != nullptr) {
-      KPROF("edge_fwd", stream, edge_fwd_mma_kernel<<<em_grid(NA), EM_THREADS, EM_FWD_SMEM, stream>>>(M, a, m->edge_frags));
+      KPROF("edge_fwd", stream, STRIVE_CUDA_LAUNCH(edge_fwd_mma_kernel, em_grid(NA), EM_THREADS, EM_FWD_SMEM, stream, M, a, m->edge_frags));
     } else {
-      KPROF("edge_fwd", stream, edge_fwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_F, stream>>>(M, a));
+      KPROF("edge_fwd", stream, STRIVE_CUDA_LAUNCH(edge_fwd_kernel, NA, EDGE_WARPS * 32, SM_EDGE_F, stream, M, a));
     }
     STRIVE_LAUNCH_CHECK();
-    KPROF("post_fwd", stream, post_fwd_kernel<<<node_blocks, NODE_THREADS, SM_NODE, stream>>>(M, a));
+    KPROF("post_fwd", stream, STRIVE_CUDA_LAUNCH(post_fwd_kernel, node_blocks, NODE_THREADS, SM_NODE, stream, M, a));
     STRIVE_LAUNCH_CHECK();
     if (t + 1 < ft) {
-      KPROF("gru_fwd", stream, gru_fwd_kernel<<<node_blocks, NODE_THREADS, SM_GRU_F, stream>>>(M, a));
+      KPROF("gru_fwd", stream, STRIVE_CUDA_LAUNCH(gru_fwd_kernel, node_blocks, NODE_THREADS, SM_GRU_F, stream, M, a));
       STRIVE_LAUNCH_CHECK();
       rc = strive_mapenc_fwd(m, map, a.tp.pose, a.tp.map_of, NA, a.tp.mapfeat + (size_t)(t + 1) * NA * 64, a.tp.mapenc_ws,
                              a.tp.mapenc_ws_bytes, stream_);
@@ -1375,18 +1394,18 @@ extern "C" int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, in
     a.t = t;
     const int has_gru = (t + 1 < ft) ? 1 : 0;
     if (has_gru) {
-      KPROF("gru_bwd", stream, gru_bwd_kernel<<<node_blocks, NODE_THREADS, SM_GRU_B, stream>>>(M, a));
+      KPROF("gru_bwd", stream, STRIVE_CUDA_LAUNCH(gru_bwd_kernel, node_blocks, NODE_THREADS, SM_GRU_B, stream, M, a));
       STRIVE_LAUNCH_CHECK();
     }
-    KPROF("post_bwd", stream, post_bwd_kernel<<<node_blocks, NODE_THREADS, SM_POST_B, stream>>>(M, a, has_gru));
+    KPROF("post_bwd", stream, STRIVE_CUDA_LAUNCH(post_bwd_kernel, node_blocks, NODE_THREADS, SM_POST_B, stream, M, a, has_gru));
     STRIVE_LAUNCH_CHECK();
     if (g_edge_impl != 0 && m->edge_frags != nullptr) {
-      KPROF("edge_bwd", stream, edge_bwd_mma_kernel<<<em_grid(NA), EM_THREADS, EM_BWD_SMEM, stream>>>(M, a, m->edge_frags));
+      KPROF("edge_bwd", stream, STRIVE_CUDA_LAUNCH(edge_bwd_mma_kernel, em_grid(NA), EM_THREADS, EM_BWD_SMEM, stream, M, a, m->edge_frags));
     } else {
-      KPROF("edge_bwd", stream, edge_bwd_kernel<<<NA, EDGE_WARPS * 32, SM_EDGE_B, stream>>>(M, a));
+      KPROF("edge_bwd", stream, STRIVE_CUDA_LAUNCH(edge_bwd_kernel, NA, EDGE_WARPS * 32, SM_EDGE_B, stream, M, a));
     }
     STRIVE_LAUNCH_CHECK();
-    KPROF("node_bwd", stream, node_bwd_kernel<<<node_blocks, NODE_THREADS, SM_NODE_B, stream>>>(M, a));
+    KPROF("node_bwd", stream, STRIVE_CUDA_LAUNCH(node_bwd_kernel, node_blocks, NODE_THREADS, SM_NODE_B, stream, M, a));
     STRIVE_LAUNCH_CHECK();
   }
   return 0;

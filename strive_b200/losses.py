@@ -206,6 +206,10 @@ class _LossFn(torch.autograd.Function):
         ctx.match_only = d_traj is None
         col = 11 if ctx.match_only else 0
         loss = terms[:, col].sum()
+        # the per-term table is a diagnostic (the drivers only print its means): without this it would require grad, and a
+        # caller copying it into a persistent buffer (`log_buf.copy_(terms)`) would chain every iteration's graph -- and its
+        # multi-GB rollout tape -- onto that buffer forever
+        ctx.mark_non_differentiable(terms)
         return loss, terms
 
     @staticmethod

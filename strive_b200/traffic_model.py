@@ -125,12 +125,17 @@ class _TapeLease(object):
     block for small requests, after which the next tape no longer fits and costs a cudaMalloc (measured: 50-180 ms stalls
     in 1 of 3 iterations of the drop-in API path)."""
     _free = {}
+    made = 0          # buffers ever allocated (diagnostic)
 
     def __init__(self, nbytes, device):
         key = (str(device), int(nbytes))
         lst = _TapeLease._free.setdefault(key, [])
         self.key = key
-        self.buf = lst.pop() if lst else torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        if lst:
+            self.buf = lst.pop()
+        else:
+            _TapeLease.made += 1
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
 
     def __del__(self):
         try:
