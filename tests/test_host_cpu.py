@@ -66,3 +66,28 @@ def test_oracle_is_not_imported_by_the_product():
         if fn.endswith('.py'):
             src = open(os.path.join(pkg, fn)).read()
             assert 'oracle' not in src.replace('the oracle', '').replace('CPU oracle', ''), fn
+
+
+def test_tape_lease_recycles_buffers_and_bounds_the_free_list():
+    """The drop-in decode leases its multi-GB rollout tape from a free list keyed by (device, size): two alternating graphs
+    need two buffers, however many iterations run; at most two idle buffers are kept per size."""
+    import gc
+    import torch
+    from strive_b200.traffic_model import _TapeLease
+    _TapeLease.release_all()
+    made0 = _TapeLease.made
+    dev = torch.device('cpu')
+    prev = None
+    ptrs = set()
+    for _ in range(10):
+        cur = _TapeLease(4096, dev)          # the new forward runs before the previous graph is dropped
+        ptrs.add(cur.buf.data_ptr())
+        prev = cur
+    assert _TapeLease.made - made0 == 2 and len(ptrs) == 2
+    held = [_TapeLease(4096, dev) for _ in range(5)]
+    del held, prev, cur
+    gc.collect()
+    assert len(_TapeLease._free[('cpu', 4096)]) == 2       # the rest went back to the allocator
+    other = _TapeLease(8192, dev)
+    assert other.buf.numel() == 8192
+    _TapeLease.release_all()
