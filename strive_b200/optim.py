@@ -101,7 +101,7 @@ class RefineLoop(object):
     def _count_launches(self):
         FT, NA = self.FT, self.NA
         chunks = (NA + 2047) // 2048
-        fwd = 1 + FT * 3 + (FT - 1) * (1 + chunks * 7)
+        fwd = 1 + FT * 3 + (FT - 1) * (1 + chunks * 8)      # init_tape; node/edge/post per step; gru + (crop_pack, conv1..6, fc) per chunk
         bwd = FT * 3 + (FT - 1)
         loss = 7
         return fwd + bwd + loss + 1
