@@ -178,3 +178,34 @@ def test_init_loop_matches_reference():
     assert float(sc['z'].double().sum()) == float(g['z_in_sum']) and float(vis.sum()) == float(g['vis_sum'])
     z = O.init_loop(sd, sc, raster, dx, INIT_W, iters, lr, FT, init_traj, vis)
     assert np.abs(z.numpy() - g['z']).max() < 1e-4
+
+
+def test_adv_loss_option_branches_match_reference():
+    """AdvGenLoss branches the main fixture does not take (adv_gen_nusc.py:118-123 attack_agt_idx, :116 crash_loss_min_infront=None,
+    crash_loss_min_time 0 / 3, veh_coll_buffer 0 / 0.2): oracle against the unmodified reference's loss, gradients and arg-mins."""
+    g = golden('losses2')
+    raster, dx, sd = world()
+    FT = int(g['FT'])
+    sc = scene_for(g)
+    ptr = sc['ptr']
+    NA = int(ptr[-1])
+    ego = torch.zeros(NA, dtype=torch.bool)
+    ego[ptr[:-1]] = True
+    lw_un = O.unnorm_att(sc['lw'])
+    mapixes = sc['map_idx'][sc['batch']]
+    tgt = O.unnorm_state(sc['ext_future'][:, :FT]).clone()
+    prior_o = (sc['prior_mu'][~ego], sc['prior_var'][~ego])
+    init_o = (sc['z'][~ego] - 0.03).clone()
+    fut_n = torch.from_numpy(g['fut_n'])
+    for name, kw in (('atk', dict(veh_coll_buffer=0.0, crash_min_t=0, crash_min_infront=None, attack_agt_idx=(ptr[:-1] + torch.tensor([2, 1, 3])))),
+                     ('noinfront', dict(veh_coll_buffer=0.2, crash_min_t=3, crash_min_infront=None))):
+        fut = O.unnorm_state(fut_n).clone().requires_grad_(True)
+        z = sc['z'][~ego].clone().requires_grad_(True)
+        ld = O.adv_gen_loss(fut, tgt, z, prior_o, init_o, ADV_W, lw_un, mapixes, ptr, raster, dx, **kw)
+        ld['loss'].backward()
+        assert abs(float(ld['loss']) - float(g[name + '_loss'])) < 1e-5 * abs(float(g[name + '_loss']))
+        gf = g[name + '_d_fut']
+        assert np.abs(fut.grad.numpy() - gf).max() < 1e-5 * max(1.0, np.abs(gf).max())
+        assert np.abs(z.grad.numpy() - g[name + '_d_z']).max() < 1e-6
+        assert [int(v) for v in ld['min_agt']] == [int(v) for v in g[name + '_min_agt']]
+        assert [int(v) for v in ld['min_t']] == [int(v) for v in g[name + '_min_t']]
