@@ -33,6 +33,11 @@ WORK = dict(scenes=64, agents=32, FT=20, group=4, raster=4096)
 CNN_MAC = {'conv1_gather': 49.0e6, 'conv2': 47.63e6, 'conv3': 43.06e6, 'conv4': 7.23e6, 'conv5': 2.65e6, 'conv6': 0.59e6, 'fc': 0.03e6,
            'tc_conv1': 49.0e6, 'tc_conv2': 47.63e6, 'tc_conv3': 43.06e6, 'tc_conv4': 7.23e6, 'tc_conv5': 2.65e6, 'tc_conv6': 0.59e6, 'tc_fc': 0.03e6}
 MAPENC_CHUNK = 2048
+
+
+def workload_desc():
+    return ('refine_traffic_optim latent Adam loop: %d scenes x %d agents x %d steps per GPU (BASELINE configs[1]), loss groups of %d scenes, '
+            'random-init weights, synthetic %dx%d raster' % (WORK['scenes'], WORK['agents'], WORK['FT'], WORK['group'], WORK['raster'], WORK['raster']))
 # per-launch (2048 crops) DRAM traffic of the encoder kernels from ONE `ncu --set full` capture: dram__bytes_read.sum + dram__bytes_write.sum
 # (profiles/r01_ncu_full_v2_encoder.txt; conv3 / conv1 re-captured after their rewrites: profiles/r01_ncu_full_v3_encoder.txt)
 NCU_TRAFFIC_BYTES = {'tc_conv2': 2.067361e9 + 0.946168e9, 'tc_conv3': 0.978821e9 + 0.421498e9, 'tc_conv1': 0.135026e9 + 1.993950e9}
@@ -196,8 +201,7 @@ def run_reference(args):
     out = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': 1000.0 * r['seconds'] / args.steps, 'higher_is_better': True, 'scaling': 'weak',
            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': 'refine_traffic_optim latent Adam loop, BASELINE configs[1] (64 scenes x 32 agents x 20 steps); '
-                                  'CPU step = bounded sample (see cpu_baseline.sample)'},
+           'config': {'workload': workload_desc(), 'cpu_step': 'bounded sample of that workload (see cpu_baseline.sample)'},
            'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
            'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(out))
@@ -359,8 +363,7 @@ def run_gpu(args):
         out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                'data': 'synthetic',
-               'config': {'workload': 'refine_traffic_optim latent Adam loop: %d scenes x %d agents x %d steps per GPU (BASELINE configs[1]), '
-                                      'loss groups of %d scenes, random-init weights, synthetic %dx%d raster' % (S, WORK['agents'], FT, WORK['group'], WORK['raster'], WORK['raster']),
+               'config': {'workload': workload_desc(),
                           'agents_per_gpu': NA, 'FT': FT, 'parallelism': 'scene-sharded replicas x%d, no collective in the loop' % world,
                           'l2': 'per-step working set (tape %.0f MB + encoder activations %.0f MB) exceeds the 126 MB L2; no explicit flush' % (
                               loop.tape_bytes / 1e6, _cabi.lib().strive_mapenc_workspace_bytes(NA) / 1e6),
