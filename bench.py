@@ -342,7 +342,9 @@ def run_gpu(args):
                 'frac': achieved / peaks['bf16_sustained'], 'traffic': traffic, 'peak_source': peaks['source'] + ' bf16 sustained (cuBLAS 8192^3)',
                 'share_of_step': tms / tot, 'avg_launch_ms': tms / launches,
                 'note': 'algorithmic FLOPs = 2*MAC*crops per launch (the bf16 hi/lo split issues 3x that many tensor MACs: ceiling of this '
-                        'precision choice = 1/3 of the dense peak), vs dense bf16 peak; traffic = ncu dram bytes per 2048-crop launch'}
+                        'precision choice = 1/3 of the dense peak), vs dense bf16 peak; traffic = ncu dram bytes per 2048-crop launch; launch durations = CUDA events '
+                        'bracketing every launch on the launch stream in %d extra iterations right after the timed region (programmatic dependent '
+                        'launch is off while events separate the launches)' % prof_steps}
         if traffic is not None:
             roof['hbm'] = {'achieved_gbs': traffic * (crops_per_launch / MAPENC_CHUNK) / avg_s / 1e9, 'peak_gbs': peaks['hbm_gbs'],
                            'frac': traffic * (crops_per_launch / MAPENC_CHUNK) / avg_s / 1e9 / peaks['hbm_gbs']}
