@@ -291,7 +291,7 @@ def run_gpu(args):
         ld = lossm(fut, z_dev, em['prior_out'])
         ld['loss'].backward()
         opt.step()
-        loss_host.copy_(ld['_terms'].detach(), non_blocking=True)
+        loss_host.copy_(lossm.last_terms.detach(), non_blocking=True)
         z_host_out.copy_(z_dev.detach(), non_blocking=True)
         torch.cuda.synchronize()
         host['z'].copy_(z_host_out)

@@ -41,7 +41,7 @@ for it in range(N):
     ld['loss'].backward()
     t.append(time.perf_counter())
     opt.step()
-    loss_host.copy_(ld['_terms'].detach(), non_blocking=True)
+    loss_host.copy_(lossm.last_terms.detach(), non_blocking=True)
     z_host_out.copy_(z_dev.detach(), non_blocking=True)
     e1.record()
     t.append(time.perf_counter())

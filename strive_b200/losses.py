@@ -284,7 +284,7 @@ class AvoidCollLoss(_Base):
         if w.get('init_z', 0.0) > 0.0:
             out['init_loss'] = terms[:, 6]
         out['loss'] = loss
-        out['_terms'] = terms
+        self.last_terms = terms          # (G, STRIVE_TERMS) raw per-group table of the last call (diagnostics; not a reference key)
         return out
 
 
@@ -346,8 +346,8 @@ class AdvGenLoss(_Base):
         loss, terms = _LossFn.apply(future_pred, z, self, prior_out[0], prior_out[1], self.init_z, None, tgt, False)
         w = self.loss_weights
         out = {'init_loss': terms[:, 6], 'motion_prior_loss': terms[:, 5], 'coll_veh_loss': terms[:, 1],
-               'coll_veh_plan_loss': terms[:, 7], 'coll_env_loss': terms[:, 3], 'adv_crash_loss': terms[:, 9], 'loss': loss,
-               '_terms': terms}
+               'coll_veh_plan_loss': terms[:, 7], 'coll_env_loss': terms[:, 3], 'adv_crash_loss': terms[:, 9], 'loss': loss}
+        self.last_terms = terms
         if return_mins:
             mins = self.plan.adv_min.cpu().numpy()
             out['min_agt'] = mins[:, 0].astype(int)

@@ -51,7 +51,7 @@ def refine_traffic_optim(scene_graph, map_idx, map_env, model, loss_weights, num
         fut = model.get_normalizer().unnormalize(dec['future_pred'])
         ld = avoid_loss(fut, cur_z, embed_info['prior_out'])
         if log is not None:
-            log(it, {k: float(torch.mean(v)) for k, v in ld.items() if not k.startswith('_')})
+            log(it, {k: float(torch.mean(v)) for k, v in ld.items()})
         ld['loss'].backward()
         opt.step()
     with torch.no_grad():
@@ -236,7 +236,7 @@ def run_adv_gen_optim(cur_z, lr, loss_weights, model, scene_graph, map_env, map_
             debug.update(g_tgt=tgt_z.grad.detach().clone(), g_other=other_z.grad.detach().clone())
         if log is not None:
             d = {'tgt_match_' + k: float(torch.mean(v)) for k, v in ld_t.items()}
-            d.update({'adv_' + k: float(torch.mean(v)) for k, v in ld_a.items() if not k.startswith('_')})
+            d.update({'adv_' + k: float(torch.mean(v)) for k, v in ld_a.items()})
             log(it, d)
         opt.step()
     cur_z = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach())
@@ -285,16 +285,17 @@ def run_find_solution_optim(cur_z, final_result_traj, future_len, lr, loss_weigh
         if debug is not None and it == 0:
             debug.update(g_tgt=tgt_z.grad.detach().clone(), g_other=other_z.grad.detach().clone())
         if log is not None:
-            d = {'tgt_' + k: float(torch.mean(v)) for k, v in ld_t.items() if not k.startswith('_')}
+            d = {'tgt_' + k: float(torch.mean(v)) for k, v in ld_t.items()}
             d.update({'other_' + k: float(torch.mean(v)) for k, v in ld_o.items()})
             log(it, d)
         opt.step()
     cur_z = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach())
+    cur_z = cur_z.unsqueeze(1)                                                     # (NA,1,D) as the reference's 3-D z (sol_optim.py:38-44)
     with torch.no_grad():
-        sol = model.decode_embedding(cur_z, embed_info, scene_graph, map_idx, map_env)
+        sol = model.decode_embedding(cur_z, embed_info, scene_graph, map_idx, map_env)    # future_pred (NA,1,FT,4), :118
     sol_traj = sol['future_pred'].clone().detach()
-    sol_traj[~tgt_mask] = nrm.normalize(other_match)[:, :sol_traj.size(1)]
-    return cur_z.unsqueeze(1), sol_traj, sol
+    sol_traj[~tgt_mask] = nrm.normalize(nrm.unnormalize(final_result_traj[~tgt_mask]))[:, :, :sol_traj.size(2)]   # :121, others keep the adversarial result
+    return cur_z, sol_traj, sol
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -177,9 +177,10 @@ class _DecodeFn(torch.autograd.Function):
         L = _cabi.lib()
         d_traj = d_traj.contiguous().float()
         d_z = torch.empty((ctx.scene.NA, 32), dtype=torch.float32, device=d_traj.device)
-        _cabi.check(L.strive_decode_bwd(ctx.model.handle, C.byref(ctx.scene.cstruct), ctx.FT, _cabi.dptr(ctx.ext),
-                                        _cabi.dptr(d_traj), _cabi.dptr(d_z), _cabi.dptr(ctx.tape), ctx.nbytes,
-                                        _cabi.stream_ptr()))
+        with torch.cuda.device(d_traj.device):
+            _cabi.check(L.strive_decode_bwd(ctx.model.handle, C.byref(ctx.scene.cstruct), ctx.FT, _cabi.dptr(ctx.ext),
+                                            _cabi.dptr(d_traj), _cabi.dptr(d_z), _cabi.dptr(ctx.tape), ctx.nbytes,
+                                            _cabi.stream_ptr()))
         return d_z, None, None, None, None, None, None, None
 
 
@@ -221,7 +222,6 @@ class TrafficModel(nn.Module):
         self.decoder_memory = nn.GRU(4, past_feat_size, 3, batch_first=True)
         self._dev_model = None
         self._dev_key = None
-        self._scene_cache = {}
 
     # ---- reference setters / getters (traffic_model.py:160-176) ----
     def set_normalizer(self, normalizer):
@@ -265,14 +265,37 @@ class TrafficModel(nn.Module):
             self._dev_key = key
         return self._dev_model
 
+    @staticmethod
+    def _sources(scene_graph, map_idx):
+        return (scene_graph.past, scene_graph.ptr, scene_graph.lw, scene_graph.sem, map_idx)
+
+    @staticmethod
+    def _cache_get(scene_graph, slot, srcs, extra=None):
+        """Cached derived object stored ON the scene graph (so it dies with it; no id()/data_ptr() reuse across batches).  An
+        entry is valid only if every source tensor is the very same object, unmodified in place since (tensor._version), and
+        of the same shape; the entry holds the sources strongly, so their identity cannot be recycled while it lives."""
+        ent = getattr(scene_graph, slot, None)
+        if ent is None or ent[0] != extra or len(ent[1]) != len(srcs):
+            return None
+        for (t, ver, shp), cur in zip(ent[1], srcs):
+            if t is not cur or cur._version != ver or tuple(cur.shape) != shp:
+                return None
+        return ent[2]
+
+    @staticmethod
+    def _cache_put(scene_graph, slot, srcs, obj, extra=None):
+        try:
+            setattr(scene_graph, slot, (extra, [(t, t._version, tuple(t.shape)) for t in srcs], obj))
+        except Exception:          # graph type without settable attributes: rebuild per call
+            pass
+
     def scene_batch(self, scene_graph, map_idx):
-        key = (id(scene_graph), int(scene_graph.past.data_ptr()), int(scene_graph.ptr.data_ptr()), int(map_idx.data_ptr()))
-        sb = self._scene_cache.get(key)
+        srcs = self._sources(scene_graph, map_idx)
+        dev = next(self.parameters()).device
+        sb = self._cache_get(scene_graph, '_strive_scene_batch', srcs, extra=str(dev))
         if sb is None:
-            if len(self._scene_cache) > 8:
-                self._scene_cache.clear()
-            sb = SceneBatch(scene_graph, map_idx, device=next(self.parameters()).device)
-            self._scene_cache[key] = sb
+            sb = SceneBatch(scene_graph, map_idx, device=dev)
+            self._cache_put(scene_graph, '_strive_scene_batch', srcs, sb, extra=str(dev))
         return sb
 
     @staticmethod
@@ -295,7 +318,24 @@ class TrafficModel(nn.Module):
             z2 = z
         mf = embed_out['map_feat'].detach().contiguous().float()
         pf = embed_out['past_feat'].detach().contiguous().float()
-        traj = _DecodeFn.apply(z2, self.device_model(), scene, self._env(map_env), mf, pf, ext_future, FT)
+        # the kernels index raw pointers: shapes the reference would reject with an IndexError are rejected here
+        if FT < 1:
+            raise RuntimeError('strive_b200: nfuture must be >= 1')
+        if z2.dim() != 2 or z2.size(0) != scene.NA or z2.size(1) != self.z_size:
+            raise RuntimeError('strive_b200: z must be (%d,%d) or (%d,1,%d), got %s' % (scene.NA, self.z_size, scene.NA, self.z_size, tuple(z.shape)))
+        for name, t in (('map_feat', mf), ('past_feat', pf)):
+            if tuple(t.shape) != (scene.NA, 64):
+                raise RuntimeError('strive_b200: embed_out[%r] must be (%d,64), got %s' % (name, scene.NA, tuple(t.shape)))
+        if ext_future is not None and (ext_future.dim() != 3 or ext_future.size(0) != scene.S or ext_future.size(1) < FT
+                                       or ext_future.size(2) < 4):
+            raise RuntimeError('strive_b200: ext_future must be (%d, >=%d, 4), got %s' % (scene.S, FT, tuple(ext_future.shape)))
+        for name, t in (('z', z2), ('map_feat', mf), ('past_feat', pf), ('ext_future', ext_future)):
+            if t is not None and t.device != scene.device:
+                raise RuntimeError('strive_b200: %s is on %s, the scene batch on %s' % (name, t.device, scene.device))
+        if ext_future is not None:
+            ext_future = ext_future[:, :FT, :4]
+        with torch.cuda.device(scene.device):
+            traj = _DecodeFn.apply(z2, self.device_model(), scene, self._env(map_env), mf, pf, ext_future, FT)
         if three_d:
             traj = traj.unsqueeze(1)
         return {'future_pred': traj}
@@ -313,9 +353,10 @@ class TrafficModel(nn.Module):
         out = torch.empty((n, 64), dtype=torch.float32, device=pose_un.device)
         nb = L.strive_mapenc_workspace_bytes(n)
         ws = torch.empty(nb, dtype=torch.uint8, device=pose_un.device)
-        _cabi.check(L.strive_mapenc_fwd(self.device_model().handle, C.byref(env.cstruct), _cabi.dptr(pose_un),
-                                        _cabi.dptr(mapixes.to(torch.int32).contiguous()), n, _cabi.dptr(out), _cabi.dptr(ws), nb,
-                                        _cabi.stream_ptr()))
+        mapixes = mapixes.to(device=pose_un.device, dtype=torch.int32).contiguous()
+        with torch.cuda.device(pose_un.device):
+            _cabi.check(L.strive_mapenc_fwd(self.device_model().handle, C.byref(env.cstruct), _cabi.dptr(pose_un), _cabi.dptr(mapixes), n,
+                                            _cabi.dptr(out), _cabi.dptr(ws), nb, _cabi.stream_ptr()))
         return out
 
     # ---- once-per-batch producers (PyTorch host code, reference :372-403, 453-486, 545-565) ----
@@ -338,12 +379,45 @@ class TrafficModel(nn.Module):
         out = self.prior_net(feat, scene_graph.past[:, -1, :4], scene_graph.sem, scene_graph.ptr)
         return out[:, :self.z_size], torch.exp(out[:, self.z_size:])
 
+    def encode_future(self, scene_graph):
+        """reference :488-522 (mlp trajectory encoder): future in the frame of the last past step, unobserved frames zeroed."""
+        NA, FT, _ = scene_graph.future.size()
+        f = scene_graph.past[:, -1, :4]
+        p = scene_graph.future[:, :, :4]
+        c, s = f[:, 2:3], f[:, 3:4]
+        dx, dy = p[:, :, 0] - f[:, 0:1], p[:, :, 1] - f[:, 1:2]
+        local = torch.stack([c * dx + s * dy, -s * dx + c * dy, p[:, :, 2] * c + p[:, :, 3] * s, p[:, :, 3] * c - p[:, :, 2] * s], 2)
+        local = torch.cat([local, scene_graph.future[:, :, 4:]], 2)
+        local = torch.where((scene_graph.future_vis == 0.0).unsqueeze(-1), torch.zeros_like(local), local)
+        local = torch.cat([local, scene_graph.future_vis.unsqueeze(-1)], -1)
+        enc_in = torch.cat([local, scene_graph.lw.unsqueeze(1).expand(NA, FT, 2)], -1)
+        enc_in = torch.cat([enc_in.reshape(NA, -1), scene_graph.sem], 1)
+        return self.future_encoder(enc_in)
+
+    def encoder(self, scene_graph, map_feat, past_feat, future_feat):
+        """posterior q(z | past, future, map), reference :524-543."""
+        feat = torch.cat([past_feat, future_feat, map_feat, scene_graph.sem], -1)
+        out = self.posterior_net(feat, scene_graph.past[:, -1, :4], scene_graph.sem, scene_graph.ptr)
+        return out[:, :self.z_size], torch.exp(out[:, self.z_size:])
+
+    @staticmethod
+    def _has(scene_graph, name):
+        try:
+            return name in scene_graph                       # torch_geometric Data / Batch
+        except TypeError:
+            return getattr(scene_graph, name, None) is not None
+
     def embed(self, scene_graph, map_idx, map_env):
+        """reference :372-403; 'posterior_out' is added whenever the graph carries a future (adv_scenario_gen.py:284 reads it)."""
         scene_graph.pos = scene_graph.past[:, -1, :4]
         map_feat = self.encode_map(scene_graph, map_idx, map_env)
         past_feat = self.encode_past(scene_graph)
         mu, var = self.prior(scene_graph, map_feat, past_feat)
-        return {'prior_out': (mu, var), 'map_feat': map_feat, 'past_feat': past_feat}
+        out = {'prior_out': (mu, var), 'map_feat': map_feat, 'past_feat': past_feat}
+        if self._has(scene_graph, 'future'):
+            future_feat = self.encode_future(scene_graph)
+            out['posterior_out'] = self.encoder(scene_graph, map_feat, past_feat, future_feat)
+        return out
 
     def rsample(self, mean, var):
         return mean + torch.randn_like(mean) * torch.sqrt(var)
@@ -351,8 +425,8 @@ class TrafficModel(nn.Module):
     def _replicated(self, scene_graph, map_idx, NS):
         """NS copies of the scene batch laid end to end (copy s owns agents [s*NA, (s+1)*NA)): scenes are independent in the
         model, so the reference's (NA, NS, ...) sample axis (traffic_model.py:352-353) is just more scenes for the kernels."""
-        key = (id(scene_graph), int(scene_graph.past.data_ptr()), int(scene_graph.ptr.data_ptr()), int(map_idx.data_ptr()), int(NS))
-        rep = self._rep_cache.get(key) if hasattr(self, '_rep_cache') else None
+        srcs = self._sources(scene_graph, map_idx)
+        rep = self._cache_get(scene_graph, '_strive_replicated', srcs, extra=int(NS))
         if rep is None:
             class _G(object):
                 pass
@@ -367,9 +441,7 @@ class TrafficModel(nn.Module):
             g.sem = scene_graph.sem.detach().repeat(NS, 1)
             g.batch = torch.repeat_interleave(torch.arange(NS * S, device=ptr.device), (g.ptr[1:] - g.ptr[:-1]))
             rep = (g, map_idx.detach().repeat(NS))
-            if not hasattr(self, '_rep_cache') or len(self._rep_cache) > 4:
-                self._rep_cache = {}
-            self._rep_cache[key] = rep
+            self._cache_put(scene_graph, '_strive_replicated', srcs, rep, extra=int(NS))
         return rep
 
     def sample_batched(self, scene_graph, map_idx, map_env, num_samples, include_mean=False, nfuture=None):

@@ -171,10 +171,10 @@ def test_c3_ragged_adv_and_solution_loops():
         wfull = {'sol_' + k: v for k, v in SOL_W.items()}
         z2, sol_traj, _ = run_find_solution_optim(z, traj, FTs, 0.05, wfull, model, graph, env, sc['map_idx'].to(dev), 4, embed,
                                                   tgt_prior, oth_prior, log=lambda it, d: slogs.append(d))
-        assert tuple(z2.shape) == (NA, 1, 32) and tuple(sol_traj.shape) == (NA, FT, 4)
+        assert tuple(z2.shape) == (NA, 1, 32) and tuple(sol_traj.shape) == (NA, 1, FT, 4)
         assert bool(torch.isfinite(z2).all()) and bool(torch.isfinite(sol_traj).all())
         # non-target agents are pinned to the adversarial result (sol_optim.py:120-121)
-        assert torch.allclose(sol_traj[~ego.to(dev)], traj[:, 0][~ego.to(dev)], atol=1e-5)
+        assert torch.allclose(sol_traj[~ego.to(dev)], traj[~ego.to(dev)], atol=1e-5)
         s0 = slogs[0]['tgt_loss'] + slogs[0]['other_loss']
         s3 = slogs[-1]['tgt_loss'] + slogs[-1]['other_loss']
         diag('c3 ragged: %d scenes (%d..%d agents), NA %d | adv loss %.3f -> %.3f in 6 iters | sol loss %.4f -> %.4f in 4 iters' % (

@@ -351,7 +351,7 @@ def test_avoid_loss_terms_and_grads_refine():
     zd = sc['z'].clone().to(dev).requires_grad_(True)
     out = mod(futd, zd, (sc['prior_mu'].to(dev), sc['prior_var'].to(dev)))
     out['loss'].backward()
-    t = out['_terms'][0].cpu()
+    t = mod.last_terms[0].cpu()
     diag('avoid(refine): loss gpu %.6f ref %.6f | veh mean %.6f/%.6f cnt %d/%d | env mean %.6f/%.6f cnt %d/%d | prior %.5f/%.5f init %.6f/%.6f' % (
         float(out['loss']), float(ref['loss']), t[1], float(ref['coll_veh_loss'].mean()), int(t[2]), ref['coll_veh_loss'].numel(),
         t[3], float(ref['coll_env_loss'].mean()), int(t[4]), ref['coll_env_loss'].numel(), t[5], float(ref['motion_prior_loss'].mean()),
@@ -387,7 +387,7 @@ def test_adv_and_sol_losses_vs_golden():
                      crash_loss_min_time=2, crash_loss_min_infront=-0.5)
     ld = adv(fut, tgt, z_o, prior_o, return_mins=True)
     ld['loss'].backward()
-    t = ld['_terms'][0].cpu()
+    t = adv.last_terms[0].cpu()
     diag('adv: loss gpu %.4f golden %.4f | means gpu [init %.4f prior %.4f veh %.5f plan %.5f env %.5f crash %.4f] golden %s | mins %s %s vs %s %s' % (
         float(ld['loss']), float(g['adv_loss']), t[6], t[5], t[1], t[7], t[3], t[9], np.array2string(g['adv_means'], precision=4),
         ld['min_agt'], ld['min_t'], g['adv_min_agt'], g['adv_min_t']))
@@ -557,7 +557,7 @@ def test_solution_loop_vs_oracle():
     assert abs(l0 - rec[0]['loss']) < 1e-3 * max(1.0, abs(rec[0]['loss']))
     assert e_t < 3e-2 and e_o < 3e-2      # 6-step BPTT after ~1e-5 forward noise (pixel flips); strict check = teacher-forced test
     assert dz.max().item() <= 2 * 0.05 * 2 + 1e-4
-    assert tuple(z.shape) == (NA, 1, 32) and tuple(sol_traj.shape) == (NA, FTm, 4)
+    assert tuple(z.shape) == (NA, 1, 32) and tuple(sol_traj.shape) == (NA, 1, FTm, 4) and tuple(out['future_pred'].shape) == (NA, 1, FTm, 4)
 
 
 def test_refine_sharded_single_rank_equals_fused_loop():
