@@ -152,6 +152,81 @@ def bicycle_step(state_un, a, ddh, veh_len):
 
 
 # --------------------------------------------------------------------------------------------
+# once-per-batch producers (embed side)
+# --------------------------------------------------------------------------------------------
+
+def interaction_net(sd, prefix, feat, pos, sem, edge_index):
+    """models/interaction_net.py:52-77 for any of prior_net / posterior_net / decoder_net (single-sample branch)."""
+    x = mlp(sd, prefix + '.mlp_in', feat, 3)
+    src, dst = edge_index[0], edge_index[1]
+    N = x.size(0)
+    D = x.size(1)
+    if src.numel() > 0:
+        rel = transform2frame(pos[dst], pos[src])
+        rel = torch.where(torch.isnan(rel), torch.zeros_like(rel), rel)
+        msg = mlp(sd, prefix + '.msg.0.edge_mlp', torch.cat([x[dst], x[src], sem[dst], sem[src], rel], dim=-1), 3)
+        idx = dst.view(-1, 1).expand(-1, msg.size(1))
+        aggr = torch.zeros((N, msg.size(1)), dtype=x.dtype).scatter_reduce(0, idx, msg, 'amax', include_self=False)
+        has_in = torch.zeros(N, dtype=torch.bool)
+        has_in[dst] = True
+        aggr = torch.where(has_in.view(-1, 1), aggr, torch.zeros_like(aggr))
+    else:
+        aggr = torch.zeros((N, D), dtype=x.dtype)
+    xu = mlp(sd, prefix + '.msg.0.update_mlp', torch.cat([x, aggr, sem], dim=-1), 2)
+    return mlp(sd, prefix + '.mlp_out', xu, 3)
+
+
+def _encode_traj(sd, prefix, frame, traj, vis, lw, sem):
+    """models/traffic_model.py:453-522 (mlp encoders): trajectory in the frame of the last past step, unobserved frames
+    zeroed (whole row), visibility and vehicle attributes appended per frame, semantic class appended once."""
+    NA, T, _ = traj.shape
+    fr = frame.unsqueeze(1).expand(NA, T, 4).reshape(NA * T, 4)
+    local = transform2frame(fr, traj[:, :, :4].reshape(NA * T, 4)).view(NA, T, 4)
+    local = torch.cat([local, traj[:, :, 4:]], dim=2)
+    local = torch.where((vis == 0.0).unsqueeze(-1), torch.zeros_like(local), local)
+    local = torch.cat([local, vis.unsqueeze(-1)], dim=-1)
+    enc_in = torch.cat([local, lw.unsqueeze(1).expand(NA, T, 2)], dim=-1)
+    enc_in = torch.cat([enc_in.reshape(NA, -1), sem], dim=1)
+    return mlp(sd, prefix, enc_in, 4)
+
+
+def encode_past(sd, past, past_vis, lw, sem):
+    """:453-486"""
+    return _encode_traj(sd, 'past_encoder', past[:, -1, :4], past, past_vis, lw, sem)
+
+
+def encode_future(sd, past, future, future_vis, lw, sem):
+    """:488-522"""
+    return _encode_traj(sd, 'future_encoder', past[:, -1, :4], future, future_vis, lw, sem)
+
+
+def prior(sd, past, map_feat, past_feat, sem, edge_index):
+    """:545-565 -> (mean, var)"""
+    out = interaction_net(sd, 'prior_net', torch.cat([past_feat, map_feat, sem], dim=-1), past[:, -1, :4], sem, edge_index)
+    return out[:, :32], torch.exp(out[:, 32:])
+
+
+def posterior(sd, past, map_feat, past_feat, future_feat, sem, edge_index):
+    """:524-543 -> (mean, var)"""
+    out = interaction_net(sd, 'posterior_net', torch.cat([past_feat, future_feat, map_feat, sem], dim=-1), past[:, -1, :4], sem,
+                          edge_index)
+    return out[:, :32], torch.exp(out[:, 32:])
+
+
+def embed(sd, scene, raster, dx, past_vis, future=None, future_vis=None):
+    """:372-403"""
+    mapixes = scene['map_idx'][scene['batch']]
+    map_feat = encode_map(sd, raster, dx, scene['past'][:, -1, :4], mapixes)
+    past_feat = encode_past(sd, scene['past'], past_vis, scene['lw'], scene['sem'])
+    out = {'map_feat': map_feat, 'past_feat': past_feat,
+           'prior_out': prior(sd, scene['past'], map_feat, past_feat, scene['sem'], scene['edge_index'])}
+    if future is not None:
+        ff = encode_future(sd, scene['past'], future, future_vis, scene['lw'], scene['sem'])
+        out['posterior_out'] = posterior(sd, scene['past'], map_feat, past_feat, ff, scene['sem'], scene['edge_index'])
+    return out
+
+
+# --------------------------------------------------------------------------------------------
 # map crop + CNN
 # --------------------------------------------------------------------------------------------
 
@@ -299,8 +374,10 @@ def coll_point(drivable, dx, cars, lw_un, mapixes, L, W):
     py = torch.where(outside, torch.zeros_like(py), py)
     nd = drivable[mapixes.view(B, 1, 1).expand(B, L, W), py, px] == 0
     num = nd.sum(dim=(1, 2))
-    ndf = nd.to(cars.dtype)
-    pt = torch.stack([(gx * ndf).sum(dim=(1, 2)), (gy * ndf).sum(dim=(1, 2))], dim=1) / num.view(B, 1)
+    # same tensor layout as the reference's reduction, (B,L,W,2) summed over (1,2) (:376-379): the mean of ~600 world coordinates
+    # of magnitude 1e2..1e3 m in float32 is only good to ~1e-4 m and the summation order shows in d(penalty)/d(centre)
+    xyw = torch.stack([gx, gy], dim=-1)
+    pt = (xyw * nd.unsqueeze(-1)).sum(dim=(1, 2)) / num.view(B, 1)
     pt[num == L * W] = float('nan')
     return pt, num
 

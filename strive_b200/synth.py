@@ -250,3 +250,53 @@ def checksum(t):
     a = t.detach().to(torch.float64).reshape(-1)
     w = torch.arange(1, a.numel() + 1, dtype=torch.float64)
     return float((a * torch.cos(w * 0.37)).sum())
+
+
+def host_producer_spec(NC=2, PT=4, FT=20):
+    """(key, shape) of the once-per-batch producer modules (reference src/models/traffic_model.py:95-148): past / future MLP
+    encoders and the prior / posterior interaction nets."""
+    spec = []
+    spec += _mlp_spec('past_encoder', [NC + PT * 9, 128, 128, 128, 64])
+    spec += _mlp_spec('future_encoder', [NC + FT * 9, 128, 128, 128, 64])
+    for name, din in (('prior_net', 64 + 64 + NC), ('posterior_net', 64 + 64 + 64 + NC)):
+        spec += _mlp_spec(name + '.mlp_in', [din, 128, 128, 128])
+        spec += _mlp_spec(name + '.msg.0.edge_mlp', [2 * (128 + NC) + 4, 128, 128, 128])
+        spec += _mlp_spec(name + '.msg.0.update_mlp', [128 + 128 + NC, 128, 128])
+        spec += _mlp_spec(name + '.mlp_out', [128, 128, 128, 64])
+    return spec
+
+
+def make_host_weights(seed=0, NC=2, PT=4, FT=20, dtype=torch.float32):
+    """Seeded state_dict entries for `host_producer_spec` (same init family as make_weights; a separate generator so the
+    decode-path weights -- and the fixtures pinned to them -- are unchanged)."""
+    g = torch.Generator().manual_seed(7000003 * (seed + 1) + FT)
+    sd = {}
+    for k, shp in host_producer_spec(NC, PT, FT):
+        is_norm = (len(shp) == 1 and k.endswith('.weight'))
+        if is_norm:
+            t = 1.0 + 0.4 * (torch.rand(shp, generator=g) - 0.5)
+        elif len(shp) == 1:
+            t = 0.2 * (torch.rand(shp, generator=g) - 0.5)
+        else:
+            bound = 1.0 / math.sqrt(int(np.prod(shp[1:])))
+            t = (2.0 * torch.rand(shp, generator=g) - 1.0) * bound
+        sd[k] = t.to(dtype)
+    return sd
+
+
+def make_future(seed, sc, FT, invis_frac=0.2, dtype=torch.float32):
+    """Observed futures for the posterior / init paths: constant-velocity continuation of `past` (normalised, (NA,FT,6)) with
+    noise, plus future_vis (NA,FT) and a past_vis (NA,PT) with a few unobserved frames (never the last past frame)."""
+    g = torch.Generator().manual_seed(seed)
+    past = sc['past']
+    NA, PT = past.size(0), past.size(1)
+    last = past[:, -1, :]
+    vel = past[:, -1, :2] - past[:, -2, :2]
+    steps = torch.arange(1, FT + 1).view(1, FT, 1).to(dtype)
+    xy = last[:, None, :2] + vel[:, None, :] * steps + 0.02 * torch.randn(NA, FT, 2, generator=g).to(dtype)
+    fut = torch.cat([xy, last[:, None, 2:].expand(NA, FT, 4)], dim=2).contiguous()
+    fvis = (torch.rand(NA, FT, generator=g) > invis_frac).to(dtype)
+    fvis[:, 0] = 1.0
+    pvis = (torch.rand(NA, PT, generator=g) > invis_frac).to(dtype)
+    pvis[:, -1] = 1.0
+    return fut, fvis, pvis
