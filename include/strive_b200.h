@@ -131,7 +131,8 @@ int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, const StriveM
                       float* traj_out, void* tape, int64_t tape_bytes, void* stream);
 int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, int32_t ft, const float* ext_future,
                       const float* d_traj, float* d_z, void* tape, int64_t tape_bytes, void* stream);
-/* test hook: copies one named tape tensor of step t to `out` (float). names: x,P,Q,aggr,past_feat,map_feat,prev,pos,loc,mem */
+/* test hook: copies one named tape tensor of step t to `out` (float). names: x,P,Q,aggr,past_feat,map_feat,prev,pos,loc,mem;
+ * "arg" copies the (NA,64) uint8 arg-max routing table of the max aggregation (local source index in the scene, 255 = none). */
 int strive_decode_tape_read(const void* tape, int32_t num_agents, int32_t ft, const char* name, int32_t t,
                             float* out, void* stream);
 

@@ -114,6 +114,15 @@ def decoder_net(sd, feat, pos, sem, edge_index, taps=None):
     out = mlp(sd, p + '.mlp_out', xu, 3)
     if taps is not None:
         taps.update(x=x, aggr=aggr, xu=xu, out=out)
+        if src.numel() > 0:
+            # arg-max routing of the max aggregation: per (target, channel) the GLOBAL index of the winning source, and the
+            # margin to the runner-up (diagnostics: a kernel may legitimately pick the other one when the margin is at rounding level)
+            dense = torch.full((N, N, msg.size(1)), float('-inf'), dtype=x.dtype)
+            dense[dst, src] = msg.detach()
+            top2 = dense.topk(min(2, N), dim=1)
+            taps['arg'] = top2.indices[:, 0]
+            taps['arg_margin'] = (top2.values[:, 0] - top2.values[:, 1]) if N > 1 else torch.full_like(top2.values[:, 0], float('inf'))
+            taps['msg_dense'] = dense
     return out
 
 

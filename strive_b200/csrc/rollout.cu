@@ -1417,6 +1417,10 @@ extern "C" int strive_decode_tape_read(const void* tape, int32_t num_agents, int
   tape_carve(&tp, (char*)tape, num_agents, ft);
   STRIVE_CHECK(t >= 0 && t < ft, STRIVE_EINVAL, "tape_read: step %d out of range", t);
   const size_t n = (size_t)num_agents;
+  if (name[0] == 'a' && name[1] == 'r' && name[2] == 'g' && name[3] == 0) {   // arg-max routing: (NA,64) uint8, raw bytes
+    STRIVE_CUDA(cudaMemcpyAsync(out, tp.arg + (size_t)t * n * 64, n * 64, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+    return 0;
+  }
   const float* src = nullptr;
   size_t w = 0;
   struct { const char* nm; const float* base; size_t width; } tab[] = {

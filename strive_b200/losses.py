@@ -272,7 +272,12 @@ class AvoidCollLoss(_Base):
 
     def forward(self, future_pred, z, prior_out):
         zz = z[:, 0, :] if z.dim() == 3 else z
-        loss, terms = _LossFn.apply(future_pred, zz, self, prior_out[0], prior_out[1], self.init_z, None, None, False)
+        # 3-D latents (B,1,D) as sol_optim.py:38-44 passes them: the reference's init term sums over dim=1 -- the size-1 SAMPLE
+        # axis -- and then averages over B*D elements (adv_gen_nusc.py:333-335), i.e. 1/D of the 2-D value.  Replicated.
+        init_scale = 1.0 / float(z.size(-1)) if z.dim() == 3 else 1.0
+        self.plan.cfg.w_init_z = float(self.loss_weights.get('init_z', 0.0)) * init_scale
+        init_z = self.init_z[:, 0, :] if self.init_z is not None and self.init_z.dim() == 3 else self.init_z
+        loss, terms = _LossFn.apply(future_pred, zz, self, prior_out[0], prior_out[1], init_z, None, None, False)
         out = {}
         w = self.loss_weights
         if w['coll_veh'] > 0.0:
@@ -282,7 +287,7 @@ class AvoidCollLoss(_Base):
         if w['motion_prior'] > 0.0:
             out['motion_prior_loss'] = terms[:, 5]
         if w.get('init_z', 0.0) > 0.0:
-            out['init_loss'] = terms[:, 6]
+            out['init_loss'] = terms[:, 6] * init_scale
         out['loss'] = loss
         self.last_terms = terms          # (G, STRIVE_TERMS) raw per-group table of the last call (diagnostics; not a reference key)
         return out

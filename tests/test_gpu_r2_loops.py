@@ -1,0 +1,164 @@
+"""GPU: the once-per-batch producers and the adversarial / solution LOOPS of the drop-in API against fixtures written by the
+unmodified reference (oracle/gen_golden_r2.py): TrafficModel.embed (prior + posterior), sample_batched(include_mean=True),
+run_adv_gen_optim(planner_name='ego') and run_find_solution_optim -- every iteration's printed loss terms, final latents,
+returned shapes, min_agt / min_t."""
+import numpy as np
+import pytest
+import torch
+
+from strive_b200 import synth
+from tests.common import world, golden, EXTENT, ADV_W, SOL_W
+from tests.test_gpu_parity import ctx, diag, to_graph
+from tests.test_r2_cpu import producers_case, full_weights, loops_case, _loop_z_check
+
+pytestmark = pytest.mark.gpu
+
+_models = {}
+
+
+def model_ft(FT):
+    """Model with ALL modules seeded (decode path + producers), nfuture = FT (the future encoder's width depends on it)."""
+    import strive_b200
+    if FT not in _models:
+        dev, _, env = ctx()
+        _, _, sd = full_weights(FT)
+        m = strive_b200.make_model(nfuture=FT, state_dict=sd, device=dev)
+        _models[FT] = m
+    return _models[FT]
+
+
+def test_embed_prior_posterior_vs_reference():
+    dev, _, env = ctx()
+    g, sc, fut, fvis, pvis, FT = producers_case()
+    m = model_ft(FT)
+    gr = to_graph(sc, dev)
+    gr.past_vis, gr.future, gr.future_vis = pvis.to(dev), fut.to(dev), fvis.to(dev)
+    with torch.no_grad():
+        e = m.embed(gr, sc['map_idx'].to(dev), env)
+    assert set(e.keys()) == {'prior_out', 'posterior_out', 'map_feat', 'past_feat'}
+    d = {'map_feat': np.abs(e['map_feat'].cpu().numpy() - g['map_feat']).max(), 'past_feat': np.abs(e['past_feat'].cpu().numpy() - g['past_feat']).max(),
+         'prior_mu': np.abs(e['prior_out'][0].cpu().numpy() - g['prior_mu']).max(), 'prior_var': np.abs(e['prior_out'][1].cpu().numpy() / g['prior_var'] - 1).max(),
+         'post_mu': np.abs(e['posterior_out'][0].cpu().numpy() - g['post_mu']).max(), 'post_var': np.abs(e['posterior_out'][1].cpu().numpy() / g['post_var'] - 1).max()}
+    diag('embed vs reference: ' + ' '.join('%s=%.2e' % kv for kv in d.items()))
+    assert d['map_feat'] < 1e-4 and d['past_feat'] < 2e-5
+    assert max(d['prior_mu'], d['prior_var'], d['post_mu'], d['post_var']) < 1e-4
+    # without a future the posterior is absent, as in the reference (:396)
+    gr2 = to_graph(sc, dev)
+    gr2.past_vis = pvis.to(dev)
+    with torch.no_grad():
+        assert 'posterior_out' not in m.embed(gr2, sc['map_idx'].to(dev), env)
+
+
+def test_sample_batched_vs_reference():
+    """The reference's own samples (rsample patched to return them) decode to the reference's futures through the NS-copy
+    rollout; include_mean puts the prior mean last; log-probs and Mahalanobis distances follow."""
+    dev, _, env = ctx()
+    g, sc, fut, fvis, pvis, FT = producers_case()
+    m = model_ft(FT)
+    gr = to_graph(sc, dev)
+    gr.past_vis = pvis.to(dev)
+    zs = torch.from_numpy(g['samp_z']).to(dev)                     # (NA,NS,32)
+    NS, nf = int(g['samp_NS']), int(g['samp_nfuture'])
+    orig = m.rsample
+    m.rsample = lambda mean, var: zs.transpose(0, 1).contiguous().clone()
+    try:
+        with torch.no_grad():
+            out = m.sample_batched(gr, sc['map_idx'].to(dev), env, NS, include_mean=True, nfuture=nf)
+    finally:
+        m.rsample = orig
+    assert tuple(out['future_pred'].shape) == g['samp_fut'].shape and tuple(out['z_samp'].shape) == g['samp_z'].shape
+    e_mu = (out['z_samp'][:, -1] - out['prior_out'][0]).abs().max().item()
+    e_f = np.abs(out['future_pred'].cpu().numpy() - g['samp_fut']).max(axis=(0, 1, 3))
+    e_lp = np.abs(out['z_logprob'].cpu().numpy() - g['samp_logprob'])[:, :-1].max()
+    e_md = np.abs(out['z_mdist'].cpu().numpy() - g['samp_mdist'])[:, :-1].max()
+    diag('sample_batched vs reference: per-step |fut| err %s | logprob %.2e mdist %.2e | mean sample err %.1e' % (
+        ' '.join('%.1e' % v for v in e_f), e_lp, e_md, e_mu))
+    assert e_mu == 0.0 and e_f[0] < 2e-6 and e_f.max() < 2e-4
+    assert e_lp < 5e-3 and e_md < 1e-3          # sums of 32 terms (z-mu)^2/var with mu, var from the fp32 prior net (1e-5)
+
+
+def _graph_with_future(sc, ego, FT, dev):
+    graph = to_graph(sc, dev)
+    fg = torch.zeros(sc['z'].size(0), FT, 6)
+    fg[ego, :, :4] = sc['ext_future'][:, :FT]
+    graph.future_gt = fg.to(dev)
+    return graph
+
+
+def test_adv_loop_vs_reference_run_adv_gen_optim():
+    from strive_b200.optim import run_adv_gen_optim
+    dev, model, env = ctx()
+    g = golden('adv_loop')
+    sc, ego, FT = loops_case(g)
+    iters, lr = int(g['iters']), float(g['lr'])
+    graph = _graph_with_future(sc, ego, FT, dev)
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev)}
+    logs = []
+    model.FT = FT
+    try:
+        z, traj, out, min_agt, min_t = run_adv_gen_optim(sc['z'].to(dev), lr, ADV_W, model, graph, env, sc['map_idx'].to(dev), iters, embed, 'ego',
+                                                          (sc['prior_mu'][ego].to(dev), sc['prior_var'][ego].to(dev)),
+                                                          (sc['prior_mu'][~ego].to(dev), sc['prior_var'][~ego].to(dev)), 1, -0.5,
+                                                          future_len=FT, veh_coll_buffer=0.1, log=lambda it, d: logs.append(d))
+    finally:
+        model.FT = 20
+    keys = ['tgt_match_loss', 'tgt_match_match_ext_loss', 'adv_loss', 'adv_init_loss', 'adv_motion_prior_loss', 'adv_coll_veh_loss',
+            'adv_coll_veh_plan_loss', 'adv_coll_env_loss', 'adv_adv_crash_loss']
+    worst = {}
+    for k in keys:
+        mine = np.array([l[k] for l in logs])
+        ref = g['t_' + k]
+        worst[k] = float(np.abs(mine - ref).max() / max(1e-3, np.abs(ref).max()))
+    tot_m = np.array([l['tgt_match_loss'] + l['adv_loss'] for l in logs])
+    tot_r = g['t_tgt_match_loss'] + g['t_adv_loss']
+    dz = (z.cpu().numpy() - g['z'])
+    diag('adv loop vs reference run_adv_gen_optim: total loss gpu %s reference %s | per-term worst rel err %s | |z| err max %.2e | mins %s %s vs %s %s' % (
+        np.array2string(tot_m, precision=3), np.array2string(tot_r, precision=3), ' '.join('%s=%.1e' % kv for kv in worst.items()),
+        np.abs(dz).max(), list(min_agt), list(min_t), list(g['min_agt']), list(g['min_t'])))
+    assert np.abs(tot_m / tot_r - 1.0).max() < 1e-3                      # every iteration
+    assert max(worst.values()) < 5e-3
+    # fp32 forward noise (crop pixel flips, 1e-5 on map_feat) reaches Adam's normalised steps: the bulk of the latents stays
+    # within 2e-3 of the reference run, every element within the 2*lr*iters an Adam run can move at all
+    assert float(np.median(np.abs(dz))) < 2e-3
+    _loop_z_check(z.cpu().numpy(), g['z'], sc['ptr'].numpy(), lr, iters, tight=5e-2, need_scenes=2)
+    assert tuple(traj.shape) == g['traj'].shape and tuple(out['future_pred'].shape) == g['final_pred'].shape
+    assert list(min_agt) == list(g['min_agt']) and list(min_t) == list(g['min_t'])
+    assert np.abs(traj[ego.to(dev), 0].cpu().numpy() - g['traj'][ego.numpy(), 0]).max() < 1e-6       # ego rows = the planner's future
+
+
+def test_sol_loop_vs_reference_run_find_solution_optim():
+    from strive_b200.optim import run_find_solution_optim
+    dev, model, env = ctx()
+    ga, g = golden('adv_loop'), golden('sol_loop')
+    sc, ego, FT = loops_case(g)
+    iters, lr, FTs = int(g['iters']), float(g['lr']), int(g['sol_FT'])
+    graph = _graph_with_future(sc, ego, FT, dev)
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev)}
+    wfull = {'sol_' + k: v for k, v in SOL_W.items()}
+    logs = []
+    model.FT = FT
+    try:
+        z, sol_traj, out = run_find_solution_optim(torch.from_numpy(ga['z']).to(dev), torch.from_numpy(ga['traj']).to(dev), FTs, lr, wfull, model,
+                                                   graph, env, sc['map_idx'].to(dev), iters, embed,
+                                                   (sc['prior_mu'][ego].to(dev), sc['prior_var'][ego].to(dev)),
+                                                   (sc['prior_mu'][~ego].to(dev), sc['prior_var'][~ego].to(dev)), log=lambda it, d: logs.append(d))
+    finally:
+        model.FT = 20
+    keys = ['tgt_loss', 'tgt_coll_veh_loss', 'tgt_coll_env_loss', 'tgt_motion_prior_loss', 'other_loss', 'other_match_ext_loss']
+    worst = {}
+    for k in keys:
+        mine = np.array([l[k] for l in logs])
+        ref = g['t_' + k]
+        worst[k] = float(np.abs(mine - ref).max() / max(1e-2, np.abs(ref).max()))
+    tot_m = np.array([l['tgt_loss'] + l['other_loss'] for l in logs])
+    tot_r = g['t_tgt_loss'] + g['t_other_loss']
+    diag('sol loop vs reference run_find_solution_optim: total loss gpu %s reference %s | per-term worst rel err %s | |z| err max %.2e' % (
+        np.array2string(tot_m, precision=4), np.array2string(tot_r, precision=4), ' '.join('%s=%.1e' % kv for kv in worst.items()),
+        np.abs(z[:, 0].cpu().numpy() - g['z'][:, 0]).max()))
+    assert np.abs(tot_m / tot_r - 1.0).max() < 1e-3
+    assert max(worst.values()) < 1e-2
+    assert tuple(z.shape) == g['z'].shape and tuple(sol_traj.shape) == g['sol_traj'].shape and tuple(out['future_pred'].shape) == g['sol_pred'].shape
+    assert float(np.median(np.abs(z[:, 0].cpu().numpy() - g['z'][:, 0]))) < 2e-3
+    _loop_z_check(z[:, 0].cpu().numpy(), g['z'][:, 0], sc['ptr'].numpy(), lr, iters, tight=5e-2, need_scenes=2)
+    # non-target agents keep the adversarial result (sol_optim.py:120-121)
+    assert np.abs(sol_traj[~ego.to(dev)].cpu().numpy() - g['sol_traj'][~ego.numpy()]).max() < 1e-5
