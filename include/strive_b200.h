@@ -197,6 +197,14 @@ int strive_loss_fwd_bwd(const StriveLossCfg* cfg, const StriveScene* sc, const S
  * g = g_a + g_b (g_b may be NULL); step_count is the 1-based step number. */
 int strive_adam_step(float* z, const float* g_a, const float* g_b, float* exp_avg, float* exp_avg_sq,
                      int64_t n, int32_t step_count, float lr, float beta1, float beta2, float eps, void* stream);
+/* Device-resident form used by the fused loops (replaces the torch.optim.Adam([tgt_z, other_z]).step() of
+ * utils/adv_gen_optim.py:72,175, utils/sol_optim.py:47,112, utils/init_optim.py:21,57): the 0-based count of completed steps
+ * lives in device memory (*step_dev, incremented by the call) so a captured CUDA graph of one iteration can be replayed;
+ * the gradient of row r (row_width elements) is g_a if row_sel == NULL or row_sel[r] != 0, else g_b -- the two adjoint
+ * sweeps of one rollout -- plus g_direct (NULL = none). */
+int strive_adam_step_dev(float* z, const float* g_a, const float* g_b, const float* g_direct, const uint8_t* row_sel,
+                         int32_t row_width, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t* step_dev, float lr,
+                         float beta1, float beta2, float eps, void* stream);
 
 /* ---- success / plausibility checks around the loop (all inputs UNNORMALISED, device) -----
  * strive_on_layer_frac: nutils.check_on_layer, src/datasets/nuscenes_utils.py:266-298 (used by compute_coll_rate_env,

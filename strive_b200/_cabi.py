@@ -46,7 +46,7 @@ class StriveLossCfg(C.Structure):
 EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_tc_trace', 'strive_tc_debug', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl', 'strive_model_edge_frag_bytes', 'strive_model_set_edge_frags', 'strive_edge_set_impl', 'strive_set_pdl',
            'strive_mapenc_workspace_bytes', 'strive_mapenc_fwd', 'strive_map_crop', 'strive_decode_tape_bytes',
            'strive_decode_fwd', 'strive_decode_bwd', 'strive_decode_tape_read', 'strive_loss_workspace_bytes',
-           'strive_loss_fwd_bwd', 'strive_adam_step', 'strive_on_layer_frac', 'strive_line_layer', 'strive_veh_iou_hits']
+           'strive_loss_fwd_bwd', 'strive_adam_step', 'strive_adam_step_dev', 'strive_on_layer_frac', 'strive_line_layer', 'strive_veh_iou_hits']
 
 
 def lib():
@@ -86,6 +86,7 @@ def lib():
     L.strive_loss_fwd_bwd.argtypes = [C.POINTER(StriveLossCfg), C.POINTER(StriveScene), C.POINTER(StriveMap), i32,
                                       vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]
     L.strive_adam_step.argtypes = [vp, vp, vp, vp, vp, i64, i32, f32, f32, f32, f32, vp]
+    L.strive_adam_step_dev.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, i64, vp, f32, f32, f32, f32, vp]
     L.strive_on_layer_frac.argtypes = [C.POINTER(StriveMap), i32, vp, vp, vp, vp, vp, i32, i32, i32, vp, vp]
     L.strive_line_layer.argtypes = [C.POINTER(StriveMap), i32, vp, vp, vp, vp, i32, i32, vp, vp, vp]
     L.strive_veh_iou_hits.argtypes = [vp, vp, i32, vp, vp, i32, i32, C.c_double, vp, vp, vp]

@@ -160,6 +160,43 @@ extern "C" int strive_adam_step(float* z, const float* g_a, const float* g_b, fl
   return 0;
 }
 
+// Device-resident variant for the fused loops: the step counter lives in device memory (so one captured CUDA graph of an
+// iteration can be replayed: no per-step host argument changes), and the gradient of a row is taken from one of two adjoint
+// sweeps -- adv / sol loops run two sweeps over one rollout tape (adv_gen_optim.py:119-130, sol_optim.py:73-77): row_sel[r] != 0
+// selects g_a, else g_b; g_direct (latent terms written by the loss kernel, zero outside its row mask) is added on top.
+__global__ void adam_dev_kernel(float* __restrict__ z, const float* __restrict__ ga, const float* __restrict__ gb,
+                                const float* __restrict__ gd, const uint8_t* __restrict__ row_sel, int width, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, const int32_t* __restrict__ step_dev, float lr, float b1, float b2,
+                                float eps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int step = *step_dev + 1;
+  const float bc1 = (float)(1.0 - pow((double)b1, (double)step));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, (double)step));
+  float g = (row_sel == nullptr || row_sel[i / width] != 0) ? ga[i] : gb[i];
+  if (gd != nullptr) g += gd[i];
+  const float mi = m[i] + (g - m[i]) * (1.0f - b1);
+  const float vi = v[i] * b2 + (1.0f - b2) * g * g;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  z[i] = z[i] - (lr / bc1) * (mi / denom);
+}
+__global__ void step_inc_kernel(int32_t* s) { *s += 1; }
+
+extern "C" int strive_adam_step_dev(float* z, const float* g_a, const float* g_b, const float* g_direct, const uint8_t* row_sel,
+                                    int32_t row_width, float* exp_avg, float* exp_avg_sq, int64_t n, int32_t* step_dev, float lr,
+                                    float beta1, float beta2, float eps, void* stream) {
+  STRIVE_CHECK(z && g_a && exp_avg && exp_avg_sq && step_dev && n > 0 && row_width > 0, STRIVE_EINVAL, "strive_adam_step_dev: bad arguments");
+  STRIVE_CHECK(row_sel == nullptr || g_b != nullptr, STRIVE_EINVAL, "strive_adam_step_dev: row_sel needs g_b");
+  KPROF("adam", (cudaStream_t)stream, adam_dev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      z, g_a, g_b, g_direct, row_sel, row_width, exp_avg, exp_avg_sq, n, step_dev, lr, beta1, beta2, eps));
+  STRIVE_LAUNCH_CHECK();
+  step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  STRIVE_LAUNCH_CHECK();
+  return 0;
+}
+
 // layout self-check for foreign-function bindings (tests compare against ctypes.sizeof / offsets)
 #include <stddef.h>
 extern "C" int strive_struct_layout(int64_t* out, int max_n) {

@@ -59,89 +59,283 @@ def refine_traffic_optim(scene_graph, map_idx, map_env, model, loss_weights, num
     return init_future_pred, cur_z, out['future_pred'].unsqueeze(1).clone().detach(), embed_info
 
 
-class RefineLoop(object):
-    """Device-resident refine iteration (decode -> AvoidCollLoss -> d/dz -> Adam)."""
+class _DeviceLoop(object):
+    """Buffers and the four C-ABI calls of one device-resident latent iteration:
+        strive_decode_fwd -> strive_loss_fwd_bwd -> strive_decode_bwd (one or two adjoint sweeps) -> strive_adam_step_dev.
+    Nothing synchronises with the host; after the first (eager) iteration the launch sequence is captured once into a CUDA
+    graph and replayed (use_graph=True): all buffers are preallocated and the Adam step count lives in device memory."""
 
-    def __init__(self, model, scene_graph, map_idx, map_env, embed_info, z_init, loss_weights, lr, FT,
-                 veh_coll_buffer=0.2, group_scene_ptr=None, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, model, scene_graph, map_idx, map_env, map_feat, past_feat, z_init, prior_mu, prior_var, lr, FT,
+                 betas=(0.9, 0.999), eps=1e-8, ext_future=None, use_graph=True):
         self.L = _cabi.lib()
         self.model = model
         self.dm = model.device_model()
         self.env = map_env
-        dev = z_init.device
         self.scene = model.scene_batch(scene_graph, map_idx)
+        dev = self.scene.device
+        self.dev = dev
         NA = self.scene.NA
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
         self.NA, self.FT, self.lr, self.betas, self.eps = NA, int(FT), float(lr), betas, float(eps)
-        self.z = z_init.detach().clone().contiguous().float()
+        self.z = f32(z_init).clone()
+        if tuple(self.z.shape) != (NA, 32):
+            raise RuntimeError('strive_b200: z must be (%d,32), got %s' % (NA, tuple(self.z.shape)))
+        self.map_feat, self.past_feat = f32(map_feat), f32(past_feat)
+        self.prior_mu, self.prior_var = f32(prior_mu), f32(prior_var)
+        self.ext = None
+        if ext_future is not None:
+            self.ext = f32(ext_future[:, :self.FT, :4])
+            if tuple(self.ext.shape) != (self.scene.S, self.FT, 4):
+                raise RuntimeError('strive_b200: ext_future must be (%d,%d,4)' % (self.scene.S, self.FT))
+        self.traj = torch.empty((NA, self.FT, 4), dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros_like(self.z)
+        self.exp_avg_sq = torch.zeros_like(self.z)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.tape_bytes = self.L.strive_decode_tape_bytes(NA, self.FT)
+        self.tape = torch.empty(self.tape_bytes, dtype=torch.uint8, device=dev)
+        self.use_graph = bool(use_graph)
+        self.graph = None
+        self.iterations = 0
+
+    # ---- the four calls
+    def _forward(self):
+        _cabi.check(self.L.strive_decode_fwd(self.dm.handle, C.byref(self.scene.cstruct), C.byref(self.env.cstruct),
+                                             _cabi.dptr(self.z), _cabi.dptr(self.map_feat), _cabi.dptr(self.past_feat),
+                                             _cabi.dptr(self.ext), self.FT, _cabi.dptr(self.traj), _cabi.dptr(self.tape),
+                                             self.tape_bytes, _cabi.stream_ptr()))
+
+    def _sweep(self, d_traj, d_z):
+        _cabi.check(self.L.strive_decode_bwd(self.dm.handle, C.byref(self.scene.cstruct), self.FT, _cabi.dptr(self.ext),
+                                             _cabi.dptr(d_traj), _cabi.dptr(d_z), _cabi.dptr(self.tape), self.tape_bytes,
+                                             _cabi.stream_ptr()))
+
+    def _adam_dev(self, g_a, g_b=None, g_direct=None, row_sel=None):
+        _cabi.check(self.L.strive_adam_step_dev(_cabi.dptr(self.z), _cabi.dptr(g_a), _cabi.dptr(g_b), _cabi.dptr(g_direct),
+                                                _cabi.dptr(row_sel), 32, _cabi.dptr(self.exp_avg), _cabi.dptr(self.exp_avg_sq),
+                                                self.z.numel(), _cabi.dptr(self.step_dev), self.lr, self.betas[0],
+                                                self.betas[1], self.eps, _cabi.stream_ptr()))
+
+    def _iteration(self):
+        raise NotImplementedError
+
+    # ---- driving
+    def step(self):
+        """One iteration.  The first one runs eagerly (lazy workspaces, function attributes); it is then captured and every
+        further call replays the graph."""
+        with torch.cuda.device(self.dev):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._iteration()
+                if self.use_graph and self.iterations == 0:
+                    self._capture()
+        self.iterations += 1
+
+    def eager_step(self):
+        """One iteration launched kernel by kernel even when a captured graph exists (per-kernel event profiling)."""
+        with torch.cuda.device(self.dev):
+            self._iteration()
+        self.iterations += 1
+
+    def _capture(self):
+        torch.cuda.synchronize(self.dev)
+        # the capture must not disturb the state the eager iteration left: a capture records launches without running them
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._iteration()
+        self.graph = g
+
+    def run(self, iters):
+        for _ in range(int(iters)):
+            self.step()
+        return self.z
+
+    def _rollout_launches(self, sweeps):
+        FT, NA = self.FT, self.NA
+        chunks = (NA + 2047) // 2048
+        fwd = 1 + FT * 3 + (FT - 1) * (1 + chunks * 8)      # init_tape; node/edge/post per step; gru + (crop_pack, conv1..6, fc) per chunk
+        bwd = FT * 3 + (FT - 1)
+        return fwd + sweeps * bwd
+
+
+class RefineLoop(_DeviceLoop):
+    """Device-resident refine iteration (decode -> AvoidCollLoss -> d/dz -> Adam), reference refine_traffic_optim.py:185-218."""
+
+    def __init__(self, model, scene_graph, map_idx, map_env, embed_info, z_init, loss_weights, lr, FT,
+                 veh_coll_buffer=0.2, group_scene_ptr=None, betas=(0.9, 0.999), eps=1e-8, use_graph=True):
+        super().__init__(model, scene_graph, map_idx, map_env, embed_info['map_feat'], embed_info['past_feat'], z_init,
+                         embed_info['prior_out'][0], embed_info['prior_out'][1], lr, FT, betas=betas, eps=eps, use_graph=use_graph)
+        dev, NA = self.dev, self.NA
         self.init_z = self.z.clone()
-        self.map_feat = embed_info['map_feat'].detach().contiguous().float()
-        self.past_feat = embed_info['past_feat'].detach().contiguous().float()
-        self.prior_mu = embed_info['prior_out'][0].detach().contiguous().float()
-        self.prior_var = embed_info['prior_out'][1].detach().contiguous().float()
         lw_un = model.get_att_normalizer().unnormalize(self.scene.lw)
         # refine builds AvoidCollLoss without ptr: one collision block per reference batch (= group)
         self.plan = LossPlan(_cabi.LOSS_AVOID, loss_weights, lw_un, self.scene.agent_map, map_env, self.scene.ptr_host, dev,
                              group_scene_ptr=group_scene_ptr, coll_by_scene=False, veh_coll_buffer=veh_coll_buffer,
                              traj_unnormalized=False)
-        self.traj = torch.empty((NA, self.FT, 4), dtype=torch.float32, device=dev)
         self.d_traj = torch.empty_like(self.traj)
         self.d_z_bptt = torch.empty((NA, 32), dtype=torch.float32, device=dev)
         self.d_z_direct = torch.empty((NA, 32), dtype=torch.float32, device=dev)
         self.terms = torch.zeros((self.plan.G, _cabi.STRIVE_TERMS), dtype=torch.float32, device=dev)
-        self.exp_avg = torch.zeros_like(self.z)
-        self.exp_avg_sq = torch.zeros_like(self.z)
-        self.tape_bytes = self.L.strive_decode_tape_bytes(NA, self.FT)
-        self.tape = torch.empty(self.tape_bytes, dtype=torch.uint8, device=dev)
-        self.step_count = 0
-        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.graph = None
         # kernels launched per iteration (counted from the launch sequence in csrc/*.cu; see DESIGN.md)
-        self.launches_per_iter = self._count_launches()
-
-    def _count_launches(self):
-        FT, NA = self.FT, self.NA
-        chunks = (NA + 2047) // 2048
-        fwd = 1 + FT * 3 + (FT - 1) * (1 + chunks * 8)      # init_tape; node/edge/post per step; gru + (crop_pack, conv1..6, fc) per chunk
-        bwd = FT * 3 + (FT - 1)
-        loss = 7
-        return fwd + bwd + loss + 1
-
-    def _forward(self):
-        _cabi.check(self.L.strive_decode_fwd(self.dm.handle, C.byref(self.scene.cstruct), C.byref(self.env.cstruct),
-                                             _cabi.dptr(self.z), _cabi.dptr(self.map_feat), _cabi.dptr(self.past_feat), None,
-                                             self.FT, _cabi.dptr(self.traj), _cabi.dptr(self.tape), self.tape_bytes,
-                                             _cabi.stream_ptr()))
+        self.launches_per_iter = self._rollout_launches(1) + 7 + 2
 
     def _loss(self):
         run_loss(self.plan, self.scene.cstruct, self.traj, self.z, self.prior_mu, self.prior_var, self.init_z,
                  d_traj=self.d_traj, d_z=self.d_z_direct, terms=self.terms)
 
     def _backward(self):
-        _cabi.check(self.L.strive_decode_bwd(self.dm.handle, C.byref(self.scene.cstruct), self.FT, None, _cabi.dptr(self.d_traj),
-                                             _cabi.dptr(self.d_z_bptt), _cabi.dptr(self.tape), self.tape_bytes,
-                                             _cabi.stream_ptr()))
+        self._sweep(self.d_traj, self.d_z_bptt)
 
     def _adam(self):
-        self.step_count += 1
-        _cabi.check(self.L.strive_adam_step(_cabi.dptr(self.z), _cabi.dptr(self.d_z_bptt), _cabi.dptr(self.d_z_direct),
-                                            _cabi.dptr(self.exp_avg), _cabi.dptr(self.exp_avg_sq), self.z.numel(),
-                                            self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
-                                            _cabi.stream_ptr()))
+        self._adam_dev(self.d_z_bptt, g_direct=self.d_z_direct)
 
-    def step(self):
+    def _iteration(self):
         self._forward()
         self._loss()
         self._backward()
         self._adam()
 
-    def run(self, iters):
-        for _ in range(iters):
-            self.step()
-        return self.z
-
     def grad(self):
         """dL/dz of the last evaluated iteration (before Adam consumed it)."""
         return self.d_z_bptt + self.d_z_direct
+
+
+class InitLoop(_DeviceLoop):
+    """Device-resident form of utils/init_optim.py:30-58: z is fitted so the decoded future matches the observed one at the
+    visible (agent, step) entries (TgtMatchingLoss with the init_* weights, incl. its :46 quirk)."""
+
+    def __init__(self, model, scene_graph, map_idx, map_env, embed_info, z_init, init_traj, traj_vis, loss_weights, lr, FT=None,
+                 prior=None, group_scene_ptr=None, use_graph=True):
+        FT = model.FT if FT is None else int(FT)
+        NA = z_init.size(0)
+        dev = z_init.device
+        mu = prior[0] if prior is not None else torch.zeros((NA, 32), device=dev)
+        var = prior[1] if prior is not None else torch.ones((NA, 32), device=dev)
+        super().__init__(model, scene_graph, map_idx, map_env, embed_info['map_feat'], embed_info['past_feat'], z_init, mu, var, lr, FT,
+                         use_graph=use_graph)
+        w = {k[5:]: v for k, v in loss_weights.items() if k[:5] == 'init_'}
+        lw_un = model.get_att_normalizer().unnormalize(self.scene.lw)
+        vis = (traj_vis[:, :FT] == 1.0)
+        self.plan = LossPlan(_cabi.LOSS_MATCH, w, lw_un, self.scene.agent_map, map_env, self.scene.ptr_host, self.dev,
+                             group_scene_ptr=group_scene_ptr, traj_unnormalized=False, match_mask=vis)
+        self.match_tgt = init_traj[:, :FT, :4].detach().to(self.dev, torch.float32).contiguous()       # NORMALISED, as the rollout
+        self.d_traj = torch.empty_like(self.traj)
+        self.g = torch.empty((self.NA, 32), dtype=torch.float32, device=self.dev)
+        self.terms = torch.zeros((self.plan.G, _cabi.STRIVE_TERMS), dtype=torch.float32, device=self.dev)
+        self.launches_per_iter = self._rollout_launches(1) + 4 + 2
+
+    def _iteration(self):
+        self._forward()
+        run_loss(self.plan, self.scene.cstruct, self.traj, None, None, None, None, match_tgt=self.match_tgt,
+                 d_traj_match=self.d_traj, terms=self.terms)
+        self._sweep(self.d_traj, self.g)
+        self._adam_dev(self.g)
+
+    def log_dict(self):
+        t = self.terms.sum(dim=0).tolist()
+        return {'match_ext_loss': t[10], 'loss': t[11]}
+
+
+class AdvLoop(_DeviceLoop):
+    """Device-resident form of utils/adv_gen_optim.py:106-175 in planner-replay mode: ONE rollout (the planner's future injected
+    for the ego rows), TgtMatchingLoss on the ego rows + AdvGenLoss on everything else in one fused loss call, TWO adjoint
+    sweeps over the same tape (the reference decodes twice with identical values and different detach masks, :119-130), and
+    one Adam step over [tgt_z ; other_z] held as a single (NA,32) buffer in graph order (= collate_tgt_other_z)."""
+
+    def __init__(self, model, scene_graph, map_idx, map_env, embed_info, z_init, planner_fut, loss_weights, lr, FT, prior,
+                 veh_coll_buffer=0.1, crash_min_t=0, crash_min_infront=None, attack_mask=None, group_scene_ptr=None, use_graph=True):
+        super().__init__(model, scene_graph, map_idx, map_env, embed_info['map_feat'], embed_info['past_feat'], z_init, prior[0], prior[1],
+                         lr, FT, ext_future=planner_fut, use_graph=use_graph)
+        dev, NA, FT = self.dev, self.NA, self.FT
+        ego = self.scene.ego_mask
+        self.ego_u8 = ego.to(torch.uint8).contiguous()
+        self.init_z = self.z.clone()
+        lw_un = model.get_att_normalizer().unnormalize(self.scene.lw)
+        mm = torch.zeros((NA, FT), dtype=torch.bool, device=dev)
+        mm[ego] = True
+        self.plan = LossPlan(_cabi.LOSS_ADV | _cabi.LOSS_MATCH, loss_weights, lw_un, self.scene.agent_map, map_env, self.scene.ptr_host, dev,
+                             group_scene_ptr=group_scene_ptr, coll_by_scene=True, veh_coll_buffer=veh_coll_buffer, crash_min_t=crash_min_t,
+                             crash_min_infront=crash_min_infront, traj_unnormalized=False, match_mask=mm)
+        if attack_mask is not None:
+            self.plan.set_attack_mask(attack_mask)
+        self.match_tgt = torch.zeros((NA, FT, 4), dtype=torch.float32, device=dev)
+        self.match_tgt[ego] = self.ext
+        self.d_traj = torch.empty_like(self.traj)
+        self.d_traj_match = torch.empty_like(self.traj)
+        self.g_tgt = torch.empty((NA, 32), dtype=torch.float32, device=dev)
+        self.g_oth = torch.empty((NA, 32), dtype=torch.float32, device=dev)
+        self.d_z_direct = torch.empty((NA, 32), dtype=torch.float32, device=dev)
+        self.terms = torch.zeros((self.plan.G, _cabi.STRIVE_TERMS), dtype=torch.float32, device=dev)
+        self.launches_per_iter = self._rollout_launches(2) + 10 + 2
+
+    def _iteration(self):
+        self._forward()
+        run_loss(self.plan, self.scene.cstruct, self.traj, self.z, self.prior_mu, self.prior_var, self.init_z, match_tgt=self.match_tgt,
+                 adv_tgt=self.ext, d_traj=self.d_traj, d_traj_match=self.d_traj_match, d_z=self.d_z_direct, terms=self.terms)
+        self._sweep(self.d_traj_match, self.g_tgt)          # target rows: matching loss
+        self._sweep(self.d_traj, self.g_oth)                # all other rows: adversarial loss
+        self._adam_dev(self.g_tgt, g_b=self.g_oth, g_direct=self.d_z_direct, row_sel=self.ego_u8)
+
+    def grads(self):
+        ego = self.scene.ego_mask
+        return self.g_tgt[ego], (self.g_oth + self.d_z_direct)[~ego]
+
+    def log_dict(self):
+        t = self.terms.sum(dim=0).tolist() if self.plan.G == 1 else self.terms.mean(dim=0).tolist()
+        return {'tgt_match_match_ext_loss': t[10], 'tgt_match_loss': t[11], 'adv_init_loss': t[6], 'adv_motion_prior_loss': t[5],
+                'adv_coll_veh_loss': t[1], 'adv_coll_veh_plan_loss': t[7], 'adv_coll_env_loss': t[3], 'adv_adv_crash_loss': t[9],
+                'adv_loss': t[0]}
+
+
+class SolLoop(_DeviceLoop):
+    """Device-resident form of utils/sol_optim.py:68-112: the target (node 0 of every scene, latent initialised at its prior
+    mean) avoids collisions (AvoidCollLoss, single_veh_idx=0, buffer 0.5) over `future_len` steps while every other agent
+    keeps matching the adversarial result over its first FTm steps; one rollout of `future_len` (>= FTm) steps, two sweeps."""
+
+    def __init__(self, model, scene_graph, map_idx, map_env, embed_info, z_init, other_match_n, loss_weights, lr, future_len, prior,
+                 group_scene_ptr=None, use_graph=True):
+        FTm = int(other_match_n.size(1))
+        if int(future_len) < FTm:
+            raise RuntimeError('strive_b200: SolLoop needs future_len >= the matched horizon (%d < %d)' % (int(future_len), FTm))
+        super().__init__(model, scene_graph, map_idx, map_env, embed_info['map_feat'], embed_info['past_feat'], z_init, prior[0], prior[1],
+                         lr, int(future_len), use_graph=use_graph)
+        dev, NA, FT = self.dev, self.NA, self.FT
+        ego = self.scene.ego_mask
+        self.ego_u8 = ego.to(torch.uint8).contiguous()
+        self.z[ego] = self.prior_mu[ego]                       # sol_optim.py:38-40
+        self.init_z = self.z.clone()
+        lw_un = model.get_att_normalizer().unnormalize(self.scene.lw)
+        mm = torch.zeros((NA, FT), dtype=torch.bool, device=dev)
+        mm[~ego, :FTm] = True
+        self.plan = LossPlan(_cabi.LOSS_AVOID | _cabi.LOSS_MATCH, loss_weights, lw_un, self.scene.agent_map, map_env, self.scene.ptr_host, dev,
+                             group_scene_ptr=group_scene_ptr, coll_by_scene=True, veh_coll_buffer=0.5, single_veh_idx=0,
+                             traj_unnormalized=False, match_mask=mm)
+        self.match_tgt = torch.zeros((NA, FT, 4), dtype=torch.float32, device=dev)
+        self.match_tgt[~ego, :FTm] = other_match_n.detach().to(dev, torch.float32)
+        self.d_traj = torch.empty_like(self.traj)
+        self.d_traj_match = torch.empty_like(self.traj)
+        self.g_tgt = torch.empty((NA, 32), dtype=torch.float32, device=dev)
+        self.g_oth = torch.empty((NA, 32), dtype=torch.float32, device=dev)
+        self.d_z_direct = torch.empty((NA, 32), dtype=torch.float32, device=dev)
+        self.terms = torch.zeros((self.plan.G, _cabi.STRIVE_TERMS), dtype=torch.float32, device=dev)
+        self.launches_per_iter = self._rollout_launches(2) + 8 + 2
+
+    def _iteration(self):
+        self._forward()
+        run_loss(self.plan, self.scene.cstruct, self.traj, self.z, self.prior_mu, self.prior_var, self.init_z, match_tgt=self.match_tgt,
+                 d_traj=self.d_traj, d_traj_match=self.d_traj_match, d_z=self.d_z_direct, terms=self.terms)
+        self._sweep(self.d_traj, self.g_tgt)                # target rows: avoid-collision loss
+        self._sweep(self.d_traj_match, self.g_oth)          # other rows: matching loss
+        self._adam_dev(self.g_tgt, g_b=self.g_oth, g_direct=self.d_z_direct, row_sel=self.ego_u8)
+
+    def grads(self):
+        ego = self.scene.ego_mask
+        return (self.g_tgt + self.d_z_direct)[ego], self.g_oth[~ego]
+
+    def log_dict(self):
+        t = self.terms.sum(dim=0).tolist() if self.plan.G == 1 else self.terms.mean(dim=0).tolist()
+        return {'tgt_coll_veh_loss': t[1], 'tgt_coll_env_loss': t[3], 'tgt_motion_prior_loss': t[5], 'tgt_init_loss': t[6], 'tgt_loss': t[0],
+                'other_match_ext_loss': t[10], 'other_loss': t[11]}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -167,37 +361,54 @@ def _ego_mask(scene_graph, NA, device):
 
 
 def run_init_optim(cur_z, init_traj, traj_vis, lr, loss_weights, model, scene_graph, map_env, map_idx, num_iters, embed_info,
-                   prior_distrib, log=None):
+                   prior_distrib, log=None, fused=True):
     """reference init_optim.py:11-68: fit z so the decoded future matches the observed one (TgtMatchingLoss with the
-    init_* weights), Adam(lr)."""
+    init_* weights), Adam(lr).  fused=True (default) runs the device-resident InitLoop (no host synchronisation unless `log`
+    is given); fused=False runs the same iteration through the drop-in modules + autograd + torch.optim.Adam."""
     from .losses import TgtMatchingLoss
-    init_traj = model.get_normalizer().unnormalize(init_traj)[traj_vis == 1.0]
-    cur_z = cur_z.clone().detach()
-    cur_z.requires_grad = True
-    opt = torch.optim.Adam([cur_z], lr=lr)
-    match_loss = TgtMatchingLoss({k[5:]: v for k, v in loss_weights.items() if k[:5] == 'init_'})
-    for it in range(num_iters):
-        opt.zero_grad()
-        dec = model.decode_embedding(cur_z, embed_info, scene_graph, map_idx, map_env)
-        fut = model.get_normalizer().unnormalize(dec['future_pred'])[traj_vis == 1.0]
-        ld = match_loss(fut, init_traj, cur_z, prior_distrib)
-        if log is not None:
-            log(it, {k: float(torch.mean(v)) for k, v in ld.items()})
-        ld['loss'].backward()
-        opt.step()
+    if fused:
+        loop = InitLoop(model, scene_graph, map_idx, map_env, embed_info, cur_z, init_traj, traj_vis, loss_weights, lr, prior=prior_distrib)
+        for it in range(num_iters):
+            loop.step()
+            if log is not None:
+                log(it, loop.log_dict())
+        cur_z = loop.z.clone().requires_grad_(True)
+    else:
+        init_traj = model.get_normalizer().unnormalize(init_traj)[traj_vis == 1.0]
+        cur_z = cur_z.clone().detach()
+        cur_z.requires_grad = True
+        opt = torch.optim.Adam([cur_z], lr=lr)
+        match_loss = TgtMatchingLoss({k[5:]: v for k, v in loss_weights.items() if k[:5] == 'init_'})
+        for it in range(num_iters):
+            opt.zero_grad()
+            dec = model.decode_embedding(cur_z, embed_info, scene_graph, map_idx, map_env)
+            fut = model.get_normalizer().unnormalize(dec['future_pred'])[traj_vis == 1.0]
+            ld = match_loss(fut, init_traj, cur_z, prior_distrib)
+            if log is not None:
+                log(it, {k: float(torch.mean(v)) for k, v in ld.items()})
+            ld['loss'].backward()
+            opt.step()
     with torch.no_grad():
         out = model.decode_embedding(cur_z, embed_info, scene_graph, map_idx, map_env)
     return cur_z, out['future_pred'].clone().detach(), out
 
 
+def _full_rows(NA, mask, rows_true, rows_false):
+    out = torch.empty((NA,) + tuple(rows_true.shape[1:]), dtype=rows_true.dtype, device=rows_true.device)
+    out[mask] = rows_true
+    out[~mask] = rows_false
+    return out
+
+
 def run_adv_gen_optim(cur_z, lr, loss_weights, model, scene_graph, map_env, map_idx, num_iters, embed_info, planner_name,
                       tgt_prior_distrib, other_prior_distrib, feasibility_time, feasibility_infront_min, planner=None,
-                      planner_viz_out=None, attack_agt_idx=None, future_len=None, veh_coll_buffer=0.1, log=None, debug=None):
+                      planner_viz_out=None, attack_agt_idx=None, future_len=None, veh_coll_buffer=0.1, log=None, debug=None, fused=True):
     """reference adv_gen_optim.py:39-211, planner replay mode (planner_name == 'ego').
 
     The reference decodes twice per iteration with identical forward values (once with other_z detached for the target's
     matching loss, once with tgt_z detached for the adversarial loss, :119-130).  Here: ONE rollout and TWO adjoint sweeps
-    over its tape (strive_decode_bwd with two seeds), which yields exactly the same gradients."""
+    over its tape (strive_decode_bwd with two seeds), which yields exactly the same gradients.  fused=True (default) runs the
+    device-resident AdvLoop; fused=False the same iteration through the drop-in modules + autograd + torch.optim.Adam."""
     from .losses import TgtMatchingLoss, AdvGenLoss
     if planner_name != 'ego':
         raise RuntimeError('strive_b200: only planner="ego" (open-loop replay) is supported; the closed-loop rule-based planner '
@@ -210,36 +421,54 @@ def run_adv_gen_optim(cur_z, lr, loss_weights, model, scene_graph, map_env, map_
         attack_agt_idx = torch.as_tensor(attack_agt_idx, device=dev).long() + ego_inds
     if future_len is None:
         future_len = model.FT
-    tgt_z = cur_z[ego_mask].clone().detach().requires_grad_(True)
-    other_z = cur_z[~ego_mask].clone().detach().requires_grad_(True)
-    opt = torch.optim.Adam([tgt_z, other_z], lr=lr)
     nrm = model.get_normalizer()
-    tgt_loss = TgtMatchingLoss(loss_weights)
-    adv_loss = AdvGenLoss(loss_weights, model.get_att_normalizer().unnormalize(scene_graph.lw), map_idx[scene_graph.batch], map_env,
-                          other_z.clone().detach(), scene_graph.ptr, veh_coll_buffer=veh_coll_buffer,
-                          crash_loss_min_time=feasibility_time, crash_loss_min_infront=feasibility_infront_min)
     planner_fut = scene_graph.future_gt[ego_mask][:, :, :4]
     assert planner_fut.size(1) == future_len
     planner_un = nrm.unnormalize(planner_fut)
-    for it in range(num_iters):
-        opt.zero_grad()
-        z_all = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach()).requires_grad_(True)
-        fut = model.decode_embedding(z_all, embed_info, scene_graph, map_idx, map_env, ext_future=planner_fut, nfuture=future_len)['future_pred']
-        fut_un = nrm.unnormalize(fut)
-        ld_t = tgt_loss(fut_un[ego_mask], planner_un, tgt_z, tgt_prior_distrib)
-        ld_a = adv_loss(fut_un, planner_un, other_z, other_prior_distrib, attack_agt_idx=attack_agt_idx)
-        g_t = torch.autograd.grad(ld_t['loss'], z_all, retain_graph=True)[0]          # adjoint sweep 1: target rows
-        g_a, g_o = torch.autograd.grad(ld_a['loss'], [z_all, other_z])               # adjoint sweep 2 + direct latent terms
-        tgt_z.grad = g_t[ego_mask]
-        other_z.grad = g_a[~ego_mask] + g_o
-        if debug is not None and it == 0:
-            debug.update(g_tgt=tgt_z.grad.detach().clone(), g_other=other_z.grad.detach().clone())
-        if log is not None:
-            d = {'tgt_match_' + k: float(torch.mean(v)) for k, v in ld_t.items()}
-            d.update({'adv_' + k: float(torch.mean(v)) for k, v in ld_a.items()})
-            log(it, d)
-        opt.step()
-    cur_z = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach())
+    adv_loss = AdvGenLoss(loss_weights, model.get_att_normalizer().unnormalize(scene_graph.lw), map_idx[scene_graph.batch], map_env,
+                          cur_z[~ego_mask].clone().detach(), scene_graph.ptr, veh_coll_buffer=veh_coll_buffer,
+                          crash_loss_min_time=feasibility_time, crash_loss_min_infront=feasibility_infront_min)
+    if fused:
+        atk = None
+        if attack_agt_idx is not None:
+            atk = torch.zeros(NA, dtype=torch.int32, device=dev)
+            atk[attack_agt_idx] = 1
+        prior = (_full_rows(NA, ego_mask, tgt_prior_distrib[0], other_prior_distrib[0]),
+                 _full_rows(NA, ego_mask, tgt_prior_distrib[1], other_prior_distrib[1]))
+        loop = AdvLoop(model, scene_graph, map_idx, map_env, embed_info, cur_z, planner_fut, loss_weights, lr, future_len, prior,
+                       veh_coll_buffer=veh_coll_buffer, crash_min_t=feasibility_time, crash_min_infront=feasibility_infront_min, attack_mask=atk)
+        for it in range(num_iters):
+            loop.step()
+            if debug is not None and it == 0:
+                gt, go = loop.grads()
+                debug.update(g_tgt=gt.clone(), g_other=go.clone())
+            if log is not None:
+                log(it, loop.log_dict())
+        cur_z = loop.z.clone()
+    else:
+        tgt_z = cur_z[ego_mask].clone().detach().requires_grad_(True)
+        other_z = cur_z[~ego_mask].clone().detach().requires_grad_(True)
+        opt = torch.optim.Adam([tgt_z, other_z], lr=lr)
+        tgt_loss = TgtMatchingLoss(loss_weights)
+        for it in range(num_iters):
+            opt.zero_grad()
+            z_all = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach()).requires_grad_(True)
+            fut = model.decode_embedding(z_all, embed_info, scene_graph, map_idx, map_env, ext_future=planner_fut, nfuture=future_len)['future_pred']
+            fut_un = nrm.unnormalize(fut)
+            ld_t = tgt_loss(fut_un[ego_mask], planner_un, tgt_z, tgt_prior_distrib)
+            ld_a = adv_loss(fut_un, planner_un, other_z, other_prior_distrib, attack_agt_idx=attack_agt_idx)
+            g_t = torch.autograd.grad(ld_t['loss'], z_all, retain_graph=True)[0]          # adjoint sweep 1: target rows
+            g_a, g_o = torch.autograd.grad(ld_a['loss'], [z_all, other_z])               # adjoint sweep 2 + direct latent terms
+            tgt_z.grad = g_t[ego_mask]
+            other_z.grad = g_a[~ego_mask] + g_o
+            if debug is not None and it == 0:
+                debug.update(g_tgt=tgt_z.grad.detach().clone(), g_other=other_z.grad.detach().clone())
+            if log is not None:
+                d = {'tgt_match_' + k: float(torch.mean(v)) for k, v in ld_t.items()}
+                d.update({'adv_' + k: float(torch.mean(v)) for k, v in ld_a.items()})
+                log(it, d)
+            opt.step()
+        cur_z = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach())
     with torch.no_grad():
         final = model.decode_embedding(cur_z, embed_info, scene_graph, map_idx, map_env, nfuture=future_len)
     final_traj = final['future_pred'].unsqueeze(1).clone().detach()
@@ -251,11 +480,12 @@ def run_adv_gen_optim(cur_z, lr, loss_weights, model, scene_graph, map_env, map_
 
 
 def run_find_solution_optim(cur_z, final_result_traj, future_len, lr, loss_weights, model, scene_graph, map_env, map_idx,
-                            num_iters, embed_info, tgt_prior_distrib, other_prior_distrib, log=None, debug=None):
+                            num_iters, embed_info, tgt_prior_distrib, other_prior_distrib, log=None, debug=None, fused=True):
     """reference sol_optim.py:19-123: the target (node 0 of every scene) avoids collisions (AvoidCollLoss, single_veh_idx=0,
     rollout of `future_len`) while the others keep matching the adversarial result (TgtMatchingLoss over model.FT steps).
     One rollout of max(future_len, FT) steps + two adjoint sweeps replaces the reference's two decodes (:73-77); the
-    rollout is causal, so its first FT steps equal the shorter decode."""
+    rollout is causal, so its first FT steps equal the shorter decode.  fused=True (default) runs the device-resident SolLoop
+    (needs future_len >= FT, as in configs/adv_gen_rule_based.cfg: 16 >= 12); fused=False the drop-in modules + autograd."""
     from .losses import AvoidCollLoss, TgtMatchingLoss
     NA = final_result_traj.size(0)
     dev = cur_z.device
@@ -263,33 +493,47 @@ def run_find_solution_optim(cur_z, final_result_traj, future_len, lr, loss_weigh
     tgt_mask = _ego_mask(scene_graph, NA, dev)
     other_match = nrm.unnormalize(final_result_traj[:, 0][~tgt_mask])            # (NA-B, FT, 4)
     FTm = other_match.size(1)
-    tgt_z = tgt_prior_distrib[0].clone().detach().requires_grad_(True)             # (B, D)  sol_optim.py:38-40
-    other_z = cur_z[~tgt_mask].reshape(NA - int(tgt_mask.sum()), -1).clone().detach().requires_grad_(True)
-    opt = torch.optim.Adam([tgt_z, other_z], lr=lr)
     w = {k[4:]: v for k, v in loss_weights.items() if k[:4] == 'sol_'}
-    avoid_loss = AvoidCollLoss(w, model.get_att_normalizer().unnormalize(scene_graph.lw), map_idx[scene_graph.batch], map_env,
-                               tgt_z.clone().detach(), veh_coll_buffer=0.5, single_veh_idx=0, ptr=scene_graph.ptr)
-    match_loss = TgtMatchingLoss(w)
-    FTd = max(int(future_len), int(FTm))
-    for it in range(num_iters):
-        opt.zero_grad()
-        z_all = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach()).requires_grad_(True)
-        fut = model.decode_embedding(z_all, embed_info, scene_graph, map_idx, map_env, nfuture=FTd)['future_pred']
-        fut_un = nrm.unnormalize(fut)
-        ld_t = avoid_loss(fut_un[:, :future_len].contiguous(), tgt_z, tgt_prior_distrib)
-        ld_o = match_loss(fut_un[~tgt_mask][:, :FTm], other_match, other_z, other_prior_distrib)
-        g_t, g_td = torch.autograd.grad(ld_t['loss'], [z_all, tgt_z], retain_graph=True)
-        g_o = torch.autograd.grad(ld_o['loss'], z_all)[0]
-        tgt_z.grad = g_t[tgt_mask] + g_td
-        other_z.grad = g_o[~tgt_mask]
-        if debug is not None and it == 0:
-            debug.update(g_tgt=tgt_z.grad.detach().clone(), g_other=other_z.grad.detach().clone())
-        if log is not None:
-            d = {'tgt_' + k: float(torch.mean(v)) for k, v in ld_t.items()}
-            d.update({'other_' + k: float(torch.mean(v)) for k, v in ld_o.items()})
-            log(it, d)
-        opt.step()
-    cur_z = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach())
+    cur_z2 = cur_z.reshape(NA, -1)
+    if fused and int(future_len) >= int(FTm):
+        prior = (_full_rows(NA, tgt_mask, tgt_prior_distrib[0], other_prior_distrib[0]),
+                 _full_rows(NA, tgt_mask, tgt_prior_distrib[1], other_prior_distrib[1]))
+        loop = SolLoop(model, scene_graph, map_idx, map_env, embed_info, cur_z2, final_result_traj[:, 0][~tgt_mask], w, lr, future_len, prior)
+        for it in range(num_iters):
+            loop.step()
+            if debug is not None and it == 0:
+                gt, go = loop.grads()
+                debug.update(g_tgt=gt.clone(), g_other=go.clone())
+            if log is not None:
+                log(it, loop.log_dict())
+        cur_z = loop.z.clone()
+    else:
+        tgt_z = tgt_prior_distrib[0].clone().detach().requires_grad_(True)             # (B, D)  sol_optim.py:38-40
+        other_z = cur_z2[~tgt_mask].clone().detach().requires_grad_(True)
+        opt = torch.optim.Adam([tgt_z, other_z], lr=lr)
+        avoid_loss = AvoidCollLoss(w, model.get_att_normalizer().unnormalize(scene_graph.lw), map_idx[scene_graph.batch], map_env,
+                                   tgt_z.clone().detach(), veh_coll_buffer=0.5, single_veh_idx=0, ptr=scene_graph.ptr)
+        match_loss = TgtMatchingLoss(w)
+        FTd = max(int(future_len), int(FTm))
+        for it in range(num_iters):
+            opt.zero_grad()
+            z_all = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach()).requires_grad_(True)
+            fut = model.decode_embedding(z_all, embed_info, scene_graph, map_idx, map_env, nfuture=FTd)['future_pred']
+            fut_un = nrm.unnormalize(fut)
+            ld_t = avoid_loss(fut_un[:, :future_len].contiguous(), tgt_z, tgt_prior_distrib)
+            ld_o = match_loss(fut_un[~tgt_mask][:, :FTm], other_match, other_z, other_prior_distrib)
+            g_t, g_td = torch.autograd.grad(ld_t['loss'], [z_all, tgt_z], retain_graph=True)
+            g_o = torch.autograd.grad(ld_o['loss'], z_all)[0]
+            tgt_z.grad = g_t[tgt_mask] + g_td
+            other_z.grad = g_o[~tgt_mask]
+            if debug is not None and it == 0:
+                debug.update(g_tgt=tgt_z.grad.detach().clone(), g_other=other_z.grad.detach().clone())
+            if log is not None:
+                d = {'tgt_' + k: float(torch.mean(v)) for k, v in ld_t.items()}
+                d.update({'other_' + k: float(torch.mean(v)) for k, v in ld_o.items()})
+                log(it, d)
+            opt.step()
+        cur_z = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach())
     cur_z = cur_z.unsqueeze(1)                                                     # (NA,1,D) as the reference's 3-D z (sol_optim.py:38-44)
     with torch.no_grad():
         sol = model.decode_embedding(cur_z, embed_info, scene_graph, map_idx, map_env)    # future_pred (NA,1,FT,4), :118

@@ -227,8 +227,14 @@ def test_decode_vs_reference_fixture(tag):
     e = np.abs(traj.detach().cpu().numpy() - ref).max(axis=(0, 2))
     with torch.no_grad():
         o32 = oracle_decode(sc, FT).numpy()
+        sd64 = {k: v.double() for k, v in sd.items()}
+        c = lambda t: t.double() if t.is_floating_point() else t
+        o64 = O.decode(sd64, c(sc['z']), c(sc['map_feat']), c(sc['past_feat']), c(sc['past'][:, -1, :]), c(sc['lw']), c(sc['sem']), sc['ptr'],
+                       sc['edge_index'], sc['map_idx'], raster, dx, FT).numpy()
     e_o = np.abs(o32 - ref).max(axis=(0, 2))
-    msg = '%s vs reference: per-step |gpu-ref| %s | |oracle-ref| %s' % (tag, ' '.join('%.1e' % v for v in e), ' '.join('%.1e' % v for v in e_o))
+    e_64 = np.abs(o32 - o64).max(axis=(0, 2))                  # what fp32 rounding alone does to THIS rollout (reference precision)
+    msg = '%s vs reference: per-step |gpu-ref| %s | |oracle32-ref| %s | |oracle32-oracle64| %s' % (
+        tag, ' '.join('%.1e' % v for v in e), ' '.join('%.1e' % v for v in e_o), ' '.join('%.1e' % v for v in e_64))
     if tag != 'g128':
         seed = torch.randn(ref.shape, generator=torch.Generator().manual_seed(int(g[tag + '_seed']) + 100))
         traj.backward(seed.to(dev))
@@ -239,4 +245,8 @@ def test_decode_vs_reference_fixture(tag):
         assert cos > 0.9995 and rel < 0.05
     diag(msg)
     assert e[0] < 2e-6
-    assert bool((e <= 10.0 * np.maximum.accumulate(np.maximum(e_o, 1e-5))).all())
+    # The CPU restatement happens to reproduce the reference's poses to the last bit here, so |oracle32-ref| is no yardstick
+    # for what rounding does.  With ~8 M nearest-pixel samples per re-encode at these sizes some crop pixels always sit within
+    # rounding of a tie: any two fp32 evaluations part ways at the first re-encode (map_feat moves by 1e-5..1e-3) and the
+    # rollout amplifies it -- the envelope is the fp32-vs-fp64 gap of the oracle itself, as for the small fixtures.
+    assert bool((e <= 10.0 * np.maximum.accumulate(e_64) + 1e-5).all())
