@@ -35,6 +35,22 @@ CNN_MAC = {'conv1_gather': 49.0e6, 'conv2': 47.63e6, 'conv3': 43.06e6, 'conv4': 
 MAPENC_CHUNK = 2048
 
 
+ADV_W = {'coll_veh': 20.0, 'coll_veh_plan': 20.0, 'coll_env': 20.0, 'init_z': 0.5, 'init_z_atk': 0.05, 'motion_prior': 1.0,
+         'motion_prior_atk': 0.005, 'motion_prior_ext': 0.0001, 'match_ext': 10.0, 'adv_crash': 2.0}      # configs/adv_gen_rule_based.cfg:34-43
+SOL_W = {'sol_motion_prior': 0.005, 'sol_coll_veh': 10.0, 'sol_coll_env': 10.0, 'sol_motion_prior_ext': 0.001, 'sol_match_ext': 10.0,
+         'sol_init_z': 0.0}                                                                              # :45-50
+INIT_W = {'init_match_ext': 10.0, 'init_motion_prior_ext': 0.01}                                       # :28-30
+ALGO_BYTES_PER_UNIT = 264e3          # 262 144 B crop gather + ~1.5 KB state / features / tape per agent*timestep*iter
+
+
+def bench_config(n_gpus):
+    """`config` of the JSON line -- the same dict in both arms (strive_b200 and --impl reference)."""
+    return {'workload': workload_desc(), 'agents_per_gpu': WORK['scenes'] * WORK['agents'], 'FT': WORK['FT'], 'loss_group_scenes': WORK['group'],
+            'parallelism': 'scene-sharded replicas x%d, no collective in the loop' % n_gpus,
+            'l2': 'inputs larger than L2: one iteration streams ~7.6 GB (rollout tape + map-encoder activations of 2048 crops x 19 re-encodes) '
+                  'through a 126 MB L2; no explicit flush'}
+
+
 def workload_desc():
     return ('refine_traffic_optim latent Adam loop: %d scenes x %d agents x %d steps per GPU (BASELINE configs[1]), loss groups of %d scenes, '
             'random-init weights, synthetic %dx%d raster' % (WORK['scenes'], WORK['agents'], WORK['FT'], WORK['group'], WORK['raster'], WORK['raster']))
@@ -201,7 +217,7 @@ def run_reference(args):
     out = {'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
            'warmup': args.warmup, 'ms_per_step': 1000.0 * r['seconds'] / args.steps, 'higher_is_better': True, 'scaling': 'weak',
            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-           'config': {'workload': workload_desc(), 'cpu_step': 'bounded sample of that workload (see cpu_baseline.sample)'},
+           'config': bench_config(args.gpus),
            'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
            'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(out))
@@ -353,32 +369,164 @@ def run_gpu(args):
             sm_ach = SMEM_BYTES_PER_CROP[top[0]] * crops_per_launch / avg_s
             roof['smem_operand'] = {'achieved_tbs': sm_ach / 1e12, 'peak_tbs': sm_peak / 1e12, 'frac': sm_ach / sm_peak,
                                     'note': 'SS-mode tcgen05 operand fetch + staging stores vs 128 B/clk/SM: the binding resource'}
+    if roof is not None:
+        # BASELINE.json asks for the fraction of the HBM roofline by name: algorithmic bytes of the WHOLE step over its duration
+        gbs = ALGO_BYTES_PER_UNIT * units_per_step / (ms / args.steps / 1000.0) / 1e9
+        roof['hbm_algorithmic'] = {'bytes_per_unit': ALGO_BYTES_PER_UNIT, 'achieved_gbs': gbs, 'peak_gbs': peaks['hbm_gbs'], 'frac': gbs / peaks['hbm_gbs'],
+                                   'note': 'whole iteration; the path is tensor / shared-memory-operand bound (intensity ~1.1 kFLOP/B), not HBM bound'}
+    launches_per_iter = loop.launches_per_iter
+    tape_bytes = loop.tape_bytes
     enc = sum(prof[k][1] for k in CNN_MAC if k in prof)
     shares = {k: round(v[1] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
+
+    extra = {}
+    if not args.no_extra_legs:
+        del loop
+        torch.cuda.empty_cache()
+        extra = extra_legs(args, model, env, dev, dist, rank, world, barrier)
 
     out = None
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            r = cpu_refine_rate(budget_s=20.0, steps=1, warmup=0)
+            r = cpu_refine_rate(budget_s=28.0, steps=3, warmup=1)
             cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
         out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                'data': 'synthetic',
-               'config': {'workload': workload_desc(),
-                          'agents_per_gpu': NA, 'FT': FT, 'parallelism': 'scene-sharded replicas x%d, no collective in the loop' % world,
-                          'l2': 'per-step working set (tape %.0f MB + encoder activations %.0f MB) exceeds the 126 MB L2; no explicit flush' % (
-                              loop.tape_bytes / 1e6, _cabi.lib().strive_mapenc_workspace_bytes(NA) / 1e6),
-                          'loss_after_timed_steps': loss_now},
+               'config': bench_config(world),
+               'working_set_mb': {'rollout_tape_incl_encoder_workspace': round(tape_bytes / 1e6),
+                                  'encoder_workspace': round(_cabi.lib().strive_mapenc_workspace_bytes(NA) / 1e6)},
+               'loss_after_timed_steps': loss_now,
                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
                        'ms_per_step': ms_e / e2e_steps, 'host_ms_each_step': wall,
                        'api': 'TrafficModel.decode_embedding + losses.AvoidCollLoss + torch.optim.Adam, inputs from pinned host memory every step'},
-               'gpu_launches': loop.launches_per_iter * args.steps,
+               'gpu_launches': launches_per_iter * args.steps,
                'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
                'kernel_time_shares': shares, 'map_encoder_share': enc / tot}
+        out.update(extra)
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _event_time(fn, dev):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return e0.elapsed_time(e1), r
+
+
+def _max_over_ranks(ms, dist, dev):
+    t = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def c3_scene(FT):
+    """BASELINE configs[2] shape: ragged scenes of U{4..40} agents until ~512, seeded."""
+    import numpy as np
+    from strive_b200 import synth
+    rng = np.random.RandomState(7)
+    sizes = []
+    while sum(sizes) < 512:
+        sizes.append(int(rng.randint(4, 41)))
+    return synth.make_scenes(3000, sizes, map_extent_m=(200.0, 800.0), M=1, FT=FT, collide_frac=0.25, offroad_frac=0.25), sizes
+
+
+def extra_legs(args, model, env, dev, dist, rank, world, barrier):
+    """Extra keys (the headline stays configs[1]):
+      c3_*            configs[2] on ONE GPU through the fused InitLoop / AdvLoop / SolLoop (planner replay), units/s each;
+      sharded_c5      ONE global batch of configs[4] (1024 scenes x 64 agents x 40 steps, loss groups of 4 scenes) partitioned over
+                      the N ranks by shard.partition_groups, refine loop, final gather_rows INSIDE the timed region (strong scaling);
+      sharded_c3_adv  the configs[2] batch (every scene its own reference batch, as configs/adv_gen_rule_based.cfg batch_size 1) over N
+                      ranks, adversarial loop + gather (strong scaling of a small batch: partial waves);
+      sharded_check   max |z_sharded - z_unsharded| of a small batch run both ways on this hardware."""
+    from strive_b200 import synth
+    from strive_b200.optim import ShardedJob, InitLoop, AdvLoop, SolLoop, RefineLoop
+    out = {}
+    # ---- configs[2], one GPU (every rank runs it; rank 0 reports)
+    FT3, FTS = 12, 16
+    sc, sizes = c3_scene(FTS)
+    g = to_graph(sc, dev)
+    NA3 = int(sc['ptr'][-1])
+    midx = sc['map_idx'].to(dev)
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev), 'prior_out': (sc['prior_mu'].to(dev), sc['prior_var'].to(dev))}
+    prior = embed['prior_out']
+    ego = torch.zeros(NA3, dtype=torch.bool)
+    ego[sc['ptr'][:-1]] = True
+    fut, fvis, _ = synth.make_future(3001, sc, FT3)
+    sol_w = {k[4:]: v for k, v in SOL_W.items()}
+    iters3 = 30
+    loops = {'init': lambda: InitLoop(model, g, midx, env, embed, sc['z'].to(dev), fut[:, :, :4].to(dev), fvis.to(dev), INIT_W, 0.1, FT=FT3, prior=prior),
+             'adv': lambda: AdvLoop(model, g, midx, env, embed, sc['z'].to(dev), sc['ext_future'][:, :FT3].to(dev), ADV_W, LR, FT3, prior, veh_coll_buffer=0.1,
+                                    crash_min_t=2, crash_min_infront=-0.5)}
+    c3 = {'agents': NA3, 'scenes': len(sizes), 'iters_timed': iters3}
+    adv_traj = None
+    for name in ('init', 'adv', 'sol'):
+        if name == 'sol':
+            loop = SolLoop(model, g, midx, env, embed, sc['z'].to(dev), adv_traj[~ego.to(dev)], sol_w, LR, FTS, prior)
+        else:
+            loop = loops[name]()
+        loop.run(3)
+        torch.cuda.synchronize(dev)
+        ms, _ = _event_time(lambda: loop.run(iters3), dev)
+        ft = loop.FT
+        c3[name] = {'units_per_s': NA3 * ft * iters3 / (ms / 1000.0), 'ms_per_iter': ms / iters3, 'FT': ft, 'launches_per_iter': loop.launches_per_iter}
+        if name == 'adv':
+            adv_traj = loop.traj.clone()
+        del loop
+    out['c3_single_gpu'] = c3
+    torch.cuda.empty_cache()
+
+    # ---- sharded configs[4]: one global batch over N ranks
+    S5, n5, FT5, grp = 1024, 64, 40, 4
+    sc5 = synth.make_scenes(5000, [n5] * S5, map_extent_m=(200.0, 800.0), M=1, FT=FT5, collide_frac=0.25, offroad_frac=0.25)
+    gptr5 = list(range(0, S5 + 1, grp))
+    job = ShardedJob('refine', model, sc5, env, REFINE_W, LR, FT5, gptr5, veh_coll_buffer=0.2)
+    job.loop.run(2)                                   # eager iteration + capture + one replay
+    it5 = 2
+    barrier()
+    ms, z5 = _event_time(lambda: job.run(it5), dev)
+    ms = _max_over_ranks(ms, dist, dev)
+    out['sharded_c5'] = {'workload': 'configs[4]: ONE batch of %d scenes x %d agents x %d steps, %d loss groups, refine loop + final gather, strong scaling' % (S5, n5, FT5, len(gptr5) - 1),
+                         'ranks': world, 'units_per_s': S5 * n5 * FT5 * it5 / (ms / 1000.0), 'ms_per_iter_incl_gather': ms / it5, 'iters_timed': it5,
+                         'agents_per_rank': job.rows_per_rank, 'imbalance_max_over_mean': job.imbalance,
+                         'tape_mb_per_rank': round(job.loop.tape_bytes / 1e6), 'gathered_rows': None if z5 is None else int(z5.size(0))}
+    del job, sc5
+    torch.cuda.empty_cache()
+
+    # ---- sharded configs[2] adversarial loop: every scene its own reference batch
+    sc3 = {k: (v[:, :FT3].contiguous() if k == 'ext_future' else v) for k, v in sc.items()}
+    gptr3 = list(range(0, len(sizes) + 1))
+    job = ShardedJob('adv', model, sc3, env, ADV_W, LR, FT3, gptr3, veh_coll_buffer=0.1, crash_min_t=2, crash_min_infront=-0.5)
+    if job.loop is not None:
+        job.loop.run(2)
+    it3 = 30
+    barrier()
+    ms, z3 = _event_time(lambda: job.run(it3), dev)
+    ms = _max_over_ranks(ms, dist, dev)
+    out['sharded_c3_adv'] = {'workload': 'configs[2]: %d agents in %d ragged scenes (one reference batch each), adversarial loop (planner replay) + final gather, strong scaling' % (NA3, len(sizes)),
+                             'ranks': world, 'units_per_s': NA3 * FT3 * it3 / (ms / 1000.0), 'ms_per_iter_incl_gather': ms / it3, 'iters_timed': it3,
+                             'agents_per_rank': job.rows_per_rank, 'imbalance_max_over_mean': job.imbalance}
+    del job
+    torch.cuda.empty_cache()
+
+    # ---- sharded == unsharded on this hardware (small batch, both ways)
+    scs = synth.make_scenes(4000, [6, 3, 8, 5, 4, 7, 2, 6], map_extent_m=(200.0, 800.0), M=1, FT=6, collide_frac=1.0, offroad_frac=1.0)
+    gps = [0, 2, 4, 6, 8]
+    zs = ShardedJob('refine', model, scs, env, REFINE_W, LR, 6, gps, veh_coll_buffer=0.2).run(4)
+    if rank == 0:
+        gs = to_graph(scs, dev)
+        es = {'map_feat': scs['map_feat'].to(dev), 'past_feat': scs['past_feat'].to(dev), 'prior_out': (scs['prior_mu'].to(dev), scs['prior_var'].to(dev))}
+        ref = RefineLoop(model, gs, scs['map_idx'].to(dev), env, es, scs['z'].to(dev), REFINE_W, LR, 6, veh_coll_buffer=0.2, group_scene_ptr=gps).run(4).cpu()
+        out['sharded_check'] = {'max_abs_diff_z_sharded_vs_unsharded': float((zs - ref).abs().max()), 'moved': float((ref - scs['z']).abs().max()),
+                                'ranks': world, 'note': 'float atomics in the loss reductions: equal to rounding, not bitwise'}
+    barrier()
+    return out
 
 
 def main():
@@ -388,6 +536,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='strive_b200', choices=['strive_b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra-legs', action='store_true', help='skip the configs[2] / sharded configs[4] legs (extra keys)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl != 'reference':
         args.warmup = 3

@@ -549,30 +549,79 @@ class _DictGraph(object):
     pass
 
 
-def refine_sharded(model, scene, map_env, loss_weights, iters, lr, FT, group_scene_ptr, veh_coll_buffer=0.2, dst=0):
-    """Refines the latents of a whole batch across the ranks of the default process group.
+class ShardedJob(object):
+    """One global batch of independent reference batches ("loss-normalisation groups") optimised across the ranks of the
+    default process group: `shard.partition_groups` gives every rank whole groups (cost-balanced), the rank runs a
+    device-resident loop on them, and `run()` ends with the gather of the optimised rows on rank `dst`.  No collective inside
+    the loop: every group gets exactly what the reference computes for that batch on its own, whatever the world size.
 
-    scene: dict of CPU tensors (ptr, past, lw, sem, map_idx, z, map_feat, past_feat, prior_mu, prior_var) describing the FULL
-    batch, identical on every rank; group_scene_ptr: scene offsets of the loss-normalisation groups (the batches the reference
-    driver would have formed).  Every rank runs a device-resident RefineLoop on the groups `shard.partition_groups` gives it;
-    rank `dst` returns the refined (NA,32) latents in batch order (CPU), the other ranks return None."""
-    import torch.distributed as dist
-    from . import shard
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank() if world > 1 else 0
-    costs = shard.group_costs(scene['ptr'], group_scene_ptr, FT)
-    mine = shard.partition_groups(costs, world)[rank]
-    sub, lgptr, agent_index = shard.shard_scenes(scene, group_scene_ptr, mine)
-    NA = int(scene['ptr'][-1])
-    if agent_index.numel() == 0:
-        return shard.gather_rows(torch.zeros((0, scene['z'].size(1)), dtype=scene['z'].dtype), agent_index, NA, dst=dst)
-    dev = map_env.device
-    g = _DictGraph()
-    for k in ('past', 'lw', 'sem', 'ptr', 'batch', 'edge_index'):
-        setattr(g, k, sub[k].to(dev))
-    embed = {'map_feat': sub['map_feat'].to(dev), 'past_feat': sub['past_feat'].to(dev),
-             'prior_out': (sub['prior_mu'].to(dev), sub['prior_var'].to(dev))}
-    loop = RefineLoop(model, g, sub['map_idx'].to(dev), map_env, embed, sub['z'].to(dev), loss_weights, lr, FT,
-                      veh_coll_buffer=veh_coll_buffer, group_scene_ptr=lgptr)
-    z = loop.run(iters)
-    return shard.gather_rows(z, agent_index, NA, dst=dst)
+    scene: dict of CPU tensors describing the FULL batch, identical on every rank (ptr, past, lw, sem, map_idx, z, map_feat,
+    past_feat, prior_mu, prior_var [, ext_future for kind='adv']).  kind: 'refine' (RefineLoop) or 'adv' (AdvLoop)."""
+
+    def __init__(self, kind, model, scene, map_env, loss_weights, lr, FT, group_scene_ptr, dst=0, use_graph=True, **loop_kw):
+        import torch.distributed as dist
+        from . import shard
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.world = self.dist.get_world_size() if self.dist is not None else 1
+        self.rank = self.dist.get_rank() if self.dist is not None else 0
+        self.dst = dst
+        self.NA = int(scene['ptr'][-1])
+        self.FT = int(FT)
+        self.zdim = int(scene['z'].size(1))
+        costs = shard.group_costs(scene['ptr'], group_scene_ptr, FT)
+        self.assign = shard.partition_groups(costs, self.world)
+        self.loads = [sum(costs[g] for g in a) for a in self.assign]
+        mine = self.assign[self.rank]
+        sub, lgptr, self.agent_index = shard.shard_scenes(scene, group_scene_ptr, mine)
+        # every rank can compute every other rank's rows: the gather needs no size exchange
+        ptr = scene['ptr']
+        self.rows_per_rank = [sum(int(ptr[int(group_scene_ptr[g + 1])]) - int(ptr[int(group_scene_ptr[g])]) for g in a) for a in self.assign]
+        self.all_index = None
+        if self.rank == dst:
+            self.all_index = [shard.group_rows(ptr, group_scene_ptr, a) for a in self.assign]
+        self.loop = None
+        self.units_local = int(self.agent_index.numel()) * self.FT
+        if self.agent_index.numel() == 0:
+            return
+        dev = map_env.device
+        g = _DictGraph()
+        for k in ('past', 'lw', 'sem', 'ptr', 'batch', 'edge_index'):
+            setattr(g, k, sub[k].to(dev))
+        embed = {'map_feat': sub['map_feat'].to(dev), 'past_feat': sub['past_feat'].to(dev),
+                 'prior_out': (sub['prior_mu'].to(dev), sub['prior_var'].to(dev))}
+        midx = sub['map_idx'].to(dev)
+        if kind == 'refine':
+            self.loop = RefineLoop(model, g, midx, map_env, embed, sub['z'].to(dev), loss_weights, lr, FT, group_scene_ptr=lgptr,
+                                   use_graph=use_graph, **loop_kw)
+        elif kind == 'adv':
+            self.loop = AdvLoop(model, g, midx, map_env, embed, sub['z'].to(dev), sub['ext_future'].to(dev), loss_weights, lr, FT,
+                                embed['prior_out'], group_scene_ptr=lgptr, use_graph=use_graph, **loop_kw)
+        else:
+            raise RuntimeError('strive_b200: unknown sharded loop kind %r' % kind)
+
+    @property
+    def imbalance(self):
+        """max / mean of the per-rank cost estimate (1.0 = perfectly balanced)."""
+        mean = sum(self.loads) / float(len(self.loads))
+        return max(self.loads) / mean if mean > 0 else 1.0
+
+    def run(self, iters):
+        """`iters` iterations on this rank's groups, then the gather; rank `dst` returns the (NA, zdim) latents in batch order
+        (a CPU tensor), the other ranks None."""
+        from . import shard
+        if self.loop is not None:
+            z = self.loop.run(iters)
+        else:
+            z = torch.zeros((0, self.zdim), dtype=torch.float32)
+        return shard.gather_rows(z, self.agent_index, self.NA, dst=self.dst, all_index=self.all_index, rows_per_rank=self.rows_per_rank)
+
+
+def refine_sharded(model, scene, map_env, loss_weights, iters, lr, FT, group_scene_ptr, veh_coll_buffer=0.2, dst=0):
+    """Refines the latents of a whole batch across the ranks of the default process group; see ShardedJob."""
+    return ShardedJob('refine', model, scene, map_env, loss_weights, lr, FT, group_scene_ptr, dst=dst, veh_coll_buffer=veh_coll_buffer).run(iters)
+
+
+def adv_sharded(model, scene, map_env, loss_weights, iters, lr, FT, group_scene_ptr, dst=0, **adv_kw):
+    """The adversarial loop (planner replay) of a whole batch of reference batches across ranks; scene['ext_future'] (S,FT,4) is
+    the planner's future per scene."""
+    return ShardedJob('adv', model, scene, map_env, loss_weights, lr, FT, group_scene_ptr, dst=dst, **adv_kw).run(iters)

@@ -58,6 +58,15 @@ PER_AGENT = ('past', 'lw', 'sem', 'z', 'prior_mu', 'prior_var', 'map_feat', 'pas
 PER_SCENE = ('map_idx', 'ext_future')
 
 
+def group_rows(ptr, group_scene_ptr, groups):
+    """Agent rows of the full batch owned by `groups` (ascending group ids), in shard order."""
+    rows = []
+    for g in groups:
+        a, b = int(ptr[int(group_scene_ptr[g])]), int(ptr[int(group_scene_ptr[g + 1])])
+        rows.append(torch.arange(a, b))
+    return torch.cat(rows) if rows else torch.zeros(0, dtype=torch.long)
+
+
 def shard_scenes(scene, group_scene_ptr, groups):
     """Sub-batch holding the scenes of `groups` (ascending group ids), renumbered from 0.
 
@@ -91,21 +100,49 @@ def shard_scenes(scene, group_scene_ptr, groups):
     return sub, local_gptr, agent_index
 
 
-def gather_rows(local_rows, agent_index, NA, dst=0):
+def gather_rows(local_rows, agent_index, NA, dst=0, all_index=None, rows_per_rank=None):
     """Collects per-agent result rows of every rank on rank `dst` in the order of the unsharded batch.
     local_rows (NA_local, ...) on any device; returns the (NA, ...) CPU tensor on `dst`, None elsewhere.
-    With torch.distributed uninitialised (single process) it is a local scatter."""
+    With torch.distributed uninitialised (single process) it is a local scatter.
+
+    The partition is deterministic, so every rank can know every rank's rows: with `all_index` (list of index tensors, needed on
+    `dst`) and `rows_per_rank` the gather is point-to-point sends of exactly-sized tensors (device tensors over NCCL / NVLink,
+    CPU tensors over gloo) -- no pickling, no size exchange.  Without them it falls back to gather_object."""
     import torch.distributed as dist
-    rows = local_rows.detach().cpu()
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        rows = local_rows.detach().cpu()
         out = torch.empty((NA,) + tuple(rows.shape[1:]), dtype=rows.dtype)
         out[agent_index] = rows
         return out
     rank, world = dist.get_rank(), dist.get_world_size()
-    parts = [None] * world if rank == dst else None
-    dist.gather_object((agent_index.cpu(), rows), parts, dst=dst)
-    if rank != dst:
-        return None
+    if rows_per_rank is None or (rank == dst and all_index is None):
+        rows = local_rows.detach().cpu()
+        parts = [None] * world if rank == dst else None
+        dist.gather_object((agent_index.cpu(), rows), parts, dst=dst)
+        if rank != dst:
+            return None
+    else:
+        nccl = dist.get_backend() == 'nccl'
+        rows = local_rows.detach()
+        rows = rows.cuda() if nccl else rows.cpu()
+        rows = rows.contiguous()
+        tail = tuple(rows.shape[1:])
+        if rank != dst:
+            if rows_per_rank[rank] > 0:
+                dist.send(rows, dst)
+            return None
+        bufs, reqs = [], []
+        for r in range(world):
+            if r == dst or rows_per_rank[r] == 0:
+                bufs.append(rows if r == dst else rows.new_zeros((0,) + tail))
+                continue
+            b = torch.empty((rows_per_rank[r],) + tail, dtype=rows.dtype, device=rows.device)
+            reqs.append(dist.irecv(b, r))
+            bufs.append(b)
+        for q in reqs:
+            q.wait()
+        parts = [(all_index[r], bufs[r].cpu()) for r in range(world)]
+        rows = rows.cpu()
     out = torch.empty((NA,) + tuple(rows.shape[1:]), dtype=rows.dtype)
     seen = torch.zeros(NA, dtype=torch.bool)
     for idx, r in parts:

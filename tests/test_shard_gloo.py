@@ -50,11 +50,18 @@ def _rank_main(rank, world, port, out_path):
         z = O.refine_loop(sd, sub, raster, dx, W, ITERS, 0.05, FT, veh_coll_buffer=0.2, groups=_groups_as_scene_lists(lgptr))
     else:
         z = torch.zeros((0, 32), dtype=torch.float64)
-    full = shard.gather_rows(z, agent_index, int(sc['ptr'][-1]), dst=0)
+    NA = int(sc['ptr'][-1])
+    full = shard.gather_rows(z, agent_index, NA, dst=0)                         # object gather (no partition knowledge needed)
+    # point-to-point gather of exactly-sized tensors: every rank derives every rank's rows from the deterministic partition
+    assign = shard.partition_groups(costs, world)
+    all_index = [shard.group_rows(sc['ptr'], GROUP_PTR, a) for a in assign]
+    assert torch.equal(all_index[rank], agent_index)
+    full2 = shard.gather_rows(z, agent_index, NA, dst=0, all_index=all_index if rank == 0 else None, rows_per_rank=[int(i.numel()) for i in all_index])
     if rank == 0:
-        torch.save({'z': full, 'assign': shard.partition_groups(costs, world)}, out_path)
+        assert torch.equal(full, full2)
+        torch.save({'z': full, 'assign': assign}, out_path)
     else:
-        assert full is None
+        assert full is None and full2 is None
     dist.barrier()
     dist.destroy_process_group()
 
