@@ -515,16 +515,32 @@ def extra_legs(args, model, env, dev, dist, rank, world, barrier):
     del job
     torch.cuda.empty_cache()
 
-    # ---- sharded == unsharded on this hardware (small batch, both ways)
+    # ---- sharded == unsharded on this hardware (small batch, both ways): first iteration strictly, then what 4 Adam steps make of it
+    from strive_b200 import shard
     scs = synth.make_scenes(4000, [6, 3, 8, 5, 4, 7, 2, 6], map_extent_m=(200.0, 800.0), M=1, FT=6, collide_frac=1.0, offroad_frac=1.0)
     gps = [0, 2, 4, 6, 8]
-    zs = ShardedJob('refine', model, scs, env, REFINE_W, LR, 6, gps, veh_coll_buffer=0.2).run(4)
+    NAs = int(scs['ptr'][-1])
+    job = ShardedJob('refine', model, scs, env, REFINE_W, LR, 6, gps, veh_coll_buffer=0.2)
+    job.run(1)
+    empty = job.loop is None
+    tr = shard.gather_rows(torch.zeros((0, 6, 4)) if empty else job.loop.traj, job.agent_index, NAs, all_index=job.all_index, rows_per_rank=job.rows_per_rank)
+    gr = shard.gather_rows(torch.zeros((0, 32)) if empty else job.loop.grad(), job.agent_index, NAs, all_index=job.all_index, rows_per_rank=job.rows_per_rank)
+    zs = job.run(3)
     if rank == 0:
         gs = to_graph(scs, dev)
         es = {'map_feat': scs['map_feat'].to(dev), 'past_feat': scs['past_feat'].to(dev), 'prior_out': (scs['prior_mu'].to(dev), scs['prior_var'].to(dev))}
-        ref = RefineLoop(model, gs, scs['map_idx'].to(dev), env, es, scs['z'].to(dev), REFINE_W, LR, 6, veh_coll_buffer=0.2, group_scene_ptr=gps).run(4).cpu()
-        out['sharded_check'] = {'max_abs_diff_z_sharded_vs_unsharded': float((zs - ref).abs().max()), 'moved': float((ref - scs['z']).abs().max()),
-                                'ranks': world, 'note': 'float atomics in the loss reductions: equal to rounding, not bitwise'}
+        ref = RefineLoop(model, gs, scs['map_idx'].to(dev), env, es, scs['z'].to(dev), REFINE_W, LR, 6, veh_coll_buffer=0.2, group_scene_ptr=gps)
+        ref.run(1)
+        d_traj = float((tr - ref.traj.cpu()).abs().max())
+        g_ref = ref.grad().cpu()
+        d_grad = float((gr - g_ref).abs().max() / g_ref.abs().max())
+        dz = (zs - ref.run(3).cpu()).abs()
+        out['sharded_check'] = {'ranks': world, 'iter1_max_abs_diff_traj': d_traj, 'iter1_max_diff_grad_over_max_grad': d_grad,
+                                'iter4_z_max_abs_diff': float(dz.max()), 'iter4_z_median_abs_diff': float(dz.median()),
+                                'iter4_z_frac_above_1e-3': float((dz > 1e-3).float().mean()), 'z_moved': float((zs - scs['z']).abs().max()),
+                                'note': 'iteration 1: same inputs, a different batch composition per rank (fp32 re-association in conv3 / float atomics in '
+                                        'the reductions); by iteration 4 Adam\'s normalised steps and nearest-pixel crops have amplified that noise -- the '
+                                        'same loop run twice UNSHARDED differs as much'}
     barrier()
     return out
 
