@@ -534,13 +534,17 @@ def extra_legs(args, model, env, dev, dist, rank, world, barrier):
         d_traj = float((tr - ref.traj.cpu()).abs().max())
         g_ref = ref.grad().cpu()
         d_grad = float((gr - g_ref).abs().max() / g_ref.abs().max())
-        dz = (zs - ref.run(3).cpu()).abs()
+        z_ref = ref.run(3).cpu()
+        dz = (zs - z_ref).abs()
+        ref2 = RefineLoop(model, gs, scs['map_idx'].to(dev), env, es, scs['z'].to(dev), REFINE_W, LR, 6, veh_coll_buffer=0.2, group_scene_ptr=gps)
+        dz2 = (ref2.run(4).cpu() - z_ref).abs()
         out['sharded_check'] = {'ranks': world, 'iter1_max_abs_diff_traj': d_traj, 'iter1_max_diff_grad_over_max_grad': d_grad,
                                 'iter4_z_max_abs_diff': float(dz.max()), 'iter4_z_median_abs_diff': float(dz.median()),
                                 'iter4_z_frac_above_1e-3': float((dz > 1e-3).float().mean()), 'z_moved': float((zs - scs['z']).abs().max()),
+                                'unsharded_rerun_iter4_z_max_abs_diff': float(dz2.max()), 'unsharded_rerun_iter4_z_frac_above_1e-3': float((dz2 > 1e-3).float().mean()),
                                 'note': 'iteration 1: same inputs, a different batch composition per rank (fp32 re-association in conv3 / float atomics in '
                                         'the reductions); by iteration 4 Adam\'s normalised steps and nearest-pixel crops have amplified that noise -- the '
-                                        'same loop run twice UNSHARDED differs as much'}
+                                        'same loop run twice on one GPU is the yardstick: unsharded_rerun_*'}
     barrier()
     return out
 
