@@ -174,6 +174,10 @@ typedef struct StriveLossCfg {
   const float* env_lin_w;      /* (G,128) */
   const float* circ_cx;        /* (NA,5) VehCollLoss centre offsets, adv_gen_nusc.py:432-437 (torch.linspace) */
   const float* lw_un;          /* (NA,2) unnormalised length/width */
+  int32_t adv_own_pred;        /* closed-loop planner mode (adv_gen_optim.py:98-103,143): the attacked trajectory is the model's OWN
+                                  prediction of the target = row ptr[s] of traj (adv_tgt may be NULL) and the crash term's gradient
+                                  w.r.t. it is written to those rows of d_traj; 0 = adv_tgt is an external constant */
+  int32_t reserved0;
 } StriveLossCfg;
 
 #define STRIVE_TERMS 16
@@ -183,7 +187,7 @@ typedef struct StriveLossCfg {
 int64_t strive_loss_workspace_bytes(int32_t num_agents, int32_t ft, int32_t num_groups);
 /* traj: (NA,FT,4) NORMALISED decoder output.  z/prior_mu/prior_var/init_z: (NA,32) rows in graph order; rows with
  * z_mask[a]==0 carry no latent term (z_mask NULL = all rows).  match_tgt (NA,FT,4) normalised + match_mask (NA,FT)
- * select the rows of the MATCH mean.  adv_tgt (S,FT,4) normalised = planner trajectory attacked by ADV.
+ * select the rows of the MATCH mean.  adv_tgt (S,FT,4) normalised = planner trajectory attacked by ADV (NULL with adv_own_pred).
  * outputs: d_traj / d_traj_match (NA,FT,4) gradients wrt the NORMALISED traj of the AVOID|ADV and MATCH modules
  * (separate seeds: the reference routes them to different latents), d_z_direct (NA,32). */
 int strive_loss_fwd_bwd(const StriveLossCfg* cfg, const StriveScene* sc, const StriveMap* map, int32_t ft,

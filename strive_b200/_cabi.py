@@ -40,7 +40,7 @@ class StriveLossCfg(C.Structure):
                 ('use_infront', C.c_int32), ('crash_min_infront', C.c_float),
                 ('attack_mask', C.c_void_p), ('adv_min_out', C.c_void_p),
                 ('env_L', C.c_void_p), ('env_W', C.c_void_p), ('env_lin_l', C.c_void_p), ('env_lin_w', C.c_void_p),
-                ('circ_cx', C.c_void_p), ('lw_un', C.c_void_p)]
+                ('circ_cx', C.c_void_p), ('lw_un', C.c_void_p), ('adv_own_pred', C.c_int32), ('reserved0', C.c_int32)]
 
 
 EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_tc_trace', 'strive_tc_debug', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl', 'strive_model_edge_frag_bytes', 'strive_model_set_edge_frags', 'strive_edge_set_impl', 'strive_set_pdl',

@@ -100,6 +100,11 @@ __device__ __forceinline__ void interp_src(int o, int FT, int& i0, int& i1, floa
 }
 
 __device__ __forceinline__ bool is_ego(const LossArgs& a, int ag) { return ag == a.ptr[a.scene_of[ag]]; }
+// trajectory attacked by the adversarial term at (scene s, step t): the external planner future, or -- closed-loop mode -- the
+// model's own prediction of the target, row ptr[s] of the rollout (adv_gen_optim.py:143)
+__device__ __forceinline__ const float* adv_tgt_at(const LossArgs& a, int s, int t) {
+  return a.cfg.adv_own_pred ? a.traj + ((size_t)a.ptr[s] * a.FT + t) * 4 : a.adv_tgt + ((size_t)s * a.FT + t) * 4;
+}
 
 // ------------------------------------------------------------------------------------------------------
 __global__ void loss_zero_kernel(LossArgs a) {
@@ -140,7 +145,7 @@ __global__ void adv_dist_kernel(LossArgs a) {
   for (int t = t0; t < a.FT; t++) {
     float p[4], q[4];
     unnorm4(a, a.traj + ((size_t)ag * a.FT + t) * 4, p);
-    unnorm4(a, a.adv_tgt + ((size_t)s * a.FT + t) * 4, q);
+    unnorm4(a, adv_tgt_at(a, s, t), q);
     const float dx = p[0] - q[0], dy = p[1] - q[1];
     const float d = sqrtf(dx * dx + dy * dy);
     a.ws.dist[(size_t)ag * a.FT + t] = d;
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(256) adv_crash_kernel(LossArgs a, int32_t* adv
           const float dd = w * (2.0f * d + crash - d * d);    // d crash / d dist
           float p[4], q[4];
           unnorm4(a, a.traj + ((size_t)ag * a.FT + t) * 4, p);
-          unnorm4(a, a.adv_tgt + ((size_t)s * a.FT + t) * 4, q);
+          unnorm4(a, adv_tgt_at(a, s, t), q);
           gx = dd * (p[0] - q[0]) / d;
           gy = dd * (p[1] - q[1]) / d;
         }
@@ -256,8 +261,22 @@ __global__ void __launch_bounds__(256) adv_crash_kernel(LossArgs a, int32_t* adv
     }
     a.ws.rew[ag] = 1.0f - wsum;    // :151-152
   }
-  if (tid == 0) {
-    for (int t = 0; t < a.FT; t++) { a.ws.gC[((size_t)p0 * a.FT + t) * 2] = 0.f; a.ws.gC[((size_t)p0 * a.FT + t) * 2 + 1] = 0.f; }
+  if (!a.cfg.adv_own_pred) {
+    if (tid == 0) {
+      for (int t = 0; t < a.FT; t++) { a.ws.gC[((size_t)p0 * a.FT + t) * 2] = 0.f; a.ws.gC[((size_t)p0 * a.FT + t) * 2 + 1] = 0.f; }
+    }
+  } else {
+    // the target's own predicted position enters every distance with the opposite sign (the "behind" test is detached, :655-671)
+    __syncthreads();
+    for (int t = tid; t < a.FT; t += 256) {
+      float gx = 0.f, gy = 0.f;
+      for (int k = 0; k < n - 1; k++) {
+        gx -= a.ws.gC[((size_t)(p0 + 1 + k) * a.FT + t) * 2];
+        gy -= a.ws.gC[((size_t)(p0 + 1 + k) * a.FT + t) * 2 + 1];
+      }
+      a.ws.gC[((size_t)p0 * a.FT + t) * 2] = gx;
+      a.ws.gC[((size_t)p0 * a.FT + t) * 2 + 1] = gy;
+    }
   }
 }
 
@@ -610,7 +629,7 @@ extern "C" int strive_loss_fwd_bwd(const StriveLossCfg* cfg, const StriveScene* 
     STRIVE_CHECK(cfg->cblock_ptr && cfg->cblock_of && cfg->circ_cx && cfg->lw_un && cfg->group_zrows, STRIVE_EINVAL, "loss: missing cfg arrays");
     STRIVE_CHECK(cfg->w_coll_env <= 0.f || (cfg->env_L && cfg->env_W && cfg->env_lin_l && cfg->env_lin_w), STRIVE_EINVAL, "loss: env grid missing");
   }
-  if (kind & STRIVE_LOSS_ADV) STRIVE_CHECK(adv_tgt != nullptr, STRIVE_EINVAL, "ADV loss needs adv_tgt");
+  if (kind & STRIVE_LOSS_ADV) STRIVE_CHECK(adv_tgt != nullptr || cfg->adv_own_pred, STRIVE_EINVAL, "ADV loss needs adv_tgt (or adv_own_pred)");
   if (kind & STRIVE_LOSS_MATCH)
     STRIVE_CHECK(match_tgt && match_mask && d_traj_match && cfg->group_match_rows, STRIVE_EINVAL, "MATCH loss needs target, mask, rows");
   STRIVE_CHECK(cfg->group_of && cfg->group_agent_ptr && cfg->num_groups > 0, STRIVE_EINVAL, "loss: group arrays missing");

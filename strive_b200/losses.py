@@ -338,9 +338,15 @@ class AdvGenLoss(_Base):
         self.row_idx = torch.nonzero(self.plan.z_mask.bool(), as_tuple=False).flatten()
 
     def forward(self, future_pred, tgt_traj, z, prior_out, return_mins=False, attack_agt_idx=None):
-        if tgt_traj.requires_grad:
-            raise RuntimeError('strive_b200: AdvGenLoss with a differentiable tgt_traj (closed-loop planner="hardcode", '
-                               'adv_gen_optim.py:143) is not supported; pass the planner trajectory detached')
+        # closed-loop planner mode (adv_gen_optim.py:98-103,143): the attacked trajectory is the model's own prediction of the
+        # target, tgt_traj = future_pred[ptr[:-1]] WITH its graph; the kernel then reads those rows of future_pred itself and
+        # folds d(loss)/d(tgt_traj) into the same rows of d(loss)/d(future_pred)
+        own = bool(tgt_traj.requires_grad)
+        if own and not getattr(self, '_own_checked', False):
+            if not torch.equal(tgt_traj.detach()[:, :, :4], future_pred.detach()[self.ptr[:-1].long()][:, :, :4]):
+                raise RuntimeError('strive_b200: a differentiable tgt_traj must be future_pred[scene_graph.ptr[:-1]] (closed-loop mode)')
+            self._own_checked = True
+        self.plan.cfg.adv_own_pred = int(own)
         if attack_agt_idx is not None:
             m = torch.zeros(self.NA, dtype=torch.int32, device=future_pred.device)
             m[attack_agt_idx] = 1

@@ -287,6 +287,106 @@ class AdvLoop(_DeviceLoop):
                 'adv_loss': t[0]}
 
 
+class AdvClosedLoop(_DeviceLoop):
+    """Closed-loop form of the adversarial iteration (planner_name == 'hardcode', adv_gen_optim.py:98-154): no planner future is
+    injected into the rollout; every iteration the CPU planner reacts to the current prediction of the other agents
+    (`planner.rollout`, :133-139), the target's latent is fitted to the planner's answer (TgtMatchingLoss) and the adversarial
+    loss attacks the model's OWN prediction of the target, whose gradient reaches the other latents through the interaction
+    net (:143-154, `adv_own_pred`).  One rollout, two sweeps.  The planner round trip overlaps the adversarial loss and its
+    adjoint sweep: the predicted futures leave on a side stream right after the rollout, the host runs the planner while the
+    device works, and only the matching loss + first sweep wait for the planner's answer.  `planner_ms` / `iter_ms` accumulate
+    host wall-clock of the planner call and of the whole iteration (planner time reported separately)."""
+
+    def __init__(self, model, scene_graph, map_idx, map_env, embed_info, z_init, planner, loss_weights, lr, FT, prior,
+                 veh_coll_buffer=0.1, crash_min_t=0, crash_min_infront=None, attack_mask=None, group_scene_ptr=None):
+        super().__init__(model, scene_graph, map_idx, map_env, embed_info['map_feat'], embed_info['past_feat'], z_init, prior[0], prior[1],
+                         lr, FT, use_graph=False)
+        import numpy as np
+        dev, NA, FT = self.dev, self.NA, self.FT
+        ego = self.scene.ego_mask
+        self.ego = ego
+        self.ego_u8 = ego.to(torch.uint8).contiguous()
+        self.init_z = self.z.clone()
+        self.planner = planner
+        self.nrm = model.get_normalizer()
+        lw_un = model.get_att_normalizer().unnormalize(self.scene.lw)
+        mm = torch.zeros((NA, FT), dtype=torch.bool, device=dev)
+        mm[ego] = True
+        common = dict(group_scene_ptr=group_scene_ptr, traj_unnormalized=False)
+        self.plan_adv = LossPlan(_cabi.LOSS_ADV, loss_weights, lw_un, self.scene.agent_map, map_env, self.scene.ptr_host, dev, coll_by_scene=True,
+                                 veh_coll_buffer=veh_coll_buffer, crash_min_t=crash_min_t, crash_min_infront=crash_min_infront, **common)
+        self.plan_adv.cfg.adv_own_pred = 1
+        if attack_mask is not None:
+            self.plan_adv.set_attack_mask(attack_mask)
+        self.plan_match = LossPlan(_cabi.LOSS_MATCH, loss_weights, lw_un, self.scene.agent_map, map_env, self.scene.ptr_host, dev, match_mask=mm, **common)
+        self.match_tgt = torch.zeros((NA, FT, 4), dtype=torch.float32, device=dev)
+        self.d_traj = torch.empty_like(self.traj)
+        self.d_traj_match = torch.empty_like(self.traj)
+        self.g_tgt = torch.empty((NA, 32), dtype=torch.float32, device=dev)
+        self.g_oth = torch.empty((NA, 32), dtype=torch.float32, device=dev)
+        self.d_z_direct = torch.empty((NA, 32), dtype=torch.float32, device=dev)
+        self.terms = torch.zeros((self.plan_adv.G, _cabi.STRIVE_TERMS), dtype=torch.float32, device=dev)
+        self.terms_m = torch.zeros((self.plan_adv.G, _cabi.STRIVE_TERMS), dtype=torch.float32, device=dev)
+        self.other_idx = torch.nonzero(~ego, as_tuple=False).flatten()
+        self.ego_idx = torch.nonzero(ego, as_tuple=False).flatten()
+        self.h_pred = torch.empty((NA - self.scene.S, FT, 4), dtype=torch.float32).pin_memory()
+        self.h_plan = torch.empty((self.scene.S, FT, 4), dtype=torch.float32).pin_memory()
+        self.side = torch.cuda.Stream(device=dev)
+        self.ev_fwd = torch.cuda.Event()
+        self.ev_copy = torch.cuda.Event()
+        ptr = self.scene.ptr_host
+        self.agt_ptr = (ptr - torch.arange(ptr.numel())).numpy()                 # cur_agt_ptr, :103
+        self.plan_t = np.linspace(model.dt, model.dt * FT, FT)                    # :104
+        self.planner_ms, self.iter_ms = 0.0, 0.0
+        self.launches_per_iter = self._rollout_launches(2) + 9 + 4 + 2
+
+    def plan(self, final=False, viz=None):
+        """planner.rollout on the others' current prediction (self.traj) -> normalised (S,FT,4) device tensor (:133-139; the final
+        call passes viz= as the reference does, :186-193)."""
+        import time
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_fwd)
+            pred_un = self.nrm.unnormalize(self.traj.index_select(0, self.other_idx))
+            self.h_pred.copy_(pred_un, non_blocking=True)
+            self.ev_copy.record(self.side)
+        self.ev_copy.synchronize()
+        t0 = time.perf_counter()
+        if final:
+            fut = self.planner.rollout(self.h_pred.numpy(), self.plan_t, self.agt_ptr, self.plan_t, viz=viz, control_all=False)
+        else:
+            fut = self.planner.rollout(self.h_pred.numpy(), self.plan_t, self.agt_ptr, self.plan_t, control_all=False)
+        self.planner_ms += 1000.0 * (time.perf_counter() - t0)
+        self.h_plan.copy_(torch.as_tensor(fut, dtype=torch.float32)[:, :, :4])
+        return self.nrm.normalize(self.h_plan.to(self.dev, non_blocking=True))
+
+    def _iteration(self):
+        import time
+        t0 = time.perf_counter()
+        self._forward()
+        self.ev_fwd.record()
+        # adversarial loss on the model's own target prediction + its adjoint sweep: queued before the host touches the planner
+        run_loss(self.plan_adv, self.scene.cstruct, self.traj, self.z, self.prior_mu, self.prior_var, self.init_z,
+                 d_traj=self.d_traj, d_z=self.d_z_direct, terms=self.terms)
+        self._sweep(self.d_traj, self.g_oth)
+        planner_fut = self.plan()                                                 # host: overlaps the work queued above
+        self.match_tgt.index_copy_(0, self.ego_idx, planner_fut)
+        run_loss(self.plan_match, self.scene.cstruct, self.traj, None, None, None, None, match_tgt=self.match_tgt,
+                 d_traj_match=self.d_traj_match, terms=self.terms_m)
+        self._sweep(self.d_traj_match, self.g_tgt)
+        self._adam_dev(self.g_tgt, g_b=self.g_oth, g_direct=self.d_z_direct, row_sel=self.ego_u8)
+        self.iter_ms += 1000.0 * (time.perf_counter() - t0)
+
+    def grads(self):
+        return self.g_tgt[self.ego], (self.g_oth + self.d_z_direct)[~self.ego]
+
+    def log_dict(self):
+        t = self.terms.sum(dim=0).tolist() if self.plan_adv.G == 1 else self.terms.mean(dim=0).tolist()
+        m = self.terms_m.sum(dim=0).tolist() if self.plan_adv.G == 1 else self.terms_m.mean(dim=0).tolist()
+        return {'tgt_match_match_ext_loss': m[10], 'tgt_match_loss': m[11], 'adv_init_loss': t[6], 'adv_motion_prior_loss': t[5],
+                'adv_coll_veh_loss': t[1], 'adv_coll_veh_plan_loss': t[7], 'adv_coll_env_loss': t[3], 'adv_adv_crash_loss': t[9],
+                'adv_loss': t[0]}
+
+
 class SolLoop(_DeviceLoop):
     """Device-resident form of utils/sol_optim.py:68-112: the target (node 0 of every scene, latent initialised at its prior
     mean) avoids collisions (AvoidCollLoss, single_veh_idx=0, buffer 0.5) over `future_len` steps while every other agent
@@ -410,9 +510,12 @@ def run_adv_gen_optim(cur_z, lr, loss_weights, model, scene_graph, map_env, map_
     over its tape (strive_decode_bwd with two seeds), which yields exactly the same gradients.  fused=True (default) runs the
     device-resident AdvLoop; fused=False the same iteration through the drop-in modules + autograd + torch.optim.Adam."""
     from .losses import TgtMatchingLoss, AdvGenLoss
-    if planner_name != 'ego':
-        raise RuntimeError('strive_b200: only planner="ego" (open-loop replay) is supported; the closed-loop rule-based planner '
-                           '(adv_gen_optim.py:133-139) is CPU host code outside the scope of this port')
+    if planner_name not in ('ego', 'hardcode'):
+        raise RuntimeError('strive_b200: planner_name must be "ego" (open-loop replay) or "hardcode" (closed loop, adv_gen_optim.py:98-104)')
+    if planner_name == 'hardcode':
+        return _run_adv_gen_closed_loop(cur_z, lr, loss_weights, model, scene_graph, map_env, map_idx, num_iters, embed_info, tgt_prior_distrib,
+                                        other_prior_distrib, feasibility_time, feasibility_infront_min, planner, planner_viz_out, attack_agt_idx,
+                                        future_len, veh_coll_buffer, log, debug, fused)
     NA = cur_z.size(0)
     dev = cur_z.device
     ego_mask = _ego_mask(scene_graph, NA, dev)
@@ -476,6 +579,89 @@ def run_adv_gen_optim(cur_z, lr, loss_weights, model, scene_graph, map_env, map_
     ld = adv_loss(nrm.unnormalize(final['future_pred']), nrm.unnormalize(final_traj[ego_inds, 0]), cur_z[~ego_mask].clone().detach(),
                   other_prior_distrib, return_mins=True)
     min_agt = ld['min_agt'] + ego_inds.cpu().numpy()
+    return cur_z, final_traj, final, min_agt, ld['min_t']
+
+
+def _run_adv_gen_closed_loop(cur_z, lr, loss_weights, model, scene_graph, map_env, map_idx, num_iters, embed_info, tgt_prior_distrib,
+                             other_prior_distrib, feasibility_time, feasibility_infront_min, planner, planner_viz_out, attack_agt_idx,
+                             future_len, veh_coll_buffer, log, debug, fused):
+    """planner_name == 'hardcode' (adv_gen_optim.py:85-104, 133-154, 186-207): `planner` is any object with the reference planner's
+    reset(init_state, veh_att, batch, B, map_idx) / rollout(agent_obs, agent_t, agent_ptr, planner_t, control_all=False[, viz=]) calls
+    (src/planners/hardcode_goalcond_nusc.py:109,178); it runs on the host as in the reference."""
+    from .losses import TgtMatchingLoss, AdvGenLoss
+    if planner is None:
+        raise RuntimeError('strive_b200: planner_name="hardcode" needs a planner object')
+    NA = cur_z.size(0)
+    dev = cur_z.device
+    B = int(map_idx.size(0))
+    ego_mask = _ego_mask(scene_graph, NA, dev)
+    ego_inds = scene_graph.ptr[:-1].long()
+    if attack_agt_idx is not None:
+        attack_agt_idx = torch.as_tensor(attack_agt_idx, device=dev).long() + ego_inds
+    if future_len is None:
+        future_len = model.FT
+    nrm = model.get_normalizer()
+    lw_un = model.get_att_normalizer().unnormalize(scene_graph.lw)
+    planner.reset(nrm.unnormalize(scene_graph.past_gt[:, -1, :]), lw_un, scene_graph.batch, B, map_idx)        # :85-89
+    adv_loss = AdvGenLoss(loss_weights, lw_un, map_idx[scene_graph.batch], map_env, cur_z[~ego_mask].clone().detach(), scene_graph.ptr,
+                          veh_coll_buffer=veh_coll_buffer, crash_loss_min_time=feasibility_time, crash_loss_min_infront=feasibility_infront_min)
+    atk = None
+    if attack_agt_idx is not None:
+        atk = torch.zeros(NA, dtype=torch.int32, device=dev)
+        atk[attack_agt_idx] = 1
+    prior = (_full_rows(NA, ego_mask, tgt_prior_distrib[0], other_prior_distrib[0]),
+             _full_rows(NA, ego_mask, tgt_prior_distrib[1], other_prior_distrib[1]))
+    loop = AdvClosedLoop(model, scene_graph, map_idx, map_env, embed_info, cur_z, planner, loss_weights, lr, future_len, prior,
+                         veh_coll_buffer=veh_coll_buffer, crash_min_t=feasibility_time, crash_min_infront=feasibility_infront_min, attack_mask=atk)
+    if fused:
+        for it in range(num_iters):
+            loop.step()
+            if debug is not None and it == 0:
+                gt, go = loop.grads()
+                debug.update(g_tgt=gt.clone(), g_other=go.clone())
+            if log is not None:
+                log(it, loop.log_dict())
+        cur_z = loop.z.clone()
+    else:
+        # the same iteration through the drop-in modules + autograd (AdvGenLoss with a differentiable tgt_traj)
+        tgt_z = cur_z[ego_mask].clone().detach().requires_grad_(True)
+        other_z = cur_z[~ego_mask].clone().detach().requires_grad_(True)
+        opt = torch.optim.Adam([tgt_z, other_z], lr=lr)
+        tgt_loss = TgtMatchingLoss(loss_weights)
+        for it in range(num_iters):
+            opt.zero_grad()
+            z_all = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach()).requires_grad_(True)
+            fut = model.decode_embedding(z_all, embed_info, scene_graph, map_idx, map_env, nfuture=future_len)['future_pred']
+            loop.traj.copy_(fut.detach())
+            loop.ev_fwd.record()
+            planner_fut = loop.plan()
+            fut_un = nrm.unnormalize(fut)
+            ld_t = tgt_loss(fut_un[ego_mask], nrm.unnormalize(planner_fut), tgt_z, tgt_prior_distrib)
+            ld_a = adv_loss(fut_un, fut_un[ego_mask], other_z, other_prior_distrib, attack_agt_idx=attack_agt_idx)
+            g_t = torch.autograd.grad(ld_t['loss'], z_all, retain_graph=True)[0]
+            g_a, g_o = torch.autograd.grad(ld_a['loss'], [z_all, other_z])
+            tgt_z.grad = g_t[ego_mask]
+            other_z.grad = g_a[~ego_mask] + g_o
+            if debug is not None and it == 0:
+                debug.update(g_tgt=tgt_z.grad.detach().clone(), g_other=other_z.grad.detach().clone())
+            if log is not None:
+                d = {'tgt_match_' + k: float(torch.mean(v)) for k, v in ld_t.items()}
+                d.update({'adv_' + k: float(torch.mean(v)) for k, v in ld_a.items()})
+                log(it, d)
+            opt.step()
+        cur_z = collate_tgt_other_z(scene_graph, tgt_z.detach(), other_z.detach())
+    with torch.no_grad():
+        final = model.decode_embedding(cur_z, embed_info, scene_graph, map_idx, map_env, nfuture=future_len)
+    loop.traj.copy_(final['future_pred'])
+    loop.ev_fwd.record()
+    planner_fut = loop.plan(final=True, viz=planner_viz_out)                         # :186-193, the planner's true reaction
+    final_traj = final['future_pred'].unsqueeze(1).clone().detach()
+    final_traj[ego_inds, 0] = planner_fut
+    ld = adv_loss(nrm.unnormalize(final['future_pred']), nrm.unnormalize(final_traj[ego_inds, 0]), cur_z[~ego_mask].clone().detach(),
+                  other_prior_distrib, return_mins=True)
+    min_agt = ld['min_agt'] + ego_inds.cpu().numpy()
+    if debug is not None:
+        debug.update(planner_ms=loop.planner_ms, iter_ms=loop.iter_ms)
     return cur_z, final_traj, final, min_agt, ld['min_t']
 
 

@@ -86,3 +86,41 @@ def init_case(FT=6):
     vis = (torch.rand(NA, FT, generator=g) > 0.25).float()
     vis[:, 0] = 1.0
     return sc, init_traj, vis
+
+
+class StubPlanner(object):
+    """Deterministic numpy stand-in for the reference's rule-based planner with its call surface (reset / rollout,
+    src/planners/hardcode_goalcond_nusc.py:109,178): the ego keeps its initial heading and speed and brakes while any other
+    agent's PREDICTED position lies in a corridor ahead of it -- so its answer reacts smoothly to the latents being optimised,
+    which is all the closed-loop adversarial loop needs from a planner.  Used unchanged by oracle/gen_golden_r2.py (with the
+    unmodified reference loop) and by the GPU tests (with the strive_b200 loop)."""
+
+    def __init__(self):
+        self.calls = 0
+
+    def reset(self, init_state, vehicle_atts, batch_mask, batch_size, map_idx, ego_idx=0):
+        st = init_state.detach().cpu().numpy()
+        bm = batch_mask.detach().cpu().numpy()
+        self.B = int(batch_size)
+        self.ego = np.stack([st[bm == b][ego_idx] for b in range(self.B)])          # (B,6) x,y,hx,hy,s,hdot
+
+    def rollout(self, agent_obs, agent_t, agent_ptr, planner_t, init_state=None, control_all=False, viz=None, coll_t=None):
+        self.calls += 1
+        obs = np.asarray(agent_obs, dtype=np.float64)                                # (NA-B, T, 4) unnormalised
+        T = obs.shape[1]
+        dt = float(planner_t[0])
+        out = np.zeros((self.B, T, 4))
+        for b in range(self.B):
+            x, y, hx, hy, s, _ = [float(v) for v in self.ego[b]]
+            others = obs[int(agent_ptr[b]):int(agent_ptr[b + 1])]
+            for t in range(T):
+                brake = 0.0
+                for o in others:
+                    dx, dy = o[t, 0] - x, o[t, 1] - y
+                    ahead, side = dx * hx + dy * hy, -dx * hy + dy * hx
+                    # smooth proximity: 1 when the agent sits right in front, fading over 15 m ahead / 2.5 m to the side
+                    brake = max(brake, float(np.exp(-max(ahead, 0.0) / 15.0 - (side / 2.5) ** 2)) if ahead > -2.0 else 0.0)
+                s = max(0.0, s - 3.0 * dt * brake)
+                x, y = x + hx * s * dt, y + hy * s * dt
+                out[b, t] = [x, y, hx, hy]
+        return torch.from_numpy(out).float()

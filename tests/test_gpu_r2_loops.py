@@ -220,3 +220,79 @@ def test_fused_init_loop_equals_autograd_path():
     dl = np.abs(res[True][1] / res[False][1] - 1.0).max()
     diag('init loop fused vs autograd path: |z| diff after 3 iterations %.3e, loss rel diff %.2e (losses %s)' % (d, dl, np.array2string(res[True][1], precision=4)))
     assert dl < 1e-4 and d < 5e-3
+
+
+@pytest.mark.parametrize('fused', [True, False])
+def test_closed_loop_adv_vs_reference_with_stub_planner(fused):
+    """planner_name='hardcode' (closed loop, adv_gen_optim.py:98-154): the CPU planner (tests.common.StubPlanner, the same object
+    the fixture generator handed to the UNMODIFIED reference loop) is re-run every iteration on the current prediction, the
+    adversarial loss attacks the model's own prediction of the target and its gradient reaches the other latents through the
+    target row (adv_own_pred).  fused=True: AdvClosedLoop (planner overlapped with the adversarial sweep); False: autograd path."""
+    from strive_b200.optim import run_adv_gen_optim
+    from tests.common import StubPlanner
+    dev, model, env = ctx()
+    g = golden('closed_loop')
+    sc, ego, FT = loops_case(g)
+    iters, lr = int(g['iters']), float(g['lr'])
+    graph = _graph_with_future(sc, ego, FT, dev)
+    graph.past_gt = graph.past
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev)}
+    planner = StubPlanner()
+    logs, dbg = [], {}
+    model.FT = FT
+    try:
+        z, traj, out, min_agt, min_t = run_adv_gen_optim(sc['z'].to(dev), lr, ADV_W, model, graph, env, sc['map_idx'].to(dev), iters, embed, 'hardcode',
+                                                          (sc['prior_mu'][ego].to(dev), sc['prior_var'][ego].to(dev)),
+                                                          (sc['prior_mu'][~ego].to(dev), sc['prior_var'][~ego].to(dev)), 1, -0.5, planner=planner,
+                                                          future_len=FT, veh_coll_buffer=0.1, log=lambda it, d: logs.append(d), debug=dbg, fused=fused)
+    finally:
+        model.FT = 20
+    assert planner.calls == iters + 1                      # once per iteration + the final true reaction (:186-193)
+    keys = ['tgt_match_loss', 'tgt_match_match_ext_loss', 'adv_loss', 'adv_motion_prior_loss', 'adv_coll_veh_loss', 'adv_coll_veh_plan_loss',
+            'adv_coll_env_loss', 'adv_adv_crash_loss']
+    worst = {}
+    for k in keys:
+        mine = np.array([l[k] for l in logs])
+        ref = g['t_' + k]
+        worst[k] = float(np.abs(mine - ref).max() / max(1e-3, np.abs(ref).max()))
+    dz = np.abs(z.cpu().numpy() - g['z'])
+    diag('closed loop [fused=%s] vs reference: tgt_match gpu %s ref %s | adv gpu %s ref %s | per-term worst rel err %s | |z| err max %.2e median %.2e | '
+         'planner %.1f ms of %.1f ms host time per iteration | mins %s %s vs %s %s' % (
+             fused, np.array2string(np.array([l['tgt_match_loss'] for l in logs]), precision=3), np.array2string(g['t_tgt_match_loss'], precision=3),
+             np.array2string(np.array([l['adv_loss'] for l in logs]), precision=2), np.array2string(g['t_adv_loss'], precision=2),
+             ' '.join('%s=%.1e' % kv for kv in worst.items()), dz.max(), float(np.median(dz)), dbg.get('planner_ms', 0.0) / (iters + 1),
+             dbg.get('iter_ms', 0.0) / max(1, iters), list(min_agt), list(min_t), list(g['min_agt']), list(g['min_t'])))
+    assert max(worst.values()) < 5e-3
+    assert float(np.median(dz)) < 2e-3 and dz.max() <= 2 * lr * iters
+    assert list(min_agt) == list(g['min_agt']) and list(min_t) == list(g['min_t'])
+    assert tuple(traj.shape) == g['traj'].shape
+    # ego rows of the returned scenario = the planner's true reaction to the final prediction
+    assert np.abs(traj[ego.to(dev), 0].cpu().numpy() - g['traj'][ego.numpy(), 0]).max() < 5e-3
+
+
+def test_closed_loop_fused_gradients_equal_autograd_path():
+    """Iteration-0 gradients of AdvClosedLoop (adv_own_pred folded into the target rows by the loss kernel, two sweeps) against
+    AdvGenLoss called with a differentiable tgt_traj under autograd."""
+    from strive_b200.optim import run_adv_gen_optim
+    from tests.common import StubPlanner
+    dev, model, env = ctx()
+    g = golden('closed_loop')
+    sc, ego, FT = loops_case(g)
+    graph = _graph_with_future(sc, ego, FT, dev)
+    graph.past_gt = graph.past
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev)}
+    res = {}
+    model.FT = FT
+    try:
+        for fused in (True, False):
+            dbg = {}
+            run_adv_gen_optim(sc['z'].to(dev), 0.05, ADV_W, model, graph, env, sc['map_idx'].to(dev), 1, embed, 'hardcode',
+                              (sc['prior_mu'][ego].to(dev), sc['prior_var'][ego].to(dev)), (sc['prior_mu'][~ego].to(dev), sc['prior_var'][~ego].to(dev)),
+                              1, -0.5, planner=StubPlanner(), future_len=FT, veh_coll_buffer=0.1, debug=dbg, fused=fused)
+            res[fused] = dbg
+    finally:
+        model.FT = 20
+    e_t = (res[True]['g_tgt'] - res[False]['g_tgt']).abs().max().item() / res[False]['g_tgt'].abs().max().item()
+    e_o = (res[True]['g_other'] - res[False]['g_other']).abs().max().item() / res[False]['g_other'].abs().max().item()
+    diag('closed loop fused vs autograd: iteration-0 gradient rel diff tgt %.2e other %.2e' % (e_t, e_o))
+    assert e_t < 1e-4 and e_o < 1e-4
