@@ -107,3 +107,36 @@ def test_two_rank_gloo_sharded_refine_equals_unsharded():
     assert sorted(g for p in got['assign'] for g in p) == [0, 1, 2, 3] and all(len(p) > 0 for p in got['assign'])
     err = (got['z'] - ref).abs().max().item()
     assert err < 1e-9, err
+
+
+def _bucket_rank(rank, world, port, out_path):
+    """world_size-2 gloo: data-parallel gradient exchange of the training step (strive_b200.train.FlatBucket)."""
+    import torch.distributed as dist
+    from strive_b200.train import FlatBucket
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(5)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.ReLU(), torch.nn.Linear(8, 3))
+    bucket = FlatBucket(net.parameters())
+    assert bucket.numel == sum(p.numel() for p in net.parameters())
+    x = torch.randn(4, 6, generator=torch.Generator().manual_seed(100 + rank))        # every rank its own batch
+    bucket.zero_grad()
+    net(x).pow(2).sum().backward()
+    local = bucket.flat_g.clone()
+    bucket.all_reduce_mean()
+    torch.save({'local': local, 'mean': bucket.flat_g.clone(), 'first_param_is_view': net[0].weight.data_ptr() == bucket.flat_p.data_ptr()},
+               out_path + '.%d' % rank)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_flat_gradient_bucket_all_reduce():
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, 'g.pt')
+        mp.spawn(_bucket_rank, args=(2, _free_port(), out), nprocs=2, join=True)
+        r0, r1 = torch.load(out + '.0'), torch.load(out + '.1')
+    want = (r0['local'] + r1['local']) / 2
+    assert (r0['local'] - r1['local']).abs().max() > 1e-3                 # the ranks really saw different batches
+    assert torch.allclose(r0['mean'], want, atol=1e-7) and torch.equal(r0['mean'], r1['mean'])
+    assert r0['first_param_is_view']
