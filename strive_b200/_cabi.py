@@ -163,9 +163,12 @@ def profile_report():
     return out
 
 
-def set_edge_impl(mma):
-    """True (default): mma.sync TF32 edge kernels; False: fp32 SIMT edge kernels (A/B verification)."""
-    lib().strive_edge_set_impl(int(bool(mma)))
+def set_edge_impl(impl):
+    """Edge-phase kernels of the rollout: 2 / True (default) = tcgen05 forward (scenes up to 129 agents) + mma.sync backward,
+    1 = mma.sync TF32 kernels both ways, 0 / False = fp32 SIMT kernels (A/B verification)."""
+    if isinstance(impl, bool):
+        impl = 2 if impl else 0
+    lib().strive_edge_set_impl(int(impl))
 
 
 def set_mapenc_impl(tensor_core):

@@ -1,0 +1,308 @@
+// Edge phase of the decoder GNN on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+// Included by rollout.cu after edge_mma.cuh (same translation unit: StepArgs / ModelDev / Tape, tc.cuh, wpipe.cuh).
+//
+// reference: src/models/interaction_net.py:139-184 (message(): edge_mlp on [x_i, x_j, sem_i, sem_j, rel], max aggregation at
+// the target :92, zeros for edge-less nodes :187-188); MLP = Linear, LayerNorm, ReLU, Linear, LayerNorm, ReLU, Linear
+// (models/common.py:26-44).
+//
+// Tile = 128 EDGES (rows) x the 128 / 64 output columns of the two dense layers.  The first layer is factorised (rollout.cu:
+// h1 = P_i + Q_j + W_rel rel) and costs 6 flops per element, so the rows are built by the CUDA cores straight into the
+// canonical K-major shared-memory operand layout; the two dense contractions
+//     D1[128 x 128] = relu(LN(h1)) . W3^T        D2[128 x 64] = relu(LN(D1 + b)) . W6^T
+// run as tcgen05.mma kind::f16 with the bf16 hi/lo split of BOTH operands (a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo, dropped
+// a_lo.w_lo ~ 2^-18: the same fidelity scheme as the map encoder), accumulating in fp32 in TMEM.  A thread owns HALF a row
+// (64 columns) of the tile in every element-wise phase -- tcgen05.ld 32x32b hands lane l of warp w row 32 (w % 4) + l, and warps
+// w, w + 4 read the two column halves of the same rows -- so LayerNorm needs one 2-float exchange per row instead of shuffles
+// and no activation ever round-trips through shared memory except as the next MMA's operand.
+// The edge list of a scene is padded so that a target's edges never straddle a tile: slot = round_up(n - 1, 8) rows per target,
+// 128 / slot targets per tile; the max / arg-max over a target's edges is then a tile-local scan of the D2 tile in shared memory.
+// Edge-MLP weights (W3, W6 hi / lo in canonical layout, 96 KB) stay resident in shared memory; one CTA per SM, persistent over
+// the tiles.  Scenes with more than 129 agents keep the mma.sync kernels (edge_mma.cuh).
+#pragma once
+
+#define ET_THREADS 256
+#define ET_W3_BYTES 32768                 // 128 (n) x 128 (k) bf16, canonical K-major: ((k>>3)*16 + (n>>3))*128 + (n&7)*16 + (k&7)*2
+#define ET_W6_BYTES 16384                 // 64 (n) x 128 (k)
+#define ET_W3H_OFF 0
+#define ET_W3L_OFF (ET_W3_BYTES)
+#define ET_W6H_OFF (2 * ET_W3_BYTES)
+#define ET_W6L_OFF (2 * ET_W3_BYTES + ET_W6_BYTES)
+#define ET_PACK_BYTES (2 * ET_W3_BYTES + 2 * ET_W6_BYTES)      // 98304
+#define ET_A_BYTES 32768                  // one precision of a 128 x 128 activation tile
+#define ET_MB_LD 68                       // row pitch (floats) of the D2 staging tile: conflict-free float4 stores at 272 B
+#define ET_SMEM (ET_PACK_BYTES + 2 * ET_A_BYTES)
+#define ET_MAX_N 129                      // scenes up to 129 agents (128 edges per target = one tile)
+
+// W: native [N][K] row-major fp32 (nn.Linear weight) -> bf16 hi and lo parts in the canonical K-major operand layout
+__global__ void edge_tc_pack_kernel(const float* __restrict__ W, int N, int K, uint8_t* __restrict__ out_hi, uint8_t* __restrict__ out_lo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * K) return;
+  const int n = idx / K, k = idx % K;
+  const float w = W[idx];
+  const __nv_bfloat16 h = __float2bfloat16_rn(w);
+  const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+  const size_t off = ((size_t)((k >> 3) * (N / 8) + (n >> 3)) * 8 + (n & 7)) * 16 + (size_t)(k & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(out_hi + off) = h;
+  *reinterpret_cast<__nv_bfloat16*>(out_lo + off) = l;
+}
+
+// Tile table of one scene batch: tiles[2 q] = scene, tiles[2 q + 1] = first (local) target of tile q; *ntiles = number of tiles.
+// One block; scenes are scanned in chunks of blockDim.x.
+__device__ __forceinline__ int et_slot(int n) { const int ne = n - 1; return ne <= 8 ? 8 : ((ne + 7) & ~7); }
+__global__ void __launch_bounds__(1024) edge_tc_tiles_kernel(const int32_t* __restrict__ ptr, int S, int32_t* __restrict__ tiles,
+                                                             int32_t* __restrict__ ntiles) {
+  __shared__ int scan[1024];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int s0 = 0; s0 < S; s0 += 1024) {
+    const int s = s0 + threadIdx.x;
+    int n = 0, tps = 1, cnt = 0;
+    if (s < S) {
+      n = ptr[s + 1] - ptr[s];
+      tps = max(1, 128 / et_slot(n));                 // (scenes above ET_MAX_N agents never reach this path)
+      cnt = (n + tps - 1) / tps;
+    }
+    scan[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const int v = threadIdx.x >= o ? scan[threadIdx.x - o] : 0;
+      __syncthreads();
+      scan[threadIdx.x] += v;
+      __syncthreads();
+    }
+    const int off = base + scan[threadIdx.x] - cnt;
+    for (int k = 0; k < cnt; k++) {
+      tiles[2 * (off + k)] = s;
+      tiles[2 * (off + k) + 1] = k * tps;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) base += scan[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *ntiles = base;
+}
+
+struct EtRow {
+  int i, j, lj;        // global target / source agent, local source index
+  bool valid;
+};
+
+// (scene, first target) of tile q -> the edge this thread's row stands for
+__device__ __forceinline__ EtRow et_row(const StepArgs& a, const int32_t* __restrict__ tiles, int q, int row, int& p0, int& n, int& slot, int& first) {
+  const int s = tiles[2 * q];
+  first = tiles[2 * q + 1];
+  p0 = a.ptr[s];
+  n = a.ptr[s + 1] - p0;
+  slot = et_slot(n);
+  const int k = row / slot, e = row - k * slot;
+  const int li = first + k;
+  EtRow r;
+  r.valid = (k < 128 / slot) && (li < n) && (e < n - 1);
+  const int lis = r.valid ? li : 0, es = r.valid ? e : 0;
+  r.lj = es + (es >= lis ? 1 : 0);
+  r.i = p0 + lis;
+  r.j = r.valid ? p0 + r.lj : r.i;
+  return r;
+}
+
+// v (this thread's 64 columns of a 128-wide row) <- relu(LayerNorm(v) * gam + bet); the other half of the row lives in the
+// thread 128 places away: partial sums meet in s_part.  Two-pass statistics as models/common.py's nn.LayerNorm (eps 1e-5).
+__device__ __forceinline__ void et_ln_relu(float (&v)[64], const float* __restrict__ s_gam, const float* __restrict__ s_bet, float* s_part, int row,
+                                           int half) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 64; c++) s += v[c];
+  s_part[half * 128 + row] = s;
+  __syncthreads();
+  const float mean = (s_part[row] + s_part[128 + row]) * (1.0f / 128.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < 64; c++) { const float d = v[c] - mean; q = fmaf(d, d, q); }
+  s_part[256 + half * 128 + row] = q;
+  __syncthreads();
+  const float rstd = 1.0f / sqrtf((s_part[256 + row] + s_part[384 + row]) * (1.0f / 128.0f) + LN_EPS);
+#pragma unroll
+  for (int c = 0; c < 64; c++) v[c] = fmaxf(fmaf((v[c] - mean) * rstd, s_gam[half * 64 + c], s_bet[half * 64 + c]), 0.f);
+}
+
+// this thread's 64 columns -> bf16 hi / lo operand rows (canonical K-major, 128 rows): 8 k-groups of 16 bytes each
+__device__ __forceinline__ void et_store_operand(const float (&v)[64], bool valid, uint8_t* sA, int row, int half) {
+#pragma unroll
+  for (int g = 0; g < 8; g++) {
+    uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = make_uint4(0u, 0u, 0u, 0u);
+    if (valid) {
+      tc::split_pack2(v[8 * g + 0], v[8 * g + 1], hi.x, lo.x);
+      tc::split_pack2(v[8 * g + 2], v[8 * g + 3], hi.y, lo.y);
+      tc::split_pack2(v[8 * g + 4], v[8 * g + 5], hi.z, lo.z);
+      tc::split_pack2(v[8 * g + 6], v[8 * g + 7], hi.w, lo.w);
+    }
+    const int unit = ((half * 8 + g) * 16 + (row >> 3)) * 8 + (row & 7);
+    *reinterpret_cast<uint4*>(sA + (size_t)unit * 16) = hi;
+    *reinterpret_cast<uint4*>(sA + ET_A_BYTES + (size_t)unit * 16) = lo;
+  }
+}
+
+// D[tmem] = A (128 x 128, hi/lo in sA) . B^T (N x 128, hi/lo packs): 8 K steps x 3 split terms, issued by one thread
+__device__ __forceinline__ void et_issue_gemm(uint32_t d_tmem, uint32_t sA_addr, uint32_t sBh_addr, uint32_t sBl_addr, int N, uint64_t* bar) {
+  const uint32_t idesc = tc::idesc_bf16_f32(128, N);
+  const uint32_t lbo_b = (uint32_t)(N / 8) * 128u;
+  const uint32_t a_hi = tc::desc_hi(128), b_hi = tc::desc_hi(128);
+  const uint32_t ah0 = tc::desc_lo(sA_addr, 2048), al0 = tc::desc_lo(sA_addr + ET_A_BYTES, 2048);
+  const uint32_t bh0 = tc::desc_lo(sBh_addr, lbo_b), bl0 = tc::desc_lo(sBl_addr, lbo_b);
+#pragma unroll
+  for (int ks = 0; ks < 8; ks++) {
+    const uint64_t ah = tc::desc_make(ah0 + ((ks * 2 * 2048) >> 4), a_hi), al = tc::desc_make(al0 + ((ks * 2 * 2048) >> 4), a_hi);
+    const uint64_t bh = tc::desc_make(bh0 + ((ks * 2 * lbo_b) >> 4), b_hi), bl = tc::desc_make(bl0 + ((ks * 2 * lbo_b) >> 4), b_hi);
+    tc::mma_bf16(d_tmem, ah, bh, idesc, ks > 0 ? 1u : 0u);
+    tc::mma_bf16(d_tmem, al, bh, idesc, 1u);
+    tc::mma_bf16(d_tmem, ah, bl, idesc, 1u);
+  }
+  tc::mma_commit(bar);
+}
+
+__global__ void __launch_bounds__(ET_THREADS, 1) edge_fwd_tc_kernel(ModelDev M, StepArgs a, const uint8_t* __restrict__ pack, const int32_t* __restrict__ tiles,
+                                                                    const int32_t* __restrict__ ntiles_p) {
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT();
+  extern __shared__ __align__(1024) uint8_t esm[];
+  uint8_t* sW = esm;
+  uint8_t* sA = esm + ET_PACK_BYTES;
+  float* mbuf = reinterpret_cast<float*>(sA);                     // D2 staging tile: aliases the operand buffer once the MMAs are done
+  __shared__ __align__(8) uint64_t bar_w, bar_mma;
+  __shared__ uint32_t tmem_base;
+  __shared__ float s_g1[128], s_b1[128], s_bias3[128], s_g4[128], s_b4[128], s_bias6[64];
+  __shared__ __align__(16) float s_wrel[4 * 128];
+  __shared__ float s_part[512];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+  const int ntiles = *ntiles_p;
+  if ((int)blockIdx.x >= ntiles) return;                           // the host sizes the grid from an upper bound of the tile count
+  if (tid < 128) {
+    s_g1[tid] = M.seg[S_E_LN1_G][tid]; s_b1[tid] = M.seg[S_E_LN1_B][tid]; s_bias3[tid] = M.seg[S_E3_B][tid];
+    s_g4[tid] = M.seg[S_E_LN4_G][tid]; s_b4[tid] = M.seg[S_E_LN4_B][tid];
+    if (tid < 64) s_bias6[tid] = M.seg[S_E6_B][tid];
+  }
+  for (int k = tid; k < 512; k += ET_THREADS) s_wrel[k] = M.seg[S_E0_T_REL][k];
+  if (tid == 0) {
+    tc::mbar_init(&bar_w, 1);
+    tc::mbar_init(&bar_mma, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(&tmem_base, 256);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  if (tid == 0) {
+    wp_mbar_expect_tx(&bar_w, ET_PACK_BYTES);
+    for (uint32_t off = 0; off < ET_PACK_BYTES; off += 32768u) wp_bulk_g2s(sW + off, pack + off, 32768u, &bar_w);
+  }
+  const uint32_t tm = tmem_base;
+  const uint32_t t_row = tm + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sW);
+  const int NA = a.NA;
+  const float* posg = a.tp.pos + (size_t)a.t * NA * 4;
+  uint32_t ph = 0;
+  bool w_ready = false;
+  for (int q = blockIdx.x; q < ntiles; q += gridDim.x) {
+    int p0, n, slot, first;
+    const EtRow r = et_row(a, tiles, q, row, p0, n, slot, first);
+    // ---- phase A: h1 = P_i + Q_j + W_rel rel (same fmaf order as the SIMT kernel), LN, ReLU -> operand tile
+    float v[64];
+    {
+      float pi[4], pj[4], rel[4];
+      const float4 a4 = __ldg(reinterpret_cast<const float4*>(posg + (size_t)r.i * 4));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(posg + (size_t)r.j * 4));
+      pi[0] = a4.x; pi[1] = a4.y; pi[2] = a4.z; pi[3] = a4.w;
+      pj[0] = b4.x; pj[1] = b4.y; pj[2] = b4.z; pj[3] = b4.w;
+      t2f_fwd(pi, pj, rel);
+#pragma unroll
+      for (int d = 0; d < 4; d++)
+        if (isnan(rel[d])) rel[d] = 0.f;                            // interaction_net.py:162
+      const float4* Pi = reinterpret_cast<const float4*>(a.tp.P + ((size_t)a.t * NA + r.i) * 128 + half * 64);
+      const float4* Qj = reinterpret_cast<const float4*>(a.tp.Q + ((size_t)a.t * NA + r.j) * 128 + half * 64);
+#pragma unroll
+      for (int c4 = 0; c4 < 16; c4++) {
+        const float4 p = __ldg(Pi + c4), qv = __ldg(Qj + c4);
+        float x[4] = {p.x + qv.x, p.y + qv.y, p.z + qv.z, p.w + qv.w};
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+          const float4 w = *reinterpret_cast<const float4*>(&s_wrel[d * 128 + half * 64 + c4 * 4]);
+          x[0] = fmaf(rel[d], w.x, x[0]); x[1] = fmaf(rel[d], w.y, x[1]); x[2] = fmaf(rel[d], w.z, x[2]); x[3] = fmaf(rel[d], w.w, x[3]);
+        }
+        v[c4 * 4] = x[0]; v[c4 * 4 + 1] = x[1]; v[c4 * 4 + 2] = x[2]; v[c4 * 4 + 3] = x[3];
+      }
+    }
+    et_ln_relu(v, s_g1, s_b1, s_part, row, half);
+    et_store_operand(v, r.valid, sA, row, half);
+    tc::fence_async_smem();
+    __syncthreads();
+    if (!w_ready) { wp_wait(&bar_w, 0); w_ready = true; }
+    if (tid == 0) {
+      tc::tc_fence_after();
+      et_issue_gemm(tm, sA_addr, sW_addr + ET_W3H_OFF, sW_addr + ET_W3L_OFF, 128, &bar_mma);
+    }
+    tc::mbar_wait(&bar_mma, ph);
+    ph ^= 1u;
+    tc::tc_fence_after();
+    // ---- phase B: D1 + bias, LN, ReLU -> operand tile (the first GEMM has completed: its operand buffer is free)
+#pragma unroll
+    for (int cc = 0; cc < 4; cc++) {
+      float t16[16];
+      tc::tmem_ld16(t_row + half * 64 + cc * 16, t16);
+#pragma unroll
+      for (int c = 0; c < 16; c++) v[cc * 16 + c] = t16[c] + s_bias3[half * 64 + cc * 16 + c];
+    }
+    et_ln_relu(v, s_g4, s_b4, s_part, row, half);
+    et_store_operand(v, r.valid, sA, row, half);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      et_issue_gemm(tm + 128, sA_addr, sW_addr + ET_W6H_OFF, sW_addr + ET_W6L_OFF, 64, &bar_mma);
+    }
+    tc::mbar_wait(&bar_mma, ph);
+    ph ^= 1u;
+    tc::tc_fence_after();
+    // ---- phase C: D2 + bias -> staging tile; max / arg-max over each target's rows (smaller source index wins ties, NaN never wins)
+#pragma unroll
+    for (int cc = 0; cc < 2; cc++) {
+      float t16[16];
+      tc::tmem_ld16(t_row + 128 + half * 32 + cc * 16, t16);
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        const int col = half * 32 + cc * 16 + c;
+        *reinterpret_cast<float4*>(mbuf + (size_t)row * ET_MB_LD + col) =
+            make_float4(t16[c] + s_bias6[col], t16[c + 1] + s_bias6[col + 1], t16[c + 2] + s_bias6[col + 2], t16[c + 3] + s_bias6[col + 3]);
+      }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    {
+      const int ch = tid & 63;
+      const int tps = 128 / slot;
+      for (int k = tid >> 6; k < tps; k += ET_THREADS / 64) {
+        const int li = first + k;
+        if (li >= n) break;
+        float best = -INFINITY;
+        int bi = 255;
+        const float* col = mbuf + (size_t)(k * slot) * ET_MB_LD + ch;
+        for (int e = 0; e < n - 1; e++) {
+          const float m = col[(size_t)e * ET_MB_LD];
+          if (m > best) { best = m; bi = e + (e >= li ? 1 : 0); }
+        }
+        a.tp.aggr[((size_t)a.t * NA + p0 + li) * 64 + ch] = bi == 255 ? 0.f : best;
+        a.tp.arg[((size_t)a.t * NA + p0 + li) * 64 + ch] = (uint8_t)bi;
+      }
+    }
+    __syncthreads();                     // the staging tile aliases the operand buffer of the next tile
+  }
+  if (!w_ready) wp_wait(&bar_w, 0);      // never leave with a bulk copy in flight
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    __syncwarp();
+    tc::tmem_dealloc(tm, 256);
+  }
+}

@@ -48,6 +48,8 @@ struct Tape {
   float* dQ;        // [NA][128]
   float* pose;      // [NA][4]  unnormalised crop pose for the map encoder
   int32_t* map_of;  // [NA]
+  int32_t* et_tiles;   // [NA][2] edge-tile table of the tcgen05 edge kernels (edge_tc.cuh): (scene, first local target)
+  int32_t* et_ntiles;  // [1]
   void* mapenc_ws;  // map encoder workspace
   int64_t mapenc_ws_bytes;
 };
@@ -85,6 +87,8 @@ static int64_t tape_carve(Tape* tp, char* base, int NA, int FT) {
   tp->dQ = (float*)take(n * 128 * 4);
   tp->pose = (float*)take(n * 4 * 4);
   tp->map_of = (int32_t*)take(n * 4);
+  tp->et_tiles = (int32_t*)take(n * 2 * 4);
+  tp->et_ntiles = (int32_t*)take(256);
   tp->mapenc_ws_bytes = strive_mapenc_workspace_bytes(NA);
   tp->mapenc_ws = (void*)take((size_t)tp->mapenc_ws_bytes);
   return (int64_t)off;
@@ -1132,6 +1136,7 @@ __global__ void __launch_bounds__(EDGE_WARPS * 32) edge_bwd_kernel(ModelDev M, S
 }
 
 #include "edge_mma.cuh"
+#include "edge_tc.cuh"
 
 // node backward: d_x = d_xupd + dP.W_xi + dQ.W_xj ; back through mlp_in; d_z += ; g_pf <- grad wrt past_feat_t
 __global__ void __launch_bounds__(NODE_THREADS, 2) node_bwd_kernel(ModelDev M, StepArgs a) {
@@ -1256,7 +1261,9 @@ static const size_t SM_GRU_B = SM_PIPE + NODE_WARPS * (6 * GRU_R * LDG + GRU_R *
 static const size_t SM_POST_B = SM_PIPE + NODE_WARPS * (NODE_R * (LDA + LDH) + 3 * NODE_R * LDH) * 4;
 static const size_t SM_NODE_B = SM_PIPE + NODE_WARPS * (NODE_R * (LDA + LDH) + 2 * NODE_R * LDH) * 4;
 
-static int g_edge_impl = 1;   // 1 = mma.sync TF32 edge kernels (default, needs the fragment packs), 0 = fp32 SIMT kernels (A/B verification)
+// 2 = tcgen05 forward (edge_tc.cuh; default; scenes up to ET_MAX_N agents) + mma.sync backward, 1 = mma.sync TF32 kernels both ways
+// (edge_mma.cuh), 0 = fp32 SIMT kernels (A/B verification)
+static int g_edge_impl = 2;
 extern "C" int strive_edge_set_impl(int impl) {
   g_edge_impl = impl;
   return 0;
@@ -1274,14 +1281,14 @@ static int em_grid(int NA) {
   return want < sms ? want : sms;
 }
 
-extern "C" int64_t strive_model_edge_frag_bytes(void) { return EM_FRAG_BYTES; }
+extern "C" int64_t strive_model_edge_frag_bytes(void) { return EM_FRAG_BYTES + ET_PACK_BYTES; }
 
 // Packs the edge-MLP matrices of the model's weight blob into mma.sync fragment order (edge_mma.cuh) inside `buf`
 // (device, 16-byte aligned, strive_model_edge_frag_bytes() bytes, owned by the caller for the lifetime of the model).
 extern "C" int strive_model_set_edge_frags(StriveModel* m, void* buf, int64_t bytes, void* stream_) {
   STRIVE_CHECK(m != nullptr && buf != nullptr, STRIVE_EINVAL, "set_edge_frags: null argument");
-  STRIVE_CHECK(bytes == EM_FRAG_BYTES && ((uintptr_t)buf & 15) == 0, STRIVE_ESIZE, "edge fragment buffer: %lld bytes (need %d, 16-byte aligned)",
-               (long long)bytes, (int)EM_FRAG_BYTES);
+  STRIVE_CHECK(bytes == EM_FRAG_BYTES + ET_PACK_BYTES && ((uintptr_t)buf & 15) == 0, STRIVE_ESIZE, "edge fragment buffer: %lld bytes (need %d, 16-byte aligned)",
+               (long long)bytes, (int)(EM_FRAG_BYTES + ET_PACK_BYTES));
   STRIVE_CHECK(m->seg_size[S_E3_T] == 128 * 128 && m->seg_size[S_E6_T] == 128 * 64 && m->seg_size[S_E6_N] == 64 * 128 && m->seg_size[S_E3_N] == 128 * 128,
                STRIVE_ESIZE, "edge MLP is not 128-128-64");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -1296,6 +1303,11 @@ extern "C" int strive_model_set_edge_frags(StriveModel* m, void* buf, int64_t by
   pack(m->seg[S_E6_N], 64, 128, EM_B6N_OFF, true);
   pack(m->seg[S_E3_N], 128, 128, EM_B3N_OFF, true);
   STRIVE_LAUNCH_CHECK();
+  // tcgen05 operand packs (edge_tc.cuh): native [out][in] matrices -> bf16 hi / lo, canonical K-major
+  uint8_t* et = b + EM_FRAG_BYTES;
+  edge_tc_pack_kernel<<<(128 * 128 + 255) / 256, 256, 0, stream>>>(m->seg[S_E3_N], 128, 128, et + ET_W3H_OFF, et + ET_W3L_OFF);
+  edge_tc_pack_kernel<<<(64 * 128 + 255) / 256, 256, 0, stream>>>(m->seg[S_E6_N], 64, 128, et + ET_W6H_OFF, et + ET_W6L_OFF);
+  STRIVE_LAUNCH_CHECK();
   m->edge_frags = b;
   return 0;
 }
@@ -1306,6 +1318,7 @@ static int set_smem_attrs() {
   STRIVE_CUDA(cudaFuncSetAttribute(edge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_EDGE_B));
   STRIVE_CUDA(cudaFuncSetAttribute(edge_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_FWD_SMEM));
   STRIVE_CUDA(cudaFuncSetAttribute(edge_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_BWD_SMEM));
+  STRIVE_CUDA(cudaFuncSetAttribute(edge_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ET_SMEM));
   STRIVE_CUDA(cudaFuncSetAttribute(node_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE));
   STRIVE_CUDA(cudaFuncSetAttribute(post_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE));
   STRIVE_CUDA(cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GRU_F));
@@ -1344,11 +1357,20 @@ extern "C" int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, co
   KPROF("init_tape", stream, STRIVE_CUDA_LAUNCH(init_tape_kernel, (NA * 64 + 255) / 256, 256, 0, stream, a, sc->past_last, map_feat0, past_feat0, sc->map_idx));
   STRIVE_LAUNCH_CHECK();
   const int node_blocks = (NA + NODE_WARPS * NODE_R - 1) / (NODE_WARPS * NODE_R);
+  const bool edge_tc = g_edge_impl == 2 && m->edge_frags != nullptr && sc->max_scene_agents <= ET_MAX_N;
+  if (edge_tc) {
+    KPROF("edge_tiles", stream, edge_tc_tiles_kernel<<<1, 1024, 0, stream>>>(sc->ptr, sc->num_scenes, a.tp.et_tiles, a.tp.et_ntiles));
+    STRIVE_LAUNCH_CHECK();
+  }
   for (int t = 0; t < ft; t++) {
     a.t = t;
     KPROF("node_fwd", stream, STRIVE_CUDA_LAUNCH(node_fwd_kernel, node_blocks, NODE_THREADS, SM_NODE, stream, M, a));
     STRIVE_LAUNCH_CHECK();
-    if (g_edge_impl != 0 && m->edge_frags != nullptr) {
+    if (edge_tc) {
+      const int grid = NA < em_grid(NA * EM_WARPS) ? NA : em_grid(NA * EM_WARPS);      // min(#SMs, upper bound of the tile count)
+      KPROF("edge_fwd", stream, STRIVE_CUDA_LAUNCH(edge_fwd_tc_kernel, grid, ET_THREADS, ET_SMEM, stream, M, a, m->edge_frags + EM_FRAG_BYTES,
+                                                   (const int32_t*)a.tp.et_tiles, (const int32_t*)a.tp.et_ntiles));
+    } else if (g_edge_impl != 0 && m->edge_frags != nullptr) {
       KPROF("edge_fwd", stream, STRIVE_CUDA_LAUNCH(edge_fwd_mma_kernel, em_grid(NA), EM_THREADS, EM_FWD_SMEM, stream, M, a, m->edge_frags));
     } else {
       KPROF("edge_fwd", stream, STRIVE_CUDA_LAUNCH(edge_fwd_kernel, NA, EDGE_WARPS * 32, SM_EDGE_F, stream, M, a));
