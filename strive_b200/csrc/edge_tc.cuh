@@ -9,8 +9,9 @@
 // h1 = P_i + Q_j + W_rel rel) and costs 6 flops per element, so the rows are built by the CUDA cores straight into the
 // canonical K-major shared-memory operand layout; the two dense contractions
 //     D1[128 x 128] = relu(LN(h1)) . W3^T        D2[128 x 64] = relu(LN(D1 + b)) . W6^T
-// run as tcgen05.mma kind::f16 with the bf16 hi/lo split of BOTH operands (a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo, dropped
-// a_lo.w_lo ~ 2^-18: the same fidelity scheme as the map encoder), accumulating in fp32 in TMEM.  A thread owns HALF a row
+// run as tcgen05.mma kind::f16 with an FP16 hi/lo split of BOTH operands (a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo, dropped
+// a_lo.w_lo ~ 2^-22; fp16 pairs carry 11 + 11 mantissa bits = the TF32 x 3 fidelity of the mma.sync kernels; bf16 pairs (8 + 8) measured
+// 1e-5 on the aggregated messages, 4x worse, and flipped arg-max routings), accumulating in fp32 in TMEM.  A thread owns HALF a row
 // (64 columns) of the tile in every element-wise phase -- tcgen05.ld 32x32b hands lane l of warp w row 32 (w % 4) + l, and warps
 // w, w + 4 read the two column halves of the same rows -- so LayerNorm needs one 2-float exchange per row instead of shuffles
 // and no activation ever round-trips through shared memory except as the next MMA's operand.
@@ -20,7 +21,8 @@
 // the tiles.  Scenes with more than 129 agents keep the mma.sync kernels (edge_mma.cuh).
 #pragma once
 
-#define ET_THREADS 256
+#define ET_CPT 32                         // columns of a row per thread (see edge_fwd_tc_kernel)
+#define ET_THREADS (128 * (128 / ET_CPT))
 #define ET_W3_BYTES 32768                 // 128 (n) x 128 (k) bf16, canonical K-major: ((k>>3)*16 + (n>>3))*128 + (n&7)*16 + (k&7)*2
 #define ET_W6_BYTES 16384                 // 64 (n) x 128 (k)
 #define ET_W3H_OFF 0
@@ -33,17 +35,20 @@
 #define ET_SMEM (ET_PACK_BYTES + 2 * ET_A_BYTES)
 #define ET_MAX_N 129                      // scenes up to 129 agents (128 edges per target = one tile)
 
-// W: native [N][K] row-major fp32 (nn.Linear weight) -> bf16 hi and lo parts in the canonical K-major operand layout
+// W: native [N][K] row-major fp32 (nn.Linear weight) -> fp16 hi and lo parts of ET_WSCALE * W in the canonical K-major operand
+// layout.  The power-of-two scale keeps the lo parts of weights of magnitude 1e-2..1e-1 in the NORMAL fp16 range (exact to undo:
+// the accumulators are multiplied by 1 / ET_WSCALE when they leave TMEM).
+#define ET_WSCALE 16.0f
 __global__ void edge_tc_pack_kernel(const float* __restrict__ W, int N, int K, uint8_t* __restrict__ out_hi, uint8_t* __restrict__ out_lo) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * K) return;
   const int n = idx / K, k = idx % K;
-  const float w = W[idx];
-  const __nv_bfloat16 h = __float2bfloat16_rn(w);
-  const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+  const float w = W[idx] * ET_WSCALE;
+  const __half h = __float2half_rn(w);
+  const __half l = __float2half_rn(w - __half2float(h));
   const size_t off = ((size_t)((k >> 3) * (N / 8) + (n >> 3)) * 8 + (n & 7)) * 16 + (size_t)(k & 7) * 2;
-  *reinterpret_cast<__nv_bfloat16*>(out_hi + off) = h;
-  *reinterpret_cast<__nv_bfloat16*>(out_lo + off) = l;
+  *reinterpret_cast<__half*>(out_hi + off) = h;
+  *reinterpret_cast<__half*>(out_lo + off) = l;
 }
 
 // Tile table of one scene batch: tiles[2 q] = scene, tiles[2 q + 1] = first (local) target of tile q; *ntiles = number of tiles.
@@ -106,38 +111,47 @@ __device__ __forceinline__ EtRow et_row(const StepArgs& a, const int32_t* __rest
   return r;
 }
 
-// v (this thread's 64 columns of a 128-wide row) <- relu(LayerNorm(v) * gam + bet); the other half of the row lives in the
-// thread 128 places away: partial sums meet in s_part.  Two-pass statistics as models/common.py's nn.LayerNorm (eps 1e-5).
-__device__ __forceinline__ void et_ln_relu(float (&v)[64], const float* __restrict__ s_gam, const float* __restrict__ s_bet, float* s_part, int row,
-                                           int half) {
+// v (this thread's CPT columns of a 128-wide row) <- relu(LayerNorm(v) * gam + bet); the other parts of the row live in the
+// threads 128, 256, ... places away: partial sums meet in s_part.  Two-pass statistics as nn.LayerNorm (eps 1e-5).
+template <int CPT>
+__device__ __forceinline__ void et_ln_relu(float (&v)[CPT], const float* __restrict__ s_gam, const float* __restrict__ s_bet, float* s_part, int row,
+                                           int part) {
+  constexpr int PARTS = 128 / CPT;
   float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < 64; c++) s += v[c];
-  s_part[half * 128 + row] = s;
+  for (int c = 0; c < CPT; c++) s += v[c];
+  s_part[part * 128 + row] = s;
   __syncthreads();
-  const float mean = (s_part[row] + s_part[128 + row]) * (1.0f / 128.0f);
+  float tot = 0.f;
+#pragma unroll
+  for (int p = 0; p < PARTS; p++) tot += s_part[p * 128 + row];
+  const float mean = tot * (1.0f / 128.0f);
   float q = 0.f;
 #pragma unroll
-  for (int c = 0; c < 64; c++) { const float d = v[c] - mean; q = fmaf(d, d, q); }
-  s_part[256 + half * 128 + row] = q;
+  for (int c = 0; c < CPT; c++) { const float d = v[c] - mean; q = fmaf(d, d, q); }
+  s_part[512 + part * 128 + row] = q;
   __syncthreads();
-  const float rstd = 1.0f / sqrtf((s_part[256 + row] + s_part[384 + row]) * (1.0f / 128.0f) + LN_EPS);
+  float qt = 0.f;
 #pragma unroll
-  for (int c = 0; c < 64; c++) v[c] = fmaxf(fmaf((v[c] - mean) * rstd, s_gam[half * 64 + c], s_bet[half * 64 + c]), 0.f);
+  for (int p = 0; p < PARTS; p++) qt += s_part[512 + p * 128 + row];
+  const float rstd = 1.0f / sqrtf(qt * (1.0f / 128.0f) + LN_EPS);
+#pragma unroll
+  for (int c = 0; c < CPT; c++) v[c] = fmaxf(fmaf((v[c] - mean) * rstd, s_gam[part * CPT + c], s_bet[part * CPT + c]), 0.f);
 }
 
-// this thread's 64 columns -> bf16 hi / lo operand rows (canonical K-major, 128 rows): 8 k-groups of 16 bytes each
-__device__ __forceinline__ void et_store_operand(const float (&v)[64], bool valid, uint8_t* sA, int row, int half) {
+// this thread's CPT columns -> fp16 hi / lo operand rows (canonical K-major, 128 rows): CPT / 8 k-groups of 16 bytes each
+template <int CPT>
+__device__ __forceinline__ void et_store_operand(const float (&v)[CPT], bool valid, uint8_t* sA, int row, int part) {
 #pragma unroll
-  for (int g = 0; g < 8; g++) {
+  for (int g = 0; g < CPT / 8; g++) {
     uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = make_uint4(0u, 0u, 0u, 0u);
     if (valid) {
-      tc::split_pack2(v[8 * g + 0], v[8 * g + 1], hi.x, lo.x);
-      tc::split_pack2(v[8 * g + 2], v[8 * g + 3], hi.y, lo.y);
-      tc::split_pack2(v[8 * g + 4], v[8 * g + 5], hi.z, lo.z);
-      tc::split_pack2(v[8 * g + 6], v[8 * g + 7], hi.w, lo.w);
+      tc::split_pack2_f16(v[8 * g + 0], v[8 * g + 1], hi.x, lo.x);
+      tc::split_pack2_f16(v[8 * g + 2], v[8 * g + 3], hi.y, lo.y);
+      tc::split_pack2_f16(v[8 * g + 4], v[8 * g + 5], hi.z, lo.z);
+      tc::split_pack2_f16(v[8 * g + 6], v[8 * g + 7], hi.w, lo.w);
     }
-    const int unit = ((half * 8 + g) * 16 + (row >> 3)) * 8 + (row & 7);
+    const int unit = ((part * (CPT / 8) + g) * 16 + (row >> 3)) * 8 + (row & 7);
     *reinterpret_cast<uint4*>(sA + (size_t)unit * 16) = hi;
     *reinterpret_cast<uint4*>(sA + ET_A_BYTES + (size_t)unit * 16) = lo;
   }
@@ -145,7 +159,7 @@ __device__ __forceinline__ void et_store_operand(const float (&v)[64], bool vali
 
 // D[tmem] = A (128 x 128, hi/lo in sA) . B^T (N x 128, hi/lo packs): 8 K steps x 3 split terms, issued by one thread
 __device__ __forceinline__ void et_issue_gemm(uint32_t d_tmem, uint32_t sA_addr, uint32_t sBh_addr, uint32_t sBl_addr, int N, uint64_t* bar) {
-  const uint32_t idesc = tc::idesc_bf16_f32(128, N);
+  const uint32_t idesc = tc::idesc_f16_f32(128, N);
   const uint32_t lbo_b = (uint32_t)(N / 8) * 128u;
   const uint32_t a_hi = tc::desc_hi(128), b_hi = tc::desc_hi(128);
   const uint32_t ah0 = tc::desc_lo(sA_addr, 2048), al0 = tc::desc_lo(sA_addr + ET_A_BYTES, 2048);
@@ -161,10 +175,44 @@ __device__ __forceinline__ void et_issue_gemm(uint32_t d_tmem, uint32_t sA_addr,
   tc::mma_commit(bar);
 }
 
-__global__ void __launch_bounds__(ET_THREADS, 1) edge_fwd_tc_kernel(ModelDev M, StepArgs a, const uint8_t* __restrict__ pack, const int32_t* __restrict__ tiles,
-                                                                    const int32_t* __restrict__ ntiles_p) {
+// one tile's worth of this thread's first-layer inputs, loaded ahead of use (the loads of tile q + grid fly while the tensor
+// core works on tile q): pq = P_i + Q_j for the thread's columns, rel = transform2frame(pos_i, pos_j)
+template <int CPT>
+struct EtPre {
+  EtRow r;
+  int p0, n, slot, first;
+  float rel[4];
+  float pq[CPT];
+};
+
+template <int CPT>
+__device__ __forceinline__ void et_prefetch(const StepArgs& a, const int32_t* __restrict__ tiles, int q, int row, int part, EtPre<CPT>& o) {
+  const int NA = a.NA;
+  o.r = et_row(a, tiles, q, row, o.p0, o.n, o.slot, o.first);
+  const float* posg = a.tp.pos + (size_t)a.t * NA * 4;
+  const float4 a4 = __ldg(reinterpret_cast<const float4*>(posg + (size_t)o.r.i * 4));
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(posg + (size_t)o.r.j * 4));
+  const float4* Pi = reinterpret_cast<const float4*>(a.tp.P + ((size_t)a.t * NA + o.r.i) * 128 + part * CPT);
+  const float4* Qj = reinterpret_cast<const float4*>(a.tp.Q + ((size_t)a.t * NA + o.r.j) * 128 + part * CPT);
+#pragma unroll
+  for (int c4 = 0; c4 < CPT / 4; c4++) {
+    const float4 p = __ldg(Pi + c4), qv = __ldg(Qj + c4);
+    o.pq[c4 * 4] = p.x + qv.x; o.pq[c4 * 4 + 1] = p.y + qv.y; o.pq[c4 * 4 + 2] = p.z + qv.z; o.pq[c4 * 4 + 3] = p.w + qv.w;
+  }
+  const float pi[4] = {a4.x, a4.y, a4.z, a4.w}, pj[4] = {b4.x, b4.y, b4.z, b4.w};
+  t2f_fwd(pi, pj, o.rel);
+#pragma unroll
+  for (int d = 0; d < 4; d++)
+    if (isnan(o.rel[d])) o.rel[d] = 0.f;                            // interaction_net.py:162
+}
+
+// CPT columns per thread: 128 / CPT threads share a row -> 128 * 128 / CPT threads.  CPT = 32 (512 threads, 16 warps) keeps twice
+// the warps in flight of CPT = 64 for the same registers per SM: the element-wise phases are latency-, not issue-bound.
+template <int CPT>
+__global__ void __launch_bounds__(128 * (128 / CPT), 1) edge_fwd_tc_kernel(ModelDev M, StepArgs a, const uint8_t* __restrict__ pack,
+                                                                          const int32_t* __restrict__ tiles, const int32_t* __restrict__ ntiles_p) {
+  constexpr int PARTS = 128 / CPT, NT = 128 * PARTS;
   STRIVE_PDL_TRIGGER();
-  STRIVE_PDL_WAIT();
   extern __shared__ __align__(1024) uint8_t esm[];
   uint8_t* sW = esm;
   uint8_t* sA = esm + ET_PACK_BYTES;
@@ -173,17 +221,17 @@ __global__ void __launch_bounds__(ET_THREADS, 1) edge_fwd_tc_kernel(ModelDev M, 
   __shared__ uint32_t tmem_base;
   __shared__ float s_g1[128], s_b1[128], s_bias3[128], s_g4[128], s_b4[128], s_bias6[64];
   __shared__ __align__(16) float s_wrel[4 * 128];
-  __shared__ float s_part[512];
+  __shared__ float s_part[1024];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = (warp & 3) * 32 + lane, half = warp >> 2;
-  const int ntiles = *ntiles_p;
-  if ((int)blockIdx.x >= ntiles) return;                           // the host sizes the grid from an upper bound of the tile count
+  const int row = (warp & 3) * 32 + lane, part = warp >> 2;
+  // ---- prologue: model constants only (weights -> shared memory, LayerNorm / bias vectors, barriers, TMEM) -- runs while the
+  // previous kernel of the stream drains; nothing the predecessor writes is touched before the wait below
   if (tid < 128) {
     s_g1[tid] = M.seg[S_E_LN1_G][tid]; s_b1[tid] = M.seg[S_E_LN1_B][tid]; s_bias3[tid] = M.seg[S_E3_B][tid];
     s_g4[tid] = M.seg[S_E_LN4_G][tid]; s_b4[tid] = M.seg[S_E_LN4_B][tid];
     if (tid < 64) s_bias6[tid] = M.seg[S_E6_B][tid];
   }
-  for (int k = tid; k < 512; k += ET_THREADS) s_wrel[k] = M.seg[S_E0_T_REL][k];
+  for (int k = tid; k < 512; k += NT) s_wrel[k] = M.seg[S_E0_T_REL][k];
   if (tid == 0) {
     tc::mbar_init(&bar_w, 1);
     tc::mbar_init(&bar_mma, 1);
@@ -200,41 +248,30 @@ __global__ void __launch_bounds__(ET_THREADS, 1) edge_fwd_tc_kernel(ModelDev M, 
   const uint32_t tm = tmem_base;
   const uint32_t t_row = tm + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t sA_addr = tc::smem_u32(sA), sW_addr = tc::smem_u32(sW);
+  STRIVE_PDL_WAIT_PTRS(tiles, ntiles_p);
+  const int ntiles = *ntiles_p;
   const int NA = a.NA;
-  const float* posg = a.tp.pos + (size_t)a.t * NA * 4;
   uint32_t ph = 0;
   bool w_ready = false;
+  EtPre<CPT> cur;
+  if ((int)blockIdx.x < ntiles) et_prefetch<CPT>(a, tiles, blockIdx.x, row, part, cur);
   for (int q = blockIdx.x; q < ntiles; q += gridDim.x) {
-    int p0, n, slot, first;
-    const EtRow r = et_row(a, tiles, q, row, p0, n, slot, first);
+    const EtRow r = cur.r;
+    const int p0 = cur.p0, n = cur.n, slot = cur.slot, first = cur.first;
     // ---- phase A: h1 = P_i + Q_j + W_rel rel (same fmaf order as the SIMT kernel), LN, ReLU -> operand tile
-    float v[64];
-    {
-      float pi[4], pj[4], rel[4];
-      const float4 a4 = __ldg(reinterpret_cast<const float4*>(posg + (size_t)r.i * 4));
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(posg + (size_t)r.j * 4));
-      pi[0] = a4.x; pi[1] = a4.y; pi[2] = a4.z; pi[3] = a4.w;
-      pj[0] = b4.x; pj[1] = b4.y; pj[2] = b4.z; pj[3] = b4.w;
-      t2f_fwd(pi, pj, rel);
+    float v[CPT];
 #pragma unroll
-      for (int d = 0; d < 4; d++)
-        if (isnan(rel[d])) rel[d] = 0.f;                            // interaction_net.py:162
-      const float4* Pi = reinterpret_cast<const float4*>(a.tp.P + ((size_t)a.t * NA + r.i) * 128 + half * 64);
-      const float4* Qj = reinterpret_cast<const float4*>(a.tp.Q + ((size_t)a.t * NA + r.j) * 128 + half * 64);
+    for (int c4 = 0; c4 < CPT / 4; c4++) {
+      float x[4] = {cur.pq[c4 * 4], cur.pq[c4 * 4 + 1], cur.pq[c4 * 4 + 2], cur.pq[c4 * 4 + 3]};
 #pragma unroll
-      for (int c4 = 0; c4 < 16; c4++) {
-        const float4 p = __ldg(Pi + c4), qv = __ldg(Qj + c4);
-        float x[4] = {p.x + qv.x, p.y + qv.y, p.z + qv.z, p.w + qv.w};
-#pragma unroll
-        for (int d = 0; d < 4; d++) {
-          const float4 w = *reinterpret_cast<const float4*>(&s_wrel[d * 128 + half * 64 + c4 * 4]);
-          x[0] = fmaf(rel[d], w.x, x[0]); x[1] = fmaf(rel[d], w.y, x[1]); x[2] = fmaf(rel[d], w.z, x[2]); x[3] = fmaf(rel[d], w.w, x[3]);
-        }
-        v[c4 * 4] = x[0]; v[c4 * 4 + 1] = x[1]; v[c4 * 4 + 2] = x[2]; v[c4 * 4 + 3] = x[3];
+      for (int d = 0; d < 4; d++) {
+        const float4 w = *reinterpret_cast<const float4*>(&s_wrel[d * 128 + part * CPT + c4 * 4]);
+        x[0] = fmaf(cur.rel[d], w.x, x[0]); x[1] = fmaf(cur.rel[d], w.y, x[1]); x[2] = fmaf(cur.rel[d], w.z, x[2]); x[3] = fmaf(cur.rel[d], w.w, x[3]);
       }
+      v[c4 * 4] = x[0]; v[c4 * 4 + 1] = x[1]; v[c4 * 4 + 2] = x[2]; v[c4 * 4 + 3] = x[3];
     }
-    et_ln_relu(v, s_g1, s_b1, s_part, row, half);
-    et_store_operand(v, r.valid, sA, row, half);
+    et_ln_relu<CPT>(v, s_g1, s_b1, s_part, row, part);
+    et_store_operand<CPT>(v, r.valid, sA, row, part);
     tc::fence_async_smem();
     __syncthreads();
     if (!w_ready) { wp_wait(&bar_w, 0); w_ready = true; }
@@ -245,16 +282,16 @@ __global__ void __launch_bounds__(ET_THREADS, 1) edge_fwd_tc_kernel(ModelDev M, 
     tc::mbar_wait(&bar_mma, ph);
     ph ^= 1u;
     tc::tc_fence_after();
-    // ---- phase B: D1 + bias, LN, ReLU -> operand tile (the first GEMM has completed: its operand buffer is free)
+    // ---- phase B: D1 / scale + bias, LN, ReLU -> operand tile (the first GEMM has completed: its operand buffer is free)
 #pragma unroll
-    for (int cc = 0; cc < 4; cc++) {
+    for (int cc = 0; cc < CPT / 16; cc++) {
       float t16[16];
-      tc::tmem_ld16(t_row + half * 64 + cc * 16, t16);
+      tc::tmem_ld16(t_row + part * CPT + cc * 16, t16);
 #pragma unroll
-      for (int c = 0; c < 16; c++) v[cc * 16 + c] = t16[c] + s_bias3[half * 64 + cc * 16 + c];
+      for (int c = 0; c < 16; c++) v[cc * 16 + c] = fmaf(t16[c], 1.0f / ET_WSCALE, s_bias3[part * CPT + cc * 16 + c]);
     }
-    et_ln_relu(v, s_g4, s_b4, s_part, row, half);
-    et_store_operand(v, r.valid, sA, row, half);
+    et_ln_relu<CPT>(v, s_g4, s_b4, s_part, row, part);
+    et_store_operand<CPT>(v, r.valid, sA, row, part);
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
@@ -262,19 +299,23 @@ __global__ void __launch_bounds__(ET_THREADS, 1) edge_fwd_tc_kernel(ModelDev M, 
       tc::tc_fence_after();
       et_issue_gemm(tm + 128, sA_addr, sW_addr + ET_W6H_OFF, sW_addr + ET_W6L_OFF, 64, &bar_mma);
     }
+    // the next tile's first-layer inputs leave L2 while the tensor core runs the second GEMM
+    if (q + (int)gridDim.x < ntiles) et_prefetch<CPT>(a, tiles, q + gridDim.x, row, part, cur);
     tc::mbar_wait(&bar_mma, ph);
     ph ^= 1u;
     tc::tc_fence_after();
-    // ---- phase C: D2 + bias -> staging tile; max / arg-max over each target's rows (smaller source index wins ties, NaN never wins)
+    // ---- phase C: D2 / scale + bias -> staging tile; max / arg-max over each target's rows (smaller source index wins ties, NaN never wins)
+    constexpr int C6 = 64 / PARTS;                                  // D2 columns per thread: 32 or 16
 #pragma unroll
-    for (int cc = 0; cc < 2; cc++) {
+    for (int cc = 0; cc < C6 / 16; cc++) {
       float t16[16];
-      tc::tmem_ld16(t_row + 128 + half * 32 + cc * 16, t16);
+      tc::tmem_ld16(t_row + 128 + part * C6 + cc * 16, t16);
 #pragma unroll
       for (int c = 0; c < 16; c += 4) {
-        const int col = half * 32 + cc * 16 + c;
+        const int col = part * C6 + cc * 16 + c;
         *reinterpret_cast<float4*>(mbuf + (size_t)row * ET_MB_LD + col) =
-            make_float4(t16[c] + s_bias6[col], t16[c + 1] + s_bias6[col + 1], t16[c + 2] + s_bias6[col + 2], t16[c + 3] + s_bias6[col + 3]);
+            make_float4(fmaf(t16[c], 1.0f / ET_WSCALE, s_bias6[col]), fmaf(t16[c + 1], 1.0f / ET_WSCALE, s_bias6[col + 1]),
+                        fmaf(t16[c + 2], 1.0f / ET_WSCALE, s_bias6[col + 2]), fmaf(t16[c + 3], 1.0f / ET_WSCALE, s_bias6[col + 3]));
       }
     }
     tc::tc_fence_before();
@@ -282,7 +323,7 @@ __global__ void __launch_bounds__(ET_THREADS, 1) edge_fwd_tc_kernel(ModelDev M, 
     {
       const int ch = tid & 63;
       const int tps = 128 / slot;
-      for (int k = tid >> 6; k < tps; k += ET_THREADS / 64) {
+      for (int k = tid >> 6; k < tps; k += NT / 64) {
         const int li = first + k;
         if (li >= n) break;
         float best = -INFINITY;

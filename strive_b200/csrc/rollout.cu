@@ -1318,7 +1318,7 @@ static int set_smem_attrs() {
   STRIVE_CUDA(cudaFuncSetAttribute(edge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_EDGE_B));
   STRIVE_CUDA(cudaFuncSetAttribute(edge_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_FWD_SMEM));
   STRIVE_CUDA(cudaFuncSetAttribute(edge_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_BWD_SMEM));
-  STRIVE_CUDA(cudaFuncSetAttribute(edge_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ET_SMEM));
+  STRIVE_CUDA(cudaFuncSetAttribute(edge_fwd_tc_kernel<ET_CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ET_SMEM));
   STRIVE_CUDA(cudaFuncSetAttribute(node_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE));
   STRIVE_CUDA(cudaFuncSetAttribute(post_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE));
   STRIVE_CUDA(cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GRU_F));
@@ -1368,7 +1368,7 @@ extern "C" int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, co
     STRIVE_LAUNCH_CHECK();
     if (edge_tc) {
       const int grid = NA < em_grid(NA * EM_WARPS) ? NA : em_grid(NA * EM_WARPS);      // min(#SMs, upper bound of the tile count)
-      KPROF("edge_fwd", stream, STRIVE_CUDA_LAUNCH(edge_fwd_tc_kernel, grid, ET_THREADS, ET_SMEM, stream, M, a, m->edge_frags + EM_FRAG_BYTES,
+      KPROF("edge_fwd", stream, STRIVE_CUDA_LAUNCH(edge_fwd_tc_kernel<ET_CPT>, grid, ET_THREADS, ET_SMEM, stream, M, a, m->edge_frags + EM_FRAG_BYTES,
                                                    (const int32_t*)a.tp.et_tiles, (const int32_t*)a.tp.et_ntiles));
     } else if (g_edge_impl != 0 && m->edge_frags != nullptr) {
       KPROF("edge_fwd", stream, STRIVE_CUDA_LAUNCH(edge_fwd_mma_kernel, em_grid(NA), EM_THREADS, EM_FWD_SMEM, stream, M, a, m->edge_frags));

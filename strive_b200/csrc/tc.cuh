@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace tc {
@@ -104,6 +105,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Instruction descriptor for kind::f16 with FP16 operands: FP16 x FP16 -> FP32 (a_format = b_format = 0), A and B K-major, dense.
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -146,6 +152,16 @@ __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, ui
   hi = *reinterpret_cast<const uint32_t*>(&h);
   const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
   const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// fp16 variant: x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 11 + 11 mantissa bits (bf16 pairs carry 8 + 8).  Values must stay
+// inside the fp16 range (|x| < 65504); a lo part below 2^-14 is subnormal and keeps an ABSOLUTE precision of 2^-25.
+__device__ __forceinline__ void split_pack2_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
