@@ -164,10 +164,10 @@ def profile_report():
 
 
 def set_edge_impl(impl):
-    """Edge-phase kernels of the rollout: 2 / True (default) = tcgen05 forward (scenes up to 129 agents) + mma.sync backward,
-    1 = mma.sync TF32 kernels both ways, 0 / False = fp32 SIMT kernels (A/B verification)."""
+    """Edge-phase kernels of the rollout: 3 / True (default) = tcgen05 forward + backward (scenes up to 129 agents), 2 = tcgen05 forward +
+    mma.sync backward, 1 = mma.sync TF32 kernels both ways, 0 / False = fp32 SIMT kernels (A/B verification)."""
     if isinstance(impl, bool):
-        impl = 2 if impl else 0
+        impl = 3 if impl else 0
     lib().strive_edge_set_impl(int(impl))
 
 

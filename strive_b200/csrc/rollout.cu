@@ -1261,9 +1261,9 @@ static const size_t SM_GRU_B = SM_PIPE + NODE_WARPS * (6 * GRU_R * LDG + GRU_R *
 static const size_t SM_POST_B = SM_PIPE + NODE_WARPS * (NODE_R * (LDA + LDH) + 3 * NODE_R * LDH) * 4;
 static const size_t SM_NODE_B = SM_PIPE + NODE_WARPS * (NODE_R * (LDA + LDH) + 2 * NODE_R * LDH) * 4;
 
-// 2 = tcgen05 forward (edge_tc.cuh; default; scenes up to ET_MAX_N agents) + mma.sync backward, 1 = mma.sync TF32 kernels both ways
-// (edge_mma.cuh), 0 = fp32 SIMT kernels (A/B verification)
-static int g_edge_impl = 2;
+// 3 = tcgen05 forward + backward (edge_tc.cuh; default; scenes up to ET_MAX_N agents, larger ones use the mma.sync kernels),
+// 2 = tcgen05 forward + mma.sync backward, 1 = mma.sync TF32 kernels both ways (edge_mma.cuh), 0 = fp32 SIMT kernels (A/B verification)
+static int g_edge_impl = 3;
 extern "C" int strive_edge_set_impl(int impl) {
   g_edge_impl = impl;
   return 0;
@@ -1319,6 +1319,7 @@ static int set_smem_attrs() {
   STRIVE_CUDA(cudaFuncSetAttribute(edge_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_FWD_SMEM));
   STRIVE_CUDA(cudaFuncSetAttribute(edge_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_BWD_SMEM));
   STRIVE_CUDA(cudaFuncSetAttribute(edge_fwd_tc_kernel<ET_CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ET_SMEM));
+  STRIVE_CUDA(cudaFuncSetAttribute(edge_bwd_tc_kernel<ETB_CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ETB_SMEM));
   STRIVE_CUDA(cudaFuncSetAttribute(node_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE));
   STRIVE_CUDA(cudaFuncSetAttribute(post_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE));
   STRIVE_CUDA(cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GRU_F));
@@ -1357,7 +1358,7 @@ extern "C" int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, co
   KPROF("init_tape", stream, STRIVE_CUDA_LAUNCH(init_tape_kernel, (NA * 64 + 255) / 256, 256, 0, stream, a, sc->past_last, map_feat0, past_feat0, sc->map_idx));
   STRIVE_LAUNCH_CHECK();
   const int node_blocks = (NA + NODE_WARPS * NODE_R - 1) / (NODE_WARPS * NODE_R);
-  const bool edge_tc = g_edge_impl == 2 && m->edge_frags != nullptr && sc->max_scene_agents <= ET_MAX_N;
+  const bool edge_tc = g_edge_impl >= 2 && m->edge_frags != nullptr && sc->max_scene_agents <= ET_MAX_N;
   if (edge_tc) {
     KPROF("edge_tiles", stream, edge_tc_tiles_kernel<<<1, 1024, 0, stream>>>(sc->ptr, sc->num_scenes, a.tp.et_tiles, a.tp.et_ntiles));
     STRIVE_LAUNCH_CHECK();
@@ -1412,6 +1413,11 @@ extern "C" int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, in
   STRIVE_CUDA(cudaMemsetAsync(a.tp.g_mem, 0, (size_t)NA * 192 * 4, stream));
   STRIVE_CUDA(cudaMemsetAsync(a.tp.d_loc, 0, (size_t)NA * 4 * 4, stream));
   const int node_blocks = (NA + NODE_WARPS * NODE_R - 1) / (NODE_WARPS * NODE_R);
+  const bool edge_tc = g_edge_impl >= 3 && m->edge_frags != nullptr && sc->max_scene_agents <= ET_MAX_N;
+  if (edge_tc) {     // the tile table depends on ptr only; rebuilt here so a backward call never relies on which forward kernel ran
+    KPROF("edge_tiles", stream, edge_tc_tiles_kernel<<<1, 1024, 0, stream>>>(sc->ptr, sc->num_scenes, a.tp.et_tiles, a.tp.et_ntiles));
+    STRIVE_LAUNCH_CHECK();
+  }
   for (int t = ft - 1; t >= 0; t--) {
     a.t = t;
     const int has_gru = (t + 1 < ft) ? 1 : 0;
@@ -1421,7 +1427,11 @@ extern "C" int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, in
     }
     KPROF("post_bwd", stream, STRIVE_CUDA_LAUNCH(post_bwd_kernel, node_blocks, NODE_THREADS, SM_POST_B, stream, M, a, has_gru));
     STRIVE_LAUNCH_CHECK();
-    if (g_edge_impl != 0 && m->edge_frags != nullptr) {
+    if (edge_tc) {
+      const int grid = NA < em_grid(NA * EM_WARPS) ? NA : em_grid(NA * EM_WARPS);
+      KPROF("edge_bwd", stream, STRIVE_CUDA_LAUNCH(edge_bwd_tc_kernel<ETB_CPT>, grid, 128 * (128 / ETB_CPT), ETB_SMEM, stream, M, a, m->edge_frags + EM_FRAG_BYTES,
+                                                   (const int32_t*)a.tp.et_tiles, (const int32_t*)a.tp.et_ntiles));
+    } else if (g_edge_impl != 0 && m->edge_frags != nullptr) {
       KPROF("edge_bwd", stream, STRIVE_CUDA_LAUNCH(edge_bwd_mma_kernel, em_grid(NA), EM_THREADS, EM_BWD_SMEM, stream, M, a, m->edge_frags));
     } else {
       KPROF("edge_bwd", stream, STRIVE_CUDA_LAUNCH(edge_bwd_kernel, NA, EDGE_WARPS * 32, SM_EDGE_B, stream, M, a));

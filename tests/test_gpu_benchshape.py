@@ -142,15 +142,16 @@ def test_teacher_forced_rollout_and_adjoint_big_scenes(tag, FT):
 
 @pytest.mark.parametrize('tag', ['n32', 'n64', 'ragged'])
 def test_edge_kernels_tensor_core_paths_vs_simt(tag):
-    """A/B of the three edge implementations (strive_edge_set_impl): 2 = tcgen05 forward (TMEM accumulators, bf16 hi/lo split) +
-    mma.sync backward, 1 = mma.sync TF32 both ways, 0 = the fp32 SIMT kernels; forward (aggr, arg-max, first-step trajectory) and
+    """A/B of the edge implementations (strive_edge_set_impl): 3 = tcgen05 forward + backward (TMEM accumulators, fp16 hi/lo split, the
+    transposed weights read through MN-major descriptors), 2 = tcgen05 forward + mma.sync backward, 1 = mma.sync TF32 both ways, 0 = the
+    fp32 SIMT kernels; forward (aggr, arg-max, first-step trajectory) and
     backward (dL/dz) at multi-tile scene sizes."""
     from strive_b200 import _cabi
     FT = 3
     sc = scene(tag, FT)
     seed = torch.randn(sc['z'].size(0), FT, 4, generator=torch.Generator().manual_seed(9))
     res = {}
-    for impl in (0, 1, 2):
+    for impl in (0, 1, 2, 3):
         _cabi.set_edge_impl(impl)
         try:
             traj, tape, NA = gpu_forward(sc, FT)
@@ -159,8 +160,8 @@ def test_edge_kernels_tensor_core_paths_vs_simt(tag):
             _, _, bwd = _lowlevel(sc, FT)
             res[impl] = (traj, aggr, arg, bwd(seed))
         finally:
-            _cabi.set_edge_impl(2)
-    for impl, name in ((1, 'mma.sync'), (2, 'tcgen05')):
+            _cabi.set_edge_impl(3)
+    for impl, name in ((1, 'mma.sync'), (2, 'tcgen05 fwd + mma.sync bwd'), (3, 'tcgen05 fwd + bwd')):
         d_aggr = (res[0][1] - res[impl][1]).abs().max().item()
         d_t0 = (res[0][0][:, 0] - res[impl][0][:, 0]).abs().max().item()
         n_arg = int((res[0][2] != res[impl][2]).sum())
