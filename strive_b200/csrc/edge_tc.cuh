@@ -619,12 +619,6 @@ __global__ void __launch_bounds__(128 * (128 / CPT), 1) edge_bwd_tc_kernel(Model
       }
 #pragma unroll
       for (int d = 0; d < 4; d++) s_drel[d * 512 + part * 128 + row] = dr[d];
-      // dQ_j += d h1
-      if (r.valid) {
-        float* dq = a.tp.dQ + (size_t)r.j * 128 + part * CPT;
-#pragma unroll
-        for (int c = 0; c < CPT; c++) atomicAdd(dq + c, d1[c]);
-      }
       // staging tile for the per-target column sums (all MMAs of this tile have completed: the operand buffers are free)
 #pragma unroll
       for (int c = 0; c < CPT; c += 4)
@@ -652,6 +646,7 @@ __global__ void __launch_bounds__(128 * (128 / CPT), 1) edge_bwd_tc_kernel(Model
     {
       const int col = tid & 127;
       const int tps = 128 / slot;
+      // dP_i = sum over the target's rows
       for (int k = tid >> 7; k < tps; k += NT / 128) {
         const int li = first + k;
         if (li >= n) break;
@@ -659,6 +654,20 @@ __global__ void __launch_bounds__(128 * (128 / CPT), 1) edge_bwd_tc_kernel(Model
         const float* cp = stg + (size_t)(k * slot) * ETB_ST_LD + col;
         for (int e = 0; e < n - 1; e++) s += cp[(size_t)e * ETB_ST_LD];
         a.tp.dP[(size_t)(p0 + li) * 128 + col] = s;
+      }
+      // dQ_j += sum over the tile's targets of the row that has j as its source: ONE atomic per (source, column) and tile instead of
+      // one per edge (the 8.1 M per-edge float atomics of a rollout step bound this kernel and its mma.sync predecessor alike:
+      // ncu stall_lg 29 %, lts RED requests 8.16 M)
+      for (int lj = tid >> 7; lj < n; lj += NT / 128) {
+        float s = 0.f;
+        for (int k = 0; k < tps; k++) {
+          const int li = first + k;
+          if (li >= n) break;
+          if (li == lj) continue;
+          const int e = lj - (lj > li ? 1 : 0);
+          s += stg[(size_t)(k * slot + e) * ETB_ST_LD + col];
+        }
+        atomicAdd(a.tp.dQ + (size_t)(p0 + lj) * 128 + col, s);
       }
     }
     __syncthreads();
