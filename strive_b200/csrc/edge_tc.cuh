@@ -590,12 +590,14 @@ __global__ void __launch_bounds__(128 * (128 / CPT), 1) edge_bwd_tc_kernel(Model
       et_issue_gemm_t(tm, sA_addr, sA_addr + ET_A_BYTES, sW_addr + ET_W3H_OFF, sW_addr + ET_W3L_OFF, 128, 8);      // D4 over D1
       tc::mma_commit(&bar_mma);
     }
-    tc::mbar_wait(&bar_mma, ph);
-    ph ^= 1u;
-    tc::tc_fence_after();
-    // ---- phase E: d h1 = LayerNorm-ReLU adjoint(D4 / s; h1 recomputed); scatter
+    // ---- phase E: d h1 = LayerNorm-ReLU adjoint(D4 / s; h1 recomputed); scatter.  The P / Q rows of the recompute leave L2 while the
+    // tensor core runs GEMM4.
     {
       float h1[CPT], d1[CPT];
+      et_h1<CPT>(a, r, rel, s_wrel, part, h1);
+      tc::mbar_wait(&bar_mma, ph);
+      ph ^= 1u;
+      tc::tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < CPT / 16; cc++) {
         float t16[16];
@@ -604,7 +606,6 @@ __global__ void __launch_bounds__(128 * (128 / CPT), 1) edge_bwd_tc_kernel(Model
         for (int c = 0; c < 16; c++) d1[cc * 16 + c] = t16[c] * (1.0f / ET_WSCALE);
       }
       tc::tc_fence_before();
-      et_h1<CPT>(a, r, rel, s_wrel, part, h1);
       et_ln_relu_bwd<CPT>(d1, h1, mean1, rstd1, s_g1, s_b1, s_red, row, part);
       if (!r.valid) {
 #pragma unroll
@@ -650,22 +651,30 @@ __global__ void __launch_bounds__(128 * (128 / CPT), 1) edge_bwd_tc_kernel(Model
       for (int k = tid >> 7; k < tps; k += NT / 128) {
         const int li = first + k;
         if (li >= n) break;
-        float s = 0.f;
         const float* cp = stg + (size_t)(k * slot) * ETB_ST_LD + col;
-        for (int e = 0; e < n - 1; e++) s += cp[(size_t)e * ETB_ST_LD];
-        a.tp.dP[(size_t)(p0 + li) * 128 + col] = s;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;                 // four independent chains: the scan is shared-memory latency bound
+        int e = 0;
+        for (; e + 4 <= n - 1; e += 4) {
+          s0 += cp[(size_t)e * ETB_ST_LD];
+          s1 += cp[(size_t)(e + 1) * ETB_ST_LD];
+          s2 += cp[(size_t)(e + 2) * ETB_ST_LD];
+          s3 += cp[(size_t)(e + 3) * ETB_ST_LD];
+        }
+        for (; e < n - 1; e++) s0 += cp[(size_t)e * ETB_ST_LD];
+        a.tp.dP[(size_t)(p0 + li) * 128 + col] = (s0 + s1) + (s2 + s3);
       }
       // dQ_j += sum over the tile's targets of the row that has j as its source: ONE atomic per (source, column) and tile instead of
       // one per edge (the 8.1 M per-edge float atomics of a rollout step bound this kernel and its mma.sync predecessor alike:
       // ncu stall_lg 29 %, lts RED requests 8.16 M)
       for (int lj = tid >> 7; lj < n; lj += NT / 128) {
         float s = 0.f;
-        for (int k = 0; k < tps; k++) {
+        const int kmax = min(tps, n - first);
+#pragma unroll 4
+        for (int k = 0; k < kmax; k++) {
           const int li = first + k;
-          if (li >= n) break;
-          if (li == lj) continue;
-          const int e = lj - (lj > li ? 1 : 0);
-          s += stg[(size_t)(k * slot + e) * ETB_ST_LD + col];
+          const int e = max(min(lj - (lj > li ? 1 : 0), n - 2), 0);    // (clamped: the li == lj term is masked below)
+          const float v = stg[(size_t)(k * slot + e) * ETB_ST_LD + col];
+          s += (li != lj) ? v : 0.f;
         }
         atomicAdd(a.tp.dQ + (size_t)(p0 + lj) * 128 + col, s);
       }
