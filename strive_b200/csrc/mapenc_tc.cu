@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __rest
 // rate reaches the math floor at N >= 128: scripts/mma_bench2.cu) and every input tile is staged once instead of once per
 // 32-channel chunk.  The hi/lo weights of both 16-channel K chunks are 204.8 KB -- more than shared memory -- so only ONE
 // chunk (102.4 KB) is resident and the K chunks are the OUTER loop over a pair of tiles whose accumulators wait in TMEM:
-//     pair p:  (t0, c) (t1, c)   [weights -> chunk 1-c]   (t0, 1-c) (t1, 1-c)        c = p & 1
+//     pair p:  (t0, c) (t1, c)   [weights -> chunk 1-c]   (t0, 1-c) (t1, 1-c)        c = parity of the GLOBAL pair index
 // so the weights are swapped once per pair and the next pair starts with the chunk that is already resident.  The swap is
 // two cp.async.bulk halves (taps 0-12 / 13-24), each issued by the loader warp as soon as the MMAs that read the old half
 // have completed (tcgen05.commit -> w_free[h]), i.e. the first half streams in while the tensor core still works on taps
@@ -881,8 +881,16 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
   __shared__ float s_gam[CIN], s_bet[CIN];
   __shared__ __align__(16) float s_ga[CIN], s_gb[CIN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // Contiguous range of tile PAIRS per CTA.  The K-chunk order of a pair follows the parity of its GLOBAL pair index: a crop has
+  // 8 tiles = 4 pairs, so the order in which a tile's two K chunks are accumulated depends only on the tile's place inside its
+  // crop -- never on the batch composition or the CTA the pair lands on (bitwise batch invariance of the forward pass).
+  static_assert(Cfg::TILES % 4 == 0, "conv3: pairs of a crop must not straddle crops and their parity must repeat per crop");
+  const int pairs_total = n * (Cfg::TILES / 2);
+  const int pair_lo = (int)(((long long)pairs_total * blockIdx.x) / gridDim.x);
+  const int pair_hi = (int)(((long long)pairs_total * (blockIdx.x + 1)) / gridDim.x);
+  const int par0 = pair_lo & 1;
   {
-    const int4* src = reinterpret_cast<const int4*>(wpack);     // K chunk 0 is resident first
+    const int4* src = reinterpret_cast<const int4*>(wpack + (size_t)par0 * T3_WCHUNK);     // the first pair's first K chunk is resident first
     for (int i = tid; i < T3_WCHUNK / 16; i += T2_THREADS) reinterpret_cast<int4*>(sW)[i] = __ldg(src + i);
   }
   for (int i = tid; i < CIN; i += T2_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
@@ -900,10 +908,8 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tm = tmem_base;
-  const int items = n * Cfg::TILES;
-  const int item_lo = (int)(((long long)items * blockIdx.x) / gridDim.x);
-  const int item_hi = (int)(((long long)items * (blockIdx.x + 1)) / gridDim.x);
-  const int npairs = (item_hi - item_lo + 1) >> 1;
+  const int item_lo = 2 * pair_lo, item_hi = 2 * pair_hi;
+  const int npairs = pair_hi - pair_lo;
 
   if (warp < T3_NPROD) {
     // ---------------- producers: same work items as tc_conv_kernel (8 channels of one input pixel), 320 threads ----------------
@@ -933,7 +939,7 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
       const int np = min(2, item_hi - (item_lo + 2 * p));
       const int s2 = np == 2 ? (r >> 1) : r, i2 = np == 2 ? (r & 1) : 0;
       item = item_lo + 2 * p + i2;
-      c2 = (p & 1) ^ s2;
+      c2 = ((p + par0) & 1) ^ s2;
     };
     auto job_base = [&](int item, int c2, int& rows_valid, int& cols_valid) -> const float* {
       const int crop = item / Cfg::TILES, tile = item - crop * Cfg::TILES;
@@ -1021,7 +1027,7 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
     // ---------------- weight loader: one swap per pair, two halves, each as soon as its old contents are dead ----------------
     if (tc::elect_one()) {
       for (int p = 0; p < npairs; p++) {
-        const uint8_t* src = wpack + (size_t)(1 - (p & 1)) * T3_WCHUNK;
+        const uint8_t* src = wpack + (size_t)(1 - ((p + par0) & 1)) * T3_WCHUNK;
         tc::mbar_wait(&w_free[0], p & 1);
         mbar_expect_tx(&w_full[0], T3_H0_TAPS * 4096);
         for (int t = 0; t < T3_H0_TAPS; t++) bulk_g2s(sW + t * 4096, src + t * 4096, 4096, &w_full[0]);
