@@ -1,12 +1,10 @@
 """Full-size GPU tests (BASELINE.json configs[1], [2], [4] per-GPU shares): the CPU oracle cannot finish these sizes in
 seconds, so they check size-independent properties of the CUDA path instead:
-  * the rollout of a scene does not depend on which other scenes share the batch, nor on their order: bitwise for the first
-    step, to fp32 re-association afterwards (conv3 visits its two K chunks in an order that alternates with the tile-pair
-    parity inside a CTA, so the position of a crop in the batch re-associates one fp32 sum: map features move by <= 1e-5,
-    and the autoregressive rollout amplifies that ~1.6x per step exactly as it amplifies the reference's own fp32 noise,
-    DESIGN.md 3);
+  * the rollout of a scene does not depend on which other scenes share the batch, nor on their order: BITWISE over the whole
+    horizon (every kernel of the forward pass accumulates in an order that depends on the item's place inside its own crop /
+    scene only; conv3's K-chunk order follows the global tile-pair parity);
   * loss-normalisation groups are independent: a sub-batch of whole groups reproduces the full batch's per-group loss terms
-    and gradient rows to that same noise level;
+    exactly and its gradient rows to the rounding noise of the float atomics in the backward pass;
   * two evaluations of the same batch give bitwise identical trajectories (no races in the forward kernels);
   * everything stays finite over the full horizon; ragged scenes (4..40 agents) run through the adv / solution loops.
 """
@@ -61,12 +59,10 @@ def subset_check(name, sc, gptr, groups, FT, full_loop, dev, model, env, cos_min
     cos = float((g_sub * g_full).sum() / (g_sub.norm() * g_full.norm() + 1e-30))
     diag('%s: groups %s alone vs inside the full batch: traj diff per step %s | loss rel err %.2e | grad cosine %.5f' % (
         name, groups, ' '.join('%.1e' % v for v in d_t.tolist()), e_loss, cos))
-    assert d_t[0].item() == 0.0                       # step 0 reads no re-encoded map feature: bitwise
-    assert d_t[1].item() < 2e-5 and d_t[:4].max().item() < 5e-4
-    assert float((tr_sub[:, :10] - tr_full[:, :10]).abs().median()) < 1e-4      # (random-init weights: chaotic beyond)
-    # gradients through 20-40 chaotic steps (random-init weights, nearest-pixel crops): direction agrees, values do not (measured
-    # cosine 0.8-0.95 at FT 20, 0.55-0.65 at FT 40, run-to-run spread from the float atomics in the backward pass)
-    assert e_loss < 5e-2 and cos > cos_min
+    assert d_t.max().item() == 0.0                    # sharded == unsharded to the last bit, over the whole horizon
+    # the forward pass is identical, so the loss terms are (the per-group sums run over the same values in the same kernels) and
+    # the gradients differ by the order of the float atomics in the backward pass only
+    assert e_loss < 1e-6 and cos > max(cos_min, 0.999)
 
 
 def full_step(loop):
