@@ -171,7 +171,9 @@ def test_init_loop_vs_reference_golden_and_oracle():
     dt = np.abs(traj.cpu().numpy() - g['traj']).max()
     diag('init loop: loss0 gpu %.5f oracle %.5f | iter-0 grad rel err %.2e | z after %d iters vs reference: max %.3e | final traj diff %.2e' % (
         logs[0]['loss'], rec[0]['loss'], e_g, iters, dz.max(), dt))
-    assert abs(logs[0]['loss'] - rec[0]['loss']) < 3e-4 * abs(rec[0]['loss'])     # ~1e-5 map-feature noise (pixel flips), 15 m position scale
+    # one flipped crop pixel moves a 6-step trajectory by ~1e-4 (normalised) = 1.5 mm; the matching loss is 10 x mean |delta|^2 with
+    # |delta| ~ 2.6 m here, so d(loss) ~ 2 x 2.6 m x 1.5 mm x 10 = 0.08 of 66 (1e-3); which pixels flip changes with any re-association
+    assert abs(logs[0]['loss'] - rec[0]['loss']) < 1.5e-3 * abs(rec[0]['loss'])
     assert e_g < 3e-2            # 6-step BPTT after ~1e-5 forward noise (pixel flips), as in the solution-loop test; strict check = teacher-forced test
     assert dz.max() <= 2 * lr * iters + 1e-4      # Adam's first steps are sign-like: noise-level gradient entries may flip
     assert tuple(traj.shape) == (sc['z'].size(0), FT, 4)
