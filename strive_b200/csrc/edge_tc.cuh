@@ -626,22 +626,41 @@ __global__ void __launch_bounds__(128 * (128 / CPT), 1) edge_bwd_tc_kernel(Model
         *reinterpret_cast<float4*>(stg + (size_t)row * ETB_ST_LD + part * CPT + c) = make_float4(d1[c], d1[c + 1], d1[c + 2], d1[c + 3]);
     }
     __syncthreads();
-    if (part == 0 && r.valid) {
-      float drel[4];
-#pragma unroll
-      for (int d = 0; d < 4; d++) {
-        float s = 0.f;
-#pragma unroll
-        for (int p = 0; p < PARTS; p++) s += s_drel[d * 512 + p * 128 + row];
-        drel[d] = ((nanmask >> d) & 1u) ? 0.f : s;
-      }
+    if (part == 0) {                                               // warps 0..3: one thread per row
       float dpi[4] = {0.f, 0.f, 0.f, 0.f}, dpj[4] = {0.f, 0.f, 0.f, 0.f};
-      t2f_bwd(pi, pj, drel, dpi, dpj);
-      const int k = row / slot;
+      if (r.valid) {
+        float drel[4];
 #pragma unroll
-      for (int d = 0; d < 4; d++) {
-        atomicAdd(a.tp.g_pos + (size_t)r.j * 4 + d, dpj[d]);
-        atomicAdd(&s_dpi[k * 4 + d], dpi[d]);
+        for (int d = 0; d < 4; d++) {
+          float s = 0.f;
+#pragma unroll
+          for (int p = 0; p < PARTS; p++) s += s_drel[d * 512 + p * 128 + row];
+          drel[d] = ((nanmask >> d) & 1u) ? 0.f : s;
+        }
+        t2f_bwd(pi, pj, drel, dpi, dpj);
+#pragma unroll
+        for (int d = 0; d < 4; d++) atomicAdd(a.tp.g_pos + (size_t)r.j * 4 + d, dpj[d]);
+      }
+      // position adjoint of the TARGET: the rows of one target are consecutive, so a warp holds at most 32 / slot + 1 targets --
+      // reduce per target with shuffles and let one lane add the sum (32 lanes hitting one shared-memory word serialise)
+      const int k = row / slot;
+      unsigned todo = 0xffffffffu;
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int kk = __shfl_sync(0xffffffffu, k, leader);
+        const bool mine = (k == kk);
+        float v[4];
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+          v[d] = mine ? dpi[d] : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v[d] += __shfl_xor_sync(0xffffffffu, v[d], o);
+        }
+        if (lane == leader) {
+#pragma unroll
+          for (int d = 0; d < 4; d++) atomicAdd(&s_dpi[kk * 4 + d], v[d]);
+        }
+        todo &= ~__ballot_sync(0xffffffffu, mine);
       }
     }
     {
@@ -673,7 +692,7 @@ __global__ void __launch_bounds__(128 * (128 / CPT), 1) edge_bwd_tc_kernel(Model
         for (int k = 0; k < kmax; k++) {
           const int li = first + k;
           const int e = max(min(lj - (lj > li ? 1 : 0), n - 2), 0);    // (clamped: the li == lj term is masked below)
-          const float v = stg[(size_t)(k * slot + e) * ETB_ST_LD + col];
+          const float v = stg[(k * slot + e) * ETB_ST_LD + col];
           s += (li != lj) ? v : 0.f;
         }
         atomicAdd(a.tp.dQ + (size_t)(p0 + lj) * 128 + col, s);
