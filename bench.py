@@ -477,7 +477,7 @@ def train_leg(env, dev, dist, rank, world, barrier, steps=3, warmup=2):
             'agent_timesteps_per_s': world * NA * FT * steps / (ms / 1000.0), 'grad_bucket_bytes': tr.bucket.numel * 4,
             'all_reduce_ms_per_step': (sum(ar) / len(ar)) if ar else 0.0, 'all_reduce_share_of_step': (sum(ar) / len(ar)) / (ms / steps) if ar else 0.0,
             'loss': float(ld['loss']), 'compute': 'PyTorch autograd (cuDNN / cuBLAS) on the package parameter tree + CUDA crop kernel; collective = one NCCL all-reduce of the flat bucket',
-            'limiter': 'the per-rank forward/backward (library kernels, small batch); the 4.4 MB all-reduce is latency-bound and < 1 % of the step'}
+            'limiter': 'the per-rank forward/backward (library kernels, small batch); all_reduce_ms is the device time from the end of this rank\'s backward to the end of the all-reduce, i.e. mostly the skew between ranks -- the 4.4 MB exchange itself is latency-bound (tens of microseconds over NVLink)'}
 
 
 def extra_legs(args, model, env, dev, dist, rank, world, barrier):
@@ -531,6 +531,7 @@ def extra_legs(args, model, env, dev, dist, rank, world, barrier):
     gptr5 = list(range(0, S5 + 1, grp))
     job = ShardedJob('refine', model, sc5, env, REFINE_W, LR, FT5, gptr5, veh_coll_buffer=0.2)
     job.loop.run(2)                                   # eager iteration + capture + one replay
+    job.run(0)                                        # untimed: the first NCCL send/recv of every pair sets up its channel (seconds)
     it5 = 2
     barrier()
     ms, z5 = _event_time(lambda: job.run(it5), dev)
@@ -548,6 +549,7 @@ def extra_legs(args, model, env, dev, dist, rank, world, barrier):
     job = ShardedJob('adv', model, sc3, env, ADV_W, LR, FT3, gptr3, veh_coll_buffer=0.1, crash_min_t=2, crash_min_infront=-0.5)
     if job.loop is not None:
         job.loop.run(2)
+    job.run(0)
     it3 = 30
     barrier()
     ms, z3 = _event_time(lambda: job.run(it3), dev)
@@ -585,9 +587,9 @@ def extra_legs(args, model, env, dev, dist, rank, world, barrier):
                                 'iter4_z_max_abs_diff': float(dz.max()), 'iter4_z_median_abs_diff': float(dz.median()),
                                 'iter4_z_frac_above_1e-3': float((dz > 1e-3).float().mean()), 'z_moved': float((zs - scs['z']).abs().max()),
                                 'unsharded_rerun_iter4_z_max_abs_diff': float(dz2.max()), 'unsharded_rerun_iter4_z_frac_above_1e-3': float((dz2 > 1e-3).float().mean()),
-                                'note': 'iteration 1: same inputs, a different batch composition per rank (fp32 re-association in conv3 / float atomics in '
-                                        'the reductions); by iteration 4 Adam\'s normalised steps and nearest-pixel crops have amplified that noise -- the '
-                                        'same loop run twice on one GPU is the yardstick: unsharded_rerun_*'}
+                                'note': 'iteration 1: same inputs, a different batch composition per rank -- the forward pass is bitwise invariant to it, the '
+                                        'gradient differs by the order of the float atomics of the backward pass; by iteration 4 Adam\'s normalised steps and the '
+                                        'nearest-pixel crops have amplified that rounding noise -- the same loop run twice on one GPU is the yardstick: unsharded_rerun_*'}
     barrier()
     # ---- configs[3]: data-parallel training step
     torch.cuda.empty_cache()
