@@ -153,8 +153,9 @@ class _DeviceLoop(object):
     def _rollout_launches(self, sweeps):
         FT, NA = self.FT, self.NA
         chunks = (NA + 2047) // 2048
-        fwd = 1 + FT * 3 + (FT - 1) * (1 + chunks * 8)      # init_tape; node/edge/post per step; gru + (crop_pack, conv1..6, fc) per chunk
-        bwd = FT * 3 + (FT - 1)
+        tiles = 1 if self.scene.max_n <= 129 else 0         # edge_tc_tiles (tcgen05 edge kernels: scenes up to 129 agents)
+        fwd = 1 + tiles + FT * 3 + (FT - 1) * (1 + chunks * 8)      # init_tape; node/edge/post per step; gru + (crop_pack, conv1..6, fc) per chunk
+        bwd = tiles + FT * 3 + (FT - 1)
         return fwd + sweeps * bwd
 
 

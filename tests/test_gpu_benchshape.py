@@ -253,3 +253,32 @@ def test_decode_vs_reference_fixture(tag):
     # rounding of a tie: any two fp32 evaluations part ways at the first re-encode (map_feat moves by 1e-5..1e-3) and the
     # rollout amplifies it -- the envelope is the fp32-vs-fp64 gap of the oracle itself, as for the small fixtures.
     assert bool((e <= 10.0 * np.maximum.accumulate(e_64) + 1e-5).all())
+
+
+def test_edge_tile_table_covers_every_slot_size_and_the_mma_fallback():
+    """Scenes of 1, 2, 9, 10, 25, 41, 65 and 129 agents put 8 / 8 / 8 / 16 / 24 / 40 / 64 / 128 rows per target into the 128-edge
+    tiles of the tcgen05 edge kernels (several tiles per scene, partly filled last tiles, a tile that is one target); a 130-agent
+    scene exceeds a tile and must fall back to the mma.sync kernels.  Forward (aggr, arg-max) and backward (dL/dz) against the fp32
+    SIMT kernels."""
+    from strive_b200 import _cabi
+    FT = 2
+    for sizes in ([1, 2, 9, 10, 25, 41, 65, 129], [130, 3]):
+        sc = synth.make_scenes(91, sizes, map_extent_m=EXTENT, M=2, FT=FT, collide_frac=1.0, offroad_frac=1.0)
+        seed = torch.randn(sc['z'].size(0), FT, 4, generator=torch.Generator().manual_seed(10))
+        res = {}
+        for impl in (0, 3):
+            _cabi.set_edge_impl(impl)
+            try:
+                traj, tape, NA = gpu_forward(sc, FT)
+                res[impl] = (traj, _tape(tape, 'aggr', 0, NA, FT, 64), read_arg(tape, 0, NA, FT), _lowlevel(sc, FT)[2](seed))
+            finally:
+                _cabi.set_edge_impl(3)
+        d_aggr = (res[0][1] - res[3][1]).abs().max().item()
+        n_arg = int((res[0][2] != res[3][2]).sum())
+        gs = res[0][3].abs().max().item()
+        d_g = (res[0][3] - res[3][3]).abs().max().item()
+        diag('edge tile table sizes %s: |aggr tc-simt| %.2e, arg-max mismatches %d of %d, |d_z| %.3e (max %.3e)' % (sizes, d_aggr, n_arg, res[0][2].numel(), d_g, gs))
+        assert d_aggr < 2e-5 and n_arg <= 2
+        assert d_g < 5e-2 * max(1.0, gs)
+        if sizes[0] == 1:
+            assert bool((res[3][1][0] == 0).all()) and bool((res[3][2][0] == 255).all())      # no in-edges: message 0, arg-max 255 (interaction_net.py:187-188)
