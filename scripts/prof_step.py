@@ -30,7 +30,7 @@ e1.record()
 torch.cuda.synchronize()
 print('%s: %.2f ms/step, loss %.4f' % (os.environ.get('STRIVE_LIB', 'default'), e0.elapsed_time(e1) / 3, float(loop.terms[:, 0].sum())))
 _cabi.profile_enable(True)
-loop.step()
+loop.eager_step()
 torch.cuda.synchronize()
 rep = _cabi.profile_report()
 tot = sum(v[1] for v in rep.values())
