@@ -43,7 +43,7 @@ class StriveLossCfg(C.Structure):
                 ('circ_cx', C.c_void_p), ('lw_un', C.c_void_p), ('adv_own_pred', C.c_int32), ('reserved0', C.c_int32)]
 
 
-EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_tc_trace', 'strive_tc_debug', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl', 'strive_model_edge_frag_bytes', 'strive_model_set_edge_frags', 'strive_edge_set_impl', 'strive_set_pdl',
+EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_tc_trace', 'strive_tc_debug', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl', 'strive_mapenc_set_split', 'strive_model_edge_frag_bytes', 'strive_model_set_edge_frags', 'strive_edge_set_impl', 'strive_set_pdl',
            'strive_mapenc_workspace_bytes', 'strive_mapenc_fwd', 'strive_map_crop', 'strive_decode_tape_bytes',
            'strive_decode_fwd', 'strive_decode_bwd', 'strive_decode_tape_read', 'strive_loss_workspace_bytes',
            'strive_loss_fwd_bwd', 'strive_adam_step', 'strive_adam_step_dev', 'strive_on_layer_frac', 'strive_line_layer', 'strive_veh_iou_hits']
@@ -68,6 +68,7 @@ def lib():
     L.strive_model_tc_bytes.restype = i64
     L.strive_model_set_tc_weights.argtypes = [vp, vp, i64]
     L.strive_mapenc_set_impl.argtypes = [C.c_int]
+    L.strive_mapenc_set_split.argtypes = [C.c_int]
     L.strive_model_edge_frag_bytes.restype = i64
     L.strive_model_set_edge_frags.argtypes = [vp, vp, i64, vp]
     L.strive_edge_set_impl.argtypes = [C.c_int]
@@ -100,6 +101,8 @@ def lib():
     if L.strive_abi_version() != 1:
         raise RuntimeError('strive_b200: ABI version mismatch')
     _verify_layout(L)
+    if os.environ.get('STRIVE_MAPENC_SPLIT') is not None:   # development switch: half-chunk pipeline of the map encoder
+        L.strive_mapenc_set_split(int(os.environ['STRIVE_MAPENC_SPLIT']))
     if os.environ.get('STRIVE_PDL') is not None:      # development switch: bit 0 rollout kernels, bit 1 map-encoder kernels
         L.strive_set_pdl(int(os.environ['STRIVE_PDL']))
     _lib = L

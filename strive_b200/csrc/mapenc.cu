@@ -360,6 +360,27 @@ extern "C" int64_t strive_mapenc_workspace_bytes(int32_t n) {
   return (int64_t)(fl * 4 + 6 * c * 2 * 8 + c * 65536 + 512);
 }
 
+// second stream of the half-chunk pipeline (one per device, created on first use; the drivers are single-threaded per device)
+static int g_mapenc_split = 1;
+extern "C" int strive_mapenc_set_split(int on) {
+  g_mapenc_split = on;
+  return 0;
+}
+static int mapenc_side_stream(cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) {
+  static cudaStream_t s[16] = {};
+  static cudaEvent_t e0[16] = {}, e1[16] = {};
+  int dev = 0;
+  STRIVE_CUDA(cudaGetDevice(&dev));
+  STRIVE_CHECK(dev >= 0 && dev < 16, STRIVE_EUNSUPPORTED, "device index %d", dev);
+  if (s[dev] == nullptr) {
+    STRIVE_CUDA(cudaStreamCreateWithFlags(&s[dev], cudaStreamNonBlocking));
+    STRIVE_CUDA(cudaEventCreateWithFlags(&e0[dev], cudaEventDisableTiming));
+    STRIVE_CUDA(cudaEventCreateWithFlags(&e1[dev], cudaEventDisableTiming));
+  }
+  *side = s[dev]; *ev_fork = e0[dev]; *ev_join = e1[dev];
+  return 0;
+}
+
 extern "C" int strive_mapenc_fwd(const StriveModel* m, const StriveMap* map, const float* pose_un, const int32_t* map_of,
                                  int32_t n, float* out_feat, void* workspace, int64_t workspace_bytes, void* stream_) {
   STRIVE_CHECK(m && map && pose_un && map_of && out_feat && workspace, STRIVE_EINVAL, "strive_mapenc_fwd: null argument");
@@ -388,21 +409,48 @@ extern "C" int strive_mapenc_fwd(const StriveModel* m, const StriveMap* map, con
     const int32_t* mo = map_of + start;
     int rc;
     if (g_mapenc_impl == 1 && m->tc_blob != nullptr) {
-      // tensor-core path (mapenc_tc.cu): conv1..conv4 on tcgen05, activations NHWC fp32
-      rc = tc_launch_conv1(map, pose, mo, m->tc_blob + m->tc_off[0], m->h_cbias[0], act[0], st[0], packed_crop, cn, stream);
+      // tensor-core path (mapenc_tc.cu): conv1..conv4 on tcgen05, activations channel-blocked fp32.
+      // The crops of a chunk are independent, so the chunk runs as TWO half-chunks on two streams (fork / join with events; inside
+      // a stream capture the side stream simply becomes a second branch of the graph): the crop gather of one half (L1 / ALU bound,
+      // no TMEM, little shared memory) is co-resident with the TMEM-read / HBM-write bound conv1 of the other, and the tail wave of
+      // every kernel is filled by the other half's next kernel.
+      auto half = [&](int h0, int hn, cudaStream_t s) -> int {
+        float* a[6];
+        double* t[6];
+        for (int i = 0; i < 6; i++) { a[i] = act[i] + kActFloats[i] * (size_t)h0; t[i] = st[i] + (size_t)h0 * 2; }
+        int r = tc_launch_conv1(map, pose + (size_t)h0 * 4, mo + h0, m->tc_blob + m->tc_off[0], m->h_cbias[0], a[0], t[0], packed_crop + (size_t)h0 * 65536, hn, s);
+        if (r) return r;
+        r = tc_launch_conv2(a[0], t[0], sg[S_GG0], sg[S_GB0], m->tc_blob + m->tc_off[1], m->h_cbias[1], a[1], t[1], hn, s);
+        if (r) return r;
+        r = tc_launch_conv3(a[1], t[1], sg[S_GG1], sg[S_GB1], m->tc_blob + m->tc_off[2], m->h_cbias[2], a[2], t[2], hn, s);
+        if (r) return r;
+        r = tc_launch_conv4(a[2], t[2], sg[S_GG2], sg[S_GB2], m->tc_blob + m->tc_off[3], m->h_cbias[3], a[3], t[3], hn, s);
+        if (r) return r;
+        r = tc_launch_conv5(a[3], t[3], sg[S_GG3], sg[S_GB3], m->tc_blob + m->tc_off[4], sg[S_CB4], a[4], t[4], hn, s);
+        if (r) return r;
+        r = tc_launch_conv6(a[4], t[4], sg[S_GG4], sg[S_GB4], m->tc_blob + m->tc_off[5], sg[S_CB5], a[5], t[5], hn, s);
+        if (r) return r;
+        return tc_launch_fc(a[5], t[5], sg[S_GG5], sg[S_GB5], m->tc_blob + m->tc_off[6], sg[S_FCB], out_feat + (size_t)(start + h0) * 64, hn, s);
+      };
+      const bool split = g_mapenc_split != 0 && g_strive_profile_on == 0 && cn >= 512;
+      if (!split) {
+        rc = half(0, cn, stream);
+        if (rc) return rc;
+        continue;
+      }
+      cudaStream_t side;
+      cudaEvent_t ev_fork, ev_join;
+      rc = mapenc_side_stream(&side, &ev_fork, &ev_join);
       if (rc) return rc;
-      rc = tc_launch_conv2(act[0], st[0], sg[S_GG0], sg[S_GB0], m->tc_blob + m->tc_off[1], m->h_cbias[1], act[1], st[1], cn, stream);
+      const int h0n = (cn / 2) & ~1;
+      STRIVE_CUDA(cudaEventRecord(ev_fork, stream));                 // after the statistics memset
+      STRIVE_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      rc = half(0, h0n, stream);
       if (rc) return rc;
-      rc = tc_launch_conv3(act[1], st[1], sg[S_GG1], sg[S_GB1], m->tc_blob + m->tc_off[2], m->h_cbias[2], act[2], st[2], cn, stream);
+      rc = half(h0n, cn - h0n, side);
       if (rc) return rc;
-      rc = tc_launch_conv4(act[2], st[2], sg[S_GG2], sg[S_GB2], m->tc_blob + m->tc_off[3], m->h_cbias[3], act[3], st[3], cn, stream);
-      if (rc) return rc;
-      rc = tc_launch_conv5(act[3], st[3], sg[S_GG3], sg[S_GB3], m->tc_blob + m->tc_off[4], sg[S_CB4], act[4], st[4], cn, stream);
-      if (rc) return rc;
-      rc = tc_launch_conv6(act[4], st[4], sg[S_GG4], sg[S_GB4], m->tc_blob + m->tc_off[5], sg[S_CB5], act[5], st[5], cn, stream);
-      if (rc) return rc;
-      rc = tc_launch_fc(act[5], st[5], sg[S_GG5], sg[S_GB5], m->tc_blob + m->tc_off[6], sg[S_FCB], out_feat + (size_t)start * 64, cn, stream);
-      if (rc) return rc;
+      STRIVE_CUDA(cudaEventRecord(ev_join, side));
+      STRIVE_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
       continue;
     } else {
       dim3 g1(C1_TILES * C1_TILES, cn);
