@@ -67,8 +67,8 @@ int64_t strive_model_tc_bytes(void);
 int strive_model_set_tc_weights(StriveModel* m, const void* blob, int64_t bytes);
 /* 1 = tensor-core map encoder (default), 0 = fp32 SIMT kernels (A/B verification only) */
 int strive_mapenc_set_impl(int impl);
-/* 1 (default): a chunk of >= 512 crops runs as two half-chunks on two streams (crop gather of one half overlaps conv1 of the other);
- * 0: one stream (A/B). */
+/* 1: a chunk of >= 512 crops runs as two half-chunks on two streams (crop gather of one half overlaps conv1 of the other);
+ * 0 (default): one stream.  Measured +0.1 % on a power-capped B200, kept as an A/B switch. */
 int strive_mapenc_set_split(int on);
 /* Edge MLP of the decoder GNN (interaction_net.py:139-184) on the warp-level tensor path: the library packs the edge-MLP
  * matrices of the weight blob into mma.sync fragment order inside `buf` (device, 16-byte aligned,

@@ -361,7 +361,7 @@ extern "C" int64_t strive_mapenc_workspace_bytes(int32_t n) {
 }
 
 // second stream of the half-chunk pipeline (one per device, created on first use; the drivers are single-threaded per device)
-static int g_mapenc_split = 1;
+static int g_mapenc_split = 0;     // measured on B200 at 2048 crops: +0.1 .. 0.2 % (the SMs sit at the 1 kW power cap: overlap lowers the clock) -> off by default
 extern "C" int strive_mapenc_set_split(int on) {
   g_mapenc_split = on;
   return 0;
@@ -410,10 +410,11 @@ extern "C" int strive_mapenc_fwd(const StriveModel* m, const StriveMap* map, con
     int rc;
     if (g_mapenc_impl == 1 && m->tc_blob != nullptr) {
       // tensor-core path (mapenc_tc.cu): conv1..conv4 on tcgen05, activations channel-blocked fp32.
-      // The crops of a chunk are independent, so the chunk runs as TWO half-chunks on two streams (fork / join with events; inside
-      // a stream capture the side stream simply becomes a second branch of the graph): the crop gather of one half (L1 / ALU bound,
-      // no TMEM, little shared memory) is co-resident with the TMEM-read / HBM-write bound conv1 of the other, and the tail wave of
-      // every kernel is filled by the other half's next kernel.
+      // The crops of a chunk are independent, so a chunk CAN run as two half-chunks on two streams (strive_mapenc_set_split(1); fork /
+      // join with events; inside a stream capture the side stream becomes a second branch of the graph): the crop gather of one half
+      // (L1 / ALU bound, no TMEM, little shared memory) is then co-resident with the TMEM-read / HBM-write bound conv1 of the other
+      // and tail waves are filled.  Measured: 56.11 -> 56.05 ms per iteration at BASELINE configs[1] -- the step is power-capped
+      // (sw_power_cap, 1.77 .. 1.95 GHz), more overlap buys a lower clock -- so the default is one stream.
       auto half = [&](int h0, int hn, cudaStream_t s) -> int {
         float* a[6];
         double* t[6];
