@@ -124,3 +124,23 @@ class StubPlanner(object):
                 x, y = x + hx * s * dt, y + hy * s * dt
                 out[b, t] = [x, y, hx, hy]
         return torch.from_numpy(out).float()
+
+
+def scenario_inputs():
+    """Seeded inputs of the scenario writer (tests/golden/scenario.json holds the reference writer's output for them)."""
+    sc = synth.make_scenes(77, [4], map_extent_m=EXTENT, M=2, FT=5, collide_frac=1.0, offroad_frac=0.0)
+    g = torch.Generator().manual_seed(78)
+    NA = sc['z'].size(0)
+
+    class SG(object):
+        pass
+    sg = SG()
+    sg.past_gt, sg.lw, sg.sem = sc['past'], sc['lw'], sc['sem']
+    kw = dict(init_fut_traj=torch.randn(NA, 5, 4, generator=g), adv_fut_traj=torch.randn(NA, 5, 4, generator=g),
+              sol_fut_traj=torch.randn(NA, 5, 4, generator=g), attack_agt=2, attack_t=3, adv_z=torch.randn(NA, 32, generator=g),
+              sol_z=torch.randn(NA, 32, generator=g), prior_distrib=(sc['prior_mu'], sc['prior_var']),
+              internal_ego_traj=torch.randn(5, 4, generator=g))
+
+    class Env(object):
+        map_list = ['map-a', 'map-b']
+    return sg, kw, Env()

@@ -186,3 +186,26 @@ def test_scene_cache_is_validated_not_pointer_keyed():
     assert TrafficModel._cache_get(g, '_slot', (a, b), extra='cuda:0') is None
     g2 = _G()                                                                            # a fresh graph never sees another's entry
     assert TrafficModel._cache_get(g2, '_slot', (a, b), extra='cuda:0') is None
+
+
+def test_scenario_json_writer_equals_reference_and_reader_round_trips(tmp_path):
+    """strive_b200.scenario_io.prepare_output_dict against the unmodified reference writer's output (utils/scenario_gen.py:189-254) on
+    the same seeded inputs: same keys in the same order, identical values; the reader (datasets/utils.py:10-38) reads it back."""
+    import json
+    import os
+    import strive_b200
+    from strive_b200 import scenario_io
+    from tests.common import scenario_inputs, GOLD
+    from strive_b200.traffic_model import MeanStdNormalizer, STATE_MEAN, STATE_STD, ATT_MEAN, ATT_STD
+    ref = json.load(open(os.path.join(GOLD, 'scenario.json')))
+    sg, kw, env = scenario_inputs()
+    model = strive_b200.TrafficModel(4, 5, 256, 2)
+    model.set_normalizer(MeanStdNormalizer(torch.tensor(STATE_MEAN), torch.tensor(STATE_STD)))
+    model.set_att_normalizer(MeanStdNormalizer(torch.tensor(ATT_MEAN), torch.tensor(ATT_STD)))
+    out = scenario_io.prepare_output_dict(sg, 1, env, 0.5, model, **kw)
+    assert list(out.keys()) == list(ref.keys())
+    assert json.loads(json.dumps(out)) == ref                     # bit-identical floats after the JSON round trip
+    scenario_io.write_scenario(str(tmp_path / 'scene_000.json'), out)
+    back = scenario_io.read_adv_scenes(str(tmp_path))
+    assert len(back) == 1 and back[0]['name'] == 'scene_000' and back[0]['map'] == 'map-b' and back[0]['attack_t'] == 3
+    assert torch.equal(back[0]['scene_fut'], torch.tensor(ref['fut_adv'])) and tuple(back[0]['veh_att'].shape) == (4, 2)
