@@ -524,6 +524,8 @@ def extra_legs(args, model, env, dev, dist, rank, world, barrier):
         del loop
     out['c3_single_gpu'] = c3
     torch.cuda.empty_cache()
+    if os.environ.get('BENCH_C3_ONLY'):               # development shortcut
+        return out
 
     # ---- sharded configs[4]: one global batch over N ranks
     S5, n5, FT5, grp = 1024, 64, 40, 4

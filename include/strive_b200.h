@@ -134,6 +134,13 @@ int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, const StriveM
                       float* traj_out, void* tape, int64_t tape_bytes, void* stream);
 int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, int32_t ft, const float* ext_future,
                       const float* d_traj, float* d_z, void* tape, int64_t tape_bytes, void* stream);
+/* Two sweeps of the same forward tape in one call: (d_traj_a -> d_z_a) and (d_traj_b -> d_z_b), results identical to two
+ * strive_decode_bwd calls.  Replaces the two backward passes of adv_gen_optim.py:119-130,170-171 / sol_optim.py:75-86,108-109
+ * (one seed per latent group).  The second sweep runs on an internal side stream with its own carry buffers inside the tape
+ * (fork / join by events on `stream`; capturable), so the pair overlaps on the device. */
+int strive_decode_bwd_pair(const StriveModel* m, const StriveScene* sc, int32_t ft, const float* ext_future,
+                           const float* d_traj_a, float* d_z_a, const float* d_traj_b, float* d_z_b,
+                           void* tape, int64_t tape_bytes, void* stream);
 /* test hook: copies one named tape tensor of step t to `out` (float). names: x,P,Q,aggr,past_feat,map_feat,prev,pos,loc,mem;
  * "arg" copies the (NA,64) uint8 arg-max routing table of the max aggregation (local source index in the scene, 255 = none). */
 int strive_decode_tape_read(const void* tape, int32_t num_agents, int32_t ft, const char* name, int32_t t,

@@ -1,0 +1,38 @@
+"""Map encoder alone on N crops under each timing-experiment flag set of strive_tc_debug (development only): per-kernel CUDA-event
+times via KPROF.  Flags: 1 no output stores, 2 no operand stores, 4 no input loads, 8 no MMAs,
+32 no weight copies (tc_gemm).  Results with any flag set are garbage by design."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import strive_b200
+from strive_b200 import synth, _cabi
+N = int(os.environ.get('N', '2048'))
+FLAGS = [int(v) for v in os.environ.get('FLAGS', '0,4,2,8,32,12,14,6').split(',')]
+dev = torch.device('cuda:0')
+raster, dx = synth.make_raster(seed=1, M=1, H=4096, W=4096)
+sd = synth.make_weights(0)
+model = strive_b200.make_model(nfuture=20, state_dict=sd, device=dev)
+env = strive_b200.MapEnv(raster, dx, device=dev)
+g = torch.Generator().manual_seed(0)
+xy = torch.rand(N, 2, generator=g) * 600 + 200
+ang = torch.rand(N, generator=g) * 6.2831853
+pose = torch.cat([xy, torch.cos(ang)[:, None], torch.sin(ang)[:, None]], 1).to(dev).contiguous()
+mapix = torch.zeros(N, dtype=torch.int32, device=dev)
+for _ in range(2):
+    f = model.encode_map_poses(pose, mapix, env)
+torch.cuda.synchronize()
+ref = f.clone()
+names = ('crop_pack', 'tc_conv1', 'tc_conv2', 'tc_conv3', 'tc_conv4', 'tc_conv5', 'tc_conv6', 'tc_fc')
+for fl in FLAGS:
+    _cabi.lib().strive_tc_debug(fl)
+    f = model.encode_map_poses(pose, mapix, env)
+    torch.cuda.synchronize()
+    _cabi.profile_enable(True)
+    for _ in range(3):
+        f = model.encode_map_poses(pose, mapix, env)
+    torch.cuda.synchronize()
+    rep = _cabi.profile_report()
+    _cabi.profile_enable(False)
+    print('flags %2d: ' % fl + '  '.join('%s %.1f' % (k.replace('tc_', ''), 1000 * rep[k][1] / rep[k][0]) for k in names if k in rep)
+          + '  | us per launch; |feat - flags0| = %.3g' % float((f - ref).abs().max()))
+_cabi.lib().strive_tc_debug(0)

@@ -45,7 +45,7 @@ class StriveLossCfg(C.Structure):
 
 EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_tc_trace', 'strive_tc_debug', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl', 'strive_mapenc_set_split', 'strive_model_edge_frag_bytes', 'strive_model_set_edge_frags', 'strive_edge_set_impl', 'strive_set_pdl',
            'strive_mapenc_workspace_bytes', 'strive_mapenc_fwd', 'strive_map_crop', 'strive_decode_tape_bytes',
-           'strive_decode_fwd', 'strive_decode_bwd', 'strive_decode_tape_read', 'strive_loss_workspace_bytes',
+           'strive_decode_fwd', 'strive_decode_bwd', 'strive_decode_bwd_pair', 'strive_decode_tape_read', 'strive_loss_workspace_bytes',
            'strive_loss_fwd_bwd', 'strive_adam_step', 'strive_adam_step_dev', 'strive_on_layer_frac', 'strive_line_layer', 'strive_veh_iou_hits']
 
 
@@ -81,6 +81,7 @@ def lib():
     L.strive_decode_tape_bytes.restype = i64
     L.strive_decode_fwd.argtypes = [vp, C.POINTER(StriveScene), C.POINTER(StriveMap), vp, vp, vp, vp, i32, vp, vp, i64, vp]
     L.strive_decode_bwd.argtypes = [vp, C.POINTER(StriveScene), i32, vp, vp, vp, vp, i64, vp]
+    L.strive_decode_bwd_pair.argtypes = [vp, C.POINTER(StriveScene), i32, vp, vp, vp, vp, vp, vp, i64, vp]
     L.strive_decode_tape_read.argtypes = [vp, i32, i32, C.c_char_p, i32, vp, vp]
     L.strive_loss_workspace_bytes.argtypes = [i32, i32, i32]
     L.strive_loss_workspace_bytes.restype = i64

@@ -1201,7 +1201,7 @@ template <int CIN, int KS, int HIN, int HOUT, int COUT, bool FINAL>
 __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
                                                              const float* __restrict__ gam, const float* __restrict__ bet,
                                                              const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
-                                                             float* __restrict__ out, double* __restrict__ out_stats, int n) {
+                                                             float* __restrict__ out, double* __restrict__ out_stats, int n, int dbg) {
   using Cfg = Tc3Cfg<CIN, KS, HIN, HOUT, COUT, FINAL>;
   constexpr int PIX = Cfg::PIX, NCH = Cfg::NCH, NBUF = Cfg::NBUF;
   static_assert(CIN % 64 == 0 && COUT % 32 == 0 && 2 * COUT <= 512, "tc_gemm tiling");
@@ -1266,12 +1266,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
           offs[j] = idx < 128 * 8 ? s_off[tpar][idx & 127] : -2;
           if (offs[j] >= 0) {
             const float* src = in + (size_t)offs[j] + (ky * HIN + kx) * CIN + c0 + (idx >> 7) * 8;
+            if (dbg & 4) { t0[j] = make_float4(1.f, 1.f, 1.f, 1.f); t1[j] = t0[j]; continue; }
             t0[j] = __ldg(reinterpret_cast<const float4*>(src));
             t1[j] = __ldg(reinterpret_cast<const float4*>(src + 4));
           }
         }
         tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
-        {
+        if (!(dbg & 32)) {
           const uint8_t* src = wpack + (size_t)kc * 2 * Cfg::W_PREC;
           const uint32_t dstw = tc::smem_u32(sWt);
           for (int i = tid; i < 2 * Cfg::W_PREC / 16; i += TC_PROD_THREADS)
@@ -1297,6 +1298,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
             }
           }
           const int unit = (kg * 16 + (m >> 3)) * 8 + (m & 7);
+          if (dbg & 2) continue;
           *reinterpret_cast<uint4*>(sA + (size_t)unit * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(sA + Cfg::A_PREC + (size_t)unit * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
@@ -1329,6 +1331,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
             const uint64_t al = tc::desc_make(a_lo0 + ((Cfg::A_PREC + j * 2 * 2048) >> 4), a_hi);
             const uint64_t bh = tc::desc_make(b_lo0 + ((j * 2 * LBO_W) >> 4), b_hi);
             const uint64_t bl = tc::desc_make(b_lo0 + ((Cfg::W_PREC + j * 2 * LBO_W) >> 4), b_hi);
+            if (dbg & 8) continue;
             tc::mma_bf16(d, ah, bh, idesc, (j > 0 || kc > 0) ? 1u : 0u);
             tc::mma_bf16(d, al, bh, idesc, 1u);
             tc::mma_bf16(d, ah, bl, idesc, 1u);
@@ -1518,7 +1521,7 @@ static int tc3_launch(const char* name, const float* in, const double* in_stats,
   const long long rows = (long long)n * Cfg::PIX;
   const int tiles = (int)((rows + 127) / 128);
   const int gx = tiles < num_sms() ? tiles : num_sms();
-  KPROF(name, stream, STRIVE_CUDA_LAUNCH(kern, gx, TC_THREADS, Cfg::SMEM, stream, in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
+  KPROF(name, stream, STRIVE_CUDA_LAUNCH(kern, gx, TC_THREADS, Cfg::SMEM, stream, in, in_stats, gam, bet, wpack, bias, out, out_stats, n, g_tc_dbg));
   STRIVE_LAUNCH_CHECK();
   return 0;
 }

@@ -52,7 +52,14 @@ struct Tape {
   int32_t* et_ntiles;  // [1]
   void* mapenc_ws;  // map encoder workspace
   int64_t mapenc_ws_bytes;
+  float* alt[9];    // second set of the nine backward carries above: the sweep strive_decode_bwd_pair runs on its side stream
 };
+
+// switches a tape view to the second carry set (forward tensors stay shared)
+static inline void tape_use_alt(Tape& tp) {
+  tp.g_prev = tp.alt[0]; tp.g_pos = tp.alt[1]; tp.g_pf = tp.alt[2]; tp.g_mem = tp.alt[3]; tp.d_loc = tp.alt[4];
+  tp.d_xupd = tp.alt[5]; tp.d_aggr = tp.alt[6]; tp.dP = tp.alt[7]; tp.dQ = tp.alt[8];
+}
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -89,6 +96,10 @@ static int64_t tape_carve(Tape* tp, char* base, int NA, int FT) {
   tp->map_of = (int32_t*)take(n * 4);
   tp->et_tiles = (int32_t*)take(n * 2 * 4);
   tp->et_ntiles = (int32_t*)take(256);
+  {
+    const size_t w[9] = {6, 4, 64, 192, 4, 64, 64, 128, 128};
+    for (int i = 0; i < 9; i++) tp->alt[i] = (float*)take(n * w[i] * 4);
+  }
   tp->mapenc_ws_bytes = strive_mapenc_workspace_bytes(NA);
   tp->mapenc_ws = (void*)take((size_t)tp->mapenc_ws_bytes);
   return (int64_t)off;
@@ -1390,34 +1401,16 @@ extern "C" int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, co
   return 0;
 }
 
-extern "C" int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, int32_t ft, const float* ext_future,
-                                 const float* d_traj, float* d_z, void* tape, int64_t tape_bytes, void* stream_) {
-  int rc = check_scene(m, sc, ft);
-  if (rc) return rc;
-  cudaStream_t stream = (cudaStream_t)stream_;
+// one adjoint sweep t = FT-1 .. 0 over the tape on `stream`; `a` carries the seed (d_traj), the output (d_z) and the carry set
+static int bwd_sweep(const StriveModel* m, const StriveScene* sc, int32_t ft, const ModelDev& M, StepArgs a, bool edge_tc, cudaStream_t stream) {
   const int NA = sc->num_agents;
-  StepArgs a;
-  const int64_t need = tape_carve(&a.tp, (char*)tape, NA, ft);
-  STRIVE_CHECK(tape_bytes >= need, STRIVE_ESIZE, "tape too small: %lld < %lld", (long long)tape_bytes, (long long)need);
-  rc = set_smem_attrs();
-  if (rc) return rc;
-  a.NA = NA; a.FT = ft; a.NC = sc->num_classes; a.t = 0;
-  a.ptr = sc->ptr; a.scene_of = sc->scene_of; a.lw = sc->lw; a.sem = sc->sem; a.z = nullptr; a.ext = ext_future;
-  a.traj = nullptr; a.d_traj = d_traj; a.d_z = d_z;
-  a.z = a.tp.z;   // the latent the forward pass ran on
-  ModelDev M = model_dev(m);
-  STRIVE_CUDA(cudaMemsetAsync(d_z, 0, (size_t)NA * ZDIM * 4, stream));
+  STRIVE_CUDA(cudaMemsetAsync(a.d_z, 0, (size_t)NA * ZDIM * 4, stream));
   STRIVE_CUDA(cudaMemsetAsync(a.tp.g_prev, 0, (size_t)NA * 6 * 4, stream));
   STRIVE_CUDA(cudaMemsetAsync(a.tp.g_pos, 0, (size_t)NA * 4 * 4, stream));
   STRIVE_CUDA(cudaMemsetAsync(a.tp.g_pf, 0, (size_t)NA * 64 * 4, stream));
   STRIVE_CUDA(cudaMemsetAsync(a.tp.g_mem, 0, (size_t)NA * 192 * 4, stream));
   STRIVE_CUDA(cudaMemsetAsync(a.tp.d_loc, 0, (size_t)NA * 4 * 4, stream));
   const int node_blocks = (NA + NODE_WARPS * NODE_R - 1) / (NODE_WARPS * NODE_R);
-  const bool edge_tc = g_edge_impl >= 3 && m->edge_frags != nullptr && sc->max_scene_agents <= ET_MAX_N;
-  if (edge_tc) {     // the tile table depends on ptr only; rebuilt here so a backward call never relies on which forward kernel ran
-    KPROF("edge_tiles", stream, edge_tc_tiles_kernel<<<1, 1024, 0, stream>>>(sc->ptr, sc->num_scenes, a.tp.et_tiles, a.tp.et_ntiles));
-    STRIVE_LAUNCH_CHECK();
-  }
   for (int t = ft - 1; t >= 0; t--) {
     a.t = t;
     const int has_gru = (t + 1 < ft) ? 1 : 0;
@@ -1441,6 +1434,85 @@ extern "C" int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, in
     STRIVE_LAUNCH_CHECK();
   }
   return 0;
+}
+
+// common part of the backward entry points: argument block on the forward tape, edge tile table
+static int bwd_setup(const StriveModel* m, const StriveScene* sc, int32_t ft, const float* ext_future, void* tape, int64_t tape_bytes,
+                     StepArgs& a, bool& edge_tc, cudaStream_t stream) {
+  int rc = check_scene(m, sc, ft);
+  if (rc) return rc;
+  const int NA = sc->num_agents;
+  const int64_t need = tape_carve(&a.tp, (char*)tape, NA, ft);
+  STRIVE_CHECK(tape_bytes >= need, STRIVE_ESIZE, "tape too small: %lld < %lld", (long long)tape_bytes, (long long)need);
+  rc = set_smem_attrs();
+  if (rc) return rc;
+  a.NA = NA; a.FT = ft; a.NC = sc->num_classes; a.t = 0;
+  a.ptr = sc->ptr; a.scene_of = sc->scene_of; a.lw = sc->lw; a.sem = sc->sem; a.ext = ext_future;
+  a.traj = nullptr; a.d_traj = nullptr; a.d_z = nullptr;
+  a.z = a.tp.z;   // the latent the forward pass ran on
+  edge_tc = g_edge_impl >= 3 && m->edge_frags != nullptr && sc->max_scene_agents <= ET_MAX_N;
+  if (edge_tc) {     // the tile table depends on ptr only; rebuilt here so a backward call never relies on which forward kernel ran
+    KPROF("edge_tiles", stream, edge_tc_tiles_kernel<<<1, 1024, 0, stream>>>(sc->ptr, sc->num_scenes, a.tp.et_tiles, a.tp.et_ntiles));
+    STRIVE_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, int32_t ft, const float* ext_future,
+                                 const float* d_traj, float* d_z, void* tape, int64_t tape_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  StepArgs a;
+  bool edge_tc = false;
+  int rc = bwd_setup(m, sc, ft, ext_future, tape, tape_bytes, a, edge_tc, stream);
+  if (rc) return rc;
+  a.d_traj = d_traj; a.d_z = d_z;
+  return bwd_sweep(m, sc, ft, model_dev(m), a, edge_tc, stream);
+}
+
+static int bwd_side_stream(cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) {
+  static cudaStream_t s[16] = {};
+  static cudaEvent_t e0[16] = {}, e1[16] = {};
+  int dev = 0;
+  STRIVE_CUDA(cudaGetDevice(&dev));
+  STRIVE_CHECK(dev >= 0 && dev < 16, STRIVE_EUNSUPPORTED, "device index %d", dev);
+  if (s[dev] == nullptr) {
+    STRIVE_CUDA(cudaStreamCreateWithFlags(&s[dev], cudaStreamNonBlocking));
+    STRIVE_CUDA(cudaEventCreateWithFlags(&e0[dev], cudaEventDisableTiming));
+    STRIVE_CUDA(cudaEventCreateWithFlags(&e1[dev], cudaEventDisableTiming));
+  }
+  *side = s[dev]; *ev_fork = e0[dev]; *ev_join = e1[dev];
+  return 0;
+}
+
+// Two adjoint sweeps of the same forward pass (the adv / sol loops route two different seeds to two groups of latents, SURVEY
+// finding 3).  The sweeps share nothing but the read-only forward tape -- the second one runs on its own carry set -- so they are
+// issued on two streams (fork / join by events: under stream capture they become two parallel branches of the graph).  Every
+// per-agent backward kernel is a single partial wave on a latency floor, so the pair costs little more than one sweep.
+extern "C" int strive_decode_bwd_pair(const StriveModel* m, const StriveScene* sc, int32_t ft, const float* ext_future,
+                                      const float* d_traj_a, float* d_z_a, const float* d_traj_b, float* d_z_b,
+                                      void* tape, int64_t tape_bytes, void* stream_) {
+  STRIVE_CHECK(d_traj_a && d_z_a && d_traj_b && d_z_b && d_z_a != d_z_b, STRIVE_EINVAL, "strive_decode_bwd_pair: two seeds and two distinct outputs are required");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  StepArgs a;
+  bool edge_tc = false;
+  int rc = bwd_setup(m, sc, ft, ext_future, tape, tape_bytes, a, edge_tc, stream);
+  if (rc) return rc;
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  rc = bwd_side_stream(&side, &ev_fork, &ev_join);
+  if (rc) return rc;
+  const ModelDev M = model_dev(m);
+  StepArgs b = a;
+  tape_use_alt(b.tp);
+  a.d_traj = d_traj_a; a.d_z = d_z_a;
+  b.d_traj = d_traj_b; b.d_z = d_z_b;
+  STRIVE_CUDA(cudaEventRecord(ev_fork, stream));                 // after the tile table, which both sweeps read
+  STRIVE_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  rc = bwd_sweep(m, sc, ft, M, a, edge_tc, stream);
+  const int rc_b = bwd_sweep(m, sc, ft, M, b, edge_tc, side);
+  STRIVE_CUDA(cudaEventRecord(ev_join, side));                   // always joined: a capture must not end with a dangling branch
+  STRIVE_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+  return rc ? rc : rc_b;
 }
 
 extern "C" int strive_decode_tape_read(const void* tape, int32_t num_agents, int32_t ft, const char* name, int32_t t,

@@ -109,6 +109,12 @@ class _DeviceLoop(object):
                                              _cabi.dptr(d_traj), _cabi.dptr(d_z), _cabi.dptr(self.tape), self.tape_bytes,
                                              _cabi.stream_ptr()))
 
+    def _sweep_pair(self, d_traj_a, d_z_a, d_traj_b, d_z_b):
+        """Both adjoint sweeps of an adv / sol iteration in one call: two parallel branches on the device."""
+        _cabi.check(self.L.strive_decode_bwd_pair(self.dm.handle, C.byref(self.scene.cstruct), self.FT, _cabi.dptr(self.ext),
+                                                  _cabi.dptr(d_traj_a), _cabi.dptr(d_z_a), _cabi.dptr(d_traj_b), _cabi.dptr(d_z_b),
+                                                  _cabi.dptr(self.tape), self.tape_bytes, _cabi.stream_ptr()))
+
     def _adam_dev(self, g_a, g_b=None, g_direct=None, row_sel=None):
         _cabi.check(self.L.strive_adam_step_dev(_cabi.dptr(self.z), _cabi.dptr(g_a), _cabi.dptr(g_b), _cabi.dptr(g_direct),
                                                 _cabi.dptr(row_sel), 32, _cabi.dptr(self.exp_avg), _cabi.dptr(self.exp_avg_sq),
@@ -273,8 +279,8 @@ class AdvLoop(_DeviceLoop):
         self._forward()
         run_loss(self.plan, self.scene.cstruct, self.traj, self.z, self.prior_mu, self.prior_var, self.init_z, match_tgt=self.match_tgt,
                  adv_tgt=self.ext, d_traj=self.d_traj, d_traj_match=self.d_traj_match, d_z=self.d_z_direct, terms=self.terms)
-        self._sweep(self.d_traj_match, self.g_tgt)          # target rows: matching loss
-        self._sweep(self.d_traj, self.g_oth)                # all other rows: adversarial loss
+        # target rows: matching loss | all other rows: adversarial loss
+        self._sweep_pair(self.d_traj_match, self.g_tgt, self.d_traj, self.g_oth)
         self._adam_dev(self.g_tgt, g_b=self.g_oth, g_direct=self.d_z_direct, row_sel=self.ego_u8)
 
     def grads(self):
@@ -425,8 +431,8 @@ class SolLoop(_DeviceLoop):
         self._forward()
         run_loss(self.plan, self.scene.cstruct, self.traj, self.z, self.prior_mu, self.prior_var, self.init_z, match_tgt=self.match_tgt,
                  d_traj=self.d_traj, d_traj_match=self.d_traj_match, d_z=self.d_z_direct, terms=self.terms)
-        self._sweep(self.d_traj, self.g_tgt)                # target rows: avoid-collision loss
-        self._sweep(self.d_traj_match, self.g_oth)          # other rows: matching loss
+        # target rows: avoid-collision loss | other rows: matching loss
+        self._sweep_pair(self.d_traj, self.g_tgt, self.d_traj_match, self.g_oth)
         self._adam_dev(self.g_tgt, g_b=self.g_oth, g_direct=self.d_z_direct, row_sel=self.ego_u8)
 
     def grads(self):

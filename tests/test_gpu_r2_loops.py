@@ -299,3 +299,47 @@ def test_closed_loop_fused_gradients_equal_autograd_path():
     e_o = (res[True]['g_other'] - res[False]['g_other']).abs().max().item() / res[False]['g_other'].abs().max().item()
     diag('closed loop fused vs autograd: iteration-0 gradient rel diff tgt %.2e other %.2e' % (e_t, e_o))
     assert e_t < 1e-4 and e_o < 1e-4
+
+
+def test_bwd_pair_equals_two_single_sweeps_eager_and_captured():
+    """strive_decode_bwd_pair (two sweeps on two streams, second carry set inside the tape) against two strive_decode_bwd calls on
+    the same forward tape with the same seeds -- launched eagerly and replayed from a captured graph (the fork / join must survive
+    capture).  The sweeps contain float atomics (dQ, g_pos): equality to rounding of the largest gradient."""
+    import ctypes as C
+    from strive_b200 import _cabi
+    from strive_b200.optim import RefineLoop
+    from tests.common import REFINE_W
+    dev, model, env = ctx()
+    sc = synth.make_scenes(41, [9, 4, 17, 6], map_extent_m=EXTENT, M=2, FT=6, collide_frac=1.0, offroad_frac=1.0)
+    embed = {'map_feat': sc['map_feat'].to(dev), 'past_feat': sc['past_feat'].to(dev), 'prior_out': (sc['prior_mu'].to(dev), sc['prior_var'].to(dev))}
+    loop = RefineLoop(model, to_graph(sc, dev), sc['map_idx'].to(dev), env, embed, sc['z'].to(dev), REFINE_W, 0.05, 6, veh_coll_buffer=0.2,
+                      use_graph=False)
+    loop._forward()
+    gen = torch.Generator().manual_seed(3)
+    sa = torch.randn(loop.traj.shape, generator=gen).to(dev)
+    sb = torch.randn(loop.traj.shape, generator=gen).to(dev)
+    sb[::2] = 0.0                                            # a seed that is zero on half of the rows, like the match seed of the loops
+    ga, gb, pa, pb = (torch.full((sa.shape[0], 32), float('nan'), device=dev) for _ in range(4))
+    loop._sweep(sa, ga)
+    loop._sweep(sb, gb)
+    loop._sweep_pair(sa, pa, sb, pb)
+    torch.cuda.synchronize()
+    scale = max(ga.abs().max().item(), gb.abs().max().item())
+    e_eager = max((pa - ga).abs().max().item(), (pb - gb).abs().max().item()) / scale
+    # captured: the side-stream branch must be part of the graph and joined before the capture ends
+    pa.fill_(float('nan')); pb.fill_(float('nan'))
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        loop._sweep_pair(sa, pa, sb, pb)
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(pa).all()) and bool(torch.isnan(pb).all())       # capture launched nothing
+    gr.replay()
+    gr.replay()
+    torch.cuda.synchronize()
+    e_graph = max((pa - ga).abs().max().item(), (pb - gb).abs().max().item()) / scale
+    diag('bwd pair vs two sweeps: rel err eager %.2e, captured+replayed %.2e (max |g| %.3g)' % (e_eager, e_graph, scale))
+    assert e_eager < 2e-6 and e_graph < 2e-6
+    # argument checking: the two outputs must be distinct buffers
+    rc = loop.L.strive_decode_bwd_pair(loop.dm.handle, C.byref(loop.scene.cstruct), loop.FT, _cabi.dptr(loop.ext), _cabi.dptr(sa), _cabi.dptr(pa),
+                                       _cabi.dptr(sb), _cabi.dptr(pa), _cabi.dptr(loop.tape), loop.tape_bytes, _cabi.stream_ptr())
+    assert rc != 0
