@@ -1350,6 +1350,27 @@ static int check_scene(const StriveModel* m, const StriveScene* sc, int ft) {
   return 0;
 }
 
+// side stream + fork / join events of device `dev`, one set per user (0: forward GRU branch, 1: second backward sweep)
+static int side_stream(int which, cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) {
+  static cudaStream_t s_[2][16] = {};
+  static cudaEvent_t e0_[2][16] = {}, e1_[2][16] = {};
+  cudaStream_t* s = s_[which];
+  cudaEvent_t *e0 = e0_[which], *e1 = e1_[which];
+  int dev = 0;
+  STRIVE_CUDA(cudaGetDevice(&dev));
+  STRIVE_CHECK(dev >= 0 && dev < 16, STRIVE_EUNSUPPORTED, "device index %d", dev);
+  if (s[dev] == nullptr) {
+    STRIVE_CUDA(cudaStreamCreateWithFlags(&s[dev], cudaStreamNonBlocking));
+    STRIVE_CUDA(cudaEventCreateWithFlags(&e0[dev], cudaEventDisableTiming));
+    STRIVE_CUDA(cudaEventCreateWithFlags(&e1[dev], cudaEventDisableTiming));
+  }
+  *side = s[dev]; *ev_fork = e0[dev]; *ev_join = e1[dev];
+  return 0;
+}
+
+static int fwd_side_stream(cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) { return side_stream(0, side, ev_fork, ev_join); }
+static int bwd_side_stream(cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) { return side_stream(1, side, ev_fork, ev_join); }
+
 extern "C" int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, const StriveMap* map, const float* z,
                                  const float* map_feat0, const float* past_feat0, const float* ext_future, int32_t ft,
                                  float* traj_out, void* tape, int64_t tape_bytes, void* stream_) {
@@ -1370,6 +1391,10 @@ extern "C" int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, co
   STRIVE_LAUNCH_CHECK();
   const int node_blocks = (NA + NODE_WARPS * NODE_R - 1) / (NODE_WARPS * NODE_R);
   const bool edge_tc = g_edge_impl >= 2 && m->edge_frags != nullptr && sc->max_scene_agents <= ET_MAX_N;
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  rc = fwd_side_stream(&side, &ev_fork, &ev_join);
+  if (rc) return rc;
   if (edge_tc) {
     KPROF("edge_tiles", stream, edge_tc_tiles_kernel<<<1, 1024, 0, stream>>>(sc->ptr, sc->num_scenes, a.tp.et_tiles, a.tp.et_ntiles));
     STRIVE_LAUNCH_CHECK();
@@ -1391,10 +1416,17 @@ extern "C" int strive_decode_fwd(const StriveModel* m, const StriveScene* sc, co
     KPROF("post_fwd", stream, STRIVE_CUDA_LAUNCH(post_fwd_kernel, node_blocks, NODE_THREADS, SM_NODE, stream, M, a));
     STRIVE_LAUNCH_CHECK();
     if (t + 1 < ft) {
-      KPROF("gru_fwd", stream, STRIVE_CUDA_LAUNCH(gru_fwd_kernel, node_blocks, NODE_THREADS, SM_GRU_F, stream, M, a));
-      STRIVE_LAUNCH_CHECK();
+      // the GRU step (loc -> mem, past_feat of t+1) and the map re-encode (pose -> map_feat of t+1) both hang off post_fwd and
+      // meet again in node_fwd(t+1): the GRU kernel -- one partial wave -- runs on the side stream beside the encoder
+      STRIVE_CUDA(cudaEventRecord(ev_fork, stream));
+      STRIVE_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+      KPROF("gru_fwd", side, STRIVE_CUDA_LAUNCH(gru_fwd_kernel, node_blocks, NODE_THREADS, SM_GRU_F, side, M, a));
+      const cudaError_t gru_err = cudaGetLastError();
+      STRIVE_CUDA(cudaEventRecord(ev_join, side));                 // joined whatever happens: a capture must not end with a dangling branch
       rc = strive_mapenc_fwd(m, map, a.tp.pose, a.tp.map_of, NA, a.tp.mapfeat + (size_t)(t + 1) * NA * 64, a.tp.mapenc_ws,
                              a.tp.mapenc_ws_bytes, stream_);
+      STRIVE_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+      STRIVE_CHECK(gru_err == cudaSuccess, 100 + (int)gru_err, "gru_fwd launch: %s", cudaGetErrorString(gru_err));
       if (rc) return rc;
     }
   }
@@ -1467,21 +1499,6 @@ extern "C" int strive_decode_bwd(const StriveModel* m, const StriveScene* sc, in
   if (rc) return rc;
   a.d_traj = d_traj; a.d_z = d_z;
   return bwd_sweep(m, sc, ft, model_dev(m), a, edge_tc, stream);
-}
-
-static int bwd_side_stream(cudaStream_t* side, cudaEvent_t* ev_fork, cudaEvent_t* ev_join) {
-  static cudaStream_t s[16] = {};
-  static cudaEvent_t e0[16] = {}, e1[16] = {};
-  int dev = 0;
-  STRIVE_CUDA(cudaGetDevice(&dev));
-  STRIVE_CHECK(dev >= 0 && dev < 16, STRIVE_EUNSUPPORTED, "device index %d", dev);
-  if (s[dev] == nullptr) {
-    STRIVE_CUDA(cudaStreamCreateWithFlags(&s[dev], cudaStreamNonBlocking));
-    STRIVE_CUDA(cudaEventCreateWithFlags(&e0[dev], cudaEventDisableTiming));
-    STRIVE_CUDA(cudaEventCreateWithFlags(&e1[dev], cudaEventDisableTiming));
-  }
-  *side = s[dev]; *ev_fork = e0[dev]; *ev_join = e1[dev];
-  return 0;
 }
 
 // Two adjoint sweeps of the same forward pass (the adv / sol loops route two different seeds to two groups of latents, SURVEY
