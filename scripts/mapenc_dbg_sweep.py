@@ -3,9 +3,13 @@ times via KPROF.  Flags: 1 no output stores, 2 no operand stores, 4 no input loa
 32 no weight copies (tc_gemm).  Results with any flag set are garbage by design."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import hashlib
 import torch
+from strive_b200 import _cabi
+if os.environ.get('STRIVE_LIB'):            # A/B against another build of the library (development only)
+    _cabi.LIB_PATH = os.environ['STRIVE_LIB']
 import strive_b200
-from strive_b200 import synth, _cabi
+from strive_b200 import synth
 N = int(os.environ.get('N', '2048'))
 FLAGS = [int(v) for v in os.environ.get('FLAGS', '0,4,2,8,32,12,14,6').split(',')]
 dev = torch.device('cuda:0')
@@ -22,6 +26,7 @@ for _ in range(2):
     f = model.encode_map_poses(pose, mapix, env)
 torch.cuda.synchronize()
 ref = f.clone()
+print('%s: feature sha1 %s' % (os.environ.get('STRIVE_LIB', 'in-tree library'), hashlib.sha1(ref.cpu().numpy().tobytes()).hexdigest()))
 names = ('crop_pack', 'tc_conv1', 'tc_conv2', 'tc_conv3', 'tc_conv4', 'tc_conv5', 'tc_conv6', 'tc_fc')
 for fl in FLAGS:
     _cabi.lib().strive_tc_debug(fl)

@@ -40,8 +40,13 @@ extern "C" int strive_tc_trace(unsigned long long* out32, int reset) {
   return 0;
 }
 
-// Timing experiments only (strive_tc_debug): bit0 epilogue skips its global stores, bit1 producers skip their shared
-// stores, bit2 producers skip their global loads, bit3 the MMA warp issues no MMAs.  Results are garbage when set.
+// Timing experiments only (strive_tc_debug, scripts/mapenc_dbg_sweep.py): bit0 epilogue skips its global stores, bit1 producers skip
+// their shared stores, bit2 producers skip their global loads, bit3 the MMA warp issues no MMAs, bit5 tc_gemm skips its weight
+// copies.  Results are garbage when set.  The flags exist only in builds with -DSTRIVE_TC_DEBUG=1 (scripts/build_variants.sh):
+// the operand producers sit at the register limit and every extra predicate costs them (measured: +3 % on conv1, spills in conv2).
+#ifndef STRIVE_TC_DEBUG
+#define STRIVE_TC_DEBUG 0
+#endif
 static int g_tc_dbg = 0;
 extern "C" int strive_tc_debug(int flags) {
   g_tc_dbg = flags;
@@ -326,6 +331,20 @@ __device__ __forceinline__ void tmem_ld48i(uint32_t taddr, int (&v)[48]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// split-phase TMEM loads for the conv1 epilogue pipeline: issue (no wait) / wait / pin the destination registers behind the wait
+__device__ __forceinline__ void tmem_ld8i_issue(uint32_t taddr, int* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_ld_wait_pin(int (&v)[N]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; i++) asm volatile("" : "+r"(v[i]));     // no use of a loaded register may be scheduled above the wait
+}
+
 __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __restrict__ packed_crop, const uint8_t* __restrict__ wpack,
                                                               const BiasArg bias, float* __restrict__ out, double* __restrict__ out_stats, int n) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -472,35 +491,46 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv1_kernel(const uint8_t* __r
       twe += TRACE_T() - tq;
       tc::tc_fence_after();
       float s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int par = 0; par < 2; par++) {
-        const int sub = half * 2 + par;     // xb = half
-        const uint32_t tb = tm + ((uint32_t)(q * 32) << 16) + a * 256 + sub * T1_NP;
-        int acc[48];
-        tmem_ld48i(tb, acc);
-        if (par == 1) {
+      // Four steps per item: (sub-tile par, channel block j) = 8 channels x 3 digit planes = 24 TMEM columns.  The load of step
+      // s + 1 is issued right after the wait for step s, so its latency hides behind the recombination and the stores of step s
+      // (one 48-column load + wait per sub-tile left this warp idle for the whole TMEM round trip: the epilogue was 93 % busy
+      // and the MMA warp waited for accumulators a quarter of the time).
+      const uint32_t tb0 = tm + ((uint32_t)(q * 32) << 16) + a * 256 + half * 2 * T1_NP;
+      int buf[2][24];
+      auto issue = [&](int st_, int (&v)[24]) {
+        const uint32_t tb = tb0 + (st_ >> 1) * T1_NP + (st_ & 1) * 8;
+        tmem_ld8i_issue(tb, &v[0]);
+        tmem_ld8i_issue(tb + 16, &v[8]);
+        tmem_ld8i_issue(tb + 32, &v[16]);
+      };
+      issue(0, buf[0]);
+#pragma unroll
+      for (int st_ = 0; st_ < 4; st_++) {
+        int (&cur)[24] = buf[st_ & 1];
+        tmem_ld_wait_pin<24>(cur);
+        if (st_ < 3) {
+          issue(st_ + 1, buf[(st_ + 1) & 1]);
+        } else {
           tc::tc_fence_before();
           tc::mbar_arrive(&acc_empty[a]);
         }
+        const int par = st_ >> 1, j = st_ & 1;
         const int oy = oy0 + oyl, ox = ox0 + half * 16 + 2 * jx + par;
         if (oy < 125 && ox < 125) {
-          float v[16];
+          float v[8];
 #pragma unroll
-          for (int c = 0; c < 16; c++) {
+          for (int c = 0; c < 8; c++) {
             // |acc_d| <= 196 * 128: the three planes recombine exactly in int32 (|t| < 1.64e9 < 2^31); ONE conversion rounds the
             // exact integer to fp32 (I2F runs on the XU pipe: 16 per output pixel, far below its rate; the magic-number
-            // conversions of the separate planes cost 3x the issue slots and the epilogue is issue-bound)
-            const int t = (acc[32 + c] * 256 + acc[16 + c]) * 256 + acc[c];
-            v[c] = fmaf(__int2float_rn(t), sc[c], bias.b[c]);
+            // conversions of the separate planes cost 3x the issue slots)
+            const int t = (cur[16 + c] * 256 + cur[8 + c]) * 256 + cur[c];
+            v[c] = fmaf(__int2float_rn(t), sc[j * 8 + c], bias.b[j * 8 + c]);
             s1 += v[c];
             s2 = fmaf(v[c], v[c], s2);
           }
           // channel-blocked activations [crop][C/8][H][W][8]: a lane stores 32 contiguous bytes per block
-#pragma unroll
-          for (int j = 0; j < 2; j++) {
-            float* dst = out + ((((size_t)crop * 2 + j) * 125 + oy) * 125 + ox) * 8;
-            tc::stg256(dst, v[j * 8], v[j * 8 + 1], v[j * 8 + 2], v[j * 8 + 3], v[j * 8 + 4], v[j * 8 + 5], v[j * 8 + 6], v[j * 8 + 7]);
-          }
+          float* dst = out + ((((size_t)crop * 2 + j) * 125 + oy) * 125 + ox) * 8;
+          tc::stg256(dst, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
         }
       }
       d1 += (double)s1;
@@ -564,7 +594,8 @@ template <int CIN, int KS, int HIN, int HOUT, int COUT, int NCH, int NBUF, bool 
 __global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
                                                              const float* __restrict__ gam, const float* __restrict__ bet,
                                                              const uint8_t* __restrict__ wpack, const BiasArg bias,
-                                                             float* __restrict__ out, double* __restrict__ out_stats, int n, int dbg) {
+                                                             float* __restrict__ out, double* __restrict__ out_stats, int n, int dbg_arg) {
+  const int dbg = STRIVE_TC_DEBUG ? dbg_arg : 0;     // timing-experiment flags: compiled out of the product build
   using Cfg = TcCfg<CIN, KS, HIN, HOUT, COUT, NCH, NBUF>;
   constexpr int PH = Cfg::PH, PW = Cfg::PW, PQ = Cfg::PQ, C2 = Cfg::C2, TAPS = Cfg::TAPS;
   constexpr int TK = CIN == 16 ? 1 : (CIN == 32 ? 2 : 3);
@@ -573,8 +604,7 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __rest
   uint8_t* sA = smem + Cfg::W_BYTES;
   __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base;
-  __shared__ float s_gam[CIN], s_bet[CIN];
-  __shared__ __align__(16) float s_ga[CIN], s_gb[CIN];
+  __shared__ __align__(16) float s_gam[CIN], s_bet[CIN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunk = (COUT == NCH) ? 0 : (int)blockIdx.y;
   {
@@ -644,6 +674,7 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __rest
     float xn[KI][8];
     unsigned okn = 0u;
     float ga[8], gb[8];
+    float cmean = 0.f, crstd = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; j++) { ga[j] = 0.f; gb[j] = 0.f; }
     if (item < item_hi) load_chunk(item, c2, xn, okn);
@@ -660,25 +691,21 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __rest
       const int crop = ci / Cfg::TILES;
       const bool new_crop = crop != cur_crop;
       if (new_crop) {
-        // GroupNorm affine of this crop, shared by all producers:  y = relu(x * ga + gb) == relu((x - mean) * rstd * gamma + beta)
+        // GroupNorm statistics of this crop: every thread derives (mean, rstd) itself -- two L2 reads and a float64 rsqrt per crop --
+        // instead of a pair of producer-wide barriers around 16..64 threads doing it for everybody (ncu: 8 % of conv4's stall
+        // samples sat on those barriers, a crop being only 8 chunk iterations there)
         cur_crop = crop;
-        asm volatile("bar.sync 1, %0;" ::"n"(T2_PROD_THREADS) : "memory");
-        if (tid < CIN) {
-          float mean, rstd;
-          gn_stats(in_stats, crop, (double)CIN * HIN * HIN, mean, rstd);
-          const float g = rstd * s_gam[tid];
-          s_ga[tid] = g;
-          s_gb[tid] = fmaf(-mean, g, s_bet[tid]);
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(T2_PROD_THREADS) : "memory");
+        gn_stats(in_stats, crop, (double)CIN * HIN * HIN, cmean, crstd);
       }
       if (C2 > 1 || new_crop) {
+        //  y = relu(x * ga + gb) == relu((x - mean) * rstd * gamma + beta)
 #pragma unroll
         for (int j = 0; j < 8; j += 4) {
-          const float4 a4 = *reinterpret_cast<const float4*>(&s_ga[cc2 * 16 + half * 8 + j]);
-          const float4 b4 = *reinterpret_cast<const float4*>(&s_gb[cc2 * 16 + half * 8 + j]);
-          ga[j] = a4.x; ga[j + 1] = a4.y; ga[j + 2] = a4.z; ga[j + 3] = a4.w;
-          gb[j] = b4.x; gb[j + 1] = b4.y; gb[j + 2] = b4.z; gb[j + 3] = b4.w;
+          const float4 g4 = *reinterpret_cast<const float4*>(&s_gam[cc2 * 16 + half * 8 + j]);
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_bet[cc2 * 16 + half * 8 + j]);
+          ga[j] = crstd * g4.x; ga[j + 1] = crstd * g4.y; ga[j + 2] = crstd * g4.z; ga[j + 3] = crstd * g4.w;
+          gb[j] = fmaf(-cmean, ga[j], b4.x); gb[j + 1] = fmaf(-cmean, ga[j + 1], b4.y);
+          gb[j + 2] = fmaf(-cmean, ga[j + 2], b4.z); gb[j + 3] = fmaf(-cmean, ga[j + 3], b4.w);
         }
       }
       const int b = cnt % NBUF;
@@ -859,6 +886,10 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __rest
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }
+// adds `bytes` to the pending transaction count of the current phase WITHOUT arriving (the caller arrives later, with everybody else)
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc),
                "r"(bytes), "r"(tc::smem_u32(bar))
@@ -878,8 +909,7 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
   uint8_t* sA = smem + T3_WCHUNK;
   __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF], acc_full[4], acc_empty[4], w_full[2], w_free[2];
   __shared__ uint32_t tmem_base;
-  __shared__ float s_gam[CIN], s_bet[CIN];
-  __shared__ __align__(16) float s_ga[CIN], s_gb[CIN];
+  __shared__ __align__(16) float s_gam[CIN], s_bet[CIN];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // Contiguous range of tile PAIRS per CTA.  The K-chunk order of a pair follows the parity of its GLOBAL pair index: a crop has
   // 8 tiles = 4 pairs, so the order in which a tile's two K chunks are accumulated depends only on the tile's place inside its
@@ -931,6 +961,7 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
       }
     }
     int cur_crop = -1;
+    float cmean = 0.f, crstd = 0.f;
     long long tw = 0, t_start = TRACE_T();
     const int njobs = 2 * (item_hi - item_lo);
     // job j of this CTA -> (tile, K chunk): pairs of tiles, K chunk outer (see the header comment)
@@ -978,25 +1009,18 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
               if (rc[k] >= 0 && row < nrv && col < ncv) asm volatile("prefetch.global.L2 [%0];" ::"l"(nbase + (row * HIN + col) * 8));
             }
           }
-          if (crop != cur_crop) {
+          if (crop != cur_crop) {     // per-thread statistics, no producer barrier (see tc_conv_kernel)
             cur_crop = crop;
-            asm volatile("bar.sync 1, %0;" ::"n"(T3_PROD_THREADS) : "memory");
-            if (tid < CIN) {
-              float mean, rstd;
-              gn_stats(in_stats, crop, (double)CIN * HIN * HIN, mean, rstd);
-              const float g = rstd * s_gam[tid];
-              s_ga[tid] = g;
-              s_gb[tid] = fmaf(-mean, g, s_bet[tid]);
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(T3_PROD_THREADS) : "memory");
+            gn_stats(in_stats, crop, (double)CIN * HIN * HIN, cmean, crstd);
           }
           float ga[8], gb[8];
 #pragma unroll
           for (int j = 0; j < 8; j += 4) {
-            const float4 a4 = *reinterpret_cast<const float4*>(&s_ga[c2 * 16 + half * 8 + j]);
-            const float4 b4 = *reinterpret_cast<const float4*>(&s_gb[c2 * 16 + half * 8 + j]);
-            ga[j] = a4.x; ga[j + 1] = a4.y; ga[j + 2] = a4.z; ga[j + 3] = a4.w;
-            gb[j] = b4.x; gb[j + 1] = b4.y; gb[j + 2] = b4.z; gb[j + 3] = b4.w;
+            const float4 g4 = *reinterpret_cast<const float4*>(&s_gam[c2 * 16 + half * 8 + j]);
+            const float4 b4 = *reinterpret_cast<const float4*>(&s_bet[c2 * 16 + half * 8 + j]);
+            ga[j] = crstd * g4.x; ga[j + 1] = crstd * g4.y; ga[j + 2] = crstd * g4.z; ga[j + 3] = crstd * g4.w;
+            gb[j] = fmaf(-cmean, ga[j], b4.x); gb[j + 1] = fmaf(-cmean, ga[j + 1], b4.y);
+            gb[j + 2] = fmaf(-cmean, ga[j + 2], b4.z); gb[j + 3] = fmaf(-cmean, ga[j + 3], b4.w);
           }
           const int b = cnt % NBUF;
           const long long tq = TRACE_T();
@@ -1201,7 +1225,8 @@ template <int CIN, int KS, int HIN, int HOUT, int COUT, bool FINAL>
 __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
                                                              const float* __restrict__ gam, const float* __restrict__ bet,
                                                              const uint8_t* __restrict__ wpack, const float* __restrict__ bias,
-                                                             float* __restrict__ out, double* __restrict__ out_stats, int n, int dbg) {
+                                                             float* __restrict__ out, double* __restrict__ out_stats, int n, int dbg_arg) {
+  const int dbg = STRIVE_TC_DEBUG ? dbg_arg : 0;     // timing-experiment flags: compiled out of the product build
   using Cfg = Tc3Cfg<CIN, KS, HIN, HOUT, COUT, FINAL>;
   constexpr int PIX = Cfg::PIX, NCH = Cfg::NCH, NBUF = Cfg::NBUF;
   static_assert(CIN % 64 == 0 && COUT % 32 == 0 && 2 * COUT <= 512, "tc_gemm tiling");
@@ -1272,12 +1297,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
           }
         }
         tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
-        if (!(dbg & 32)) {
-          const uint8_t* src = wpack + (size_t)kc * 2 * Cfg::W_PREC;
-          const uint32_t dstw = tc::smem_u32(sWt);
-          for (int i = tid; i < 2 * Cfg::W_PREC / 16; i += TC_PROD_THREADS)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstw + (uint32_t)i * 16u), "l"(src + (size_t)i * 16) : "memory");
-          asm volatile("cp.async.commit_group;" ::: "memory");
+        if (tid == 0 && !(dbg & 32)) {
+          // the chunk's hi/lo weights are contiguous in the pack: ONE bulk copy whose bytes are counted on the stage's `full`
+          // barrier (the per-thread cp.async loop it replaces held a quarter of this kernel's stall samples)
+          mbar_expect_tx_only(&full[b], 2 * Cfg::W_PREC);
+          bulk_g2s(sWt, wpack + (size_t)kc * 2 * Cfg::W_PREC, 2 * Cfg::W_PREC, &full[b]);
         }
 #pragma unroll
         for (int j = 0; j < NIT; j++) {
@@ -1302,7 +1326,6 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const float* __rest
           *reinterpret_cast<uint4*>(sA + (size_t)unit * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(sA + Cfg::A_PREC + (size_t)unit * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
         tc::fence_async_smem();
         tc::mbar_arrive(&full[b]);
       }

@@ -140,3 +140,36 @@ def test_two_rank_gloo_flat_gradient_bucket_all_reduce():
     assert (r0['local'] - r1['local']).abs().max() > 1e-3                 # the ranks really saw different batches
     assert torch.allclose(r0['mean'], want, atol=1e-7) and torch.equal(r0['mean'], r1['mean'])
     assert r0['first_param_is_view']
+
+
+def _empty_rank_main(rank, world, port, out_path):
+    """More ranks than groups: the partition leaves ranks without rows; both gather paths must cope (N = 8 with 4 groups)."""
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    ptr = torch.tensor([0, 3, 5, 9])
+    gptr = [0, 3]                                                   # ONE group of three scenes
+    assign = shard.partition_groups(shard.group_costs(ptr, gptr, 4), world)
+    all_index = [shard.group_rows(ptr, gptr, a) for a in assign]
+    rows_per_rank = [int(i.numel()) for i in all_index]
+    mine = all_index[rank]
+    z = (mine.to(torch.float32)[:, None] * 10 + torch.arange(2)[None]).contiguous()        # row r -> [10 r, 10 r + 1]; (0,2) on the empty rank
+    a = shard.gather_rows(z, mine, 9, dst=0)
+    b = shard.gather_rows(z, mine, 9, dst=0, all_index=all_index if rank == 0 else None, rows_per_rank=rows_per_rank)
+    if rank == 0:
+        torch.save({'a': a, 'b': b, 'rows_per_rank': rows_per_rank}, out_path)
+    else:
+        assert a is None and b is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_with_an_empty_rank():
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, 'g.pt')
+        mp.spawn(_empty_rank_main, args=(2, _free_port(), out), nprocs=2, join=True)
+        got = torch.load(out)
+    assert sorted(got['rows_per_rank']) == [0, 9]
+    want = torch.arange(9, dtype=torch.float32)[:, None] * 10 + torch.arange(2)[None]
+    assert torch.equal(got['a'], want) and torch.equal(got['b'], want)
