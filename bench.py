@@ -59,6 +59,11 @@ def workload_desc():
 NCU_TRAFFIC_BYTES = {'tc_conv2': 2.067361e9 + 0.946168e9, 'tc_conv3': 0.978821e9 + 0.421498e9, 'tc_conv1': 0.135026e9 + 1.993950e9}
 # shared-memory operand bytes one launch moves (tcgen05 SS-mode operand fetch + producer stores), the resource that actually binds
 # these kernels: conv2 per 128-pixel tile = 25 taps x (4096 A_hi + 2048 B + 4096 A_lo + 1024 B) + 42.6 KB staged input
+# + the bytes the same kernels move through the SAME L1 / shared-memory data path as global loads of the input tile and global
+# stores of the output tile (unified L1/shared SRAM, 128 B/clk/SM for everything): conv2 per tile 42.6 KB in + 16 KB out
+SM_PATH_EXTRA_BYTES_PER_CROP = {'tc_conv2': 32 * (665 * 16 * 4 + 128 * 32 * 4),
+                                'tc_conv3': 8 * (2 * 665 * 16 * 4 + 128 * 64 * 4),
+                                'tc_conv1': 32 * (666 * 4 + 512 * 16 * 4)}
 SMEM_BYTES_PER_CROP = {'tc_conv2': 32 * (25 * (4096 + 2048 + 4096 + 1024) + 665 * 16 * 4),
                        'tc_conv3': 8 * 2 * (25 * (4096 + 4096 + 4096 + 2048) + 665 * 16 * 4 + 25600),
                        'tc_conv1': 32 * (28 * (4096 + 1536) + 21312)}
@@ -368,7 +373,12 @@ def run_gpu(args):
             sm_peak = 148 * 128.0 * (clocks.get('sm_mhz') or 1965.0) * 1e6      # 128 B/clk/SM operand fetch (scripts/mma_bench2.cu)
             sm_ach = SMEM_BYTES_PER_CROP[top[0]] * crops_per_launch / avg_s
             roof['smem_operand'] = {'achieved_tbs': sm_ach / 1e12, 'peak_tbs': sm_peak / 1e12, 'frac': sm_ach / sm_peak,
-                                    'note': 'SS-mode tcgen05 operand fetch + staging stores vs 128 B/clk/SM: the binding resource'}
+                                    'note': 'SS-mode tcgen05 operand fetch + staging stores vs 128 B/clk/SM'}
+            dp_ach = (SMEM_BYTES_PER_CROP[top[0]] + SM_PATH_EXTRA_BYTES_PER_CROP[top[0]]) * crops_per_launch / avg_s
+            roof['sm_datapath'] = {'achieved_tbs': dp_ach / 1e12, 'peak_tbs': sm_peak / 1e12, 'frac': dp_ach / sm_peak,
+                                   'note': 'smem_operand + the global loads of the input tile and the global stores of the output tile, which cross the same '
+                                           'L1/shared data path (128 B/clk/SM at the sampled SM clock): the binding resource -- by the kernels\' own cycle '
+                                           'counters conv2 runs at 0.97 and conv3 at 0.975 of it (DESIGN.md 9)'}
     if roof is not None:
         # BASELINE.json asks for the fraction of the HBM roofline by name: algorithmic bytes of the WHOLE step over its duration
         gbs = ALGO_BYTES_PER_UNIT * units_per_step / (ms / args.steps / 1000.0) / 1e9
