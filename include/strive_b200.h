@@ -45,6 +45,9 @@ int64_t strive_profile_report(char* buf, int64_t cap);
 /* ---- tcgen05 primitive self-test (tests only): A (128,32), B (32,32), X0/X1 (144,8) fp32 (rounded to bf16 inside);
  * D0 = A B^T, D1[m] = [X0[m+1] | X1[m+3]] B[:, :16]^T, both (128,32) fp32. */
 int strive_tc_selftest(const float* A, const float* B, const float* X0, const float* X1, float* D0, float* D1, void* stream);
+/* CTA-pair variant (tcgen05 cta_group::2, cluster of two CTAs): A (256,32), B (n,32) fp32 (rounded to bf16 inside), D = A B^T (256,n), n = 64 or 128;
+ * CTA r stages rows [128 r, +128) of A and rows [n/2 r, +n/2) of B; flag (device int32): bit r set = CTA r timed out (bounded waits). */
+int strive_tc_selftest_pair(const float* A, const float* B, float* D, int32_t* flag, int32_t n, void* stream);
 /* Pipeline diagnostics of the tensor-core convolutions: out32 = [4 kernels conv1..conv4][8] SM-cycle counters summed over
  * CTAs since the last reset ([0] producers blocked on a ring slot, [1] producer total, [2] MMA warp starved, [3] MMA warp
  * blocked on an accumulator, [4] MMA total, [5] epilogue idle, [6] epilogue total, [7] CTAs).  No reference counterpart. */
@@ -70,6 +73,9 @@ int strive_mapenc_set_impl(int impl);
 /* 1: a chunk of >= 512 crops runs as two half-chunks on two streams (crop gather of one half overlaps conv1 of the other);
  * 0 (default): one stream.  Measured +0.1 % on a power-capped B200, kept as an A/B switch. */
 int strive_mapenc_set_split(int on);
+/* conv3 of the tensor-core encoder on CTA pairs (tcgen05 cta_group::2, clusters of two CTAs): 1 = on, 0 = single-CTA kernel.  Same
+ * outputs bit for bit; needs the pair weight pack that strive_model_set_tc_weights receives as the last segment of its blob. */
+int strive_mapenc_set_pair(int on);
 /* Edge MLP of the decoder GNN (interaction_net.py:139-184) on the warp-level tensor path: the library packs the edge-MLP
  * matrices of the weight blob into mma.sync fragment order inside `buf` (device, 16-byte aligned,
  * strive_model_edge_frag_bytes() bytes, owned by the caller for the lifetime of the model).  Without it -- or with

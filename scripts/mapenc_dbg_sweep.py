@@ -26,6 +26,14 @@ for _ in range(2):
     f = model.encode_map_poses(pose, mapix, env)
 torch.cuda.synchronize()
 ref = f.clone()
+if os.environ.get('STRIVE_MAPENC_PAIR') == '1':      # A/B of conv3 on CTA pairs against the single-CTA kernel, same process
+    _cabi.lib().strive_mapenc_set_pair(0)
+    f1 = model.encode_map_poses(pose, mapix, env)
+    _cabi.lib().strive_mapenc_set_pair(1)
+    f2 = model.encode_map_poses(pose, mapix, env)
+    torch.cuda.synchronize()
+    print('conv3 pair kernel vs single-CTA kernel: max |feature diff| %.3e (max |feature| %.3f); pair kernel run to run %.1e' % (
+        float((f1 - ref).abs().max()), float(ref.abs().max()), float((f2 - ref).abs().max())))
 print('%s: feature sha1 %s' % (os.environ.get('STRIVE_LIB', 'in-tree library'), hashlib.sha1(ref.cpu().numpy().tobytes()).hexdigest()))
 names = ('crop_pack', 'tc_conv1', 'tc_conv2', 'tc_conv3', 'tc_conv4', 'tc_conv5', 'tc_conv6', 'tc_fc')
 for fl in FLAGS:
@@ -41,3 +49,12 @@ for fl in FLAGS:
     print('flags %2d: ' % fl + '  '.join('%s %.1f' % (k.replace('tc_', ''), 1000 * rep[k][1] / rep[k][0]) for k in names if k in rep)
           + '  | us per launch; |feat - flags0| = %.3g' % float((f - ref).abs().max()))
 _cabi.lib().strive_tc_debug(0)
+if os.environ.get('TRACE'):
+    _cabi.tc_trace(True)
+    f = model.encode_map_poses(pose, mapix, env)
+    torch.cuda.synchronize()
+    tr = _cabi.tc_trace(True)
+    t = tr[2]
+    ct = max(t[7], 1)
+    print('conv3 trace (kcycles per traced CTA): producer wait-empty %.0f / total %.0f | mma wait-full %.0f wait-acc %.0f wait-weights(pair kernel)/epi-wait %.0f / total %.0f | CTAs %d' % (
+        t[0] / ct / 1e3, t[1] / ct / 1e3, t[2] / ct / 1e3, t[3] / ct / 1e3, t[5] / ct / 1e3, t[4] / ct / 1e3, t[7]))

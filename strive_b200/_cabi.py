@@ -43,7 +43,7 @@ class StriveLossCfg(C.Structure):
                 ('circ_cx', C.c_void_p), ('lw_un', C.c_void_p), ('adv_own_pred', C.c_int32), ('reserved0', C.c_int32)]
 
 
-EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_tc_trace', 'strive_tc_debug', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl', 'strive_mapenc_set_split', 'strive_model_edge_frag_bytes', 'strive_model_set_edge_frags', 'strive_edge_set_impl', 'strive_set_pdl',
+EXPORTS = ['strive_last_error', 'strive_abi_version', 'strive_struct_layout', 'strive_profile_enable', 'strive_profile_report', 'strive_tc_selftest', 'strive_tc_selftest_pair', 'strive_tc_trace', 'strive_tc_debug', 'strive_model_layout', 'strive_model_create', 'strive_model_destroy', 'strive_model_tc_bytes', 'strive_model_set_tc_weights', 'strive_mapenc_set_impl', 'strive_mapenc_set_split', 'strive_mapenc_set_pair', 'strive_model_edge_frag_bytes', 'strive_model_set_edge_frags', 'strive_edge_set_impl', 'strive_set_pdl',
            'strive_mapenc_workspace_bytes', 'strive_mapenc_fwd', 'strive_map_crop', 'strive_decode_tape_bytes',
            'strive_decode_fwd', 'strive_decode_bwd', 'strive_decode_bwd_pair', 'strive_decode_tape_read', 'strive_loss_workspace_bytes',
            'strive_loss_fwd_bwd', 'strive_adam_step', 'strive_adam_step_dev', 'strive_on_layer_frac', 'strive_line_layer', 'strive_veh_iou_hits']
@@ -69,6 +69,7 @@ def lib():
     L.strive_model_set_tc_weights.argtypes = [vp, vp, i64]
     L.strive_mapenc_set_impl.argtypes = [C.c_int]
     L.strive_mapenc_set_split.argtypes = [C.c_int]
+    L.strive_mapenc_set_pair.argtypes = [C.c_int]
     L.strive_model_edge_frag_bytes.restype = i64
     L.strive_model_set_edge_frags.argtypes = [vp, vp, i64, vp]
     L.strive_edge_set_impl.argtypes = [C.c_int]
@@ -95,6 +96,7 @@ def lib():
     L.strive_struct_layout.argtypes = [C.POINTER(i64), C.c_int]
     L.strive_profile_enable.argtypes = [C.c_int]
     L.strive_tc_selftest.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.strive_tc_selftest_pair.argtypes = [vp, vp, vp, vp, i32, vp]
     L.strive_tc_trace.argtypes = [vp, C.c_int]
     L.strive_tc_debug.argtypes = [C.c_int]
     L.strive_profile_report.argtypes = [C.c_char_p, i64]
@@ -104,6 +106,8 @@ def lib():
     _verify_layout(L)
     if os.environ.get('STRIVE_MAPENC_SPLIT') is not None:   # development switch: half-chunk pipeline of the map encoder
         L.strive_mapenc_set_split(int(os.environ['STRIVE_MAPENC_SPLIT']))
+    if os.environ.get('STRIVE_MAPENC_PAIR') is not None:    # A/B switch: conv3 on CTA pairs (tcgen05 cta_group::2)
+        L.strive_mapenc_set_pair(int(os.environ['STRIVE_MAPENC_PAIR']))
     if os.environ.get('STRIVE_PDL') is not None:      # development switch: bit 0 rollout kernels, bit 1 map-encoder kernels
         L.strive_set_pdl(int(os.environ['STRIVE_PDL']))
     _lib = L

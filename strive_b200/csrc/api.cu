@@ -103,12 +103,14 @@ extern "C" int strive_model_create(const float* blob, int64_t blob_floats, const
 
 extern "C" void strive_model_destroy(StriveModel* m) { delete m; }
 
-// tensor-core weight blob: [conv1 10752 B int8 digit planes + 16 fp32 scales][conv2 51200 B][conv3 2 x 102400 B][conv4 147456 B][conv5][conv6][fc]  (layouts in mapenc_tc.cu)
-static const int64_t kTcBytes[7] = {7 * 2 * 48 * 16 + 64, 1 * (1 * 25 * 2 * 1024), 2 * (2 * 25 * 2 * 1024), 2 * (4 * 9 * 2 * 1024),
-                                    9 * 2 * 128 * 64 * 2, 18 * 2 * 128 * 64 * 2, 8 * 2 * 64 * 64 * 2};
+// tensor-core weight blob: [conv1 10752 B int8 digit planes + 16 fp32 scales][conv2 51200 B][conv3 2 x 102400 B][conv4 147456 B][conv5][conv6][fc]
+// [conv3 for CTA pairs: 2 ranks x 2 K chunks x 25 taps x 2048 B]  (layouts in mapenc_tc.cu)
+#define TC_SEGS 8
+static const int64_t kTcBytes[TC_SEGS] = {7 * 2 * 48 * 16 + 64, 1 * (1 * 25 * 2 * 1024), 2 * (2 * 25 * 2 * 1024), 2 * (4 * 9 * 2 * 1024),
+                                          9 * 2 * 128 * 64 * 2, 18 * 2 * 128 * 64 * 2, 8 * 2 * 64 * 64 * 2, 2 * 2 * 25 * 2048};
 extern "C" int64_t strive_model_tc_bytes(void) {
   int64_t t = 0;
-  for (int i = 0; i < 7; i++) t += kTcBytes[i];
+  for (int i = 0; i < TC_SEGS; i++) t += kTcBytes[i];
   return t;
 }
 extern "C" int strive_model_set_tc_weights(StriveModel* m, const void* blob, int64_t bytes) {
@@ -126,7 +128,7 @@ extern "C" int strive_model_set_tc_weights(StriveModel* m, const void* blob, int
   }
   m->tc_blob = (const uint8_t*)blob;
   int64_t off = 0;
-  for (int i = 0; i < 7; i++) { m->tc_off[i] = off; off += kTcBytes[i]; }
+  for (int i = 0; i < TC_SEGS; i++) { m->tc_off[i] = off; off += kTcBytes[i]; }
   return 0;
 }
 

@@ -130,7 +130,7 @@ struct StriveModel {
   int in0_rows;   // rows of IN0_T (= 64+64+NC+32+2 rounded up to 4)
   int u0_rows;    // rows of U0_T  (= 64+64+NC rounded up to 4)
   const uint8_t* tc_blob;   // bf16 hi/lo conv weights in UMMA canonical layout (strive_model_set_tc_weights) or null
-  int64_t tc_off[7];        // byte offsets of conv1..conv6, fc inside tc_blob
+  int64_t tc_off[8];        // byte offsets of conv1..conv6, fc, conv3-for-CTA-pairs inside tc_blob
   float h_cbias[4][64];     // host copies of the conv1..conv4 biases (kernel arguments of the tensor-core convolutions)
   const uint8_t* edge_frags; // mma.sync weight fragment packs of the edge MLP (strive_model_set_edge_frags) or null
 };

@@ -341,7 +341,7 @@ int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_
                     double* out_stats, uint8_t* packed_crop, int n, cudaStream_t stream);
 int tc_launch_conv2(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
                     float* out, double* out_stats, int n, cudaStream_t stream);
-int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
+int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const uint8_t* wpack_pair, const float* bias,
                     float* out, double* out_stats, int n, cudaStream_t stream);
 int tc_launch_conv4(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* bias,
                     float* out, double* out_stats, int n, cudaStream_t stream);
@@ -423,7 +423,7 @@ extern "C" int strive_mapenc_fwd(const StriveModel* m, const StriveMap* map, con
         if (r) return r;
         r = tc_launch_conv2(a[0], t[0], sg[S_GG0], sg[S_GB0], m->tc_blob + m->tc_off[1], m->h_cbias[1], a[1], t[1], hn, s);
         if (r) return r;
-        r = tc_launch_conv3(a[1], t[1], sg[S_GG1], sg[S_GB1], m->tc_blob + m->tc_off[2], m->h_cbias[2], a[2], t[2], hn, s);
+        r = tc_launch_conv3(a[1], t[1], sg[S_GG1], sg[S_GB1], m->tc_blob + m->tc_off[2], m->tc_blob + m->tc_off[7], m->h_cbias[2], a[2], t[2], hn, s);
         if (r) return r;
         r = tc_launch_conv4(a[2], t[2], sg[S_GG2], sg[S_GB2], m->tc_blob + m->tc_off[3], m->h_cbias[3], a[3], t[3], hn, s);
         if (r) return r;

@@ -16,6 +16,8 @@
 #define STRIVE_PDL_CLASS 2   // bit of strive_set_pdl() that enables programmatic dependent launch for this file's kernels
 #include "common.cuh"
 #include "tc.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 #define TC_NPROD 11
 #define TC_MMA_WARP 11
@@ -1205,6 +1207,390 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
 }
 
 // ======================================================================================================
+// conv3 on CTA PAIRS (tcgen05 cta_group::2).  A cluster of two CTAs on one TPC works on one crop at a time: the leader (rank 0)
+// owns tiles 0-3, the follower tiles 4-7, each as two tile pairs with the K-chunk-outer schedule of tc_conv3_kernel above (the
+// order in which a tile accumulates its two K chunks is the same function of the tile's place in its crop: batch-invariant).
+// ONE M = 256 MMA covers a leader tile and a follower tile, and every B operand is split across the pair: CTA r stages, per tap and
+// K chunk, ONE 64-row block  Z_r = [W_hi rows 32r..32r+31 ; W_lo rows 32r..32r+31]  (2 KB instead of the 4 KB [W_hi ; W_lo]):
+//     D[:, 0:128]  += A_hi * [Z_0 ; Z_1]^T                  N = 128: columns  hi(0:32) | lo(0:32) | hi(32:64) | lo(32:64)
+//     D[:, 32:96]  += A_lo * [Z_0[0:32] ; Z_1[0:32]]^T      N = 64 on the SAME block: the W_hi rows, landing on lo(0:32) | hi(32:64)
+// and the epilogue adds column c to column c + 32 (channels 0-31) resp. 64 + c' to 96 + c' (channels 32-63).  An SM thus fetches
+// 3 KB instead of 6 KB of weights per tap and K chunk through its 128 B/clk data path, and a chunk is 50 KB per CTA: taps 0-12 of
+// BOTH chunks stay resident, only taps 13-24 (24 KB) are swapped once per tile pair -- behind the 13 resident taps of the next job --
+// and three operand buffers fit.  (Small terms are summed apart from the hi x hi products here, so the results differ from the
+// single-CTA kernel in the last bits; both are batch-invariant.)
+// Only the leader issues MMAs.  Cross-CTA signalling:
+//   full[b], acc_empty[k], w_full live in the LEADER: local arrivals + one remote arrival per follower warp / loader
+//   empty[b], acc_full[k], w_free are signalled by tcgen05.commit multicast to the same barrier in BOTH CTAs
+// ======================================================================================================
+#define T3P_NBUF 3
+#define T3P_TAP_BYTES 2048
+#define T3P_CHUNK_BYTES (25 * T3P_TAP_BYTES)                 // one K chunk of one rank in the weight pack
+#define T3P_R0_BYTES (T3_H0_TAPS * T3P_TAP_BYTES)            // taps 0..12 of one chunk (resident for both chunks)
+#define T3P_R1_BYTES ((25 - T3_H0_TAPS) * T3P_TAP_BYTES)     // taps 13..24 of the current chunk (swapped)
+#define T3P_WBYTES (2 * T3P_R0_BYTES + T3P_R1_BYTES)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrival on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(tc::smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// wait on a local barrier that also receives arrivals from the peer CTA (cluster-scope acquire)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = tc::smem_u32(bar);
+  uint32_t ok = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(a), "r"(parity), "r"(4000u)
+                 : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc),
+               "l"(bdesc), "r"(idesc), "r"(accumulate)
+               : "memory");
+}
+// completion of all MMAs issued so far -> one arrival on `bar` in BOTH CTAs of the pair
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(tc::smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3_pair_kernel(const float* __restrict__ in, const double* __restrict__ in_stats,
+                                                                                             const float* __restrict__ gam, const float* __restrict__ bet,
+                                                                                             const uint8_t* __restrict__ wpack, const BiasArg bias,
+                                                                                             float* __restrict__ out, double* __restrict__ out_stats, int n) {
+  using Cfg = TcCfg<32, 5, 61, 29, 64, 64, T3P_NBUF>;
+  constexpr int CIN = 32, KS = 5, HIN = 61, HOUT = 29, COUT = 64, NCH = 64, NBUF = T3P_NBUF;
+  constexpr int PH = Cfg::PH, PW = Cfg::PW, PQ = Cfg::PQ, TAPS = Cfg::TAPS;
+  static_assert(Cfg::TILES == 8, "conv3 pair kernel: a crop is 4 tiles per CTA = 2 tile pairs of alternating parity");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem;                          // [taps 0-12 of chunk 0][taps 0-12 of chunk 1][taps 13-24 of the current chunk]
+  uint8_t* sW1 = smem + 2 * T3P_R0_BYTES;
+  uint8_t* sA = smem + T3P_WBYTES;
+  __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF], acc_full[4], acc_empty[4], w_full, w_free;
+  __shared__ uint32_t tmem_base;
+  __shared__ __align__(16) float s_gam[CIN], s_bet[CIN];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int ncl = (int)(gridDim.x >> 1), cl = (int)(blockIdx.x >> 1);
+  const int crop_lo = (int)(((long long)n * cl) / ncl), crop_hi = (int)(((long long)n * (cl + 1)) / ncl);
+  const int npairs = 2 * (crop_hi - crop_lo);            // local pair p: crop crop_lo + p / 2, tiles 4 rank + 2 (p & 1) + {0, 1}; parity p & 1
+  const uint8_t* wrank = wpack + (size_t)rank * 2 * T3P_CHUNK_BYTES;
+  {
+    // resident: taps 0-12 of both chunks; the first pair starts with K chunk 0: its taps 13-24
+    for (int i = tid; i < T3P_WBYTES / 16; i += T2_THREADS) {
+      const int byte = i * 16;
+      const int src = byte < T3P_R0_BYTES ? byte : (byte < 2 * T3P_R0_BYTES ? T3P_CHUNK_BYTES + (byte - T3P_R0_BYTES) : T3P_R0_BYTES + (byte - 2 * T3P_R0_BYTES));
+      reinterpret_cast<int4*>(sW)[i] = __ldg(reinterpret_cast<const int4*>(wrank + src));
+    }
+  }
+  for (int i = tid; i < CIN; i += T2_THREADS) { s_gam[i] = gam[i]; s_bet[i] = bet[i]; }
+  if (tid == 0) {
+    for (int b = 0; b < NBUF; b++) { tc::mbar_init(&full[b], leader ? T3_PROD_THREADS / 2 + T3_NPROD / 2 : 1); tc::mbar_init(&empty[b], 1); }
+    for (int a = 0; a < 4; a++) { tc::mbar_init(&acc_full[a], 1); tc::mbar_init(&acc_empty[a], leader ? 128 + 4 : 1); }
+    tc::mbar_init(&w_full, leader ? 2 : 1);
+    tc::mbar_init(&w_free, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == T2_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(&tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc::fence_async_smem();
+  STRIVE_PDL_TRIGGER();
+  STRIVE_PDL_WAIT_PTRS(in, in_stats);          // prologue above: weights / GroupNorm affine (constants), barriers, TMEM; below: the previous kernel's output
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                          // the peer's barriers are initialised before anything arrives on them
+  tc::tc_fence_after();
+  const uint32_t tm = tmem_base;
+  auto item_of = [&](int p, int i2) { return (crop_lo + (p >> 1)) * Cfg::TILES + 4 * (int)rank + 2 * (p & 1) + i2; };
+
+  if (warp < T3_NPROD) {
+    // ---------------- producers: TWO groups of five warps take the jobs alternately ----------------
+    // A job is "load the patch, wait for it, transform, store, fence" -- the proxy fence waits for every outstanding load of the
+    // thread, so one group cannot prefetch across jobs; with two groups one job's load latency hides behind the other job's
+    // arithmetic (with the B bytes halved the MMAs no longer cover for it: one group left the tensor core starved 30 % of the time).
+    // Work item = 8 channels (one channel block, 32 bytes) of one input pixel, two passes of 5 + 4 item slots per thread.
+    constexpr int GT = T3_PROD_THREADS / 2;                                    // 160 threads per group
+    constexpr int NPIX = PH * PW, NITEM = NPIX * 2;
+    constexpr int KI = (NITEM + GT - 1) / GT;                                  // 9
+    constexpr int KA = (KI + 1) / 2;                                           // 5 slots in the first pass, KI - KA in the second
+    constexpr int CG = PH * 2 * PQ * 16;
+    const int grp = tid / GT, gt = tid - grp * GT;
+    const int half = tid & 1;
+    // one register per item slot: (operand-buffer offset << 12) | (patch row << 6) | patch column; row 63 = no item (never valid)
+    static_assert(PH < 63 && PW < 64 && Cfg::A_PREC_BYTES < (1 << 19), "item slot packing");
+    uint32_t pk[KI];
+#pragma unroll
+    for (int k = 0; k < KI; k++) {
+      const int i = gt + k * GT;
+      pk[k] = ((uint32_t)Cfg::DUMP_OFF << 12) | (63u << 6);
+      if (i < NITEM) {
+        const int p = i >> 1;
+        const int row = p / PW, col = p - row * PW;
+        pk[k] = ((uint32_t)(((row * 2 + (col & 1)) * PQ + (col >> 1)) * 16 + half * CG) << 12) | ((uint32_t)row << 6) | (uint32_t)col;
+      }
+    }
+    int cur_crop = -1;
+    float cmean = 0.f, crstd = 0.f;
+    const int njobs = 4 * npairs;
+    auto decode = [&](int j, int& item, int& c2) {       // job j -> (tile, K chunk): pairs of tiles, K chunk outer
+      const int p = j >> 2, r = j & 3;
+      item = item_of(p, r & 1);
+      c2 = (p & 1) ^ (r >> 1);
+    };
+    auto job_base = [&](int item, int c2, int& rows_valid, int& cols_valid) -> const float* {
+      const int crop = item / Cfg::TILES, tile = item - crop * Cfg::TILES;
+      const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
+      rows_valid = HIN - 2 * ty0;
+      cols_valid = HIN - 2 * tx0;
+      return in + ((((size_t)crop * (CIN / 8) + c2 * 2 + half) * HIN + 2 * ty0) * HIN + 2 * tx0) * 8;
+    };
+    for (int cnt = grp; cnt < njobs; cnt += 2) {
+      int item, c2;
+      decode(cnt, item, c2);
+      const int crop = item / Cfg::TILES;
+      int rows_valid, cols_valid;
+      const float* base = job_base(item, c2, rows_valid, cols_valid);
+      if (crop != cur_crop) {
+        cur_crop = crop;
+        gn_stats(in_stats, crop, (double)CIN * HIN * HIN, cmean, crstd);
+      }
+      float ga[8], gb[8];
+#pragma unroll
+      for (int j = 0; j < 8; j += 4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(&s_gam[c2 * 16 + half * 8 + j]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&s_bet[c2 * 16 + half * 8 + j]);
+        ga[j] = crstd * g4.x; ga[j + 1] = crstd * g4.y; ga[j + 2] = crstd * g4.z; ga[j + 3] = crstd * g4.w;
+        gb[j] = fmaf(-cmean, ga[j], b4.x); gb[j + 1] = fmaf(-cmean, ga[j + 1], b4.y);
+        gb[j + 2] = fmaf(-cmean, ga[j + 2], b4.z); gb[j + 3] = fmaf(-cmean, ga[j + 3], b4.w);
+      }
+      const int b = cnt % NBUF;
+      uint8_t* dst = sA + (size_t)b * Cfg::A_BYTES;
+#pragma unroll
+      for (int pass = 0; pass < 2; pass++) {
+        const int k0 = pass ? KA : 0, k1 = pass ? KI : KA;
+        float x[KA][8];
+        unsigned ok = 0u;
+#pragma unroll
+        for (int k = k0; k < k1; k++) {
+          const int row = (int)((pk[k] >> 6) & 63u), col = (int)(pk[k] & 63u);
+          if (row < rows_valid && col < cols_valid) {
+            ok |= 1u << k;
+            tc::ldg256(base + (row * HIN + col) * 8, x[k - k0]);
+          }
+        }
+        if (pass == 0) {
+          if (cnt + 2 < njobs) {      // this group's next job towards L2
+            int nitem, nc2, nrv, ncv;
+            decode(cnt + 2, nitem, nc2);
+            const float* nbase = job_base(nitem, nc2, nrv, ncv);
+#pragma unroll
+            for (int k = 0; k < KI; k++) {
+              const int row = (int)((pk[k] >> 6) & 63u), col = (int)(pk[k] & 63u);
+              if (row < nrv && col < ncv) asm volatile("prefetch.global.L2 [%0];" ::"l"(nbase + (row * HIN + col) * 8));
+            }
+          }
+          tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
+        }
+#pragma unroll
+        for (int k = k0; k < k1; k++) {
+          const bool okk = (ok >> k) & 1u;
+          float y[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) y[j] = okk ? fmaxf(fmaf(x[k - k0][j], ga[j], gb[j]), 0.f) : 0.f;
+          uint4 hi, lo;
+          tc::split_pack2(y[0], y[1], hi.x, lo.x);
+          tc::split_pack2(y[2], y[3], hi.y, lo.y);
+          tc::split_pack2(y[4], y[5], hi.z, lo.z);
+          tc::split_pack2(y[6], y[7], hi.w, lo.w);
+          *reinterpret_cast<uint4*>(dst + (pk[k] >> 12)) = hi;                      // items beyond the patch land in the dump slot
+          *reinterpret_cast<uint4*>(dst + Cfg::A_PREC_BYTES + (pk[k] >> 12)) = lo;
+        }
+      }
+      tc::fence_async_smem();
+      if (leader) {
+        tc::mbar_arrive(&full[b]);
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&full[b], 0);
+      }
+    }
+    if (tid == 0 && leader) trace_add(2, 7, 1);
+  } else if (warp == T3_LOAD_WARP) {
+    // ---------------- weight loader: taps 13-24 of this CTA's half of the other K chunk, once per pair ----------------
+    if (tc::elect_one()) {
+      for (int p = 0; p < npairs; p++) {
+        const uint8_t* src = wrank + (size_t)(1 - (p & 1)) * T3P_CHUNK_BYTES + T3P_R0_BYTES;
+        tc::mbar_wait(&w_free, p & 1);
+        mbar_expect_tx(&w_full, T3P_R1_BYTES);
+        bulk_g2s(sW1, src, T3P_R1_BYTES, &w_full);
+        if (!leader) {
+          tc::mbar_wait(&w_full, p & 1);
+          mbar_arrive_cluster(&w_full, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == T2_MMA_WARP) {
+    if (leader) {
+      const uint32_t idesc1 = tc::idesc_bf16_f32(256, 2 * NCH), idesc2 = tc::idesc_bf16_f32(256, NCH);
+      constexpr uint32_t LBO_A = PH * 2 * PQ * 16, SBO_A = 64 * PQ;
+      int cnt = 0;
+      long long twf = 0, twa = 0, tww = 0, t_start = TRACE_T();
+      for (int p = 0; p < npairs; p++) {
+        for (int s2 = 0; s2 < 2; s2++) {
+          const int cc = (p & 1) ^ s2;                     // K chunk of these two jobs
+          for (int i2 = 0; i2 < 2; i2++, cnt++) {
+            const int k = (p & 1) * 2 + i2;
+            const uint32_t d = tm + k * (2 * NCH);
+            const long long tq0 = TRACE_T();
+            if (s2 == 0) mbar_wait_cluster(&acc_empty[k], ((p >> 1) & 1) ^ 1);
+            const int b = cnt % NBUF;
+            const long long tq1 = TRACE_T();
+            mbar_wait_cluster(&full[b], (cnt / NBUF) & 1);
+            twa += tq1 - tq0; twf += TRACE_T() - tq1;
+            const bool after_swap = (s2 == 1 && i2 == 0), before_swap = (s2 == 0 && i2 == 1);
+            tc::tc_fence_after();
+            const uint32_t a_lo0 = tc::desc_lo(tc::smem_u32(sA + (size_t)b * Cfg::A_BYTES), LBO_A);
+            const uint32_t b0_lo0 = tc::desc_lo(tc::smem_u32(sW) + cc * T3P_R0_BYTES, 1024), b1_lo0 = tc::desc_lo(tc::smem_u32(sW1), 1024);
+            const uint32_t a_hi = tc::desc_hi(SBO_A), b_hi = tc::desc_hi(128);
+            if (tc::elect_one()) {
+#pragma unroll
+              for (int tap = 0; tap < T3_H0_TAPS; tap++) {
+                const int ky = tap / KS, kx = tap % KS;
+                const uint32_t al0 = a_lo0 + ((((ky * 2 + (kx & 1)) * PQ + (kx >> 1)) * 16) >> 4);
+                const uint64_t ah = tc::desc_make(al0, a_hi), al = tc::desc_make(al0 + (Cfg::A_PREC_BYTES >> 4), a_hi);
+                const uint64_t bd = tc::desc_make(b0_lo0 + ((tap * T3P_TAP_BYTES) >> 4), b_hi);
+                mma_bf16_pair(d, ah, bd, idesc1, (tap > 0 || s2 > 0) ? 1u : 0u);
+                mma_bf16_pair(d + 32, al, bd, idesc2, 1u);
+              }
+            }
+            __syncwarp();
+            if (after_swap) {
+              const long long tq3 = TRACE_T();
+              mbar_wait_cluster(&w_full, p & 1);
+              tww += TRACE_T() - tq3;
+              tc::tc_fence_after();
+            }
+            if (tc::elect_one()) {
+#pragma unroll
+              for (int tap = T3_H0_TAPS; tap < TAPS; tap++) {
+                const int ky = tap / KS, kx = tap % KS;
+                const uint32_t al0 = a_lo0 + ((((ky * 2 + (kx & 1)) * PQ + (kx >> 1)) * 16) >> 4);
+                const uint64_t ah = tc::desc_make(al0, a_hi), al = tc::desc_make(al0 + (Cfg::A_PREC_BYTES >> 4), a_hi);
+                const uint64_t bd = tc::desc_make(b1_lo0 + (((tap - T3_H0_TAPS) * T3P_TAP_BYTES) >> 4), b_hi);
+                mma_bf16_pair(d, ah, bd, idesc1, 1u);
+                mma_bf16_pair(d + 32, al, bd, idesc2, 1u);
+              }
+              if (before_swap) mma_commit_pair(&w_free);
+              mma_commit_pair(&empty[b]);
+              if (s2 == 1) mma_commit_pair(&acc_full[k]);
+            }
+            __syncwarp();
+          }
+        }
+      }
+      if (lane == 0) { trace_add(2, 2, twf); trace_add(2, 3, twa); trace_add(2, 4, TRACE_T() - t_start); trace_add(2, 5, tww); }
+    }
+  } else if (warp >= T2_EPI_WARP0) {
+    // ---------------- epilogue: as in tc_conv3_kernel; the follower reports each drained accumulator to the leader ----------------
+    const int q = warp - T2_EPI_WARP0;
+    const int m = q * 32 + lane;
+    int cur_crop = -1;
+    double d1 = 0.0, d2 = 0.0;
+    for (int p = 0; p < npairs; p++) {
+      for (int i2 = 0; i2 < 2; i2++) {
+        const int item = item_of(p, i2);
+        const int crop = item / Cfg::TILES, tile = item % Cfg::TILES;
+        const int ty0 = (tile / Cfg::TILES_X) * 16, tx0 = (tile % Cfg::TILES_X) * 8;
+        const int k = (p & 1) * 2 + i2;
+        if (crop != cur_crop) {
+          if (cur_crop >= 0) {
+            d1 = warp_sum_f64(d1);
+            d2 = warp_sum_f64(d2);
+            if (lane == 0) {
+              atomicAdd(out_stats + (size_t)cur_crop * 2, d1);
+              atomicAdd(out_stats + (size_t)cur_crop * 2 + 1, d2);
+            }
+          }
+          cur_crop = crop;
+          d1 = 0.0;
+          d2 = 0.0;
+        }
+        tc::mbar_wait(&acc_full[k], (p >> 1) & 1);
+        tc::tc_fence_after();
+        const int oy = ty0 + (m >> 3), ox = tx0 + (m & 7);
+        const bool ok = oy < HOUT && ox < HOUT;
+        const uint32_t tbase = tm + ((uint32_t)(q * 32) << 16) + k * (2 * NCH);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int h = 0; h < NCH / 16; h++) {
+          float vh[16], vl[16];
+          const int colh = h * 16 < 32 ? h * 16 : 32 + h * 16;     // channel block -> column of its hi x hi sums; the small terms sit 32 columns on
+          tc::tmem_ld16(tbase + colh, vh);
+          tc::tmem_ld16(tbase + colh + 32, vl);
+          if (h == NCH / 16 - 1) {
+            tc::tc_fence_before();
+            if (leader) {
+              tc::mbar_arrive(&acc_empty[k]);
+            } else {
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(&acc_empty[k], 0);
+            }
+          }
+          if (ok) {
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+              vh[c] = (vh[c] + vl[c]) + bias.b[h * 16 + c];
+              s1 += vh[c];
+              s2 = fmaf(vh[c], vh[c], s2);
+            }
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const int ch0 = h * 16 + j * 8;
+              float* dst = out + ((((size_t)crop * (COUT / 8) + (ch0 >> 3)) * HOUT + oy) * HOUT + ox) * 8;
+              tc::stg256(dst, vh[j * 8], vh[j * 8 + 1], vh[j * 8 + 2], vh[j * 8 + 3], vh[j * 8 + 4], vh[j * 8 + 5], vh[j * 8 + 6], vh[j * 8 + 7]);
+            }
+          }
+        }
+        d1 += (double)s1;
+        d2 += (double)s2;
+      }
+    }
+    if (cur_crop >= 0) {
+      d1 = warp_sum_f64(d1);
+      d2 = warp_sum_f64(d2);
+      if (lane == 0) {
+        atomicAdd(out_stats + (size_t)cur_crop * 2, d1);
+        atomicAdd(out_stats + (size_t)cur_crop * 2 + 1, d2);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();          // no CTA leaves (or frees tensor memory) while the peer may still signal its barriers or its MMAs write here
+  if (warp == T2_MMA_WARP) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512u) : "memory");
+  }
+}
+
+// ======================================================================================================
 // conv5 / conv6 / fc: small spatial extent (6x6, 2x2, 1x1 outputs) -> rows of many crops are packed into M = 128 tiles and
 // the A operand is gathered explicitly (im2col rows written straight into the canonical K-major layout, 64-wide K chunks).
 // GEMM:  out[m][n] = sum_k relu(GN(in))[row m, tap(k), c(k)] * W[n][k],   k = tap * CIN + c,  NHWC in/out.
@@ -1507,20 +1893,51 @@ int tc_launch_conv2(const float* in, const double* in_stats, const float* gam, c
                     float* out, double* out_stats, int n, cudaStream_t stream) {
   return tc_launch<16, 5, 125, 61, 32, 32, 3, true>("tc_conv2", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
 }
-int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* h_bias,
-                    float* out, double* out_stats, int n, cudaStream_t stream) {
+// conv3 kernel choice (strive_mapenc_set_pair): 1 = CTA-pair kernel (tcgen05 cta_group::2), 0 = single-CTA kernel
+static int g_conv3_pair = 0;
+extern "C" int strive_mapenc_set_pair(int on) {
+  g_conv3_pair = on ? 1 : 0;
+  return 0;
+}
+
+int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const uint8_t* wpack_pair,
+                    const float* h_bias, float* out, double* out_stats, int n, cudaStream_t stream) {
   using Cfg = TcCfg<32, 5, 61, 29, 64, 64, T3_NBUF>;
   constexpr size_t SMEM = (size_t)T3_WCHUNK + (size_t)T3_NBUF * Cfg::A_BYTES;
-  static_assert(SMEM <= 225 * 1024, "conv3 shared memory");
+  constexpr size_t SMEM_PAIR = (size_t)T3P_WBYTES + (size_t)T3P_NBUF * Cfg::A_BYTES;
+  static_assert(SMEM <= 225 * 1024 && SMEM_PAIR <= 225 * 1024, "conv3 shared memory");
   static bool attr = false;
+  static int max_clusters = 0;
   if (!attr) {
     STRIVE_CUDA(cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    STRIVE_CUDA(cudaFuncSetAttribute(tc_conv3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
+    // how many CTA pairs can be resident at once (a GPC with an odd number of usable SMs leaves one of them without a partner)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * num_sms());
+    cfg.blockDim = dim3(T2_THREADS);
+    cfg.dynamicSmemBytes = SMEM_PAIR;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, tc_conv3_pair_kernel, &cfg) != cudaSuccess) {
+      (void)cudaGetLastError();
+      max_clusters = 0;
+    }
+    if (getenv("STRIVE_TC_VERBOSE")) fprintf(stderr, "strive_b200: conv3 pair kernel: %d CTA pairs resident on %d SMs\n", max_clusters, num_sms());
     attr = true;
+  }
+  const BiasArg bias = make_bias(h_bias, 64);
+  if (g_conv3_pair && wpack_pair != nullptr && 2 * max_clusters >= num_sms() - 8) {
+    int ncl = max_clusters < n ? max_clusters : n;       // one crop is the unit of work of a pair
+    KPROF("tc_conv3", stream, STRIVE_CUDA_LAUNCH(tc_conv3_pair_kernel, 2 * ncl, T2_THREADS, SMEM_PAIR, stream, in, in_stats, gam, bet, wpack_pair, bias, out, out_stats, n));
+    STRIVE_LAUNCH_CHECK();
+    return 0;
   }
   const int items = n * Cfg::TILES;
   int gx = num_sms();
   if (gx > (items + 1) / 2) gx = (items + 1) / 2;
-  const BiasArg bias = make_bias(h_bias, 64);
   KPROF("tc_conv3", stream, STRIVE_CUDA_LAUNCH(tc_conv3_kernel, gx, T2_THREADS, SMEM, stream, in, in_stats, gam, bet, wpack, bias, out, out_stats, n));
   STRIVE_LAUNCH_CHECK();
   return 0;

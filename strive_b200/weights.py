@@ -162,4 +162,9 @@ def pack_tc_weights(sd):
         out.append(gemm_pack(w.permute(0, 2, 3, 1).reshape(w.size(0), -1)))
     wf = g('map_feature.weight').reshape(64, 128, 2, 2)                     # flatten index of the reference = c*4 + y*2 + x
     out.append(gemm_pack(wf.permute(0, 2, 3, 1).reshape(64, -1)))           # NHWC order: k = (y*2+x)*128 + c
+    # conv3 once more for the CTA-pair kernel (tcgen05 cta_group::2: each CTA of a pair stages HALF of every B operand):
+    # [rank 2][c2 2][tap 25][khalf 2][64 rows][8 k] with rows = W_hi rows 32 rank .. 32 rank + 31, then W_lo rows 32 rank .. 32 rank + 31
+    w = g('map_conv.6.weight')
+    hi, lo = [p.reshape(8, 8, 2, 2, 8, 25).permute(2, 5, 3, 0, 1, 4) for p in _split(w)]     # (c2, tap, khalf, ngroup, r, k)
+    out.append(_bytes(torch.stack([torch.cat([hi[:, :, :, 4 * rank:4 * rank + 4], lo[:, :, :, 4 * rank:4 * rank + 4]], dim=3) for rank in (0, 1)])))
     return torch.cat(out)
