@@ -73,8 +73,9 @@ int strive_mapenc_set_impl(int impl);
 /* 1: a chunk of >= 512 crops runs as two half-chunks on two streams (crop gather of one half overlaps conv1 of the other);
  * 0 (default): one stream.  Measured +0.1 % on a power-capped B200, kept as an A/B switch. */
 int strive_mapenc_set_split(int on);
-/* conv3 of the tensor-core encoder on CTA pairs (tcgen05 cta_group::2, clusters of two CTAs): 1 = on, 0 = single-CTA kernel.  Same
- * outputs bit for bit; needs the pair weight pack that strive_model_set_tc_weights receives as the last segment of its blob. */
+/* conv3 of the tensor-core encoder on CTA pairs (tcgen05 cta_group::2, clusters of two CTAs): 1 = on (default), 0 = single-CTA kernel
+ * (A/B; also the automatic fallback when the device cannot hold ~74 CTA pairs at once).  The two kernels agree to fp32 re-association
+ * level (1e-5 on the features); each is bitwise reproducible and batch-invariant. */
 int strive_mapenc_set_pair(int on);
 /* Edge MLP of the decoder GNN (interaction_net.py:139-184) on the warp-level tensor path: the library packs the edge-MLP
  * matrices of the weight blob into mma.sync fragment order inside `buf` (device, 16-byte aligned,

@@ -74,6 +74,21 @@ __device__ __forceinline__ void gn_stats(const double* __restrict__ st, int crop
   rstd = (float)(1.0 / sqrt(var + 1e-5));
 }
 
+// Per-CTA table of the GroupNorm statistics (mean, rstd) of the crops a CTA works on, filled ONCE in the prologue by the first 64
+// threads (one crop per thread): the float64 division + rsqrt behind gn_stats saturate the FP64 pipe when every producer warp runs
+// them at every crop change (ncu: 16 % of the stall samples of conv3), and a producer-wide barrier around one warp doing it for
+// everybody stalls ten warps.  A CTA's crops are a contiguous range; ranges longer than the table fall back to gn_stats.
+#define GN_TAB 64
+__device__ __forceinline__ void gn_table_fill(float* s_cm, float* s_cr, const double* __restrict__ st, int crop_first, int crop_last, double cnt, int tid) {
+  if (tid < GN_TAB && crop_first + tid <= crop_last) gn_stats(st, crop_first + tid, cnt, s_cm[tid], s_cr[tid]);
+}
+__device__ __forceinline__ void gn_table_get(const float* s_cm, const float* s_cr, const double* __restrict__ st, int crop, int crop_first, double cnt,
+                                             float& mean, float& rstd) {
+  const int i = crop - crop_first;
+  if (i < GN_TAB) { mean = s_cm[i]; rstd = s_cr[i]; }
+  else gn_stats(st, crop, cnt, mean, rstd);
+}
+
 // ======================================================================================================
 // conv1: 4 -> 16, k7 s2 on the INTEGER tensor path (tcgen05.mma kind::i8, s32 accumulators).
 // The input is the binary crop -- exact as int8 {0,1}.  Each output channel's weights are written in 31-bit fixed point
@@ -623,14 +638,17 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __rest
   tc::fence_async_smem();
   STRIVE_PDL_TRIGGER();
   STRIVE_PDL_WAIT_PTRS(in, in_stats);          // prologue above: weights / GroupNorm affine (constants), barriers, TMEM; below: the previous kernel's output
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tm = tmem_base;
   const int items = n * Cfg::TILES;
   // contiguous item range per CTA: consecutive tiles of the same crop share the GroupNorm statistics and L2 lines
   const int item_lo = (int)(((long long)items * blockIdx.x) / gridDim.x);
   const int item_hi = (int)(((long long)items * (blockIdx.x + 1)) / gridDim.x);
+  const int crop_first = item_lo / Cfg::TILES;
+  __shared__ float s_cm[GN_TAB], s_cr[GN_TAB];
+  gn_table_fill(s_cm, s_cr, in_stats, crop_first, (item_hi - 1) / Cfg::TILES, (double)CIN * HIN * HIN, tid);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tm = tmem_base;
 
   if (warp < T2_NPROD) {
     // ---------------- producers ----------------
@@ -693,11 +711,9 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv_kernel(const float* __rest
       const int crop = ci / Cfg::TILES;
       const bool new_crop = crop != cur_crop;
       if (new_crop) {
-        // GroupNorm statistics of this crop: every thread derives (mean, rstd) itself -- two L2 reads and a float64 rsqrt per crop --
-        // instead of a pair of producer-wide barriers around 16..64 threads doing it for everybody (ncu: 8 % of conv4's stall
-        // samples sat on those barriers, a crop being only 8 chunk iterations there)
+        // GroupNorm statistics of this crop from the CTA's table (no producer-wide barrier, no float64 arithmetic in the loop)
         cur_crop = crop;
-        gn_stats(in_stats, crop, (double)CIN * HIN * HIN, cmean, crstd);
+        gn_table_get(s_cm, s_cr, in_stats, crop, crop_first, (double)CIN * HIN * HIN, cmean, crstd);
       }
       if (C2 > 1 || new_crop) {
         //  y = relu(x * ga + gb) == relu((x - mean) * rstd * gamma + beta)
@@ -936,12 +952,15 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
   tc::fence_async_smem();
   STRIVE_PDL_TRIGGER();
   STRIVE_PDL_WAIT_PTRS(in, in_stats);          // prologue above: weights / GroupNorm affine (constants), barriers, TMEM; below: the previous kernel's output
+  const int item_lo = 2 * pair_lo, item_hi = 2 * pair_hi;
+  const int npairs = pair_hi - pair_lo;
+  const int crop_first = item_lo / Cfg::TILES;
+  __shared__ float s_cm[GN_TAB], s_cr[GN_TAB];
+  gn_table_fill(s_cm, s_cr, in_stats, crop_first, (item_hi - 1) / Cfg::TILES, (double)CIN * HIN * HIN, tid);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tm = tmem_base;
-  const int item_lo = 2 * pair_lo, item_hi = 2 * pair_hi;
-  const int npairs = pair_hi - pair_lo;
 
   if (warp < T3_NPROD) {
     // ---------------- producers: same work items as tc_conv_kernel (8 channels of one input pixel), 320 threads ----------------
@@ -1011,9 +1030,9 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
               if (rc[k] >= 0 && row < nrv && col < ncv) asm volatile("prefetch.global.L2 [%0];" ::"l"(nbase + (row * HIN + col) * 8));
             }
           }
-          if (crop != cur_crop) {     // per-thread statistics, no producer barrier (see tc_conv_kernel)
+          if (crop != cur_crop) {     // statistics from the CTA's table, no producer barrier (see tc_conv_kernel)
             cur_crop = crop;
-            gn_stats(in_stats, crop, (double)CIN * HIN * HIN, cmean, crstd);
+            gn_table_get(s_cm, s_cr, in_stats, crop, crop_first, (double)CIN * HIN * HIN, cmean, crstd);
           }
           float ga[8], gb[8];
 #pragma unroll
@@ -1215,8 +1234,8 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
 //     D[:, 0:128]  += A_hi * [Z_0 ; Z_1]^T                  N = 128: columns  hi(0:32) | lo(0:32) | hi(32:64) | lo(32:64)
 //     D[:, 32:96]  += A_lo * [Z_0[0:32] ; Z_1[0:32]]^T      N = 64 on the SAME block: the W_hi rows, landing on lo(0:32) | hi(32:64)
 // and the epilogue adds column c to column c + 32 (channels 0-31) resp. 64 + c' to 96 + c' (channels 32-63).  An SM thus fetches
-// 3 KB instead of 6 KB of weights per tap and K chunk through its 128 B/clk data path, and a chunk is 50 KB per CTA: taps 0-12 of
-// BOTH chunks stay resident, only taps 13-24 (24 KB) are swapped once per tile pair -- behind the 13 resident taps of the next job --
+// 3 KB instead of 6 KB of weights per tap and K chunk through its 128 B/clk data path, and a chunk is 50 KB per CTA: taps 0-16 of
+// BOTH chunks stay resident, only taps 17-24 (16 KB) are swapped once per tile pair -- behind the 17 resident taps of the next job --
 // and three operand buffers fit.  (Small terms are summed apart from the hi x hi products here, so the results differ from the
 // single-CTA kernel in the last bits; both are batch-invariant.)
 // Only the leader issues MMAs.  Cross-CTA signalling:
@@ -1226,8 +1245,9 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
 #define T3P_NBUF 3
 #define T3P_TAP_BYTES 2048
 #define T3P_CHUNK_BYTES (25 * T3P_TAP_BYTES)                 // one K chunk of one rank in the weight pack
-#define T3P_R0_BYTES (T3_H0_TAPS * T3P_TAP_BYTES)            // taps 0..12 of one chunk (resident for both chunks)
-#define T3P_R1_BYTES ((25 - T3_H0_TAPS) * T3P_TAP_BYTES)     // taps 13..24 of the current chunk (swapped)
+#define T3P_H0_TAPS 17
+#define T3P_R0_BYTES (T3P_H0_TAPS * T3P_TAP_BYTES)           // taps 0..16 of one chunk (resident for both chunks)
+#define T3P_R1_BYTES ((25 - T3P_H0_TAPS) * T3P_TAP_BYTES)    // taps 17..24 of the current chunk (swapped)
 #define T3P_WBYTES (2 * T3P_R0_BYTES + T3P_R1_BYTES)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -1276,7 +1296,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3
   constexpr int PH = Cfg::PH, PW = Cfg::PW, PQ = Cfg::PQ, TAPS = Cfg::TAPS;
   static_assert(Cfg::TILES == 8, "conv3 pair kernel: a crop is 4 tiles per CTA = 2 tile pairs of alternating parity");
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sW = smem;                          // [taps 0-12 of chunk 0][taps 0-12 of chunk 1][taps 13-24 of the current chunk]
+  uint8_t* sW = smem;                          // [taps 0-16 of chunk 0][taps 0-16 of chunk 1][taps 17-24 of the current chunk]
   uint8_t* sW1 = smem + 2 * T3P_R0_BYTES;
   uint8_t* sA = smem + T3P_WBYTES;
   __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF], acc_full[4], acc_empty[4], w_full, w_free;
@@ -1290,7 +1310,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3
   const int npairs = 2 * (crop_hi - crop_lo);            // local pair p: crop crop_lo + p / 2, tiles 4 rank + 2 (p & 1) + {0, 1}; parity p & 1
   const uint8_t* wrank = wpack + (size_t)rank * 2 * T3P_CHUNK_BYTES;
   {
-    // resident: taps 0-12 of both chunks; the first pair starts with K chunk 0: its taps 13-24
+    // resident: taps 0-16 of both chunks; the first pair starts with K chunk 0: its taps 17-24
     for (int i = tid; i < T3P_WBYTES / 16; i += T2_THREADS) {
       const int byte = i * 16;
       const int src = byte < T3P_R0_BYTES ? byte : (byte < 2 * T3P_R0_BYTES ? T3P_CHUNK_BYTES + (byte - T3P_R0_BYTES) : T3P_R0_BYTES + (byte - 2 * T3P_R0_BYTES));
@@ -1312,6 +1332,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3
   tc::fence_async_smem();
   STRIVE_PDL_TRIGGER();
   STRIVE_PDL_WAIT_PTRS(in, in_stats);          // prologue above: weights / GroupNorm affine (constants), barriers, TMEM; below: the previous kernel's output
+  __shared__ float s_cm[GN_TAB], s_cr[GN_TAB];
+  gn_table_fill(s_cm, s_cr, in_stats, crop_lo, crop_hi - 1, (double)CIN * HIN * HIN, tid);
   tc::tc_fence_before();
   __syncthreads();
   cluster_sync_all();                          // the peer's barriers are initialised before anything arrives on them
@@ -1324,11 +1346,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3
     // A job is "load the patch, wait for it, transform, store, fence" -- the proxy fence waits for every outstanding load of the
     // thread, so one group cannot prefetch across jobs; with two groups one job's load latency hides behind the other job's
     // arithmetic (with the B bytes halved the MMAs no longer cover for it: one group left the tensor core starved 30 % of the time).
-    // Work item = 8 channels (one channel block, 32 bytes) of one input pixel, two passes of 5 + 4 item slots per thread.
+    // Work item = 8 channels (one channel block, 32 bytes) of one input pixel, 9 item slots per thread in three batches.
     constexpr int GT = T3_PROD_THREADS / 2;                                    // 160 threads per group
     constexpr int NPIX = PH * PW, NITEM = NPIX * 2;
     constexpr int KI = (NITEM + GT - 1) / GT;                                  // 9
-    constexpr int KA = (KI + 1) / 2;                                           // 5 slots in the first pass, KI - KA in the second
+    constexpr int KB = 3;                                                      // item slots per load batch
+    static_assert(KI == 3 * KB, "conv3 pair producers: three batches of three item slots");
     constexpr int CG = PH * 2 * PQ * 16;
     const int grp = tid / GT, gt = tid - grp * GT;
     const int half = tid & 1;
@@ -1368,7 +1391,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3
       const float* base = job_base(item, c2, rows_valid, cols_valid);
       if (crop != cur_crop) {
         cur_crop = crop;
-        gn_stats(in_stats, crop, (double)CIN * HIN * HIN, cmean, crstd);
+        gn_table_get(s_cm, s_cr, in_stats, crop, crop_lo, (double)CIN * HIN * HIN, cmean, crstd);
       }
       float ga[8], gb[8];
 #pragma unroll
@@ -1381,47 +1404,55 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3
       }
       const int b = cnt % NBUF;
       uint8_t* dst = sA + (size_t)b * Cfg::A_BYTES;
+      // three batches of three item slots: the loads of batch i + 1 are in flight while batch i is transformed (inside a job nothing
+      // fences; only the end-of-job proxy fence waits for outstanding loads)
+      float xa[KB][8], xb[KB][8];          // two rotating batch buffers
+      unsigned ok = 0u;
+      auto load_batch = [&](int bt, float (&x)[KB][8]) {
 #pragma unroll
-      for (int pass = 0; pass < 2; pass++) {
-        const int k0 = pass ? KA : 0, k1 = pass ? KI : KA;
-        float x[KA][8];
-        unsigned ok = 0u;
-#pragma unroll
-        for (int k = k0; k < k1; k++) {
-          const int row = (int)((pk[k] >> 6) & 63u), col = (int)(pk[k] & 63u);
+        for (int k = 0; k < KB; k++) {
+          const uint32_t e = pk[bt * KB + k];
+          const int row = (int)((e >> 6) & 63u), col = (int)(e & 63u);
           if (row < rows_valid && col < cols_valid) {
-            ok |= 1u << k;
-            tc::ldg256(base + (row * HIN + col) * 8, x[k - k0]);
+            ok |= 1u << (bt * KB + k);
+            tc::ldg256(base + (row * HIN + col) * 8, x[k]);
           }
         }
-        if (pass == 0) {
-          if (cnt + 2 < njobs) {      // this group's next job towards L2
-            int nitem, nc2, nrv, ncv;
-            decode(cnt + 2, nitem, nc2);
-            const float* nbase = job_base(nitem, nc2, nrv, ncv);
+      };
+      auto transform_batch = [&](int bt, const float (&x)[KB][8]) {
 #pragma unroll
-            for (int k = 0; k < KI; k++) {
-              const int row = (int)((pk[k] >> 6) & 63u), col = (int)(pk[k] & 63u);
-              if (row < nrv && col < ncv) asm volatile("prefetch.global.L2 [%0];" ::"l"(nbase + (row * HIN + col) * 8));
-            }
-          }
-          tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
-        }
-#pragma unroll
-        for (int k = k0; k < k1; k++) {
-          const bool okk = (ok >> k) & 1u;
+        for (int k = 0; k < KB; k++) {
+          const uint32_t e = pk[bt * KB + k];
+          const bool okk = (ok >> (bt * KB + k)) & 1u;
           float y[8];
 #pragma unroll
-          for (int j = 0; j < 8; j++) y[j] = okk ? fmaxf(fmaf(x[k - k0][j], ga[j], gb[j]), 0.f) : 0.f;
+          for (int j = 0; j < 8; j++) y[j] = okk ? fmaxf(fmaf(x[k][j], ga[j], gb[j]), 0.f) : 0.f;
           uint4 hi, lo;
           tc::split_pack2(y[0], y[1], hi.x, lo.x);
           tc::split_pack2(y[2], y[3], hi.y, lo.y);
           tc::split_pack2(y[4], y[5], hi.z, lo.z);
           tc::split_pack2(y[6], y[7], hi.w, lo.w);
-          *reinterpret_cast<uint4*>(dst + (pk[k] >> 12)) = hi;                      // items beyond the patch land in the dump slot
-          *reinterpret_cast<uint4*>(dst + Cfg::A_PREC_BYTES + (pk[k] >> 12)) = lo;
+          *reinterpret_cast<uint4*>(dst + (e >> 12)) = hi;                          // items beyond the patch land in the dump slot
+          *reinterpret_cast<uint4*>(dst + Cfg::A_PREC_BYTES + (e >> 12)) = lo;
+        }
+      };
+      load_batch(0, xa);
+      load_batch(1, xb);
+      if (cnt + 2 < njobs) {      // this group's next job towards L2
+        int nitem, nc2, nrv, ncv;
+        decode(cnt + 2, nitem, nc2);
+        const float* nbase = job_base(nitem, nc2, nrv, ncv);
+#pragma unroll
+        for (int k = 0; k < KI; k++) {
+          const int row = (int)((pk[k] >> 6) & 63u), col = (int)(pk[k] & 63u);
+          if (row < nrv && col < ncv) asm volatile("prefetch.global.L2 [%0];" ::"l"(nbase + (row * HIN + col) * 8));
         }
       }
+      tc::mbar_wait(&empty[b], ((cnt / NBUF) & 1) ^ 1);
+      transform_batch(0, xa);
+      load_batch(2, xa);
+      transform_batch(1, xb);
+      transform_batch(2, xa);
       tc::fence_async_smem();
       if (leader) {
         tc::mbar_arrive(&full[b]);
@@ -1432,7 +1463,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3
     }
     if (tid == 0 && leader) trace_add(2, 7, 1);
   } else if (warp == T3_LOAD_WARP) {
-    // ---------------- weight loader: taps 13-24 of this CTA's half of the other K chunk, once per pair ----------------
+    // ---------------- weight loader: taps 17-24 of this CTA's half of the other K chunk, once per pair ----------------
     if (tc::elect_one()) {
       for (int p = 0; p < npairs; p++) {
         const uint8_t* src = wrank + (size_t)(1 - (p & 1)) * T3P_CHUNK_BYTES + T3P_R0_BYTES;
@@ -1471,7 +1502,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3
             const uint32_t a_hi = tc::desc_hi(SBO_A), b_hi = tc::desc_hi(128);
             if (tc::elect_one()) {
 #pragma unroll
-              for (int tap = 0; tap < T3_H0_TAPS; tap++) {
+              for (int tap = 0; tap < T3P_H0_TAPS; tap++) {
                 const int ky = tap / KS, kx = tap % KS;
                 const uint32_t al0 = a_lo0 + ((((ky * 2 + (kx & 1)) * PQ + (kx >> 1)) * 16) >> 4);
                 const uint64_t ah = tc::desc_make(al0, a_hi), al = tc::desc_make(al0 + (Cfg::A_PREC_BYTES >> 4), a_hi);
@@ -1489,11 +1520,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3
             }
             if (tc::elect_one()) {
 #pragma unroll
-              for (int tap = T3_H0_TAPS; tap < TAPS; tap++) {
+              for (int tap = T3P_H0_TAPS; tap < TAPS; tap++) {
                 const int ky = tap / KS, kx = tap % KS;
                 const uint32_t al0 = a_lo0 + ((((ky * 2 + (kx & 1)) * PQ + (kx >> 1)) * 16) >> 4);
                 const uint64_t ah = tc::desc_make(al0, a_hi), al = tc::desc_make(al0 + (Cfg::A_PREC_BYTES >> 4), a_hi);
-                const uint64_t bd = tc::desc_make(b1_lo0 + (((tap - T3_H0_TAPS) * T3P_TAP_BYTES) >> 4), b_hi);
+                const uint64_t bd = tc::desc_make(b1_lo0 + (((tap - T3P_H0_TAPS) * T3P_TAP_BYTES) >> 4), b_hi);
                 mma_bf16_pair(d, ah, bd, idesc1, 1u);
                 mma_bf16_pair(d + 32, al, bd, idesc2, 1u);
               }
@@ -1893,8 +1924,8 @@ int tc_launch_conv2(const float* in, const double* in_stats, const float* gam, c
                     float* out, double* out_stats, int n, cudaStream_t stream) {
   return tc_launch<16, 5, 125, 61, 32, 32, 3, true>("tc_conv2", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
 }
-// conv3 kernel choice (strive_mapenc_set_pair): 1 = CTA-pair kernel (tcgen05 cta_group::2), 0 = single-CTA kernel
-static int g_conv3_pair = 0;
+// conv3 kernel choice (strive_mapenc_set_pair): 1 = CTA-pair kernel (tcgen05 cta_group::2, default), 0 = single-CTA kernel
+static int g_conv3_pair = 1;
 extern "C" int strive_mapenc_set_pair(int on) {
   g_conv3_pair = on ? 1 : 0;
   return 0;

@@ -78,6 +78,17 @@ def test_sample_batched_vs_reference():
     assert e_lp < 5e-3 and e_md < 1e-3          # sums of 32 terms (z-mu)^2/var with mu, var from the fp32 prior net (1e-5)
 
 
+def _gpu_loop_z_check(z, z_ref, ptr, lr, iters):
+    """Final latents of a GPU Adam loop against the reference's run.  Which crop pixels / near-tie arg-max routings flip is a property
+    of the rounding of the whole forward pass (it changes with any re-association in any kernel), and one flipped sign of a small
+    gradient moves an element by a full lr: so the check is distributional -- the bulk agrees tightly (the callers assert the median),
+    at most 3 % of the elements are off by more than ONE Adam step, at least one scene stays within one step everywhere, nothing
+    leaves the 2 lr iters an Adam run can move at all."""
+    dz = np.abs(z - z_ref)
+    assert float((dz > lr).mean()) < 0.03, float((dz > lr).mean())
+    _loop_z_check(z, z_ref, ptr, lr, iters, tight=lr, need_scenes=1)
+
+
 def _graph_with_future(sc, ego, FT, dev):
     graph = to_graph(sc, dev)
     fg = torch.zeros(sc['z'].size(0), FT, 6)
@@ -126,7 +137,7 @@ def test_adv_loop_vs_reference_run_adv_gen_optim(fused):
     # fp32 forward noise (crop pixel flips, 1e-5 on map_feat) reaches Adam's normalised steps: the bulk of the latents stays
     # within 2e-3 of the reference run, every element within the 2*lr*iters an Adam run can move at all
     assert float(np.median(np.abs(dz))) < 2e-3
-    _loop_z_check(z.cpu().numpy(), g['z'], sc['ptr'].numpy(), lr, iters, tight=5e-2, need_scenes=2)
+    _gpu_loop_z_check(z.cpu().numpy(), g['z'], sc['ptr'].numpy(), lr, iters)
     assert tuple(traj.shape) == g['traj'].shape and tuple(out['future_pred'].shape) == g['final_pred'].shape
     assert list(min_agt) == list(g['min_agt']) and list(min_t) == list(g['min_t'])
     assert np.abs(traj[ego.to(dev), 0].cpu().numpy() - g['traj'][ego.numpy(), 0]).max() < 1e-6       # ego rows = the planner's future
@@ -167,7 +178,7 @@ def test_sol_loop_vs_reference_run_find_solution_optim(fused):
     assert max(v for k, v in worst.items() if not k.startswith('other')) < 5e-3 and max(worst['other_loss'], worst['other_match_ext_loss']) < 5e-2
     assert tuple(z.shape) == g['z'].shape and tuple(sol_traj.shape) == g['sol_traj'].shape and tuple(out['future_pred'].shape) == g['sol_pred'].shape
     assert float(np.median(np.abs(z[:, 0].cpu().numpy() - g['z'][:, 0]))) < 2e-3
-    _loop_z_check(z[:, 0].cpu().numpy(), g['z'][:, 0], sc['ptr'].numpy(), lr, iters, tight=5e-2, need_scenes=2)
+    _gpu_loop_z_check(z[:, 0].cpu().numpy(), g['z'][:, 0], sc['ptr'].numpy(), lr, iters)
     # non-target agents keep the adversarial result (sol_optim.py:120-121)
     assert np.abs(sol_traj[~ego.to(dev)].cpu().numpy() - g['sol_traj'][~ego.numpy()]).max() < 1e-5
 

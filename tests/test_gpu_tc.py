@@ -90,7 +90,7 @@ def test_conv3_on_cta_pairs_matches_the_single_cta_kernel():
         sub = [model.encode_map_poses(pose[:n].contiguous(), mapix[:n].contiguous(), env).clone() for n in (1, 3, 150)]
         torch.cuda.synchronize()
     finally:
-        L.strive_mapenc_set_pair(0)
+        L.strive_mapenc_set_pair(1)          # the default
     d = (f_pair - f_single).abs().max().item()
     diag('conv3 on CTA pairs vs single-CTA kernel: max |feature diff| %.2e on %d crops (max |feature| %.2f)' % (d, N, f_single.abs().max().item()))
     assert torch.equal(f_pair, f_pair2)
