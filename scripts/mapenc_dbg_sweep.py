@@ -26,14 +26,15 @@ for _ in range(2):
     f = model.encode_map_poses(pose, mapix, env)
 torch.cuda.synchronize()
 ref = f.clone()
-if os.environ.get('STRIVE_MAPENC_PAIR') == '1':      # A/B of conv3 on CTA pairs against the single-CTA kernel, same process
+if os.environ.get('STRIVE_MAPENC_PAIR', '0') != '0':      # A/B of the CTA-pair kernels against the single-CTA kernels, same process
+    mask = int(os.environ['STRIVE_MAPENC_PAIR'])
     _cabi.lib().strive_mapenc_set_pair(0)
     f1 = model.encode_map_poses(pose, mapix, env)
-    _cabi.lib().strive_mapenc_set_pair(1)
+    _cabi.lib().strive_mapenc_set_pair(mask)
     f2 = model.encode_map_poses(pose, mapix, env)
     torch.cuda.synchronize()
-    print('conv3 pair kernel vs single-CTA kernel: max |feature diff| %.3e (max |feature| %.3f); pair kernel run to run %.1e' % (
-        float((f1 - ref).abs().max()), float(ref.abs().max()), float((f2 - ref).abs().max())))
+    print('pair kernels (mask %d) vs single-CTA kernels: max |feature diff| %.3e (max |feature| %.3f); pair kernels run to run %.1e' % (
+        mask, float((f1 - ref).abs().max()), float(ref.abs().max()), float((f2 - ref).abs().max())))
 print('%s: feature sha1 %s' % (os.environ.get('STRIVE_LIB', 'in-tree library'), hashlib.sha1(ref.cpu().numpy().tobytes()).hexdigest()))
 names = ('crop_pack', 'tc_conv1', 'tc_conv2', 'tc_conv3', 'tc_conv4', 'tc_conv5', 'tc_conv6', 'tc_fc')
 for fl in FLAGS:

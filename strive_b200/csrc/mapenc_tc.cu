@@ -1920,17 +1920,39 @@ static int tc_launch(const char* name, const float* in, const double* in_stats, 
   return 0;
 }
 
+// conv3 kernel choice (strive_mapenc_set_pair): 1 = CTA-pair kernel (tcgen05 cta_group::2, default), 0 = single-CTA kernel.
+// (conv2 was built the same way -- Z_r of 32 rows, four operand buffers, four accumulators, outputs within 1e-5 of the single-CTA
+// kernel -- and measured 825 us against 765 us per 2048 crops: with the B bytes halved its MMAs need 1880 cycles per tile, but the
+// producers + the epilogue of that layer need ~3100 whatever the MMA side does.  Removed.)
+static int g_pair_mask = 1;
+extern "C" int strive_mapenc_set_pair(int on) {
+  g_pair_mask = on ? 1 : 0;
+  return 0;
+}
+// how many CTA pairs of `kern` can be resident at once (a GPC with an odd number of usable SMs leaves one of them without a partner)
+template <typename K>
+static int max_resident_pairs(K kern, size_t smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * num_sms());
+  cfg.blockDim = dim3(T2_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int nc = 0;
+  if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess) {
+    (void)cudaGetLastError();
+    nc = 0;
+  }
+  return nc;
+}
+
 int tc_launch_conv2(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const float* h_bias,
                     float* out, double* out_stats, int n, cudaStream_t stream) {
   return tc_launch<16, 5, 125, 61, 32, 32, 3, true>("tc_conv2", in, in_stats, gam, bet, wpack, h_bias, out, out_stats, n, stream);
 }
-// conv3 kernel choice (strive_mapenc_set_pair): 1 = CTA-pair kernel (tcgen05 cta_group::2, default), 0 = single-CTA kernel
-static int g_conv3_pair = 1;
-extern "C" int strive_mapenc_set_pair(int on) {
-  g_conv3_pair = on ? 1 : 0;
-  return 0;
-}
-
 int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, const float* bet, const uint8_t* wpack, const uint8_t* wpack_pair,
                     const float* h_bias, float* out, double* out_stats, int n, cudaStream_t stream) {
   using Cfg = TcCfg<32, 5, 61, 29, 64, 64, T3_NBUF>;
@@ -1942,25 +1964,12 @@ int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, c
   if (!attr) {
     STRIVE_CUDA(cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     STRIVE_CUDA(cudaFuncSetAttribute(tc_conv3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
-    // how many CTA pairs can be resident at once (a GPC with an odd number of usable SMs leaves one of them without a partner)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * num_sms());
-    cfg.blockDim = dim3(T2_THREADS);
-    cfg.dynamicSmemBytes = SMEM_PAIR;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, tc_conv3_pair_kernel, &cfg) != cudaSuccess) {
-      (void)cudaGetLastError();
-      max_clusters = 0;
-    }
+    max_clusters = max_resident_pairs(tc_conv3_pair_kernel, SMEM_PAIR);
     if (getenv("STRIVE_TC_VERBOSE")) fprintf(stderr, "strive_b200: conv3 pair kernel: %d CTA pairs resident on %d SMs\n", max_clusters, num_sms());
     attr = true;
   }
   const BiasArg bias = make_bias(h_bias, 64);
-  if (g_conv3_pair && wpack_pair != nullptr && 2 * max_clusters >= num_sms() - 8) {
+  if ((g_pair_mask & 1) && wpack_pair != nullptr && 2 * max_clusters >= num_sms() - 8) {
     int ncl = max_clusters < n ? max_clusters : n;       // one crop is the unit of work of a pair
     KPROF("tc_conv3", stream, STRIVE_CUDA_LAUNCH(tc_conv3_pair_kernel, 2 * ncl, T2_THREADS, SMEM_PAIR, stream, in, in_stats, gam, bet, wpack_pair, bias, out, out_stats, n));
     STRIVE_LAUNCH_CHECK();
