@@ -65,7 +65,7 @@ SM_PATH_EXTRA_BYTES_PER_CROP = {'tc_conv2': 32 * (665 * 16 * 4 + 128 * 32 * 4),
                                 'tc_conv3': 8 * (2 * 665 * 16 * 4 + 128 * 64 * 4),
                                 'tc_conv1': 32 * (666 * 4 + 512 * 16 * 4)}
 SMEM_BYTES_PER_CROP = {'tc_conv2': 32 * (25 * (4096 + 2048 + 4096 + 1024) + 665 * 16 * 4),
-                       'tc_conv3': 8 * 2 * (25 * (4096 + 4096 + 4096 + 2048) + 665 * 16 * 4 + 25600),
+                       'tc_conv3': 8 * 2 * (25 * (4096 + 2048 + 4096 + 1024) + 665 * 16 * 4 + 4096),      # CTA-pair kernel: half of every B operand per SM
                        'tc_conv1': 32 * (28 * (4096 + 1536) + 21312)}
 
 
@@ -377,8 +377,8 @@ def run_gpu(args):
             dp_ach = (SMEM_BYTES_PER_CROP[top[0]] + SM_PATH_EXTRA_BYTES_PER_CROP[top[0]]) * crops_per_launch / avg_s
             roof['sm_datapath'] = {'achieved_tbs': dp_ach / 1e12, 'peak_tbs': sm_peak / 1e12, 'frac': dp_ach / sm_peak,
                                    'note': 'smem_operand + the global loads of the input tile and the global stores of the output tile, which cross the same '
-                                           'L1/shared data path (128 B/clk/SM at the sampled SM clock): the binding resource -- by the kernels\' own cycle '
-                                           'counters conv2 runs at 0.97 and conv3 at 0.975 of it (DESIGN.md 9)'}
+                                           'L1/shared data path (128 B/clk/SM at the sampled SM clock); by the kernel\'s own cycle counters conv2 runs at 0.98 of it -- and at '
+                                           'the instruction-issue capacity of its producer warps, the two limits are equally high (DESIGN.md 9)'}
     if roof is not None:
         # BASELINE.json asks for the fraction of the HBM roofline by name: algorithmic bytes of the WHOLE step over its duration
         gbs = ALGO_BYTES_PER_UNIT * units_per_step / (ms / args.steps / 1000.0) / 1e9
