@@ -75,7 +75,7 @@ int strive_mapenc_set_impl(int impl);
 int strive_mapenc_set_split(int on);
 /* conv3 of the tensor-core encoder on CTA pairs (tcgen05 cta_group::2, clusters of two CTAs): 1 = on (default), 0 = single-CTA kernel
  * (A/B; also the automatic fallback when the device cannot hold ~74 CTA pairs at once).  The two kernels agree to fp32 re-association
- * level (1e-5 on the features); each is bitwise reproducible and batch-invariant. */
+ * level (1e-5 on the features); each is bitwise reproducible and batch-invariant.  2 = pairs even when fewer of them fit (tools). */
 int strive_mapenc_set_pair(int on);
 /* Edge MLP of the decoder GNN (interaction_net.py:139-184) on the warp-level tensor path: the library packs the edge-MLP
  * matrices of the weight blob into mma.sync fragment order inside `buf` (device, 16-byte aligned,

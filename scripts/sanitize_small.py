@@ -6,6 +6,8 @@ import torch
 import strive_b200
 from strive_b200 import synth
 from strive_b200.optim import RefineLoop, AdvLoop
+from strive_b200 import _cabi
+_cabi.lib().strive_mapenc_set_pair(2)          # conv3 on CTA pairs whatever residency the tool leaves
 dev = torch.device('cuda:0')
 raster, dx = synth.make_raster(seed=3, M=2, H=1280, W=1280)
 sd = synth.make_weights(0)

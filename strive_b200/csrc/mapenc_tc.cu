@@ -1926,7 +1926,7 @@ static int tc_launch(const char* name, const float* in, const double* in_stats, 
 // producers + the epilogue of that layer need ~3100 whatever the MMA side does.  Removed.)
 static int g_pair_mask = 1;
 extern "C" int strive_mapenc_set_pair(int on) {
-  g_pair_mask = on ? 1 : 0;
+  g_pair_mask = on == 2 ? 3 : (on ? 1 : 0);     // 2 = pairs even when fewer than ~74 of them fit at once (tests under tools that limit residency)
   return 0;
 }
 // how many CTA pairs of `kern` can be resident at once (a GPC with an odd number of usable SMs leaves one of them without a partner)
@@ -1969,7 +1969,7 @@ int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, c
     attr = true;
   }
   const BiasArg bias = make_bias(h_bias, 64);
-  if ((g_pair_mask & 1) && wpack_pair != nullptr && 2 * max_clusters >= num_sms() - 8) {
+  if ((g_pair_mask & 1) && wpack_pair != nullptr && (2 * max_clusters >= num_sms() - 8 || ((g_pair_mask & 2) && max_clusters >= 1))) {
     int ncl = max_clusters < n ? max_clusters : n;       // one crop is the unit of work of a pair
     KPROF("tc_conv3", stream, STRIVE_CUDA_LAUNCH(tc_conv3_pair_kernel, 2 * ncl, T2_THREADS, SMEM_PAIR, stream, in, in_stats, gam, bet, wpack_pair, bias, out, out_stats, n));
     STRIVE_LAUNCH_CHECK();
