@@ -1234,8 +1234,8 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
 //     D[:, 0:128]  += A_hi * [Z_0 ; Z_1]^T                  N = 128: columns  hi(0:32) | lo(0:32) | hi(32:64) | lo(32:64)
 //     D[:, 32:96]  += A_lo * [Z_0[0:32] ; Z_1[0:32]]^T      N = 64 on the SAME block: the W_hi rows, landing on lo(0:32) | hi(32:64)
 // and the epilogue adds column c to column c + 32 (channels 0-31) resp. 64 + c' to 96 + c' (channels 32-63).  An SM thus fetches
-// 3 KB instead of 6 KB of weights per tap and K chunk through its 128 B/clk data path, and a chunk is 50 KB per CTA: taps 0-16 of
-// BOTH chunks stay resident, only taps 17-24 (16 KB) are swapped once per tile pair -- behind the 17 resident taps of the next job --
+// 3 KB instead of 6 KB of weights per tap and K chunk through its 128 B/clk data path, and a chunk is 50 KB per CTA: taps 0-20 of
+// BOTH chunks stay resident, only taps 21-24 (8 KB) are swapped once per tile pair -- behind the 21 resident taps of the next job --
 // and three operand buffers fit.  (Small terms are summed apart from the hi x hi products here, so the results differ from the
 // single-CTA kernel in the last bits; both are batch-invariant.)
 // Only the leader issues MMAs.  Cross-CTA signalling:
@@ -1245,9 +1245,9 @@ __global__ void __launch_bounds__(T2_THREADS) tc_conv3_kernel(const float* __res
 #define T3P_NBUF 3
 #define T3P_TAP_BYTES 2048
 #define T3P_CHUNK_BYTES (25 * T3P_TAP_BYTES)                 // one K chunk of one rank in the weight pack
-#define T3P_H0_TAPS 17
-#define T3P_R0_BYTES (T3P_H0_TAPS * T3P_TAP_BYTES)           // taps 0..16 of one chunk (resident for both chunks)
-#define T3P_R1_BYTES ((25 - T3P_H0_TAPS) * T3P_TAP_BYTES)    // taps 17..24 of the current chunk (swapped)
+#define T3P_H0_TAPS 21
+#define T3P_R0_BYTES (T3P_H0_TAPS * T3P_TAP_BYTES)           // taps 0..20 of one chunk (resident for both chunks)
+#define T3P_R1_BYTES ((25 - T3P_H0_TAPS) * T3P_TAP_BYTES)    // taps 21..24 of the current chunk (swapped)
 #define T3P_WBYTES (2 * T3P_R0_BYTES + T3P_R1_BYTES)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -1296,7 +1296,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3
   constexpr int PH = Cfg::PH, PW = Cfg::PW, PQ = Cfg::PQ, TAPS = Cfg::TAPS;
   static_assert(Cfg::TILES == 8, "conv3 pair kernel: a crop is 4 tiles per CTA = 2 tile pairs of alternating parity");
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sW = smem;                          // [taps 0-16 of chunk 0][taps 0-16 of chunk 1][taps 17-24 of the current chunk]
+  uint8_t* sW = smem;                          // [taps 0-20 of chunk 0][taps 0-20 of chunk 1][taps 21-24 of the current chunk]
   uint8_t* sW1 = smem + 2 * T3P_R0_BYTES;
   uint8_t* sA = smem + T3P_WBYTES;
   __shared__ __align__(8) uint64_t full[NBUF], empty[NBUF], acc_full[4], acc_empty[4], w_full, w_free;
@@ -1310,7 +1310,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3
   const int npairs = 2 * (crop_hi - crop_lo);            // local pair p: crop crop_lo + p / 2, tiles 4 rank + 2 (p & 1) + {0, 1}; parity p & 1
   const uint8_t* wrank = wpack + (size_t)rank * 2 * T3P_CHUNK_BYTES;
   {
-    // resident: taps 0-16 of both chunks; the first pair starts with K chunk 0: its taps 17-24
+    // resident: taps 0-20 of both chunks; the first pair starts with K chunk 0: its taps 21-24
     for (int i = tid; i < T3P_WBYTES / 16; i += T2_THREADS) {
       const int byte = i * 16;
       const int src = byte < T3P_R0_BYTES ? byte : (byte < 2 * T3P_R0_BYTES ? T3P_CHUNK_BYTES + (byte - T3P_R0_BYTES) : T3P_R0_BYTES + (byte - 2 * T3P_R0_BYTES));
@@ -1463,7 +1463,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS) tc_conv3
     }
     if (tid == 0 && leader) trace_add(2, 7, 1);
   } else if (warp == T3_LOAD_WARP) {
-    // ---------------- weight loader: taps 17-24 of this CTA's half of the other K chunk, once per pair ----------------
+    // ---------------- weight loader: taps 21-24 of this CTA's half of the other K chunk, once per pair ----------------
     if (tc::elect_one()) {
       for (int p = 0; p < npairs; p++) {
         const uint8_t* src = wrank + (size_t)(1 - (p & 1)) * T3P_CHUNK_BYTES + T3P_R0_BYTES;
