@@ -75,6 +75,17 @@ inline cudaError_t strive_launch(int pdl_class, void (*kern)(KArgs...), dim3 gri
 
 #define STRIVE_CUDA_LAUNCH(kern, grid, block, smem, stream, ...) (void)strive_launch(STRIVE_PDL_CLASS, kern, dim3(grid), dim3(block), (size_t)(smem), stream, __VA_ARGS__)
 
+// Function attributes (opt-in dynamic shared memory) belong to a device, not to the process: every launcher keeps a bitmask of the
+// devices it has configured (one process per GPU is the intended use; a process that drives several devices must still work).
+static inline bool strive_first_use_on_device(unsigned* done_mask, int* dev_out = nullptr) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) dev = 0;
+  if (dev_out) *dev_out = dev;
+  if (*done_mask & (1u << dev)) return false;
+  *done_mask |= 1u << dev;
+  return true;
+}
+
 enum StriveErr { STRIVE_OK = 0, STRIVE_EINVAL = 1, STRIVE_ESIZE = 2, STRIVE_EUNSUPPORTED = 3 };
 
 // ------------------------------------------------------------------------------------------------------

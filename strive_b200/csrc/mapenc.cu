@@ -318,10 +318,9 @@ static int launch_conv(const char* name, const float* in, const double* in_stats
   using Cfg = ConvCfg<CIN, COUT, KS, HIN, HOUT, TH, TW, G, CC, COC, PXT, FINAL>;
   static_assert(CIN % CC == 0 && COUT % COC == 0 && COC % 4 == 0 && (TH % PXT) == 0, "bad conv tiling");
   auto kern = conv_gn_kernel<CIN, COUT, KS, HIN, HOUT, TH, TW, G, CC, COC, PXT, FINAL, IN_NHWC>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned attr_done = 0;
+  if (strive_first_use_on_device(&attr_done)) {
     STRIVE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    attr_done = true;
   }
   dim3 grid(Cfg::TILES, (n + G - 1) / G, COUT / COC);
   KPROF(name, stream, kern<<<grid, Cfg::NTHREADS, Cfg::SMEM, stream>>>(in, in_stats, gam, bet, Wk, bias, out, out_stats, n));

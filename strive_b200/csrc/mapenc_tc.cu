@@ -1878,11 +1878,10 @@ static BiasArg make_bias(const float* h_bias, int nb) {
 
 int tc_launch_conv1(const StriveMap* map, const float* pose, const int32_t* map_of, const uint8_t* wpack, const float* h_bias, float* out,
                     double* out_stats, uint8_t* packed_crop, int n, cudaStream_t stream) {
-  static bool attr = false;
+  static unsigned attr = 0;
   const size_t smem = T1_WBYTES + T1_NBUF * T1_PATCH_BYTES;
-  if (!attr) {
+  if (strive_first_use_on_device(&attr)) {
     STRIVE_CUDA(cudaFuncSetAttribute(tc_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   STRIVE_CHECK(map->packed != nullptr, STRIVE_EINVAL, "tensor-core map encoder needs StriveMap.packed");
   STRIVE_CHECK(map->packed_pitch >= map->W && (map->packed_pitch & 15) == 0 && ((uintptr_t)map->packed & 15) == 0, STRIVE_EINVAL, "StriveMap.packed_pitch must be >= W and a multiple of 16, packed 16-byte aligned");
@@ -1904,10 +1903,9 @@ static int tc_launch(const char* name, const float* in, const double* in_stats, 
   static_assert(COUT % NCH == 0 && (NCH == 32 || NCH == 64) && CIN % 16 == 0, "tc conv tiling");
   static_assert(Cfg::SMEM <= 225 * 1024, "tc conv shared memory");
   auto kern = tc_conv_kernel<CIN, KS, HIN, HOUT, COUT, NCH, NBUF, OUT_BLK>;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned attr = 0;
+  if (strive_first_use_on_device(&attr)) {
     STRIVE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    attr = true;
   }
   const int items = n * Cfg::TILES;
   int gx = num_sms() / (COUT / NCH);
@@ -1959,15 +1957,18 @@ int tc_launch_conv3(const float* in, const double* in_stats, const float* gam, c
   constexpr size_t SMEM = (size_t)T3_WCHUNK + (size_t)T3_NBUF * Cfg::A_BYTES;
   constexpr size_t SMEM_PAIR = (size_t)T3P_WBYTES + (size_t)T3P_NBUF * Cfg::A_BYTES;
   static_assert(SMEM <= 225 * 1024 && SMEM_PAIR <= 225 * 1024, "conv3 shared memory");
-  static bool attr = false;
-  static int max_clusters = 0;
-  if (!attr) {
+  static unsigned attr = 0;
+  static int max_clusters_dev[32] = {};
+  int dev = 0;
+  if (strive_first_use_on_device(&attr, &dev)) {
+    int max_clusters = 0;
     STRIVE_CUDA(cudaFuncSetAttribute(tc_conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     STRIVE_CUDA(cudaFuncSetAttribute(tc_conv3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
     max_clusters = max_resident_pairs(tc_conv3_pair_kernel, SMEM_PAIR);
     if (getenv("STRIVE_TC_VERBOSE")) fprintf(stderr, "strive_b200: conv3 pair kernel: %d CTA pairs resident on %d SMs\n", max_clusters, num_sms());
-    attr = true;
+    max_clusters_dev[dev] = max_clusters;
   }
+  const int max_clusters = max_clusters_dev[dev];
   const BiasArg bias = make_bias(h_bias, 64);
   if ((g_pair_mask & 1) && wpack_pair != nullptr && (2 * max_clusters >= num_sms() - 8 || ((g_pair_mask & 2) && max_clusters >= 1))) {
     int ncl = max_clusters < n ? max_clusters : n;       // one crop is the unit of work of a pair
@@ -1993,10 +1994,9 @@ static int tc3_launch(const char* name, const float* in, const double* in_stats,
   using Cfg = Tc3Cfg<CIN, KS, HIN, HOUT, COUT, FINAL>;
   static_assert(Cfg::SMEM <= 226 * 1024, "tc gemm shared memory");
   auto kern = tc_gemm_kernel<CIN, KS, HIN, HOUT, COUT, FINAL>;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned attr = 0;
+  if (strive_first_use_on_device(&attr)) {
     STRIVE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    attr = true;
   }
   const long long rows = (long long)n * Cfg::PIX;
   const int tiles = (int)((rows + 127) / 128);

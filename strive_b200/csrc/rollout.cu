@@ -1324,8 +1324,8 @@ extern "C" int strive_model_set_edge_frags(StriveModel* m, void* buf, int64_t by
 }
 
 static int set_smem_attrs() {
-  static bool done = false;
-  if (done) return 0;
+  static unsigned done = 0;
+  if (!strive_first_use_on_device(&done)) return 0;
   STRIVE_CUDA(cudaFuncSetAttribute(edge_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_EDGE_B));
   STRIVE_CUDA(cudaFuncSetAttribute(edge_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_FWD_SMEM));
   STRIVE_CUDA(cudaFuncSetAttribute(edge_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EM_BWD_SMEM));
@@ -1337,7 +1337,6 @@ static int set_smem_attrs() {
   STRIVE_CUDA(cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_GRU_B));
   STRIVE_CUDA(cudaFuncSetAttribute(post_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_POST_B));
   STRIVE_CUDA(cudaFuncSetAttribute(node_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_NODE_B));
-  done = true;
   return 0;
 }
 
