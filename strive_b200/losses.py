@@ -172,12 +172,13 @@ def run_loss(plan, scene_struct, traj, z_full, prior_mu, prior_var, init_z, matc
     if terms is None:
         terms = torch.empty((plan.G, _cabi.STRIVE_TERMS), dtype=torch.float32, device=dev)
     ws = plan.workspace(FT)
-    _cabi.check(L.strive_loss_fwd_bwd(C.byref(plan.cfg), C.byref(scene_struct), C.byref(plan.env.cstruct), FT,
-                                      _cabi.dptr(traj), _cabi.dptr(z_full), _cabi.dptr(prior_mu), _cabi.dptr(prior_var),
-                                      _cabi.dptr(init_z), _cabi.dptr(plan.z_mask), _cabi.dptr(match_tgt),
-                                      _cabi.dptr(plan.match_mask), _cabi.dptr(adv_tgt), _cabi.dptr(d_traj),
-                                      _cabi.dptr(d_traj_match), _cabi.dptr(d_z), _cabi.dptr(terms), _cabi.dptr(ws),
-                                      ws.numel(), _cabi.stream_ptr()))
+    with torch.cuda.device(traj.device):
+        _cabi.check(L.strive_loss_fwd_bwd(C.byref(plan.cfg), C.byref(scene_struct), C.byref(plan.env.cstruct), FT,
+                                          _cabi.dptr(traj), _cabi.dptr(z_full), _cabi.dptr(prior_mu), _cabi.dptr(prior_var),
+                                          _cabi.dptr(init_z), _cabi.dptr(plan.z_mask), _cabi.dptr(match_tgt),
+                                          _cabi.dptr(plan.match_mask), _cabi.dptr(adv_tgt), _cabi.dptr(d_traj),
+                                          _cabi.dptr(d_traj_match), _cabi.dptr(d_z), _cabi.dptr(terms), _cabi.dptr(ws),
+                                          ws.numel(), _cabi.stream_ptr()))
     return d_traj, d_traj_match, d_z, terms
 
 

@@ -50,8 +50,9 @@ def check_on_layer(map_env, layer, cars, lw, mapixes):
     lin_w = torch.linspace(-1.0, 1.0, W, device=dev)
     out = torch.empty(B, dtype=torch.float32, device=dev)
     mo = mapixes.detach().to(dev, torch.int32).contiguous()
-    _cabi.check(_cabi.lib().strive_on_layer_frac(C.byref(env.cstruct), int(layer), _cabi.dptr(cars), _cabi.dptr(lw), _cabi.dptr(mo),
-                                                 _cabi.dptr(lin_l), _cabi.dptr(lin_w), L, W, B, _cabi.dptr(out), _cabi.stream_ptr()))
+    with torch.cuda.device(out.device):
+        _cabi.check(_cabi.lib().strive_on_layer_frac(C.byref(env.cstruct), int(layer), _cabi.dptr(cars), _cabi.dptr(lw), _cabi.dptr(mo),
+                                                     _cabi.dptr(lin_l), _cabi.dptr(lin_w), L, W, B, _cabi.dptr(out), _cabi.stream_ptr()))
     return out
 
 
@@ -98,8 +99,9 @@ def check_line_layer(map_env, layer, start, end, mapixes):
     hit = torch.zeros(B, dtype=torch.uint8, device=dev)
     oob = torch.zeros(1, dtype=torch.int32, device=dev)
     mo = mapixes.detach().to(dev, torch.int32).contiguous()
-    _cabi.check(_cabi.lib().strive_line_layer(C.byref(env.cstruct), int(layer), _cabi.dptr(start), _cabi.dptr(end), _cabi.dptr(mo),
-                                              _cabi.dptr(lin01), NL, B, _cabi.dptr(hit), _cabi.dptr(oob), _cabi.stream_ptr()))
+    with torch.cuda.device(hit.device):
+        _cabi.check(_cabi.lib().strive_line_layer(C.byref(env.cstruct), int(layer), _cabi.dptr(start), _cabi.dptr(end), _cabi.dptr(mo),
+                                                  _cabi.dptr(lin01), NL, B, _cabi.dptr(hit), _cabi.dptr(oob), _cabi.stream_ptr()))
     if int(oob.item()) != 0:
         raise RuntimeError('strive_b200.check_line_layer: %d samples index outside the raster '
                            '(the reference raises IndexError here, nuscenes_utils.py:329)' % int(oob.item()))
@@ -113,8 +115,9 @@ def _iou_hits(traj_a, lw_a, traj_b, lw_b, want_iou=False):
     nb = tb.size(0)
     hit = torch.zeros((na, nb, T), dtype=torch.uint8, device=dev)
     iou = torch.zeros((na, nb, T), dtype=torch.float32, device=dev) if want_iou else None
-    _cabi.check(_cabi.lib().strive_veh_iou_hits(_cabi.dptr(ta), _cabi.dptr(la), na, _cabi.dptr(tb), _cabi.dptr(lb), nb, T,
-                                                float(VEH_COLL_THRESH), _cabi.dptr(hit), _cabi.dptr(iou), _cabi.stream_ptr()))
+    with torch.cuda.device(hit.device):
+        _cabi.check(_cabi.lib().strive_veh_iou_hits(_cabi.dptr(ta), _cabi.dptr(la), na, _cabi.dptr(tb), _cabi.dptr(lb), nb, T,
+                                                    float(VEH_COLL_THRESH), _cabi.dptr(hit), _cabi.dptr(iou), _cabi.stream_ptr()))
     return hit, iou
 
 

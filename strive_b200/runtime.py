@@ -31,16 +31,17 @@ class DeviceModel(object):
         self.num_classes = num_classes
         arr = (C.c_int64 * len(sizes))(*sizes)
         h = C.c_void_p()
-        _cabi.check(L.strive_model_create(_cabi.dptr(self.blob), self.blob.numel(), arr, len(sizes), num_classes, C.byref(h)))
-        self.handle = h
         tcb = pack_tc_weights(state_dict)
         if tcb.numel() != L.strive_model_tc_bytes():
             raise RuntimeError('strive_b200: tensor-core weight packing size mismatch')
-        self.tc_blob = tcb.to(device)
-        _cabi.check(L.strive_model_set_tc_weights(h, _cabi.dptr(self.tc_blob), self.tc_blob.numel()))
-        # mma.sync fragment packs of the edge MLP, packed on the device from the blob (csrc/edge_mma.cuh)
-        self.edge_frags = torch.empty(L.strive_model_edge_frag_bytes(), dtype=torch.uint8, device=device)
-        _cabi.check(L.strive_model_set_edge_frags(h, _cabi.dptr(self.edge_frags), self.edge_frags.numel(), _cabi.stream_ptr()))
+        with torch.cuda.device(self.blob.device):       # the library works on the CURRENT device: make it the model's
+            _cabi.check(L.strive_model_create(_cabi.dptr(self.blob), self.blob.numel(), arr, len(sizes), num_classes, C.byref(h)))
+            self.handle = h
+            self.tc_blob = tcb.to(device)
+            _cabi.check(L.strive_model_set_tc_weights(h, _cabi.dptr(self.tc_blob), self.tc_blob.numel()))
+            # mma.sync fragment packs of the edge MLP, packed on the device from the blob (csrc/edge_mma.cuh)
+            self.edge_frags = torch.empty(L.strive_model_edge_frag_bytes(), dtype=torch.uint8, device=device)
+            _cabi.check(L.strive_model_set_edge_frags(h, _cabi.dptr(self.edge_frags), self.edge_frags.numel(), _cabi.stream_ptr()))
 
     def __del__(self):
         try:
@@ -85,8 +86,9 @@ class MapEnv(object):
         """(N,4) unnormalised poses -> (N,C,256,256) uint8 (reference get_map_obs, nuscenes_utils.py:236-264)."""
         n = pose_un.size(0)
         out = torch.empty((n, self.num_layers, self.L, self.W), dtype=torch.uint8, device=self.device)
-        _cabi.check(_cabi.lib().strive_map_crop(C.byref(self.cstruct), _cabi.dptr(pose_un.contiguous().float()),
-                                                _cabi.dptr(_i32(mapixes, self.device)), n, _cabi.dptr(out), _cabi.stream_ptr()))
+        pose_c, mix = pose_un.contiguous().float(), _i32(mapixes, self.device)
+        with torch.cuda.device(out.device):
+            _cabi.check(_cabi.lib().strive_map_crop(C.byref(self.cstruct), _cabi.dptr(pose_c), _cabi.dptr(mix), n, _cabi.dptr(out), _cabi.stream_ptr()))
         return out
 
     def get_map_crop(self, scene_graph, map_idx, bounds=None, L=None, W=None):

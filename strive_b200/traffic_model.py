@@ -165,9 +165,10 @@ class _DecodeFn(torch.autograd.Function):
         lease = _TapeLease(nbytes, z.device)
         tape = lease.buf
         ext = None if ext_future is None else ext_future.detach().contiguous().float()
-        _cabi.check(L.strive_decode_fwd(model.handle, C.byref(scene.cstruct), C.byref(env.cstruct), _cabi.dptr(z),
-                                        _cabi.dptr(map_feat), _cabi.dptr(past_feat), _cabi.dptr(ext), FT,
-                                        _cabi.dptr(traj), _cabi.dptr(tape), nbytes, _cabi.stream_ptr()))
+        with torch.cuda.device(z.device):
+            _cabi.check(L.strive_decode_fwd(model.handle, C.byref(scene.cstruct), C.byref(env.cstruct), _cabi.dptr(z),
+                                            _cabi.dptr(map_feat), _cabi.dptr(past_feat), _cabi.dptr(ext), FT,
+                                            _cabi.dptr(traj), _cabi.dptr(tape), nbytes, _cabi.stream_ptr()))
         ctx.model, ctx.scene, ctx.tape, ctx.nbytes, ctx.ext, ctx.FT = model, scene, tape, nbytes, ext, FT
         ctx.lease = lease        # returned to the free list when this node is freed
         return traj
