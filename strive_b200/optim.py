@@ -147,7 +147,9 @@ class _DeviceLoop(object):
         torch.cuda.synchronize(self.dev)
         # the capture must not disturb the state the eager iteration left: a capture records launches without running them
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # an explicit capture stream on THIS loop's device: torch.cuda.graph's default capture stream is one class-wide stream on the
+        # device of the first capture of the process, and entering it would switch the current device away from the loop's tensors
+        with torch.cuda.graph(g, stream=torch.cuda.Stream(device=self.dev)):
             self._iteration()
         self.graph = g
 
