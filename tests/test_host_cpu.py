@@ -91,3 +91,22 @@ def test_tape_lease_recycles_buffers_and_bounds_the_free_list():
     other = _TapeLease(8192, dev)
     assert other.buf.numel() == 8192
     _TapeLease.release_all()
+
+
+def test_conv3_cta_pair_weight_pack_is_the_split_of_the_single_cta_pack():
+    """pack_tc_weights: the last blob segment holds conv3 for the CTA-pair kernel -- per CTA rank, K chunk and tap ONE 64-row block
+    [W_hi rows 32r..32r+31 ; W_lo rows 32r..32r+31] in the same K-major layout -- i.e. exactly the rows of the single-CTA pack
+    ([khalf][prec][64 rows][8 k]) regrouped; sizes agree with the library's blob layout."""
+    from strive_b200 import _cabi, synth, weights
+    blob = weights.pack_tc_weights(synth.make_weights(0))
+    sizes = [7 * 2 * 48 * 16 + 64, 51200, 204800, 2 * (4 * 9 * 2 * 1024), 9 * 2 * 128 * 64 * 2, 18 * 2 * 128 * 64 * 2, 8 * 2 * 64 * 64 * 2,
+             2 * 2 * 25 * 2048]
+    assert blob.numel() == sum(sizes) == _cabi.lib().strive_model_tc_bytes()
+    off = [0]
+    for v in sizes:
+        off.append(off[-1] + v)
+    std = blob[off[2]:off[3]].view(torch.int16).reshape(2, 25, 2, 2, 64, 8)          # (c2, tap, khalf, prec, row, k)
+    pair = blob[off[7]:off[8]].view(torch.int16).reshape(2, 2, 25, 2, 64, 8)         # (rank, c2, tap, khalf, row, k)
+    for rank in (0, 1):
+        assert torch.equal(pair[rank][:, :, :, :32], std[:, :, :, 0, 32 * rank:32 * rank + 32])      # W_hi rows of this rank
+        assert torch.equal(pair[rank][:, :, :, 32:], std[:, :, :, 1, 32 * rank:32 * rank + 32])      # W_lo rows of this rank
