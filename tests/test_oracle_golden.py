@@ -209,3 +209,66 @@ def test_adv_loss_option_branches_match_reference():
         assert np.abs(z.grad.numpy() - g[name + '_d_z']).max() < 1e-6
         assert [int(v) for v in ld['min_agt']] == [int(v) for v in g[name + '_min_agt']]
         assert [int(v) for v in ld['min_t']] == [int(v) for v in g[name + '_min_t']]
+
+
+def test_rect_iou_against_an_independent_construction():
+    """Second, structurally different computation of the intersection area the reference gets from shapely (absent here): the
+    intersection of two convex quadrilaterals is the convex hull of {corners of A inside B} + {corners of B inside A} + {edge x edge
+    crossing points} (scipy.spatial.ConvexHull), against the oracle's Sutherland-Hodgman clipping, on random rotated rectangles
+    of vehicle proportions incl. touching / containing / disjoint configurations."""
+    from scipy.spatial import ConvexHull
+    from oracle import metrics_oracle as MO
+
+    def inside(p, quad):      # CCW quad, closed
+        for e in range(4):
+            a, b = quad[e], quad[(e + 1) % 4]
+            if (b[0] - a[0]) * (p[1] - a[1]) - (b[1] - a[1]) * (p[0] - a[0]) < -1e-12:
+                return False
+        return True
+
+    def seg_x(p, q, a, b):
+        r, s = q - p, b - a
+        den = r[0] * s[1] - r[1] * s[0]
+        if abs(den) < 1e-14:
+            return None
+        t = ((a[0] - p[0]) * s[1] - (a[1] - p[1]) * s[0]) / den
+        u = ((a[0] - p[0]) * r[1] - (a[1] - p[1]) * r[0]) / den
+        return p + t * r if (0.0 <= t <= 1.0 and 0.0 <= u <= 1.0) else None
+
+    def area(quad):
+        x, y = quad[:, 0], quad[:, 1]
+        return 0.5 * abs(float(np.sum(x * np.roll(y, -1) - np.roll(x, -1) * y)))
+
+    rng = np.random.RandomState(11)
+    worst, nonzero = 0.0, 0
+    for it in range(400):
+        l1, w1, l2, w2 = rng.uniform(3.5, 6.0), rng.uniform(1.6, 2.4), rng.uniform(3.5, 12.0), rng.uniform(1.6, 3.0)
+        a1, a2 = rng.uniform(-np.pi, np.pi, 2)
+        c2 = rng.uniform(-5.0, 5.0, 2) if it % 5 else np.zeros(2)          # every fifth pair concentric (containment / crossings)
+        A = np.asarray(MO.get_corners(np.array([0.0, 0.0, np.cos(a1), np.sin(a1)], dtype=np.float32), np.array([l1, w1], dtype=np.float32)), dtype=np.float64)
+        B = np.asarray(MO.get_corners(np.array([c2[0], c2[1], np.cos(a2), np.sin(a2)], dtype=np.float32), np.array([l2, w2], dtype=np.float32)), dtype=np.float64)
+        if 0.5 * float(np.sum(A[:, 0] * np.roll(A[:, 1], -1) - np.roll(A[:, 0], -1) * A[:, 1])) < 0:      # make both CCW for inside()
+            A = A[::-1]
+        if 0.5 * float(np.sum(B[:, 0] * np.roll(B[:, 1], -1) - np.roll(B[:, 0], -1) * B[:, 1])) < 0:
+            B = B[::-1]
+        pts = [p for p in A if inside(p, B)] + [p for p in B if inside(p, A)]
+        for i in range(4):
+            for j in range(4):
+                x = seg_x(A[i], A[(i + 1) % 4], B[j], B[(j + 1) % 4])
+                if x is not None:
+                    pts.append(x)
+        inter = 0.0
+        if len(pts) >= 3:
+            P = np.unique(np.round(np.array(pts), 12), axis=0)
+            if len(P) >= 3:
+                try:
+                    inter = float(ConvexHull(P).volume)
+                except Exception:          # degenerate (collinear) point set: zero area
+                    inter = 0.0
+        union = area(A) + area(B) - inter
+        ref = inter / union if union > 0 else 0.0
+        got = MO.rect_iou(A, B)
+        worst = max(worst, abs(got - ref))
+        nonzero += ref > 0
+    assert nonzero > 150, nonzero
+    assert worst < 1e-9, worst
